@@ -1,0 +1,225 @@
+"""Pins the oracle itself: finite differences (fp64) and an independent torch-autograd transcription.
+The reference has no tests/goldens (parity unpinned), so these are what stand behind the oracle."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fql_oracle as O
+
+
+def small_cfg(**kw):
+    cfg = dict(O.DEFAULT_CONFIG)
+    cfg.update(actor_hidden_dims=(24, 24, 24, 24), value_hidden_dims=(24, 24, 24, 24))
+    cfg.update(kw)
+    return cfg
+
+
+def setup(cfg, B=6, F=5, A=3, dtype=np.float64, seed=0):
+    params = O.init_params(seed, F, A, cfg, dtype=dtype, jitter=0.1, target_equals_critic=False)
+    batch = O.make_batch(seed + 1, B, F, A, dtype)
+    noise = O.make_noise(seed + 2, B, A, dtype)
+    return params, batch, noise
+
+
+@pytest.mark.parametrize('kw', [
+    dict(), dict(q_agg='min', alpha=10.0), dict(normalize_q_loss=True), dict(actor_layer_norm=True),
+    dict(layer_norm=False), dict(flow_steps=3, discount=0.995),
+])
+def test_finite_differences(kw):
+    cfg = small_cfg(**kw)
+    params, batch, noise = setup(cfg)
+    # push some actor outputs outside [-1,1] so the clip gate is exercised
+    params['modules_actor_onestep_flow']['mlp']['Dense_4']['bias'] += np.array([1.2, -0.1, 0.0])
+    loss, info, grads = O.total_loss(params, cfg, batch, noise)
+    rng = np.random.default_rng(5)
+    leaves = O.tree_leaves(params)
+    gl = dict(O.tree_leaves(grads))
+    eps = 1e-6
+    for path, arr in leaves:
+        g = gl[path]
+        for _ in range(3):
+            idx = tuple(rng.integers(0, s) for s in arr.shape)
+            old = arr[idx]
+            arr[idx] = old + eps
+            lp = O.total_loss(params, cfg, batch, noise, with_grads=False)[0]
+            arr[idx] = old - eps
+            lm = O.total_loss(params, cfg, batch, noise, with_grads=False)[0]
+            arr[idx] = old
+            fd = (lp - lm) / (2 * eps)
+            if path[0] == 'modules_target_critic':
+                # stored-params-only module: the true derivative is non-zero but the algorithm stops it
+                assert g[idx] == 0.0
+                continue
+            # stop-gradient structure: stored-param uses of critic/bc_flow/onestep contribute to FD but not to the
+            # algorithm's gradient, so compare against a FD that perturbs only the grad_params copy (below)
+    # proper check: FD on a loss where stored and grad params are separated
+    _fd_separated(cfg, params, batch, noise, grads)
+
+
+def _fd_separated(cfg, params, batch, noise, grads):
+    """FD of L(grad_params; stored_params) w.r.t. grad_params only, emulating `params=grad_params` routing."""
+    stored = copy.deepcopy(params)
+
+    def loss_of(gp):
+        return _routed_loss(gp, stored, cfg, batch, noise)
+
+    rng = np.random.default_rng(11)
+    gl = dict(O.tree_leaves(grads))
+    eps = 1e-6
+    gp = copy.deepcopy(params)
+    for path, arr in O.tree_leaves(gp):
+        for _ in range(4):
+            idx = tuple(rng.integers(0, s) for s in arr.shape)
+            old = arr[idx]
+            arr[idx] = old + eps
+            lp = loss_of(gp)
+            arr[idx] = old - eps
+            lm = loss_of(gp)
+            arr[idx] = old
+            fd = (lp - lm) / (2 * eps)
+            assert abs(fd - gl[path][idx]) <= 1e-6 * max(1.0, abs(fd)) + 1e-8, (path, idx, fd, gl[path][idx])
+
+
+def _routed_loss(gp, sp, cfg, batch, noise):
+    """total_loss with explicit routing: which calls see grad_params (gp) and which see stored params (sp);
+    agents/fql.py:25,28,36,58,64,65,70,82."""
+    obs, act, nobs = batch['observations'], batch['actions'], batch['next_observations']
+    na = np.clip(O.actor_forward(sp['modules_actor_onestep_flow'], cfg, nobs, noise['z_next']), -1, 1)
+    nq = O.critic_forward(sp['modules_target_critic'], cfg, nobs, na)
+    nq = nq.min(0) if cfg['q_agg'] == 'min' else nq.mean(0)
+    tq = batch['rewards'] + cfg['discount'] * batch['masks'] * nq
+    q = O.critic_forward(gp['modules_critic'], cfg, obs, act)
+    cl = ((q - tq) ** 2).mean()
+    x0, t = noise['x0'], noise['t']
+    xt = (1 - t) * x0 + t * act
+    pred = O.actor_forward(gp['modules_actor_bc_flow'], cfg, obs, xt, t)
+    bc = ((pred - (act - x0)) ** 2).mean()
+    tgt = O.compute_flow_actions(sp, cfg, obs, noise['z'])
+    api = O.actor_forward(gp['modules_actor_onestep_flow'], cfg, obs, noise['z'])
+    dl = ((api - tgt) ** 2).mean()
+    qs = O.critic_forward(sp['modules_critic'], cfg, obs, np.clip(api, -1, 1))
+    qm = qs.mean(0)
+    ql = -qm.mean()
+    if cfg['normalize_q_loss']:
+        lam = 1 / np.abs(O.critic_forward(sp['modules_critic'], cfg, obs, np.clip(
+            O.actor_forward(sp['modules_actor_onestep_flow'], cfg, obs, noise['z']), -1, 1)).mean(0)).mean()
+        ql = lam * ql
+    return cl + bc + cfg['alpha'] * dl + ql
+
+
+# ---------------- independent torch-autograd transcription ----------------
+def _t_mlp(p, x, ln):
+    n = O.n_dense(p)
+    for i in range(n):
+        W, b = p[f'Dense_{i}']['kernel'], p[f'Dense_{i}']['bias']
+        if W.ndim == 3:
+            x = torch.matmul(x, W) + b[:, None, :]
+        else:
+            x = x @ W + b
+        if i + 1 < n:
+            x = torch.nn.functional.gelu(x, approximate='tanh')
+            if ln:
+                sc, bi = p[f'LayerNorm_{i}']['scale'], p[f'LayerNorm_{i}']['bias']
+                mu = x.mean(-1, keepdim=True)
+                var = (x * x).mean(-1, keepdim=True) - mu * mu
+                xh = (x - mu) / torch.sqrt(var.clamp_min(0) + 1e-6)
+                x = xh * (sc[:, None, :] if W.ndim == 3 else sc) + (bi[:, None, :] if W.ndim == 3 else bi)
+    return x
+
+
+def _to_torch(t, grad):
+    if isinstance(t, dict):
+        return {k: _to_torch(v, grad) for k, v in t.items()}
+    return torch.tensor(t, dtype=torch.float64, requires_grad=grad)
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(q_agg='min', alpha=10.0), dict(normalize_q_loss=True, alpha=1000.0),
+                                dict(actor_layer_norm=True)])
+def test_against_torch_autograd(kw):
+    cfg = small_cfg(**kw)
+    params, batch, noise = setup(cfg, B=9, F=7, A=4, seed=3)
+    loss, info, grads = O.total_loss(params, cfg, batch, noise)
+    gp = _to_torch(params, True)
+    sp = _to_torch(params, False)
+    b = {k: torch.tensor(v) for k, v in batch.items()}
+    nz = {k: torch.tensor(v) for k, v in noise.items()}
+    cat = lambda *a: torch.cat(a, -1)
+    aln, cln = cfg['actor_layer_norm'], cfg['layer_norm']
+    obs, act, nobs = b['observations'], b['actions'], b['next_observations']
+    na = _t_mlp(sp['modules_actor_onestep_flow']['mlp'], cat(nobs, nz['z_next']), aln).clamp(-1, 1)
+    nq = _t_mlp(sp['modules_target_critic']['value_net'], cat(nobs, na), cln)[..., 0]
+    nq = nq.min(0).values if cfg['q_agg'] == 'min' else nq.mean(0)
+    tq = b['rewards'] + cfg['discount'] * b['masks'] * nq
+    q = _t_mlp(gp['modules_critic']['value_net'], cat(obs, act), cln)[..., 0]
+    cl = ((q - tq) ** 2).mean()
+    x0, t = nz['x0'], nz['t']
+    pred = _t_mlp(gp['modules_actor_bc_flow']['mlp'], cat(obs, (1 - t) * x0 + t * act, t), aln)
+    bc = ((pred - (act - x0)) ** 2).mean()
+    a = nz['z']
+    for i in range(cfg['flow_steps']):
+        tt = torch.full((obs.shape[0], 1), i / cfg['flow_steps'], dtype=torch.float64)
+        a = a + _t_mlp(sp['modules_actor_bc_flow']['mlp'], cat(obs, a, tt), aln) / cfg['flow_steps']
+    tgt = a.clamp(-1, 1)
+    api = _t_mlp(gp['modules_actor_onestep_flow']['mlp'], cat(obs, nz['z']), aln)
+    dl = ((api - tgt) ** 2).mean()
+    qm = _t_mlp(sp['modules_critic']['value_net'], cat(obs, api.clamp(-1, 1)), cln)[..., 0].mean(0)
+    ql = -qm.mean()
+    if cfg['normalize_q_loss']:
+        ql = ql * (1 / qm.abs().mean()).detach()
+    total = cl + bc + cfg['alpha'] * dl + ql
+    total.backward()
+    assert abs(total.item() - loss) < 1e-10 * max(1, abs(loss))
+    np.testing.assert_allclose(info['critic/critic_loss'], cl.item(), rtol=1e-12)
+    np.testing.assert_allclose(info['actor/distill_loss'], dl.item(), rtol=1e-12)
+    np.testing.assert_allclose(info['actor/q_loss'], ql.item(), rtol=1e-12)
+    gl = dict(O.tree_leaves(grads))
+    for path, tg in O.tree_leaves(gp):
+        ref = tg.grad.numpy() if tg.grad is not None else np.zeros(tg.shape)
+        np.testing.assert_allclose(gl[path], ref, rtol=1e-9, atol=1e-12, err_msg=str(path))
+
+
+def test_adam_polyak_against_torch():
+    cfg = small_cfg()
+    params, batch, noise = setup(cfg, seed=4)
+    state = O.init_state(params, warm=True)
+    new_state, info, grads = O.update(copy.deepcopy(state), cfg, batch, noise)
+    # torch.optim.Adam is the same arithmetic as optax.adam (eps outside the sqrt, bias-corrected)
+    for net in ('modules_critic', 'modules_actor_bc_flow'):
+        for path, p in O.tree_leaves(state['params'][net]):
+            g = dict(O.tree_leaves(grads[net]))[path]
+            tp = torch.tensor(p.copy(), requires_grad=True)
+            opt = torch.optim.Adam([tp], lr=cfg['lr'], betas=(0.9, 0.999), eps=1e-8)
+            tp.grad = torch.tensor(g)
+            opt.state[tp] = dict(step=torch.tensor(float(state['count'])),
+                                 exp_avg=torch.tensor(dict(O.tree_leaves(state['mu'][net]))[path].copy()),
+                                 exp_avg_sq=torch.tensor(dict(O.tree_leaves(state['nu'][net]))[path].copy()))
+            opt.step()
+            np.testing.assert_allclose(dict(O.tree_leaves(new_state['params'][net]))[path], tp.detach().numpy(),
+                                       rtol=1e-12, atol=1e-15)
+    # Polyak uses pre-step critic (F6); target Adam step is a no-op (F7)
+    for path, tp_old in O.tree_leaves(state['params']['modules_target_critic']):
+        p_old = dict(O.tree_leaves(state['params']['modules_critic']))[path]
+        np.testing.assert_allclose(dict(O.tree_leaves(new_state['params']['modules_target_critic']))[path],
+                                   cfg['tau'] * p_old + (1 - cfg['tau']) * tp_old, rtol=1e-15)
+    assert new_state['count'] == state['count'] + 1 and new_state['step'] == state['step'] + 1
+    # grad stats: L1 norm of per-leaf L2 norms, zeros of the target critic included
+    leaves = [g for _, g in O.tree_leaves(grads)]
+    assert np.isclose(info['grad/norm'], sum(np.linalg.norm(l.ravel()) for l in leaves))
+    assert info['grad/max'] == max(l.max() for l in leaves) and info['grad/min'] == min(l.min() for l in leaves)
+
+
+def test_fp32_vs_fp64_gap():
+    """Calibrates the 1e-5 tolerance: the fp32 restatement sits ~1e-6 from fp64 on tensor-norm-relative error."""
+    cfg = dict(O.DEFAULT_CONFIG)
+    cfg.update(actor_hidden_dims=(128,) * 4, value_hidden_dims=(128,) * 4)
+    params, batch, noise = setup(cfg, B=64, F=29, A=8, seed=9)
+    l64, i64, g64 = O.total_loss(params, cfg, batch, noise)
+    c = lambda t: O.cast_tree(t, np.float32)
+    l32, i32, g32 = O.total_loss(c(params), cfg, c(batch), c(noise))
+    assert abs(l32 - l64) / abs(l64) < 1e-5
+    for (path, a), (_, b) in zip(O.tree_leaves(g64), O.tree_leaves(g32)):
+        if path[0] == 'modules_target_critic':
+            continue
+        assert np.abs(a - b).max() / np.abs(a).max() < 2e-5, path
