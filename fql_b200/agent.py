@@ -1,0 +1,389 @@
+"""FQLAgent: host-side mirror of the reference agent API (agents/fql.py) over the libfql_b200 C ABI.
+
+Same surface as the reference class (`create`, `update`, `sample_actions`, `total_loss`, `compute_flow_actions`,
+`target_update` semantics, `network.params / opt_state / step`, `rng`, `config`) and the same parameter layout
+(SURVEY 8a), so the training loop of main.py:159-165,216,225,284 runs unchanged.  Differences, all deliberate:
+  * state lives in flat device arenas and is updated IN PLACE; `update` returns `(self, info)` so the caller's
+    `agent, info = agent.update(batch)` rebind still works (the reference returns a new pytree, fql.py:133);
+  * `info` values are fetched lazily from a pinned host ring (like jax's async dispatch: reading a value syncs);
+  * noise comes from a device Philox generator keyed by (agent.rng, step); jax threefry streams are not reproduced
+    (SURVEY 8c).  Parity tests inject the five noise tensors explicitly via `noise=`.
+There is no CPU path: everything below calls CUDA through fql_b200._lib.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import get_config  # noqa: F401  (re-export, agents/fql.py:249)
+
+INFO_KEYS = ('critic/critic_loss', 'critic/q_mean', 'critic/q_max', 'critic/q_min', 'actor/actor_loss', 'actor/bc_flow_loss',
+             'actor/distill_loss', 'actor/q_loss', 'actor/q', 'actor/mse', 'grad/max', 'grad/min', 'grad/norm')
+NOISE_KEYS = ('z_next', 'x0', 't', 'z', 'z_metric')
+_BATCH_KEYS = ('observations', 'actions', 'next_observations', 'rewards', 'masks')
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class LazyInfo(dict):
+    """dict of the 13 training metrics; values materialise (one event sync) on first access."""
+
+    def __init__(self, keys, host_buf, event, seed_index=None):
+        super().__init__()
+        self._keys, self._buf, self._ev, self._seed = keys, host_buf, event, seed_index
+        self._ready = False
+
+    def _fill(self):
+        if not self._ready:
+            self._ev.synchronize()
+            arr = self._buf.numpy().reshape(-1, _lib.NUM_INFO)
+            for i, k in enumerate(self._keys):
+                dict.__setitem__(self, k, float(arr[0, i]) if arr.shape[0] == 1 else arr[:, i].copy())
+            self._ready = True
+
+    def __getitem__(self, k):
+        self._fill()
+        return dict.__getitem__(self, k)
+
+    def __iter__(self):
+        self._fill()
+        return dict.__iter__(self)
+
+    def items(self):
+        self._fill()
+        return dict.items(self)
+
+    def keys(self):
+        self._fill()
+        return dict.keys(self)
+
+    def values(self):
+        self._fill()
+        return dict.values(self)
+
+    def __len__(self):
+        return len(self._keys)
+
+    def __contains__(self, k):
+        return k in self._keys
+
+    def __repr__(self):
+        self._fill()
+        return dict.__repr__(self)
+
+
+class TrainStateView:
+    """`agent.network`: params / opt_state / step with the reference's nesting (utils/flax_utils.py:53-70)."""
+
+    def __init__(self, agent):
+        self._a = agent
+
+    @property
+    def params(self):
+        return self._a._tree(self._a._params)
+
+    @property
+    def opt_state(self):
+        a = self._a
+        return ({'count': a._count, 'mu': a._tree(a._mu), 'nu': a._tree(a._nu)}, {})
+
+    @property
+    def grads(self):
+        return self._a._tree(self._a._grads)
+
+    @property
+    def step(self):
+        return int(self._a._count.item()) + 1  # TrainState.step starts at 1 (flax_utils.py:81), count at 0
+
+
+class FQLAgent:
+    """Flow Q-learning agent on one B200 (or one data-parallel rank)."""
+
+    # ------------------------------------------------------------------ construction (agents/fql.py:173-246)
+    @classmethod
+    def create(cls, seed, ex_observations, ex_actions, config, *, num_seeds=1, device=None, precision='fp32',
+               process_group=None):
+        self = cls.__new__(cls)
+        cfg = dict(config)
+        if cfg.get('encoder') is not None:
+            raise NotImplementedError('visual encoders (config 5, impala_small) are not built yet: see DESIGN.md scope table')
+        ex_observations = np.asarray(ex_observations)
+        ex_actions = np.asarray(ex_actions)
+        ob_dims = tuple(ex_observations.shape[1:])
+        if len(ob_dims) != 1:
+            raise NotImplementedError(f'state observations only (got ob_dims={ob_dims})')
+        ah, vh = tuple(cfg['actor_hidden_dims']), tuple(cfg['value_hidden_dims'])
+        if len(set(ah + vh)) != 1 or len(ah) != len(vh):
+            raise NotImplementedError('actor/value hidden dims must be one common width and depth')
+        cfg['ob_dims'], cfg['action_dim'] = ob_dims, int(ex_actions.shape[-1])
+        self.config = cfg
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        self.num_seeds = int(num_seeds)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self._precision = {'fp32': _lib.PRECISION_FP32, 'bf16': _lib.PRECISION_BF16_TC}[precision]
+        self._hidden, self._num_hidden = ah[0], len(ah)
+        self._lib = _lib.lib()
+        ctx = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.fql_context_create(C.byref(ctx)), 'fql_context_create')
+        self._ctx = ctx
+        self._hp = _lib.make_hparams(lr=cfg['lr'], discount=cfg['discount'], tau=cfg['tau'], alpha=cfg['alpha'])
+        self._dims_cache = {}
+        d = self._dims(int(cfg.get('batch_size', 256)))
+        self._leaves, self._arena = _lib.layout(d)
+        S = self.num_seeds
+        self._params = torch.zeros(S, self._arena, dtype=torch.float32, device=self.device)
+        self._mu = torch.zeros_like(self._params)
+        self._nu = torch.zeros_like(self._params)
+        self._grads = torch.zeros_like(self._params)
+        self._count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._shadow = None
+        self._bufs = {}
+        self._ring, self._ring_i = [], 0
+        self._init_params(seed)
+        # agent.rng: a (2,) uint32 key; noise for update k comes from Philox(key, k)
+        ss = np.random.SeedSequence(int(seed) if np.ndim(seed) == 0 else [int(x) for x in np.ravel(seed)])
+        self.rng = ss.generate_state(2, dtype=np.uint32)
+        self.network = TrainStateView(self)
+        return self
+
+    def _dims(self, batch):
+        if batch not in self._dims_cache:
+            c = self.config
+            self._dims_cache[batch] = _lib.make_dims(
+                batch, c['ob_dims'][0], c['action_dim'], global_batch=batch * self.world, hidden=self._hidden,
+                num_hidden=self._num_hidden, critic_layer_norm=c['layer_norm'], actor_layer_norm=c['actor_layer_norm'],
+                q_agg=c['q_agg'], normalize_q_loss=c['normalize_q_loss'], flow_steps=c['flow_steps'],
+                num_seeds=self.num_seeds, precision=self._precision)
+        return self._dims_cache[batch]
+
+    def _init_params(self, seed):
+        """default_init = variance_scaling(1,'fan_avg','uniform') (utils/networks.py:9-11); Dense bias 0, LN scale 1 / bias 0;
+        target critic <- critic (fql.py:241-242).  Same distribution as Flax, different random stream."""
+        rng = np.random.default_rng(np.random.SeedSequence(int(seed)).spawn(1)[0]) if np.ndim(seed) == 0 else np.random.default_rng(0)
+        host = np.zeros((self.num_seeds, self._arena), np.float32)
+        for lf in self._leaves:
+            if lf['net'] == 'target_critic':
+                continue
+            n = lf['ens'] * lf['rows'] * lf['cols']
+            sl = slice(lf['offset'], lf['offset'] + n)
+            if lf['is_kernel']:
+                lim = np.sqrt(6.0 / (lf['rows'] + lf['cols']))
+                host[:, sl] = rng.uniform(-lim, lim, (self.num_seeds, n)).astype(np.float32)
+            elif lf['name'] == 'scale':
+                host[:, sl] = 1.0
+        self._params.copy_(torch.from_numpy(host))
+        self._copy_critic_to_target()
+
+    def _net_range(self, net):
+        offs = [lf['offset'] for lf in self._leaves if lf['net'] == net]
+        nxt = [lf['offset'] for lf in self._leaves if lf['offset'] > max(offs)]
+        return min(offs), (min(nxt) if nxt else self._arena)
+
+    def _copy_critic_to_target(self):
+        c0, c1 = self._net_range('critic')
+        t0, t1 = self._net_range('target_critic')
+        self._params[:, t0:t1] = self._params[:, c0:c1]
+
+    def _tree(self, arena):
+        """Nested dict of views with the reference layout: modules_<net>/{mlp|value_net}/{Dense_i|LayerNorm_i}/{kernel|bias|scale}."""
+        out = {}
+        S = self.num_seeds
+        for lf in self._leaves:
+            net = out.setdefault('modules_' + lf['net'], {})
+            sub = net.setdefault('value_net' if 'critic' in lf['net'] else 'mlp', {})
+            mod = sub.setdefault(lf['module'], {})
+            n = lf['ens'] * lf['rows'] * lf['cols']
+            shape = ((lf['rows'], lf['cols']) if lf['is_kernel'] else (lf['cols'],))
+            if lf['ens'] > 1:
+                shape = (lf['ens'],) + shape
+            v = arena[:, lf['offset']:lf['offset'] + n]
+            mod[lf['name']] = v.view((S,) + shape) if S > 1 else v.view(shape)
+        return out
+
+    # ------------------------------------------------------------------ state import/export
+    def load_tree(self, params=None, mu=None, nu=None, count=None):
+        """Copy nested dicts of arrays (numpy/torch, reference layout) into the arenas."""
+        for src, dst in ((params, self._params), (mu, self._mu), (nu, self._nu)):
+            if src is None:
+                continue
+            views = self._tree(dst)
+
+            def rec(s, v):
+                for k in s:
+                    if isinstance(s[k], dict):
+                        rec(s[k], v[k])
+                    else:
+                        v[k].copy_(torch.as_tensor(np.asarray(s[k], dtype=np.float32)))
+            rec(src, views)
+        if count is not None:
+            self._count.fill_(int(count))
+        return self
+
+    def export_tree(self, which='params'):
+        arena = {'params': self._params, 'mu': self._mu, 'nu': self._nu, 'grads': self._grads}[which]
+
+        def rec(v):
+            return {k: rec(x) if isinstance(x, dict) else x.detach().cpu().numpy().copy() for k, x in v.items()}
+        return rec(self._tree(arena))
+
+    def state_dict(self):
+        """flax.serialization.to_state_dict(agent) nesting (utils/flax_utils.py:171-173; SURVEY 5 checkpoint row)."""
+        return {'rng': np.asarray(self.rng, np.uint32).copy(),
+                'network': {'step': self.network.step, 'params': self.export_tree('params'),
+                            'opt_state': {'0': {'count': int(self._count.item()), 'mu': self.export_tree('mu'),
+                                                'nu': self.export_tree('nu')}, '1': {}}}}
+
+    def load_state_dict(self, sd):
+        net = sd['network']
+        self.load_tree(net['params'], net['opt_state']['0']['mu'], net['opt_state']['0']['nu'], net['opt_state']['0']['count'])
+        self.rng = np.asarray(sd['rng'], np.uint32).copy()
+        return self
+
+    # ------------------------------------------------------------------ buffers
+    def _step_bufs(self, B):
+        if B in self._bufs:
+            return self._bufs[B]
+        d = self._dims(B)
+        S, F, A = self.num_seeds, self.config['ob_dims'][0], self.config['action_dim']
+        shapes = dict(observations=(S, B, F), actions=(S, B, A), next_observations=(S, B, F), rewards=(S, B), masks=(S, B),
+                      z_next=(S, B, A), x0=(S, B, A), t=(S, B, 1), z=(S, B, A), z_metric=(S, B, A))
+        dev = {k: torch.empty(s, dtype=torch.float32, device=self.device) for k, s in shapes.items()}
+        pin = {k: torch.empty(s, dtype=torch.float32).pin_memory() for k, s in shapes.items()}
+        ws_bytes = int(self._lib.fql_workspace_bytes(C.byref(d)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        fb = _lib.FqlBatch(*[dev[k].data_ptr() for k in _BATCH_KEYS + NOISE_KEYS])
+        st = _lib.FqlState(self._params.data_ptr(), self._mu.data_ptr(), self._nu.data_ptr(), self._grads.data_ptr(),
+                           self._count.data_ptr(), self._shadow.data_ptr() if self._shadow is not None else None)
+        info = torch.zeros(S, _lib.NUM_INFO, dtype=torch.float32, device=self.device)
+        raw = torch.zeros(S, _lib.NUM_RAW, dtype=torch.float32, device=self.device)
+        self._bufs[B] = dict(d=d, dev=dev, pin=pin, ws=ws, ws_bytes=ws_bytes, fb=fb, st=st, info=info, raw=raw)
+        return self._bufs[B]
+
+    def _stage(self, bufs, batch, noise, step_for_noise):
+        S = self.num_seeds
+        h2d = 0
+        for k in _BATCH_KEYS:
+            h2d += self._stage_one(bufs, k, batch[k])
+        if noise is not None:
+            for k in NOISE_KEYS:
+                h2d += self._stage_one(bufs, k, noise[k])
+        else:
+            dev = bufs['dev']
+            seed = int(self.rng[0]) | (int(self.rng[1]) << 32)
+            _lib.check(self._lib.fql_fill_noise(C.byref(bufs['d']), C.c_uint64(seed), C.c_uint64(step_for_noise),
+                                                _ptr(dev['z_next']), _ptr(dev['x0']), _ptr(dev['t']), _ptr(dev['z']),
+                                                _ptr(dev['z_metric']), self._stream()), 'fql_fill_noise')
+        return h2d
+
+    def _stage_one(self, bufs, k, src):
+        dst = bufs['dev'][k]
+        if isinstance(src, torch.Tensor) and src.is_cuda:
+            dst.copy_(src.reshape(dst.shape), non_blocking=True)
+            return 0
+        t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32))
+        pin = bufs['pin'][k]
+        pin.copy_(t.reshape(pin.shape))
+        dst.copy_(pin, non_blocking=True)
+        return pin.numel() * 4
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _info_out(self, info_dev):
+        i = self._ring_i % 64
+        if i >= len(self._ring):
+            self._ring.append((torch.empty(info_dev.shape, dtype=torch.float32).pin_memory(), torch.cuda.Event()))
+        host, ev = self._ring[i]
+        self._ring_i += 1
+        host.copy_(info_dev, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return LazyInfo(INFO_KEYS, host, ev)
+
+    # ------------------------------------------------------------------ the hot path (agents/fql.py:122-133)
+    def update(self, batch, noise=None):
+        """One training step.  `batch`: dict of host numpy arrays (main.py:201) or torch tensors, [B,...] (or [S,B,...]
+        when num_seeds>1).  Returns (self, info)."""
+        B = int(np.shape(batch['actions'])[-2])
+        bufs = self._step_bufs(B)
+        with torch.cuda.device(self.device):
+            self.last_h2d_bytes = self._stage(bufs, batch, noise, self._host_step)
+            self._host_step += 1
+            a = (self._ctx, C.byref(bufs['d']), C.byref(self._hp))
+            if self.world == 1:
+                _lib.check(self._lib.fql_update_step(*a, C.byref(bufs['fb']), C.byref(bufs['st']), _ptr(bufs['info']),
+                                                     _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_update_step')
+            else:
+                import torch.distributed as dist
+                _lib.check(self._lib.fql_step_grads(*a, C.byref(bufs['fb']), C.byref(bufs['st']), _ptr(bufs['raw']),
+                                                    _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_step_grads')
+                t0, _ = self._net_range('target_critic')
+                dist.all_reduce(self._grads[:, :t0], op=dist.ReduceOp.SUM, group=self.pg)
+                dist.all_reduce(bufs['raw'][:, :9], op=dist.ReduceOp.SUM, group=self.pg)
+                dist.all_reduce(bufs['raw'][:, 9:11], op=dist.ReduceOp.MAX, group=self.pg)
+                _lib.check(self._lib.fql_step_apply(*a, C.byref(bufs['st']), _ptr(bufs['raw']), _ptr(bufs['info']),
+                                                    _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_step_apply')
+            return self, self._info_out(bufs['info'])
+
+    _host_step = 0
+    last_h2d_bytes = 0
+
+    def total_loss(self, batch, grad_params=None, rng=None, noise=None):
+        """Forward-only losses (agents/fql.py:94-111 as called by main.py:284): returns (loss, info[10 keys])."""
+        B = int(np.shape(batch['actions'])[-2])
+        bufs = self._step_bufs(B)
+        with torch.cuda.device(self.device):
+            self._stage(bufs, batch, noise, (1 << 62) + self._host_step)
+            _lib.check(self._lib.fql_total_loss(self._ctx, C.byref(bufs['d']), C.byref(self._hp), C.byref(bufs['fb']),
+                                                C.byref(bufs['st']), _ptr(bufs['info']), _ptr(bufs['ws']), bufs['ws_bytes'],
+                                                self._stream()), 'fql_total_loss')
+            info = self._info_out(bufs['info'])
+        vals = {k: info[k] for k in INFO_KEYS[:10]}
+        return vals['critic/critic_loss'] + vals['actor/actor_loss'], vals
+
+    # ------------------------------------------------------------------ agents/fql.py:135-171
+    def _fwd_call(self, fn, observations, noises):
+        obs = torch.as_tensor(np.asarray(observations, dtype=np.float32) if not isinstance(observations, torch.Tensor) else observations)
+        F, A, S = self.config['ob_dims'][0], self.config['action_dim'], self.num_seeds
+        lead = tuple(obs.shape[:-1])
+        obs = obs.to(self.device, torch.float32).reshape(S, -1, F).contiguous()
+        rows = obs.shape[1]
+        nz = torch.as_tensor(noises).to(self.device, torch.float32).reshape(S, rows, A).contiguous()
+        d = self._dims(int(self.config.get('batch_size', 256)))
+        wsb = int(self._lib.fql_forward_workspace_bytes(C.byref(d), rows))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+        out = torch.empty(S, rows, A, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self._ctx, C.byref(d), _ptr(self._params), _ptr(self._shadow), _ptr(obs), _ptr(nz), _ptr(out), rows,
+                          _ptr(ws), wsb, self._stream()), fn.__name__)
+        return out.reshape(lead + (A,))
+
+    def sample_actions(self, observations, seed=None, temperature=1.0, noise=None):
+        """clip(actor_onestep_flow(obs, z)), z ~ N(0, I) of shape obs.shape[:-1] + (A,).  `temperature` is accepted and
+        ignored exactly like the reference (fql.py:140).  Returns a host numpy array (np.array-able, evaluation.py:150)."""
+        lead = tuple(np.shape(observations)[:-1])
+        A = self.config['action_dim']
+        if noise is None:
+            key = np.ravel(np.asarray(seed if seed is not None else self.rng)).astype(np.uint64)
+            g = torch.Generator(device='cpu').manual_seed(int(key[0]) ^ (int(key[-1]) << 32) if key.size else 0)
+            noise = torch.randn(lead + (A,), generator=g, dtype=torch.float32)
+        return self._fwd_call(self._lib.fql_sample_actions, observations, noise).cpu().numpy()
+
+    def compute_flow_actions(self, observations, noises):
+        return self._fwd_call(self._lib.fql_compute_flow_actions, observations, noises).cpu().numpy()
+
+    def __del__(self):
+        try:
+            if getattr(self, '_ctx', None):
+                self._lib.fql_context_destroy(self._ctx)
+        except Exception:
+            pass

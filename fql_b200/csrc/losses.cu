@@ -1,0 +1,311 @@
+// losses.cu -- the non-GEMM arithmetic of FQLAgent.total_loss (agents/fql.py:22-111): input assembly, TD target,
+// loss reductions and the loss-side gradients.  One CTA per seed for the reductions (deterministic order).
+#include "step.cuh"
+
+namespace {
+
+__device__ __forceinline__ float clip1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
+
+template <int OP>  // 0 sum, 1 max
+__device__ float block_reduce(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = OP == 0 ? warp_sum(v) : warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float x = lane < nw ? sh[lane] : (OP == 0 ? 0.f : -INFINITY);
+    x = OP == 0 ? warp_sum(x) : warp_max(x);
+    if (lane == 0) sh[0] = x;
+  }
+  __syncthreads();
+  float r = sh[0];
+  return r;
+}
+
+// Builds every first-layer input of the step (concats of networks.py:191,229-231) + vel (fql.py:55-56).
+__global__ void prep_kernel(StepShape sh, FqlBatch b, WsPtrs w) {
+  const int row = blockIdx.x;  // s*B + r
+  const int s = row / sh.B, r = row % sh.B;
+  const int F = sh.F, A = sh.A, B = sh.B;
+  const int KO = F + A, KF = F + A + 1, KC = F + A;
+  const float* obs = b.observations + (int64_t)row * F;
+  const float* nobs = b.next_observations + (int64_t)row * F;
+  const float* act = b.actions + (int64_t)row * A;
+  const float* zn = b.z_next + (int64_t)row * A;
+  const float* x0 = b.x0 + (int64_t)row * A;
+  const float* z = b.z + (int64_t)row * A;
+  const float* zm = b.z_metric + (int64_t)row * A;
+  const float t = b.t[row];
+  float* xo0 = w.XO + ((int64_t)s * 3 * B + r) * KO;
+  float* xo1 = xo0 + (int64_t)B * KO;
+  float* xo2 = xo1 + (int64_t)B * KO;
+  float* xf0 = w.XF + ((int64_t)s * 2 * B + r) * KF;
+  float* xf1 = xf0 + (int64_t)B * KF;
+  float* xc0 = w.XC + ((int64_t)(0 * sh.S + s) * B + r) * KC;
+  float* xc1 = w.XC + ((int64_t)(1 * sh.S + s) * B + r) * KC;
+  float* xc2 = w.XC + ((int64_t)(2 * sh.S + s) * B + r) * KC;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float o = obs[c], no = nobs[c];
+    xo0[c] = no; xo1[c] = o; xo2[c] = o;
+    xf0[c] = o; xf1[c] = o;
+    xc0[c] = no; xc1[c] = o; xc2[c] = o;
+  }
+  for (int c = threadIdx.x; c < A; c += blockDim.x) {
+    float a = act[c], x = x0[c];
+    xo0[F + c] = zn[c]; xo1[F + c] = z[c]; xo2[F + c] = zm[c];
+    xf0[F + c] = (1.0f - t) * x + t * a;
+    xf1[F + c] = z[c];
+    xc1[F + c] = a;
+    w.vel[(int64_t)row * A + c] = a - x;
+  }
+  if (threadIdx.x == 0) {
+    xf0[F + A] = t;
+    xf1[F + A] = 0.0f;  // Euler step 0: t = 0/flow_steps (fql.py:167)
+  }
+}
+
+// After the one-step actor pass on rows {(s',z_next), (s,z), (s,z')}: clip and scatter the actions into the critic
+// inputs (fql.py:25-26, 69-70) and reduce the logging mse (fql.py:82-83).
+__global__ void post_onestep_kernel(StepShape sh, FqlBatch b, WsPtrs w, float* raw) {
+  __shared__ float red[32];
+  const int s = blockIdx.x;
+  const int F = sh.F, A = sh.A, B = sh.B, KC = F + A;
+  const float* out = w.O_out + (int64_t)s * 3 * B * A;
+  float mse = 0.f;
+  for (int i = threadIdx.x; i < B * A; i += blockDim.x) {
+    const int r = i / A, c = i % A;
+    w.XC[((int64_t)(0 * sh.S + s) * B + r) * KC + F + c] = clip1(out[i]);
+    w.XC[((int64_t)(2 * sh.S + s) * B + r) * KC + F + c] = clip1(out[(int64_t)B * A + i]);
+    float d = clip1(out[(int64_t)2 * B * A + i]) - b.actions[(int64_t)s * B * A + i];
+    mse += d * d;
+  }
+  mse = block_reduce<0>(mse, red);
+  if (threadIdx.x == 0) raw[s * FQL_NUM_RAW + RAW_MSE] = mse;
+}
+
+// TD target + critic loss gradient (fql.py:28-44) and the actor's Q statistics / dQ seed (fql.py:70-76).
+// qout: [3][S][2][B]  (0: target critic on (s',a'), 1: critic on (s,a), 2: critic on (s, clip a_pi))
+__global__ void critic_post_kernel(StepShape sh, FqlHparams hp, FqlBatch b, WsPtrs w, float* raw) {
+  __shared__ float red[32];
+  const int s = blockIdx.x;
+  const int B = sh.B, S = sh.S;
+  const float* q_t = w.C_out + ((int64_t)(0 * S + s) * 2) * B;
+  const float* q_c = w.C_out + ((int64_t)(1 * S + s) * 2) * B;
+  const float* q_p = w.C_out + ((int64_t)(2 * S + s) * 2) * B;
+  const float inv_2gb = 1.0f / (2.0f * (float)sh.GB);
+  float sq = 0.f, qs = 0.f, qmx = -INFINITY, qmn = INFINITY, ps = 0.f, pa = 0.f;
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    const float t0 = q_t[r], t1 = q_t[B + r];
+    const float nq = sh.q_agg_min ? fminf(t0, t1) : (t0 + t1) * 0.5f;
+    const float y = b.rewards[(int64_t)s * B + r] + hp.discount * b.masks[(int64_t)s * B + r] * nq;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float q = q_c[h * B + r];
+      const float d = q - y;
+      sq += d * d;
+      qs += q;
+      qmx = fmaxf(qmx, q);
+      qmn = fminf(qmn, q);
+      w.dq[((int64_t)s * 2 + h) * B + r] = 2.0f * d * inv_2gb;
+    }
+    const float qp = (q_p[r] + q_p[B + r]) * 0.5f;
+    ps += qp;
+    pa += fabsf(qp);
+  }
+  sq = block_reduce<0>(sq, red);
+  qs = block_reduce<0>(qs, red);
+  ps = block_reduce<0>(ps, red);
+  pa = block_reduce<0>(pa, red);
+  qmx = block_reduce<1>(qmx, red);
+  qmn = -block_reduce<1>(-qmn, red);
+  // lam = 1/mean|q| over the (global) batch, stop-gradient (fql.py:74-76)
+  float lam = 1.0f;
+  if (sh.normalize_q_loss) lam = 1.0f / (pa / (float)sh.GB);
+  if (threadIdx.x == 0) {
+    float* rw = raw + s * FQL_NUM_RAW;
+    rw[RAW_CRITIC_SQ] = sq; rw[RAW_Q_SUM] = qs; rw[RAW_QPI_SUM] = ps; rw[RAW_QPI_ABS] = pa;
+    rw[RAW_Q_MAX] = qmx; rw[RAW_Q_NEGMIN] = -qmn;
+  }
+  const float dqs = -lam * inv_2gb;
+  for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) w.dqs[(int64_t)s * 2 * B + i] = dqs;
+}
+
+// BC flow-matching loss gradient (fql.py:58-59): pred rows are rows [0,B) of the bc-flow pass output.
+__global__ void bc_post_kernel(StepShape sh, WsPtrs w, float* raw) {
+  __shared__ float red[32];
+  const int s = blockIdx.x;
+  const int A = sh.A, B = sh.B;
+  const float* pred = w.F_out + (int64_t)s * 2 * B * A;
+  const float scale = 2.0f / ((float)sh.GB * (float)A);
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < B * A; i += blockDim.x) {
+    float d = pred[i] - w.vel[(int64_t)s * B * A + i];
+    sq += d * d;
+    w.dpred[(int64_t)s * B * A + i] = scale * d;
+  }
+  sq = block_reduce<0>(sq, red);
+  if (threadIdx.x == 0) raw[s * FQL_NUM_RAW + RAW_BC_SQ] = sq;
+}
+
+// One Euler step (fql.py:166-169): a += v / flow_steps on the Euler rows of XF; t column <- (i+1)/flow_steps;
+// after the last step: target = clip(a) (fql.py:170).
+__global__ void euler_update_kernel(StepShape sh, WsPtrs w, int step) {
+  const int A = sh.A, B = sh.B, KF = sh.F + sh.A + 1;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)sh.S * B * A) return;
+  const int c = (int)(i % A);
+  const int64_t row = i / A;
+  const int s = (int)(row / B), r = (int)(row % B);
+  float* xf = w.XF + ((int64_t)s * 2 * B + B + r) * KF;
+  const float v = w.F_out[((int64_t)s * 2 * B + B + r) * A + c];
+  const float a = xf[sh.F + c] + v / (float)sh.flow_steps;
+  xf[sh.F + c] = a;
+  if (c == 0) xf[sh.F + A] = (float)((double)(step + 1) / (double)sh.flow_steps);
+  if (step == sh.flow_steps - 1) w.target[i] = clip1(a);
+}
+
+// Distillation loss + dL/da_pi (fql.py:65-79): da = alpha*2(a_pi-target)/(GB*A) + [dQ/da through clip].
+// dX0: [S][2][B][KC] input-gradient of the critic(s, clip a_pi) pass; the two heads are summed (input broadcast).
+__global__ void actor_grad_kernel(StepShape sh, FqlHparams hp, WsPtrs w, float* raw) {
+  __shared__ float red[32];
+  const int s = blockIdx.x;
+  const int A = sh.A, B = sh.B, KC = sh.F + sh.A;
+  const float* api = w.O_out + ((int64_t)s * 3 * B + B) * A;
+  const float scale = hp.alpha * 2.0f / ((float)sh.GB * (float)A);
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < B * A; i += blockDim.x) {
+    const int r = i / A, c = i % A;
+    const float a = api[i];
+    const float d = a - w.target[(int64_t)s * B * A + i];
+    sq += d * d;
+    const float g0 = w.dX0[(((int64_t)s * 2 + 0) * B + r) * KC + sh.F + c];
+    const float g1 = w.dX0[(((int64_t)s * 2 + 1) * B + r) * KC + sh.F + c];
+    const float inside = (a >= -1.0f && a <= 1.0f) ? 1.0f : 0.0f;
+    w.dapi[(int64_t)s * B * A + i] = scale * d + (g0 + g1) * inside;
+  }
+  sq = block_reduce<0>(sq, red);
+  if (threadIdx.x == 0) raw[s * FQL_NUM_RAW + RAW_DISTILL_SQ] = sq;
+}
+
+// info[13] from the (all-reduced) raw accumulators + gradient statistics.
+__global__ void finalize_info_kernel(StepShape sh, FqlHparams hp, const float* raw, const float* gstats, float* info,
+                                     int with_grad_stats) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= sh.S) return;
+  const float* rw = raw + s * FQL_NUM_RAW;
+  float* o = info + s * FQL_NUM_INFO;
+  const float gb = (float)sh.GB, A = (float)sh.A;
+  const float critic_loss = rw[RAW_CRITIC_SQ] / (2.0f * gb);
+  const float bc = rw[RAW_BC_SQ] / (gb * A);
+  const float distill = rw[RAW_DISTILL_SQ] / (gb * A);
+  const float q = rw[RAW_QPI_SUM] / gb;
+  float q_loss = -q;
+  if (sh.normalize_q_loss) q_loss = (1.0f / (rw[RAW_QPI_ABS] / gb)) * q_loss;
+  o[0] = critic_loss;
+  o[1] = rw[RAW_Q_SUM] / (2.0f * gb);
+  o[2] = rw[RAW_Q_MAX];
+  o[3] = -rw[RAW_Q_NEGMIN];
+  o[4] = bc + hp.alpha * distill + q_loss;
+  o[5] = bc;
+  o[6] = distill;
+  o[7] = q_loss;
+  o[8] = q;
+  o[9] = rw[RAW_MSE] / (gb * A);
+  if (with_grad_stats) {
+    o[10] = gstats[s * 4 + 0];
+    o[11] = gstats[s * 4 + 1];
+    o[12] = gstats[s * 4 + 2];
+  } else {
+    o[10] = o[11] = o[12] = 0.f;
+  }
+}
+
+// clip(x) elementwise (fql.py:152)
+__global__ void clip_kernel(const float* in, float* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = clip1(in[i]);
+}
+
+// generic concat of up to 3 row blocks into X [rows, k0+k1+k2]; x2 may be a scalar constant column
+__global__ void concat_kernel(const float* x0, int k0, const float* x1, int k1, float c2, int k2, float* out, int64_t rows) {
+  const int K = k0 + k1 + k2;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const int64_t r = i / K;
+  const int c = (int)(i % K);
+  out[i] = c < k0 ? x0[r * k0 + c] : (c < k0 + k1 ? x1[r * k1 + (c - k0)] : c2);
+}
+
+// Euler step for the standalone compute_flow_actions entry: X [rows, F+A+1] in place
+__global__ void euler_inplace_kernel(float* X, const float* v, int F, int A, int64_t rows, int step, int nsteps, float* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * A) return;
+  const int64_t r = i / A;
+  const int c = (int)(i % A);
+  float* x = X + r * (F + A + 1);
+  const float a = x[F + c] + v[i] / (float)nsteps;
+  x[F + c] = a;
+  if (c == 0) x[F + A] = (float)((double)(step + 1) / (double)nsteps);
+  if (step == nsteps - 1) out[i] = clip1(a);
+}
+
+}  // namespace
+
+int launch_prep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, cudaStream_t st) {
+  prep_kernel<<<sh.S * sh.B, 64, 0, st>>>(sh, b, w);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+int launch_post_onestep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st) {
+  post_onestep_kernel<<<sh.S, 1024, 0, st>>>(sh, b, w, raw);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st) {
+  critic_post_kernel<<<sh.S, 1024, 0, st>>>(sh, hp, b, w, raw);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+int launch_bc_post(const StepShape& sh, const WsPtrs& w, float* raw, cudaStream_t st) {
+  bc_post_kernel<<<sh.S, 1024, 0, st>>>(sh, w, raw);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+int launch_euler_update(const StepShape& sh, const WsPtrs& w, int step, cudaStream_t st) {
+  const int64_t n = (int64_t)sh.S * sh.B * sh.A;
+  euler_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sh, w, step);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w, float* raw, cudaStream_t st) {
+  actor_grad_kernel<<<sh.S, 1024, 0, st>>>(sh, hp, w, raw);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+int launch_finalize_info(const StepShape& sh, const FqlHparams& hp, const float* raw, const float* gstats, float* info,
+                         int with_grad_stats, cudaStream_t st) {
+  finalize_info_kernel<<<(sh.S + 63) / 64, 64, 0, st>>>(sh, hp, raw, gstats, info, with_grad_stats);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+int launch_clip(const float* in, float* out, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  clip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+int launch_concat(const float* x0, int k0, const float* x1, int k1, float c2, int k2, float* out, int64_t rows, cudaStream_t st) {
+  const int64_t n = rows * (k0 + k1 + k2);
+  if (n == 0) return 0;
+  concat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x0, k0, x1, k1, c2, k2, out, rows);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+int launch_euler_inplace(float* X, const float* v, int F, int A, int64_t rows, int step, int nsteps, float* out, cudaStream_t st) {
+  const int64_t n = rows * A;
+  if (n == 0) return 0;
+  euler_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(X, v, F, A, rows, step, nsteps, out);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}

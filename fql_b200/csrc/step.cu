@@ -1,0 +1,728 @@
+// step.cu -- arena layout, workspace map and the stream-level schedule of FQLAgent.update (agents/fql.py:122-133).
+//
+// Schedule of one step (three streams, forked/joined with events; capturable into a CUDA graph):
+//   S0: prep -> onestep actor on {(s',z_next),(s,z),(s,z')} (fql.py:25,65,82) -> {target critic, critic(s,a),
+//       critic(s,clip a_pi)} x 2 heads as ONE grouped pass (fql.py:28,36,70) -> TD/Q post -> critic input-gradient
+//       -> [join Euler] distill + dL/da_pi -> onestep backward
+//   S1: bc-flow on {(s,x_t,t), Euler step 0} -> Euler steps 1..n-1 (fql.py:155-171)      <- longest dependent chain
+//   S2: BC loss + bc-flow backward (fql.py:58-59); critic backward (fql.py:36-37)
+//   S0: join -> grad stats + Adam + Polyak (optim.cu) -> info
+#include "step.cuh"
+
+#include <stdarg.h>
+
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void fql_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layout
+// ---------------------------------------------------------------------------------------------------------
+int fql_validate_dims(const FqlDims* d) {
+  FQL_REQUIRE(d != nullptr, "dims is NULL");
+  FQL_REQUIRE(d->batch >= 1 && d->global_batch >= d->batch, "batch=%d global_batch=%d", d->batch, d->global_batch);
+  FQL_REQUIRE(d->obs_dim >= 1 && d->action_dim >= 1, "obs_dim=%d action_dim=%d", d->obs_dim, d->action_dim);
+  FQL_REQUIRE(d->hidden >= 1 && d->num_hidden >= 1 && d->num_hidden + 1 <= FQL_MAXL, "hidden=%d num_hidden=%d", d->hidden, d->num_hidden);
+  FQL_REQUIRE(d->num_seeds >= 1, "num_seeds=%d", d->num_seeds);
+  FQL_REQUIRE(d->flow_steps >= 1, "flow_steps=%d", d->flow_steps);
+  FQL_REQUIRE(d->precision == FQL_PRECISION_FP32 || d->precision == FQL_PRECISION_BF16_TC, "precision=%d", d->precision);
+  FQL_REQUIRE(!(d->normalize_q_loss && d->global_batch != d->batch),
+              "normalize_q_loss with a data-parallel split needs a global |q| exchange inside the step: not supported; "
+              "shard seeds instead (SURVEY 8e)");
+  return 0;
+}
+
+int fql_build_layout(const FqlDims* d, Layout* L) {
+  FQL_TRY(fql_validate_dims(d));
+  memset(L, 0, sizeof(*L));
+  const int F = d->obs_dim, A = d->action_dim, H = d->hidden, NL = d->num_hidden + 1;
+  int64_t off = 0;
+  int nl = 0;
+  auto add_leaf = [&](int net, int64_t n) {
+    int64_t o = off;
+    L->leaf_blk[nl] = (int)(off / FQL_LEAF_PAD);
+    L->leaf_net[nl] = net;
+    nl++;
+    off += round_up64(n, FQL_LEAF_PAD);
+    return o;
+  };
+  for (int n = 0; n < FQL_NUM_NETS; n++) {
+    NetView& v = L->net[n];
+    v.n_layers = NL;
+    v.hidden = H;
+    const bool critic = (n == FQL_NET_CRITIC || n == FQL_NET_TARGET_CRITIC);
+    v.ens = critic ? 2 : 1;
+    v.ln = critic ? d->critic_layer_norm : d->actor_layer_norm;
+    v.in_dim = (n == FQL_NET_ACTOR_BC_FLOW) ? F + A + 1 : F + A;
+    v.out_dim = critic ? 1 : A;
+    v.begin = off;
+    const int extra = v.ln ? 4 : 2;
+    FQL_REQUIRE(nl + NL * extra <= FQL_MAX_LEAVES, "too many leaves");
+    for (int l = 0; l < NL; l++) {
+      const int64_t K = v.k_of(l), N = v.n_of(l);
+      v.off_w[l] = add_leaf(n, v.ens * K * N);
+      v.off_b[l] = add_leaf(n, v.ens * N);
+      if (v.ln && l + 1 < NL) {
+        v.off_lns[l] = add_leaf(n, v.ens * N);
+        v.off_lnb[l] = add_leaf(n, v.ens * N);
+      }
+    }
+    v.end = off;
+  }
+  L->arena = off;
+  L->n_leaves = nl;
+  L->leaf_blk[nl] = (int)(off / FQL_LEAF_PAD);
+  return 0;
+}
+
+StepShape make_shape(const FqlDims* d) {
+  StepShape s;
+  s.S = d->num_seeds; s.B = d->batch; s.GB = d->global_batch; s.F = d->obs_dim; s.A = d->action_dim;
+  s.H = d->hidden; s.NH = d->num_hidden;
+  s.q_agg_min = d->q_agg_min; s.normalize_q_loss = d->normalize_q_loss; s.flow_steps = d->flow_steps;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct Carver {
+  char* base;
+  size_t off = 0;
+  float* take(int64_t nfloats) {
+    off = (off + 255) & ~(size_t)255;
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += (size_t)nfloats * sizeof(float);
+    return p;
+  }
+};
+
+void carve_pass(Carver& c, PassBuf* pb, int G, int Mcap, int H, int NH, int out_dim, bool ln, bool need_z) {
+  pb->G = G;
+  pb->Mcap = Mcap;
+  for (int l = 0; l < NH; l++) {
+    pb->Z[l] = (need_z || ln) ? c.take((int64_t)G * Mcap * H) : nullptr;
+    pb->Hh[l] = c.take((int64_t)G * Mcap * H);
+    pb->mu[l] = ln ? c.take((int64_t)G * Mcap) : nullptr;
+    pb->rstd[l] = ln ? c.take((int64_t)G * Mcap) : nullptr;
+  }
+  pb->out = c.take((int64_t)G * Mcap * out_dim);
+}
+}  // namespace
+
+size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w) {
+  Carver c{reinterpret_cast<char*>(base)};
+  const int64_t S = d->num_seeds, B = d->batch, F = d->obs_dim, A = d->action_dim, H = d->hidden;
+  const int NH = d->num_hidden;
+  memset(w, 0, sizeof(*w));
+  w->XO = c.take(S * 3 * B * (F + A));
+  w->XF = c.take(S * 2 * B * (F + A + 1));
+  w->XC = c.take(3 * S * B * (F + A));
+  w->vel = c.take(S * B * A);
+  carve_pass(c, &w->pO, (int)S, (int)(3 * B), (int)H, NH, (int)A, d->actor_layer_norm, true);
+  carve_pass(c, &w->pF, (int)S, (int)(2 * B), (int)H, NH, (int)A, d->actor_layer_norm, true);
+  carve_pass(c, &w->pC, (int)(3 * S * 2), (int)B, (int)H, NH, 1, d->critic_layer_norm, true);
+  w->O_out = w->pO.out;
+  w->F_out = w->pF.out;
+  w->C_out = w->pC.out;
+  w->dq = c.take(S * 2 * B);
+  w->dqs = c.take(S * 2 * B);
+  w->dpred = c.take(S * B * A);
+  w->dapi = c.take(S * B * A);
+  w->target = c.take(S * B * A);
+  w->dX0 = c.take(S * 2 * B * (F + A));
+  w->raw_local = c.take(S * FQL_NUM_RAW);
+  w->gstats = c.take(S * 4);
+  w->partials = c.take(S * (int64_t)L.leaf_blk[L.n_leaves] * 4);
+  for (int i = 0; i < 2; i++) {
+    w->dC[i] = c.take(S * 2 * B * H);
+    w->dCp[i] = c.take(S * 2 * B * H);
+    w->dF[i] = c.take(S * B * H);
+    w->dO[i] = c.take(S * B * H);
+  }
+  return c.off + 256;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// grouped MLP forward / backward in FQL_PRECISION_FP32
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct FwdSpec {
+  int P;
+  const NetView* nv[FQL_MAXP];
+  const float* params;
+  int64_t arena;
+  int S, E, M, H;
+  const float* X0;  // [P][S][Mcap0][K0]
+  int Mcap0, r0_in;
+  PassBuf* buf;
+  int r0;
+  int save_z;
+};
+
+int mlp_forward(const FwdSpec& f, cudaStream_t st) {
+  const NetView& n0 = *f.nv[0];
+  const int NL = n0.n_layers;
+  const int64_t Mcap = f.buf->Mcap;
+  for (int l = 0; l < NL; l++) {
+    const int K = n0.k_of(l), N = n0.n_of(l);
+    const bool last = (l == NL - 1);
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = f.P; a.S = f.S; a.E = f.E; a.M = f.M; a.N = N; a.K = K;
+    for (int p = 0; p < f.P; p++) {
+      if (l == 0) a.A.base[p] = f.X0 + ((int64_t)p * f.S * f.Mcap0 + f.r0_in) * K;
+      else a.A.base[p] = f.buf->Hh[l - 1] + ((int64_t)p * f.S * f.E * Mcap + f.r0) * f.H;
+      a.B.base[p] = f.params + f.nv[p]->off_w[l];
+      a.bias.base[p] = f.params + f.nv[p]->off_b[l];
+    }
+    if (l == 0) { a.A.stride_s = (int64_t)f.Mcap0 * K; a.A.stride_e = 0; a.lda = K; }
+    else { a.A.stride_s = (int64_t)f.E * Mcap * f.H; a.A.stride_e = Mcap * f.H; a.lda = f.H; }
+    a.B.stride_s = f.arena; a.B.stride_e = (int64_t)K * N; a.ldb = N;
+    a.bias.stride_s = f.arena; a.bias.stride_e = N;
+    a.out.stride_s = (int64_t)f.E * Mcap * N; a.out.stride_e = Mcap * N; a.ldo = N;
+    a.out_pre.stride_s = a.out.stride_s; a.out_pre.stride_e = a.out.stride_e; a.ld_pre = N;
+    for (int p = 0; p < f.P; p++) {
+      const int64_t goff = ((int64_t)p * f.S * f.E * Mcap + f.r0) * N;
+      if (last) a.out.base[p] = f.buf->out + goff;
+      else if (n0.ln) a.out.base[p] = f.buf->Z[l] + goff;
+      else {
+        a.out.base[p] = f.buf->Hh[l] + goff;
+        a.out_pre.base[p] = f.save_z ? f.buf->Z[l] + goff : nullptr;
+      }
+    }
+    a.act_gelu = (!last && !n0.ln) ? 1 : 0;
+    FQL_TRY(launch_gemm(a, st));
+    if (!last && n0.ln) {
+      ActLnArgs r;
+      memset(&r, 0, sizeof(r));
+      r.P = f.P; r.S = f.S; r.E = f.E; r.M = f.M; r.N = N; r.ld = N; r.ln = 1;
+      for (int p = 0; p < f.P; p++) {
+        const int64_t goff = ((int64_t)p * f.S * f.E * Mcap + f.r0);
+        r.Z.base[p] = f.buf->Z[l] + goff * N;
+        r.H.base[p] = f.buf->Hh[l] + goff * N;
+        r.mu.base[p] = f.buf->mu[l] + goff;
+        r.rstd.base[p] = f.buf->rstd[l] + goff;
+        r.scale.base[p] = f.params + f.nv[p]->off_lns[l];
+        r.lnbias.base[p] = f.params + f.nv[p]->off_lnb[l];
+      }
+      r.Z.stride_s = (int64_t)f.E * Mcap * N; r.Z.stride_e = Mcap * N;
+      r.H.stride_s = r.Z.stride_s; r.H.stride_e = r.Z.stride_e;
+      r.mu.stride_s = (int64_t)f.E * Mcap; r.mu.stride_e = Mcap;
+      r.rstd.stride_s = r.mu.stride_s; r.rstd.stride_e = r.mu.stride_e;
+      r.scale.stride_s = f.arena; r.scale.stride_e = N;
+      r.lnbias.stride_s = f.arena; r.lnbias.stride_e = N;
+      FQL_TRY(launch_act_ln_fwd(r, st));
+    }
+  }
+  return 0;
+}
+
+struct BwdSpec {
+  const NetView* nv;
+  const float* params;
+  float* grads;  // NULL: no parameter gradients (dgrad-only pass)
+  int64_t arena;
+  int S, E, M, H;
+  const float* X0;  // already offset to (problem, first row); [S][Mcap0][K0]
+  int Mcap0;
+  const PassBuf* buf;
+  int p, r0;        // problem index / first row inside buf
+  const float* dOut;  // [S][E][M][out_dim]
+  float* dpp[2];      // [S][E][M][H]
+  float* dX0;         // optional [S][E][M][K0]
+};
+
+int mlp_backward(const BwdSpec& b, cudaStream_t st) {
+  const NetView& n = *b.nv;
+  const int NL = n.n_layers;
+  const int64_t Mcap = b.buf->Mcap;
+  const int64_t goff_rows = ((int64_t)b.p * b.S * b.E * Mcap + b.r0);  // row offset of this problem inside buf
+  const float* dZ = b.dOut;
+  int ldz = n.out_dim;
+  int cur = 0;
+  for (int l = NL - 1; l >= 0; l--) {
+    const int K = n.k_of(l), N = n.n_of(l);
+    const int64_t dz_ss = (int64_t)b.E * b.M * ldz, dz_se = (int64_t)b.M * ldz;
+    if (b.grads) {
+      GemmArgs a;  // dW[K,N] = A_l^T[K,M] * dZ[M,N]
+      memset(&a, 0, sizeof(a));
+      a.P = 1; a.S = b.S; a.E = b.E; a.M = K; a.N = N; a.K = b.M;
+      a.trans_a = 1;
+      if (l == 0) { a.A.base[0] = b.X0; a.A.stride_s = (int64_t)b.Mcap0 * K; a.A.stride_e = 0; a.lda = K; }
+      else { a.A.base[0] = b.buf->Hh[l - 1] + goff_rows * b.H; a.A.stride_s = (int64_t)b.E * Mcap * b.H; a.A.stride_e = Mcap * b.H; a.lda = b.H; }
+      a.B.base[0] = dZ; a.B.stride_s = dz_ss; a.B.stride_e = dz_se; a.ldb = ldz;
+      a.out.base[0] = b.grads + n.off_w[l]; a.out.stride_s = b.arena; a.out.stride_e = (int64_t)K * N; a.ldo = N;
+      FQL_TRY(launch_gemm(a, st));
+      ColSumArgs c;  // db[N] = sum_rows dZ
+      memset(&c, 0, sizeof(c));
+      c.P = 1; c.S = b.S; c.E = b.E; c.M = b.M; c.N = N; c.ld = ldz;
+      c.X.base[0] = dZ; c.X.stride_s = dz_ss; c.X.stride_e = dz_se;
+      c.out.base[0] = b.grads + n.off_b[l]; c.out.stride_s = b.arena; c.out.stride_e = N;
+      FQL_TRY(launch_colsum(c, st));
+    }
+    if (l == 0 && !b.dX0) break;
+    GemmArgs a;  // dH_{l-1}[M,K] = dZ[M,N] * W_l^T
+    memset(&a, 0, sizeof(a));
+    a.P = 1; a.S = b.S; a.E = b.E; a.M = b.M; a.N = K; a.K = N;
+    a.A.base[0] = dZ; a.A.stride_s = dz_ss; a.A.stride_e = dz_se; a.lda = ldz;
+    a.trans_b = 1;
+    a.B.base[0] = b.params + n.off_w[l]; a.B.stride_s = b.arena; a.B.stride_e = (int64_t)K * N; a.ldb = N;
+    if (l == 0) {
+      a.out.base[0] = b.dX0; a.out.stride_s = (int64_t)b.E * b.M * K; a.out.stride_e = (int64_t)b.M * K; a.ldo = K;
+      FQL_TRY(launch_gemm(a, st));
+      break;
+    }
+    float* dst = b.dpp[cur];
+    a.out.base[0] = dst; a.out.stride_s = (int64_t)b.E * b.M * b.H; a.out.stride_e = (int64_t)b.M * b.H; a.ldo = b.H;
+    const float* Zprev = b.buf->Z[l - 1] + goff_rows * b.H;
+    const int64_t z_ss = (int64_t)b.E * Mcap * b.H, z_se = Mcap * b.H;
+    if (!n.ln) {  // dZ_{l-1} = dH_{l-1} * gelu'(Z_{l-1}) fused into the dgrad epilogue
+      a.mulz.base[0] = Zprev; a.mulz.stride_s = z_ss; a.mulz.stride_e = z_se; a.ld_mulz = b.H;
+      FQL_TRY(launch_gemm(a, st));
+    } else {
+      FQL_TRY(launch_gemm(a, st));
+      if (b.grads) {
+        ColSumArgs c;
+        memset(&c, 0, sizeof(c));
+        c.P = 1; c.S = b.S; c.E = b.E; c.M = b.M; c.N = b.H; c.ld = b.H;
+        c.X.base[0] = dst; c.X.stride_s = a.out.stride_s; c.X.stride_e = a.out.stride_e;
+        c.out.base[0] = b.grads + n.off_lnb[l - 1]; c.out.stride_s = b.arena; c.out.stride_e = b.H;
+        FQL_TRY(launch_colsum(c, st));
+        // NB: colsum addresses Z/mu/rstd rows with X's row index, so they must share X's row pitch: Z rows of this
+        // problem are contiguous per (s,e) with pitch H, same as dst.
+        c.Z.base[0] = Zprev; c.Z.stride_s = z_ss; c.Z.stride_e = z_se;
+        c.mu.base[0] = b.buf->mu[l - 1] + goff_rows; c.mu.stride_s = (int64_t)b.E * Mcap; c.mu.stride_e = Mcap;
+        c.rstd.base[0] = b.buf->rstd[l - 1] + goff_rows; c.rstd.stride_s = c.mu.stride_s; c.rstd.stride_e = c.mu.stride_e;
+        c.out.base[0] = b.grads + n.off_lns[l - 1];
+        FQL_TRY(launch_colsum(c, st));
+      }
+      ActLnBwdArgs r;
+      memset(&r, 0, sizeof(r));
+      r.P = 1; r.S = b.S; r.E = b.E; r.M = b.M; r.N = b.H; r.ld = b.H;
+      r.dH.base[0] = dst; r.dH.stride_s = a.out.stride_s; r.dH.stride_e = a.out.stride_e;
+      r.dZ.base[0] = dst; r.dZ.stride_s = a.out.stride_s; r.dZ.stride_e = a.out.stride_e;
+      r.Z.base[0] = Zprev; r.Z.stride_s = z_ss; r.Z.stride_e = z_se;
+      r.scale.base[0] = b.params + n.off_lns[l - 1]; r.scale.stride_s = b.arena; r.scale.stride_e = b.H;
+      FQL_TRY(launch_act_ln_bwd(r, st));
+    }
+    dZ = dst;
+    ldz = b.H;
+    cur ^= 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// context: internal streams / events / cached graphs
+// ---------------------------------------------------------------------------------------------------------
+struct GraphEntry {
+  std::vector<unsigned char> key;
+  cudaGraphExec_t exec;
+};
+struct FqlContext {
+  cudaStream_t s1 = nullptr, s2 = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::vector<GraphEntry> graphs;
+  int use_graph = 1;
+};
+
+extern "C" int fql_context_create(FqlContext** out) {
+  FQL_REQUIRE(out != nullptr, "out is NULL");
+  FqlContext* c = new FqlContext();
+  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s1, cudaStreamNonBlocking));
+  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking));
+  for (auto& e : c->ev) FQL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  const char* g = getenv("FQL_B200_GRAPH");
+  if (g && g[0] == '0') c->use_graph = 0;
+  *out = c;
+  return 0;
+}
+
+extern "C" int fql_context_destroy(FqlContext* c) {
+  if (!c) return 0;
+  for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->s1) cudaStreamDestroy(c->s1);
+  if (c->s2) cudaStreamDestroy(c->s2);
+  delete c;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct StepCall {
+  const FqlDims* d;
+  const FqlHparams* hp;
+  const FqlBatch* b;
+  const FqlState* st;
+  float* raw;
+  float* info;
+  void* ws;
+  size_t ws_bytes;
+  int do_grads, do_backward, do_apply;
+};
+
+int check_common(const FqlDims* d, const void* ws, size_t ws_bytes, Layout* L, WsPtrs* w) {
+  FQL_TRY(fql_build_layout(d, L));
+  const size_t need = carve_workspace(d, *L, nullptr, w);
+  FQL_REQUIRE(ws != nullptr && ws_bytes >= need, "workspace too small: have %zu need %zu", ws_bytes, need);
+  FQL_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  carve_workspace(d, *L, const_cast<void*>(ws), w);
+  return 0;
+}
+
+int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
+  Layout L;
+  WsPtrs w;
+  FQL_TRY(check_common(c.d, c.ws, c.ws_bytes, &L, &w));
+  FQL_REQUIRE(c.d->precision == FQL_PRECISION_FP32, "FQL_PRECISION_BF16_TC step is not built into this library version");
+  const StepShape sh = make_shape(c.d);
+  const FqlHparams hp = *c.hp;
+  const int S = sh.S, B = sh.B, H = sh.H;
+  float* raw = c.raw ? c.raw : w.raw_local;
+  const float* P = c.st->params;
+
+  if (c.do_grads) {
+    const FqlBatch& b = *c.b;
+    cudaStream_t S1 = ctx->s1, S2 = ctx->s2;
+    cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4];
+    FQL_TRY(launch_zero(raw, (int64_t)S * FQL_NUM_RAW, S0));
+    FQL_TRY(launch_prep(sh, b, w, S0));
+    FQL_CHECK_CUDA(cudaEventRecord(ev_prep, S0));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S1, ev_prep, 0));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_prep, 0));
+
+    // ---- S1: bc-flow network on {BC rows, Euler rows}, then the Euler chain
+    FwdSpec fF;
+    memset(&fF, 0, sizeof(fF));
+    fF.P = 1; fF.nv[0] = &L.net[FQL_NET_ACTOR_BC_FLOW]; fF.params = P; fF.arena = L.arena;
+    fF.S = S; fF.E = 1; fF.M = 2 * B; fF.H = H; fF.X0 = w.XF; fF.Mcap0 = 2 * B; fF.r0_in = 0;
+    fF.buf = &w.pF; fF.r0 = 0; fF.save_z = 1;
+    FQL_TRY(mlp_forward(fF, S1));
+    FQL_CHECK_CUDA(cudaEventRecord(ev_f0, S1));
+    fF.M = B; fF.r0_in = B; fF.r0 = B; fF.save_z = 0;
+    for (int i = 0; i < sh.flow_steps; i++) {
+      FQL_TRY(launch_euler_update(sh, w, i, S1));
+      if (i + 1 < sh.flow_steps) FQL_TRY(mlp_forward(fF, S1));
+    }
+    FQL_CHECK_CUDA(cudaEventRecord(ev_euler, S1));
+
+    // ---- S0: one-step actor, then the grouped critic pass
+    FwdSpec fO;
+    memset(&fO, 0, sizeof(fO));
+    fO.P = 1; fO.nv[0] = &L.net[FQL_NET_ACTOR_ONESTEP_FLOW]; fO.params = P; fO.arena = L.arena;
+    fO.S = S; fO.E = 1; fO.M = 3 * B; fO.H = H; fO.X0 = w.XO; fO.Mcap0 = 3 * B; fO.r0_in = 0;
+    fO.buf = &w.pO; fO.r0 = 0; fO.save_z = 1;
+    FQL_TRY(mlp_forward(fO, S0));
+    FQL_TRY(launch_post_onestep(sh, b, w, raw, S0));
+    FwdSpec fC;
+    memset(&fC, 0, sizeof(fC));
+    fC.P = 3; fC.nv[0] = &L.net[FQL_NET_TARGET_CRITIC]; fC.nv[1] = &L.net[FQL_NET_CRITIC]; fC.nv[2] = &L.net[FQL_NET_CRITIC];
+    fC.params = P; fC.arena = L.arena; fC.S = S; fC.E = 2; fC.M = B; fC.H = H; fC.X0 = w.XC; fC.Mcap0 = B; fC.r0_in = 0;
+    fC.buf = &w.pC; fC.r0 = 0; fC.save_z = 1;
+    FQL_TRY(mlp_forward(fC, S0));
+    FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0));
+    FQL_CHECK_CUDA(cudaEventRecord(ev_cpost, S0));
+
+    // ---- S2: BC loss + bc-flow backward, critic backward
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_f0, 0));
+    FQL_TRY(launch_bc_post(sh, w, raw, S2));
+    if (c.do_backward) {
+      BwdSpec bF;
+      memset(&bF, 0, sizeof(bF));
+      bF.nv = &L.net[FQL_NET_ACTOR_BC_FLOW]; bF.params = P; bF.grads = c.st->grads; bF.arena = L.arena;
+      bF.S = S; bF.E = 1; bF.M = B; bF.H = H; bF.X0 = w.XF; bF.Mcap0 = 2 * B; bF.buf = &w.pF; bF.p = 0; bF.r0 = 0;
+      bF.dOut = w.dpred; bF.dpp[0] = w.dF[0]; bF.dpp[1] = w.dF[1];
+      FQL_TRY(mlp_backward(bF, S2));
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_cpost, 0));
+      BwdSpec bC;
+      memset(&bC, 0, sizeof(bC));
+      bC.nv = &L.net[FQL_NET_CRITIC]; bC.params = P; bC.grads = c.st->grads; bC.arena = L.arena;
+      bC.S = S; bC.E = 2; bC.M = B; bC.H = H; bC.X0 = w.XC + (int64_t)1 * S * B * (sh.F + sh.A); bC.Mcap0 = B;
+      bC.buf = &w.pC; bC.p = 1; bC.r0 = 0; bC.dOut = w.dq; bC.dpp[0] = w.dC[0]; bC.dpp[1] = w.dC[1];
+      FQL_TRY(mlp_backward(bC, S2));
+    }
+    FQL_CHECK_CUDA(cudaEventRecord(ev_s2, S2));
+
+    // ---- S0: critic input gradient (stored params: no weight grads, fql.py:70), distill, onestep backward
+    if (c.do_backward) {
+      BwdSpec bQ;
+      memset(&bQ, 0, sizeof(bQ));
+      bQ.nv = &L.net[FQL_NET_CRITIC]; bQ.params = P; bQ.grads = nullptr; bQ.arena = L.arena;
+      bQ.S = S; bQ.E = 2; bQ.M = B; bQ.H = H; bQ.X0 = w.XC + (int64_t)2 * S * B * (sh.F + sh.A); bQ.Mcap0 = B;
+      bQ.buf = &w.pC; bQ.p = 2; bQ.r0 = 0; bQ.dOut = w.dqs; bQ.dpp[0] = w.dCp[0]; bQ.dpp[1] = w.dCp[1]; bQ.dX0 = w.dX0;
+      FQL_TRY(mlp_backward(bQ, S0));
+    }
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_euler, 0));
+    FQL_TRY(launch_actor_grad(sh, hp, w, raw, S0));
+    if (c.do_backward) {
+      BwdSpec bO;
+      memset(&bO, 0, sizeof(bO));
+      bO.nv = &L.net[FQL_NET_ACTOR_ONESTEP_FLOW]; bO.params = P; bO.grads = c.st->grads; bO.arena = L.arena;
+      bO.S = S; bO.E = 1; bO.M = B; bO.H = H; bO.X0 = w.XO + (int64_t)B * (sh.F + sh.A); bO.Mcap0 = 3 * B;
+      bO.buf = &w.pO; bO.p = 0; bO.r0 = B; bO.dOut = w.dapi; bO.dpp[0] = w.dO[0]; bO.dpp[1] = w.dO[1];
+      FQL_TRY(mlp_backward(bO, S0));
+    }
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
+  }
+
+  if (c.do_apply) {
+    FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, c.st->count, w.partials,
+                                     c.st->shadow, S0));
+    FQL_TRY(launch_grad_stats_final(L, S, w.partials, w.gstats, c.st->count, S0));
+  }
+  if (c.info) FQL_TRY(launch_finalize_info(sh, hp, raw, w.gstats, c.info, c.do_apply, S0));
+  return 0;
+}
+
+// Run `c` through a cached CUDA graph when possible (the ~150 launches of a B=256 step are launch-bound otherwise).
+int run_step(FqlContext* ctx, const StepCall& c, void* stream) {
+  FQL_REQUIRE(ctx != nullptr, "context is NULL");
+  FQL_REQUIRE(c.d && c.hp && c.st, "NULL argument");
+  cudaStream_t S0 = reinterpret_cast<cudaStream_t>(stream);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  FQL_CHECK_CUDA(cudaStreamIsCapturing(S0, &cap));
+  if (!ctx->use_graph || cap != cudaStreamCaptureStatusNone) return enqueue_step(ctx, c, S0);
+
+  std::vector<unsigned char> key;
+  auto push = [&](const void* p, size_t n) { key.insert(key.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
+  push(c.d, sizeof(FqlDims));
+  push(c.hp, sizeof(FqlHparams));
+  if (c.b) push(c.b, sizeof(FqlBatch));
+  push(c.st, sizeof(FqlState));
+  push(&c.raw, sizeof(void*)); push(&c.info, sizeof(void*)); push(&c.ws, sizeof(void*)); push(&c.ws_bytes, sizeof(size_t));
+  int flags[3] = {c.do_grads, c.do_backward, c.do_apply};
+  push(flags, sizeof(flags));
+  push(&S0, sizeof(S0));
+  GraphEntry* seen = nullptr;
+  for (auto& g : ctx->graphs)
+    if (g.key == key) {
+      if (g.exec) {
+        FQL_CHECK_CUDA(cudaGraphLaunch(g.exec, S0));
+        return 0;
+      }
+      seen = &g;
+    }
+  if (!seen) {
+    // First sight of this argument set: run eagerly (this also lets the driver load every kernel outside a capture);
+    // the second call captures, later calls replay.
+    if (ctx->graphs.size() >= 16) {
+      if (ctx->graphs.front().exec) cudaGraphExecDestroy(ctx->graphs.front().exec);
+      ctx->graphs.erase(ctx->graphs.begin());
+    }
+    ctx->graphs.push_back({key, nullptr});
+    return enqueue_step(ctx, c, S0);
+  }
+  // validate eagerly (errors must not surface in the middle of a capture)
+  {
+    Layout L;
+    WsPtrs w;
+    FQL_TRY(check_common(c.d, c.ws, c.ws_bytes, &L, &w));
+    FQL_REQUIRE(c.d->precision == FQL_PRECISION_FP32, "FQL_PRECISION_BF16_TC step is not built into this library version");
+  }
+  FQL_CHECK_CUDA(cudaStreamBeginCapture(S0, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_step(ctx, c, S0);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(S0, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  FQL_CHECK_CUDA(e);
+  cudaGraphExec_t exec = nullptr;
+  FQL_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
+  seen->exec = exec;
+  FQL_CHECK_CUDA(cudaGraphLaunch(exec, S0));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int fql_update_step(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlBatch* batch,
+                               const FqlState* st, float* info, void* workspace, size_t ws_bytes, void* stream) {
+  FQL_REQUIRE(batch != nullptr, "batch is NULL");
+  StepCall c{d, hp, batch, st, nullptr, info, workspace, ws_bytes, 1, 1, 1};
+  return run_step(ctx, c, stream);
+}
+
+extern "C" int fql_step_grads(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlBatch* batch,
+                              const FqlState* st, float* raw, void* workspace, size_t ws_bytes, void* stream) {
+  FQL_REQUIRE(batch != nullptr && raw != nullptr, "batch/raw is NULL");
+  StepCall c{d, hp, batch, st, raw, nullptr, workspace, ws_bytes, 1, 1, 0};
+  return run_step(ctx, c, stream);
+}
+
+extern "C" int fql_step_apply(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlState* st, const float* raw,
+                              float* info, void* workspace, size_t ws_bytes, void* stream) {
+  FQL_REQUIRE(raw != nullptr, "raw is NULL");
+  StepCall c{d, hp, nullptr, st, const_cast<float*>(raw), info, workspace, ws_bytes, 0, 0, 1};
+  return run_step(ctx, c, stream);
+}
+
+extern "C" int fql_total_loss(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlBatch* batch,
+                              const FqlState* st, float* info, void* workspace, size_t ws_bytes, void* stream) {
+  FQL_REQUIRE(batch != nullptr && info != nullptr, "batch/info is NULL");
+  StepCall c{d, hp, batch, st, nullptr, info, workspace, ws_bytes, 1, 0, 0};
+  return run_step(ctx, c, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// standalone forward entry points
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+size_t carve_forward(const FqlDims* d, int rows, int ens, int in_dim, int out_dim, bool ln, void* base, float** X, PassBuf* pb) {
+  Carver c{reinterpret_cast<char*>(base)};
+  *X = c.take((int64_t)d->num_seeds * rows * in_dim);
+  carve_pass(c, pb, d->num_seeds * ens, rows, d->hidden, d->num_hidden, out_dim, ln, false);
+  return c.off + 256;
+}
+}  // namespace
+
+extern "C" size_t fql_forward_workspace_bytes(const FqlDims* d, int32_t rows) {
+  if (fql_validate_dims(d)) return 0;
+  float* X;
+  PassBuf pb;
+  return carve_forward(d, rows, 2, d->obs_dim + d->action_dim + 1, d->action_dim > 1 ? d->action_dim : 1, true, nullptr, &X, &pb);
+}
+
+static int forward_net(const FqlDims* d, const Layout& L, int net, const float* params, const float* X, PassBuf* pb, int rows,
+                       cudaStream_t st) {
+  FwdSpec f;
+  memset(&f, 0, sizeof(f));
+  f.P = 1; f.nv[0] = &L.net[net]; f.params = params; f.arena = L.arena;
+  f.S = d->num_seeds; f.E = L.net[net].ens; f.M = rows; f.H = d->hidden; f.X0 = X; f.Mcap0 = rows; f.buf = pb;
+  return mlp_forward(f, st);
+}
+
+extern "C" int fql_mlp_forward(FqlContext*, const FqlDims* d, int32_t net, const float* params, const float* x, float* y,
+                               int32_t rows, void* workspace, size_t ws_bytes, void* stream) {
+  Layout L;
+  FQL_TRY(fql_build_layout(d, &L));
+  FQL_REQUIRE(net >= 0 && net < FQL_NUM_NETS && rows >= 1, "bad net/rows");
+  FQL_REQUIRE(d->precision == FQL_PRECISION_FP32, "fql_mlp_forward: FP32 only");
+  const NetView& nv = L.net[net];
+  float* X;
+  PassBuf pb;
+  const size_t need = carve_forward(d, rows, nv.ens, nv.in_dim, nv.out_dim, nv.ln, nullptr, &X, &pb);
+  FQL_REQUIRE(workspace && ws_bytes >= need, "workspace too small: have %zu need %zu", ws_bytes, need);
+  carve_forward(d, rows, nv.ens, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FQL_TRY(forward_net(d, L, net, params, x, &pb, rows, st));
+  FQL_CHECK_CUDA(cudaMemcpyAsync(y, pb.out, sizeof(float) * (size_t)d->num_seeds * nv.ens * rows * nv.out_dim,
+                                 cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int fql_sample_actions(FqlContext*, const FqlDims* d, const float* params, const void*, const float* obs,
+                                  const float* noise, float* actions_out, int32_t rows, void* workspace, size_t ws_bytes,
+                                  void* stream) {
+  Layout L;
+  FQL_TRY(fql_build_layout(d, &L));
+  FQL_REQUIRE(rows >= 1, "rows=%d", rows);
+  FQL_REQUIRE(d->precision == FQL_PRECISION_FP32, "fql_sample_actions: FP32 only in this library version");
+  const NetView& nv = L.net[FQL_NET_ACTOR_ONESTEP_FLOW];
+  float* X;
+  PassBuf pb;
+  const size_t need = carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, nullptr, &X, &pb);
+  FQL_REQUIRE(workspace && ws_bytes >= need, "workspace too small: have %zu need %zu", ws_bytes, need);
+  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t R = (int64_t)d->num_seeds * rows;
+  FQL_TRY(launch_concat(obs, d->obs_dim, noise, d->action_dim, 0.f, 0, X, R, st));
+  FQL_TRY(forward_net(d, L, FQL_NET_ACTOR_ONESTEP_FLOW, params, X, &pb, rows, st));
+  FQL_TRY(launch_clip(pb.out, actions_out, R * d->action_dim, st));
+  return 0;
+}
+
+extern "C" int fql_compute_flow_actions(FqlContext*, const FqlDims* d, const float* params, const void*, const float* obs,
+                                        const float* noise, float* actions_out, int32_t rows, void* workspace, size_t ws_bytes,
+                                        void* stream) {
+  Layout L;
+  FQL_TRY(fql_build_layout(d, &L));
+  FQL_REQUIRE(rows >= 1, "rows=%d", rows);
+  FQL_REQUIRE(d->precision == FQL_PRECISION_FP32, "fql_compute_flow_actions: FP32 only in this library version");
+  const NetView& nv = L.net[FQL_NET_ACTOR_BC_FLOW];
+  float* X;
+  PassBuf pb;
+  const size_t need = carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, nullptr, &X, &pb);
+  FQL_REQUIRE(workspace && ws_bytes >= need, "workspace too small: have %zu need %zu", ws_bytes, need);
+  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t R = (int64_t)d->num_seeds * rows;
+  FQL_TRY(launch_concat(obs, d->obs_dim, noise, d->action_dim, 0.f, 1, X, R, st));
+  for (int i = 0; i < d->flow_steps; i++) {
+    FQL_TRY(forward_net(d, L, FQL_NET_ACTOR_BC_FLOW, params, X, &pb, rows, st));
+    FQL_TRY(launch_euler_inplace(X, pb.out, d->obs_dim, d->action_dim, R, i, d->flow_steps, actions_out, st));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// misc API
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int fql_version(void) { return FQL_ABI_VERSION; }
+extern "C" const char* fql_last_error(void) { return g_err; }
+extern "C" const char* fql_info_name(int i) {
+  static const char* names[FQL_NUM_INFO] = {
+      "critic/critic_loss", "critic/q_mean", "critic/q_max", "critic/q_min", "actor/actor_loss", "actor/bc_flow_loss",
+      "actor/distill_loss", "actor/q_loss", "actor/q", "actor/mse", "grad/max", "grad/min", "grad/norm"};
+  return (i >= 0 && i < FQL_NUM_INFO) ? names[i] : nullptr;
+}
+extern "C" int64_t fql_arena_floats(const FqlDims* d) {
+  Layout L;
+  if (fql_build_layout(d, &L)) return -1;
+  return L.arena;
+}
+extern "C" size_t fql_workspace_bytes(const FqlDims* d) {
+  Layout L;
+  if (fql_build_layout(d, &L)) return 0;
+  WsPtrs w;
+  return carve_workspace(d, L, nullptr, &w);
+}
+extern "C" size_t fql_shadow_bytes(const FqlDims* d) {
+  (void)d;
+  return 0;
+}
+extern "C" int fql_refresh_shadow(const FqlDims*, const float*, void*, void*) { return 0; }
+
+extern "C" int fql_layout(const FqlDims* d, FqlLeaf* leaves, int32_t cap, int32_t* n_leaves) {
+  Layout L;
+  FQL_TRY(fql_build_layout(d, &L));
+  int n = 0;
+  auto put = [&](int net, int layer, int kind, int ens, int rows, int cols, int64_t off) {
+    if (leaves && n < cap) leaves[n] = FqlLeaf{net, layer, kind, ens, rows, cols, off};
+    n++;
+  };
+  for (int t = 0; t < FQL_NUM_NETS; t++) {
+    const NetView& v = L.net[t];
+    for (int l = 0; l < v.n_layers; l++) {
+      put(t, l, FQL_LEAF_KERNEL, v.ens, v.k_of(l), v.n_of(l), v.off_w[l]);
+      put(t, l, FQL_LEAF_BIAS, v.ens, 1, v.n_of(l), v.off_b[l]);
+      if (v.ln && l + 1 < v.n_layers) {
+        put(t, l, FQL_LEAF_LN_SCALE, v.ens, 1, v.n_of(l), v.off_lns[l]);
+        put(t, l, FQL_LEAF_LN_BIAS, v.ens, 1, v.n_of(l), v.off_lnb[l]);
+      }
+    }
+  }
+  if (n_leaves) *n_leaves = n;
+  FQL_REQUIRE(!leaves || n <= cap, "leaf table too small: need %d", n);
+  return 0;
+}
