@@ -25,7 +25,8 @@ class FqlDims(C.Structure):
 
 
 class FqlHparams(C.Structure):
-    _fields_ = [(n, C.c_float) for n in ('lr', 'beta1', 'beta2', 'eps', 'discount', 'tau', 'alpha', 'reserved')]
+    _fields_ = [(n, C.c_float) for n in ('lr', 'beta1', 'beta2', 'eps', 'discount', 'tau', 'alpha', 'one_minus_beta1',
+                                         'one_minus_beta2', 'one_minus_tau')] + [('reserved', C.c_float * 2)]
 
 
 class FqlLeaf(C.Structure):
@@ -54,6 +55,7 @@ _SIGS = {
     'fql_info_name': (C.c_char_p, [C.c_int]),
     'fql_context_create': (C.c_int, [C.POINTER(C.c_void_p)]),
     'fql_context_destroy': (C.c_int, [C.c_void_p]),
+    'fql_launch_count': (C.c_longlong, [C.c_void_p]),
     'fql_arena_floats': (C.c_int64, [C.POINTER(FqlDims)]),
     'fql_layout': (C.c_int, [C.POINTER(FqlDims), C.POINTER(FqlLeaf), C.c_int32, C.POINTER(C.c_int32)]),
     'fql_workspace_bytes': (C.c_size_t, [C.POINTER(FqlDims)]),
@@ -117,6 +119,7 @@ def make_dims(batch, obs_dim, action_dim, *, global_batch=None, hidden=512, num_
 def make_hparams(lr=3e-4, discount=0.99, tau=0.005, alpha=300.0, beta1=0.9, beta2=0.999, eps=1e-8):
     h = FqlHparams()
     h.lr, h.beta1, h.beta2, h.eps, h.discount, h.tau, h.alpha = lr, beta1, beta2, eps, discount, tau, alpha
+    h.one_minus_beta1, h.one_minus_beta2, h.one_minus_tau = 1.0 - beta1, 1.0 - beta2, 1.0 - tau  # double, then rounded
     return h
 
 

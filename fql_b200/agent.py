@@ -269,22 +269,6 @@ class FQLAgent:
         self._bufs[B] = dict(d=d, dev=dev, pin=pin, ws=ws, ws_bytes=ws_bytes, fb=fb, st=st, info=info, raw=raw)
         return self._bufs[B]
 
-    def _stage(self, bufs, batch, noise, step_for_noise):
-        S = self.num_seeds
-        h2d = 0
-        for k in _BATCH_KEYS:
-            h2d += self._stage_one(bufs, k, batch[k])
-        if noise is not None:
-            for k in NOISE_KEYS:
-                h2d += self._stage_one(bufs, k, noise[k])
-        else:
-            dev = bufs['dev']
-            seed = int(self.rng[0]) | (int(self.rng[1]) << 32)
-            _lib.check(self._lib.fql_fill_noise(C.byref(bufs['d']), C.c_uint64(seed), C.c_uint64(step_for_noise),
-                                                _ptr(dev['z_next']), _ptr(dev['x0']), _ptr(dev['t']), _ptr(dev['z']),
-                                                _ptr(dev['z_metric']), self._stream()), 'fql_fill_noise')
-        return h2d
-
     def _stage_one(self, bufs, k, src):
         dst = bufs['dev'][k]
         if isinstance(src, torch.Tensor) and src.is_cuda:
@@ -313,10 +297,29 @@ class FQLAgent:
     def update(self, batch, noise=None):
         """One training step.  `batch`: dict of host numpy arrays (main.py:201) or torch tensors, [B,...] (or [S,B,...]
         when num_seeds>1).  Returns (self, info)."""
+        bufs = self.stage(batch, noise)
+        return self, self.step(bufs, fill_noise=noise is None)
+
+    def stage(self, batch, noise=None):
+        """Copy one batch (and optionally explicit noise) into the static device buffers of its batch size."""
         B = int(np.shape(batch['actions'])[-2])
         bufs = self._step_bufs(B)
         with torch.cuda.device(self.device):
-            self.last_h2d_bytes = self._stage(bufs, batch, noise, self._host_step)
+            h2d = 0
+            for k in _BATCH_KEYS:
+                h2d += self._stage_one(bufs, k, batch[k])
+            if noise is not None:
+                for k in NOISE_KEYS:
+                    h2d += self._stage_one(bufs, k, noise[k])
+            self.last_h2d_bytes = h2d
+        return bufs
+
+    def step(self, bufs, fill_noise=True):
+        """Enqueue one update on the staged buffers: [device noise] -> fql_update_step (or the data-parallel split with
+        an NCCL all-reduce of the gradient arena in between) -> async copy of the 13 metrics to pinned host memory."""
+        with torch.cuda.device(self.device):
+            if fill_noise:
+                self._fill_noise(bufs, self._host_step)
             self._host_step += 1
             a = (self._ctx, C.byref(bufs['d']), C.byref(self._hp))
             if self.world == 1:
@@ -332,17 +335,28 @@ class FQLAgent:
                 dist.all_reduce(bufs['raw'][:, 9:11], op=dist.ReduceOp.MAX, group=self.pg)
                 _lib.check(self._lib.fql_step_apply(*a, C.byref(bufs['st']), _ptr(bufs['raw']), _ptr(bufs['info']),
                                                     _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_step_apply')
-            return self, self._info_out(bufs['info'])
+            return self._info_out(bufs['info'])
+
+    def _fill_noise(self, bufs, step_for_noise):
+        dev = bufs['dev']
+        seed = int(self.rng[0]) | (int(self.rng[1]) << 32)
+        _lib.check(self._lib.fql_fill_noise(C.byref(bufs['d']), C.c_uint64(seed), C.c_uint64(step_for_noise),
+                                            _ptr(dev['z_next']), _ptr(dev['x0']), _ptr(dev['t']), _ptr(dev['z']),
+                                            _ptr(dev['z_metric']), self._stream()), 'fql_fill_noise')
+
+    def launch_count(self):
+        """Kernels this agent's context has enqueued so far (graph replays count their kernel nodes)."""
+        return int(self._lib.fql_launch_count(self._ctx))
 
     _host_step = 0
     last_h2d_bytes = 0
 
     def total_loss(self, batch, grad_params=None, rng=None, noise=None):
         """Forward-only losses (agents/fql.py:94-111 as called by main.py:284): returns (loss, info[10 keys])."""
-        B = int(np.shape(batch['actions'])[-2])
-        bufs = self._step_bufs(B)
         with torch.cuda.device(self.device):
-            self._stage(bufs, batch, noise, (1 << 62) + self._host_step)
+            bufs = self.stage(batch, noise)
+            if noise is None:
+                self._fill_noise(bufs, (1 << 62) + self._host_step)
             _lib.check(self._lib.fql_total_loss(self._ctx, C.byref(bufs['d']), C.byref(self._hp), C.byref(bufs['fb']),
                                                 C.byref(bufs['st']), _ptr(bufs['info']), _ptr(bufs['ws']), bufs['ws_bytes'],
                                                 self._stream()), 'fql_total_loss')

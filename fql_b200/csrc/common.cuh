@@ -20,7 +20,12 @@ void fql_set_error(const char* fmt, ...);
       return 1;                                                                                    \
     }                                                                                              \
   } while (0)
-#define FQL_CHECK_LAUNCH() FQL_CHECK_CUDA(cudaGetLastError())
+extern thread_local long long g_fql_launches;  // kernels enqueued by this thread (diagnostics: fql_launch_count)
+#define FQL_CHECK_LAUNCH()                 \
+  do {                                     \
+    g_fql_launches++;                      \
+    FQL_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
 #define FQL_REQUIRE(cond, ...)       \
   do {                               \
     if (!(cond)) {                   \

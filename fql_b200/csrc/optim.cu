@@ -25,9 +25,16 @@ __global__ void __launch_bounds__(256) adam_polyak_stats_kernel(Layout L, FqlHpa
     if (threadIdx.x == 0) { part[0] = 0.f; part[1] = 0.f; part[2] = 0.f; }
     return;
   }
-  const float t = (float)(count[0] + 1);
-  const float bc1 = 1.0f - powf(hp.beta1, t);
-  const float bc2 = 1.0f - powf(hp.beta2, t);
+  // optax bias_correction: 1 - decay**count in float32.  A correctly rounded float pow (via double) once per CTA: one ulp
+  // of pow(0.999f, t) is 7.5e-6 of (1 - 0.999^8), so a sloppy powf would show up in the parameters.
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)(count[0] + 1);
+    s_bc[0] = 1.0f - (float)pow((double)hp.beta1, t);
+    s_bc[1] = 1.0f - (float)pow((double)hp.beta2, t);
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2 = s_bc[1];
   float4 g = *reinterpret_cast<const float4*>(grads + base + off);
   float4 p = *reinterpret_cast<const float4*>(params + base + off);
   float4 m = *reinterpret_cast<const float4*>(mu + base + off);
@@ -41,8 +48,8 @@ __global__ void __launch_bounds__(256) adam_polyak_stats_kernel(Layout L, FqlHpa
     mx = fmaxf(mx, gi);
     mn = fminf(mn, gi);
     sq += gi * gi;
-    mr[i] = hp.beta1 * mr[i] + (1.0f - hp.beta1) * gi;
-    vr[i] = hp.beta2 * vr[i] + (1.0f - hp.beta2) * gi * gi;
+    mr[i] = hp.beta1 * mr[i] + hp.one_minus_beta1 * gi;
+    vr[i] = hp.beta2 * vr[i] + hp.one_minus_beta2 * gi * gi;
     const float mhat = mr[i] / bc1;
     const float vhat = vr[i] / bc2;
     pn[i] = pr[i] + (-hp.lr * (mhat / (sqrtf(vhat) + hp.eps)));
@@ -53,7 +60,7 @@ __global__ void __launch_bounds__(256) adam_polyak_stats_kernel(Layout L, FqlHpa
   if (off >= cri.begin && off < cri.end) {  // Polyak with the pre-step critic values still in registers
     const int64_t toff = base + off - cri.begin + tgt.begin;
     float4 tp = *reinterpret_cast<const float4*>(params + toff);
-    const float omt = 1.0f - hp.tau;
+    const float omt = hp.one_minus_tau;
     tp.x = pr[0] * hp.tau + tp.x * omt;
     tp.y = pr[1] * hp.tau + tp.y * omt;
     tp.z = pr[2] * hp.tau + tp.z * omt;

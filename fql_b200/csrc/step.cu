@@ -17,6 +17,7 @@
 // errors
 // ---------------------------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
+thread_local long long g_fql_launches = 0;
 void fql_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -332,17 +333,22 @@ int mlp_backward(const BwdSpec& b, cudaStream_t st) {
 struct GraphEntry {
   std::vector<unsigned char> key;
   cudaGraphExec_t exec;
+  long long kernels;  // kernel nodes in the captured graph
 };
 struct FqlContext {
-  cudaStream_t s1 = nullptr, s2 = nullptr;
+  cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr;  // s0 stands in for the caller's stream when that is the legacy default
   cudaEvent_t ev[8] = {};
   std::vector<GraphEntry> graphs;
   int use_graph = 1;
+  long long launches = 0;  // kernels enqueued through this context
 };
+
+extern "C" long long fql_launch_count(FqlContext* c) { return c ? c->launches : -1; }
 
 extern "C" int fql_context_create(FqlContext** out) {
   FQL_REQUIRE(out != nullptr, "out is NULL");
   FqlContext* c = new FqlContext();
+  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking));
   FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s1, cudaStreamNonBlocking));
   FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking));
   for (auto& e : c->ev) FQL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -356,6 +362,7 @@ extern "C" int fql_context_destroy(FqlContext* c) {
   if (!c) return 0;
   for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->s0) cudaStreamDestroy(c->s0);
   if (c->s1) cudaStreamDestroy(c->s1);
   if (c->s2) cudaStreamDestroy(c->s2);
   delete c;
@@ -493,13 +500,15 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
 }
 
 // Run `c` through a cached CUDA graph when possible (the ~150 launches of a B=256 step are launch-bound otherwise).
-int run_step(FqlContext* ctx, const StepCall& c, void* stream) {
-  FQL_REQUIRE(ctx != nullptr, "context is NULL");
-  FQL_REQUIRE(c.d && c.hp && c.st, "NULL argument");
-  cudaStream_t S0 = reinterpret_cast<cudaStream_t>(stream);
+int run_step_on(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   FQL_CHECK_CUDA(cudaStreamIsCapturing(S0, &cap));
-  if (!ctx->use_graph || cap != cudaStreamCaptureStatusNone) return enqueue_step(ctx, c, S0);
+  if (!ctx->use_graph || cap != cudaStreamCaptureStatusNone) {
+    const long long before = g_fql_launches;
+    const int rc0 = enqueue_step(ctx, c, S0);
+    ctx->launches += g_fql_launches - before;
+    return rc0;
+  }
 
   std::vector<unsigned char> key;
   auto push = [&](const void* p, size_t n) { key.insert(key.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
@@ -516,6 +525,7 @@ int run_step(FqlContext* ctx, const StepCall& c, void* stream) {
     if (g.key == key) {
       if (g.exec) {
         FQL_CHECK_CUDA(cudaGraphLaunch(g.exec, S0));
+        ctx->launches += g.kernels;
         return 0;
       }
       seen = &g;
@@ -527,8 +537,11 @@ int run_step(FqlContext* ctx, const StepCall& c, void* stream) {
       if (ctx->graphs.front().exec) cudaGraphExecDestroy(ctx->graphs.front().exec);
       ctx->graphs.erase(ctx->graphs.begin());
     }
-    ctx->graphs.push_back({key, nullptr});
-    return enqueue_step(ctx, c, S0);
+    ctx->graphs.push_back({key, nullptr, 0});
+    const long long before = g_fql_launches;
+    const int rc0 = enqueue_step(ctx, c, S0);
+    ctx->launches += g_fql_launches - before;
+    return rc0;
   }
   // validate eagerly (errors must not surface in the middle of a capture)
   {
@@ -538,7 +551,9 @@ int run_step(FqlContext* ctx, const StepCall& c, void* stream) {
     FQL_REQUIRE(c.d->precision == FQL_PRECISION_FP32, "FQL_PRECISION_BF16_TC step is not built into this library version");
   }
   FQL_CHECK_CUDA(cudaStreamBeginCapture(S0, cudaStreamCaptureModeThreadLocal));
+  const long long before = g_fql_launches;
   int rc = enqueue_step(ctx, c, S0);
+  const long long nk = g_fql_launches - before;
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(S0, &graph);
   if (rc) {
@@ -550,8 +565,26 @@ int run_step(FqlContext* ctx, const StepCall& c, void* stream) {
   FQL_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
   cudaGraphDestroy(graph);
   seen->exec = exec;
+  seen->kernels = nk;
   FQL_CHECK_CUDA(cudaGraphLaunch(exec, S0));
+  ctx->launches += nk;
   return 0;
+}
+
+
+// The legacy default stream (what torch hands out by default) can neither be captured nor forked from with non-blocking
+// streams safely, so the step runs on the context's own stream, ordered after / before the caller's stream with events.
+int run_step(FqlContext* ctx, const StepCall& c, void* stream) {
+  FQL_REQUIRE(ctx != nullptr, "context is NULL");
+  FQL_REQUIRE(c.d && c.hp && c.st, "NULL argument");
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  if (user != nullptr && user != cudaStreamLegacy) return run_step_on(ctx, c, user);
+  FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[6], user));
+  FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s0, ctx->ev[6], 0));
+  const int rc = run_step_on(ctx, c, ctx->s0);
+  FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[7], ctx->s0));
+  FQL_CHECK_CUDA(cudaStreamWaitEvent(user, ctx->ev[7], 0));
+  return rc;
 }
 
 }  // namespace

@@ -59,7 +59,10 @@ typedef struct FqlDims {
 typedef struct FqlHparams {
   float lr, beta1, beta2, eps;
   float discount, tau, alpha;
-  float reserved;
+  /* (1-beta1), (1-beta2), (1-tau) evaluated in double on the host and then rounded, as the reference's Python-float
+   * arithmetic does (optax `(1 - decay) * g`, fql.py:116 `tp * (1 - tau)`): 1.0f-0.999f differs from (float)0.001 by 1.3e-5. */
+  float one_minus_beta1, one_minus_beta2, one_minus_tau;
+  float reserved[2];
 } FqlHparams;
 
 typedef struct FqlLeaf {
@@ -107,6 +110,7 @@ const char* fql_last_error(void);
 const char* fql_info_name(int i);
 int fql_context_create(FqlContext** out);
 int fql_context_destroy(FqlContext* ctx);
+long long fql_launch_count(FqlContext* ctx); /* kernels enqueued through ctx so far (graph replays included) */
 
 /* ---- layout: replaces the pytree structure built by FQLAgent.create (agents/fql.py:205-242) ------------- */
 int64_t fql_arena_floats(const FqlDims* d);                         /* floats per seed (leaves padded to 32) */

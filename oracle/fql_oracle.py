@@ -318,15 +318,20 @@ def grad_stats(grads):
 
 
 def adam_update(params, grads, mu, nu, count, lr, b1=0.9, b2=0.999, eps=1e-8):
-    """optax.adam (scale_by_adam + scale(-lr)) then optax.apply_updates; count is the PRE-update int32."""
+    """optax.adam (scale_by_adam + scale(-lr)) then optax.apply_updates; count is the PRE-update int32.
+    optax's bias_correction evaluates `1 - decay**count` with a Python-float decay and an int32 count array, i.e. in
+    float32 (jax default dtype) -- pow(0.999f, t) -- and that is restated here in float32 for every oracle dtype: at
+    small t it differs from the double value by ~1e-5 relative, which is the reference's arithmetic, not noise."""
     t = count + 1
+    bc1 = np.float32(1) - np.power(np.float32(b1), np.float32(t))
+    bc2 = np.float32(1) - np.power(np.float32(b2), np.float32(t))
 
     def leaf(p, g, m, v):
         dt = p.dtype.type
         m2 = dt(b1) * m + dt(1 - b1) * g
         v2 = dt(b2) * v + dt(1 - b2) * g * g
-        mhat = m2 / dt(1 - b1 ** t)
-        vhat = v2 / dt(1 - b2 ** t)
+        mhat = m2 / dt(bc1)
+        vhat = v2 / dt(bc2)
         upd = -dt(lr) * (mhat / (np.sqrt(vhat) + dt(eps)))
         return p + upd, m2, v2
 
@@ -402,7 +407,7 @@ def init_state(params, warm=False, seed=0):
     if warm:
         rng = np.random.default_rng(seed + 77)
         mu = tree_map(lambda p: (1e-3 * rng.standard_normal(p.shape)).astype(p.dtype), params)
-        nu = tree_map(lambda p: (1e-6 * rng.random(p.shape)).astype(p.dtype), params)
+        nu = tree_map(lambda p: (1e-6 * (0.5 + rng.random(p.shape))).astype(p.dtype), params)  # |m|/sqrt(v) = O(1)
         # target-critic moments are identically zero in a real run (zero grads)
         mu['modules_target_critic'] = _zeros_like_tree(params['modules_target_critic'])
         nu['modules_target_critic'] = _zeros_like_tree(params['modules_target_critic'])

@@ -48,3 +48,16 @@ def stack_trees(trees):
     if isinstance(trees[0], dict):
         return {k: stack_trees([t[k] for t in trees]) for k in trees[0]}
     return np.stack(trees, 0)
+
+
+def info_close(key, got, ref_info, tol):
+    """Scalars that are means of signed quantities (q, q_loss, q_mean) cancel: their tolerance is relative to the scale
+    of the quantity being averaged (max |q|), not to the possibly near-zero mean itself."""
+    r = float(ref_info[key])
+    scale = max(abs(r), 1e-3)
+    if key in ('actor/q', 'actor/q_loss', 'critic/q_mean', 'actor/actor_loss'):
+        qs = max(abs(float(ref_info['critic/q_max'])), abs(float(ref_info['critic/q_min'])), abs(float(ref_info['actor/q'])))
+        if key == 'actor/q_loss' and abs(float(ref_info['actor/q'])) > 0:
+            qs *= abs(r) / abs(float(ref_info['actor/q']))       # lam factor when normalize_q_loss
+        scale = max(scale, qs)
+    assert abs(got - r) <= tol * scale, (key, got, r, scale)

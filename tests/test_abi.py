@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(L):
 
 def test_struct_sizes_match_header(L):
     assert C.sizeof(L.FqlDims) == 16 * 4
-    assert C.sizeof(L.FqlHparams) == 8 * 4
+    assert C.sizeof(L.FqlHparams) == 12 * 4
     assert C.sizeof(L.FqlBatch) == 10 * 8
     assert C.sizeof(L.FqlState) == 6 * 8
     assert C.sizeof(L.FqlLeaf) == 6 * 4 + 8

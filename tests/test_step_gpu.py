@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import fql_oracle as O
-from tests.helpers import cuda_agent_from_state, f32, make_case, rel_err, stack_trees
+from tests.helpers import cuda_agent_from_state, f32, info_close, make_case, rel_err, stack_trees
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -46,9 +46,7 @@ def check_update(agent, cfg, state, batch, noise, seeds=None):
     for si in range(S):
         pick = (lambda x: x) if S == 1 else (lambda x: x[si])
         for k in O.INFO_KEYS:
-            v = info[k] if S == 1 else info[k][si]
-            r = float(ref_infos[si][k])
-            assert abs(v - r) <= TOL * max(abs(r), 1e-3) * 3, (k, v, r)
+            info_close(k, info[k] if S == 1 else info[k][si], ref_infos[si], 3 * TOL)
         for which, ref in (('grads', ref_grads[si]), ('params', ref_states[si]['params']), ('mu', ref_states[si]['mu']),
                            ('nu', ref_states[si]['nu'])):
             for (path, r), (_, g) in zip(O.tree_leaves(ref), O.tree_leaves(got[which])):
@@ -86,7 +84,7 @@ def test_two_consecutive_steps_and_graph_replay():
         st, info_ref, _ = O.update(st, cfg, ba, nz)
         _, info = agent.update(f32(ba), noise=f32(nz))
         for k in O.INFO_KEYS:
-            assert abs(info[k] - float(info_ref[k])) <= 5e-5 * max(abs(float(info_ref[k])), 1e-3), (i, k)
+            info_close(k, info[k], info_ref, 5e-5)
         got = agent.export_tree('params')
         for (path, r), (_, g) in zip(O.tree_leaves(st['params']), O.tree_leaves(got)):
             assert rel_err(g, r) <= 1e-5 * (i + 1), (i, path)
@@ -112,8 +110,8 @@ def test_total_loss_forward_only():
     loss, info = agent.total_loss(f32(batch), noise=f32(noise))
     ref_loss, ref_info, _ = O.total_loss(state['params'], cfg, batch, noise, with_grads=False)
     assert abs(loss - ref_loss) <= 1e-5 * abs(ref_loss)
-    for k, v in ref_info.items():
-        assert abs(info[k] - float(v)) <= 1e-5 * max(abs(float(v)), 1e-3), k
+    for k in ref_info:
+        info_close(k, info[k], ref_info, 3 * TOL)
     after = agent.export_tree('params')
     for (_, a), (_, b) in zip(O.tree_leaves(before), O.tree_leaves(after)):
         assert np.array_equal(a, b)
@@ -155,8 +153,7 @@ def test_large_batch_properties():
     agent.load_tree(f32(state['params']), f32(state['mu']), f32(state['nu']), state['count'])
     _, info = agent.update(f32(big_b), noise=f32(big_n))
     for k in O.INFO_KEYS:
-        r = float(info_ref[k])
-        assert abs(info[k] - r) <= 3e-5 * max(abs(r), 1e-3), (k, info[k], r)
+        info_close(k, info[k], info_ref, 3 * TOL)
     got = agent.export_tree('grads')
     for (path, r), (_, g) in zip(O.tree_leaves(grads_ref), O.tree_leaves(got)):
         assert rel_err(g, r) <= TOL, path
