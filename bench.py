@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- FQL update throughput on B200 (the metric BASELINE.json names), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload antmaze-large] [--batch 256] [--seeds 1]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (N > 1, one rank per GPU)
+  python bench.py --impl reference ...       CPU arm: the oracle's fp32 restatement of the reference on the host cores
+
+A "step" is one FQLAgent.update (agents/fql.py:122-133) on one synthetic batch of the named OGBench shape.
+  value   device-timed samples/s with the batch already resident in HBM (CUDA events around every step, max over ranks)
+  e2e     the same through the public API `agent.update(host_batch)`: pinned H2D of the batch + D2H of the 13 metrics
+N > 1 is data parallel, weak scaling: every rank holds `--batch` rows of a global batch of N*batch, gradients are
+all-reduced over NCCL, value = global samples/s.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # BASELINE.json configs 1-4 (state-based); SURVEY 8d hyper-parameters
+    'cube-single': dict(F=28, A=5, cfg=dict(alpha=300.0)),
+    'antmaze-large': dict(F=29, A=8, cfg=dict(q_agg='min', alpha=10.0)),
+    'humanoidmaze-medium': dict(F=69, A=21, cfg=dict(discount=0.995, alpha=30.0)),
+    'puzzle-4x4': dict(F=83, A=5, cfg=dict(normalize_q_loss=True, alpha=1000.0)),  # F=83 assumed (unverified)
+}
+
+
+def flops_per_sample(F, A, H=512):
+    """Algorithmic FLOPs of one update per sample: MACs x2 of the Dense layers only."""
+    G = lambda d, o: 2 * (d * H + 3 * H * H + H * o)
+    d_bc, d_os, d_c = F + A + 1, F + A, F + A
+    fwd = 11 * G(d_bc, A) + 3 * G(d_os, A) + 6 * G(d_c, 1)
+    bwd = (2 * G(d_bc, A) - 2 * d_bc * H) + (2 * G(d_os, A) - 2 * d_os * H) + 2 * (2 * G(d_c, 1) - 2 * d_c * H) \
+        + 2 * (G(d_c, 1) - 2 * F * H)
+    return fwd + bwd
+
+
+def hbm_bytes_per_step(p_train, p_target, B, F, A):
+    """Algorithmic HBM bytes of one update: Adam 28 B/param, Polyak 8 B/target param (fused with Adam's read of
+    the critic), every weight read once by the GEMMs (4 B), the batch."""
+    return 28 * p_train + 8 * p_target + 4 * (p_train + p_target) + B * (2 * F + A + 2) * 4
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return dict(hbm=p['hbm_gbs'], tc=p.get('bf16_tflops_sustained', p['bf16_tflops']), src='measured (MEASURED_PEAKS.json)')
+    except Exception:
+        return dict(hbm=6650.0, tc=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
+        if not rows:
+            return None
+        sm = sorted(int(r[0]) for r in rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(rows[0][1]), reasons=reasons, samples=len(rows))
+
+
+def make_host_batches(n, B, F, A, seeds, seed0=0):
+    import numpy as np
+    out = []
+    for i in range(n):
+        rng = np.random.default_rng(seed0 + i)
+        shp = (seeds, B) if seeds > 1 else (B,)
+        rew = -(rng.random(shp) >= 0.01).astype(np.float32)
+        out.append(dict(
+            observations=rng.standard_normal(shp + (F,), dtype=np.float32),
+            actions=np.clip(rng.uniform(-1, 1, shp + (A,)), -1 + 1e-5, 1 - 1e-5).astype(np.float32),
+            next_observations=rng.standard_normal(shp + (F,), dtype=np.float32),
+            rewards=rew, masks=(rew != 0).astype(np.float32), terminals=np.zeros(shp, np.float32)))
+    return out
+
+
+def cpu_reference_arm(wl, B, steps, warmup, budget_s=20.0):
+    """The reference's CPU path: JAX is not installed, so this is oracle/fql_torch_cpu.py, the fp32 torch-CPU
+    restatement of FQLAgent.update (autograd, MKL, every host core), same shapes and hyper-parameters.  kind='port'."""
+    import numpy as np
+    import torch
+    from oracle import fql_oracle as O
+    from oracle.fql_torch_cpu import TorchCpuAgent
+    cfg = dict(O.DEFAULT_CONFIG)
+    cfg.update(wl['cfg'])
+    F, A = wl['F'], wl['A']
+    agent = TorchCpuAgent(O.init_params(1, F, A, cfg, dtype=np.float32), cfg)
+    batches = make_host_batches(4, B, F, A, 1)
+    noises = [O.make_noise(i, B, A, np.float32) for i in range(4)]
+    for i in range(max(1, min(warmup, 3))):
+        agent.update(batches[i % 4], noises[i % 4])
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        info, _ = agent.update(batches[i % 4], noises[i % 4])
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 3:
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(ms_per_step=med * 1e3, steps_measured=len(times), cores=torch.get_num_threads(), loss=info['critic/critic_loss'])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='antmaze-large', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=256, help='rows per GPU (per seed)')
+    ap.add_argument('--seeds', type=int, default=1, help='independent agents vectorised on each GPU')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    F, A = wl['F'], wl['A']
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    config = dict(workload=f'{args.workload}-shaped synthetic (obs {F}, act {A}), FQL update, batch {args.batch}/GPU, '
+                           f'{args.seeds} seed(s)/GPU, 4x512 MLPs, flow_steps 10, ' + ', '.join(f'{k}={v}' for k, v in wl['cfg'].items()),
+                  batch_per_gpu=args.batch, global_batch=args.batch * max(world, 1), seeds_per_gpu=args.seeds,
+                  parallelism=f'dp{world}' if world > 1 else 'single', l2='flushed between timed steps (256 MiB write)')
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        r = cpu_reference_arm(wl, args.batch, args.steps, args.warmup)
+        sps = 1e3 / r['ms_per_step']
+        val = sps * args.batch
+        sample = f"{r['steps_measured']} full updates of the same workload at batch {args.batch} (median), fp32 torch-CPU (MKL, autograd)"
+        print(json.dumps(dict(
+            impl='reference', metric='fql_update_samples_per_sec', value=val, unit='samples/s', steps_per_sec=sps, n_gpus=0,
+            steps=r['steps_measured'], warmup=min(args.warmup, 2), ms_per_step=r['ms_per_step'], higher_is_better=True,
+            scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', config=config,
+            cpu_baseline=dict(value=val, unit='samples/s', cores=r['cores'], kind='port', sample=sample),
+            e2e=dict(value=val, unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+            note='reference JAX is not installable here (no jax/flax/optax, no network): CPU restatement of the reference, '
+                 'not JAX/XLA')))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fql_b200 import FQLAgent, get_config
+
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+        pg = dist.group.WORLD
+    cfg = get_config()
+    cfg.update(wl['cfg'])
+    cfg['batch_size'] = args.batch
+    agent = FQLAgent.create(0, np.zeros((1, F), np.float32), np.zeros((1, A), np.float32), cfg, num_seeds=args.seeds,
+                            precision=args.precision, process_group=pg)
+    batches = make_host_batches(8, args.batch, F, A, args.seeds, seed0=1000 * rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    stream = torch.cuda.Stream()  # a real (non-legacy) stream: the library captures its step graph on it
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        # ---------------- device-resident leg: `value`
+        bufs = agent.stage(batches[0])
+        for _ in range(W):
+            agent.step(bufs)
+        barrier()
+        l0 = agent.launch_count()
+        clocks = ClockSampler(local_rank) if rank == 0 else None
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        for i in range(K):
+            flush.zero_()
+            ev[i][0].record()
+            info = agent.step(bufs)
+            ev[i][1].record()
+        barrier()
+        clk = clocks.stop() if clocks else None
+        launches = agent.launch_count() - l0
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        last_loss = float(np.ravel(info['critic/critic_loss'])[0])
+        assert np.isfinite(last_loss), 'non-finite loss in the timed region'
+        # L2-warm variant (no flush), reported beside the headline
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            agent.step(bufs)
+        e1.record()
+        barrier()
+        warm_ms = e0.elapsed_time(e1)
+
+        # ---------------- end-to-end leg: public API, host batches, pinned H2D + D2H of the metrics every step
+        for i in range(W):
+            agent.update(batches[i % 8])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            _, info = agent.update(batches[i % 8])
+        _ = info['critic/critic_loss']  # materialise the last step's metrics (every step's D2H copy has been issued)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        h2d = agent.last_h2d_bytes
+
+    if world > 1:
+        t = torch.tensor([dev_ms, warm_ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, warm_ms, e2e_ms = [float(x) for x in t.tolist()]
+        e2e_s = e2e_ms / 1e3
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    n = max(world, 1)
+    samples_per_step = args.batch * args.seeds * n
+    ms_per_step = dev_ms / K
+    value = samples_per_step / (ms_per_step / 1e3)
+    peaks = load_peaks()
+    leaves = agent._leaves
+    cnt = lambda pred: sum(l['ens'] * l['rows'] * l['cols'] for l in leaves if pred(l))
+    p_train, p_target = cnt(lambda l: l['net'] != 'target_critic'), cnt(lambda l: l['net'] == 'target_critic')
+    flops_gpu = flops_per_sample(F, A) * args.batch * args.seeds               # per GPU per step
+    bytes_gpu = (hbm_bytes_per_step(p_train, p_target, args.batch, F, A)) * args.seeds
+    t_s = ms_per_step / 1e3
+    t_tc, t_hbm = flops_gpu / (peaks['tc'] * 1e12), bytes_gpu / (peaks['hbm'] * 1e9)
+    if t_hbm >= t_tc:
+        roof = dict(bound='hbm', achieved=bytes_gpu / t_s / 1e9, peak=peaks['hbm'], unit='GB/s')
+    else:
+        roof = dict(bound='tensor', achieved=flops_gpu / t_s / 1e12, peak=peaks['tc'], unit='TFLOP/s')
+    roof['frac'] = roof['achieved'] / roof['peak']
+    roof.update(traffic=None, scope='whole update step (one CUDA graph); per-kernel shares in profiles/', peak_source=peaks['src'],
+                algorithmic_flops_per_step_per_gpu=flops_gpu, algorithmic_bytes_per_step_per_gpu=bytes_gpu,
+                tensor_tflops_achieved=flops_gpu / t_s / 1e12, tensor_frac=flops_gpu / t_s / 1e12 / peaks['tc'],
+                hbm_gbs_achieved=bytes_gpu / t_s / 1e9, t_min_us=max(t_tc, t_hbm) * 1e6,
+                arithmetic='fp32 FFMA (parity mode)' if args.precision == 'fp32' else 'bf16 tcgen05, fp32 accumulate')
+    out = dict(metric='fql_update_samples_per_sec', value=value, unit='samples/s', steps_per_sec=1e3 / ms_per_step, n_gpus=n,
+               steps=K, warmup=W, ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None,
+               dtype='f32' if args.precision == 'fp32' else 'bf16', data='synthetic', config=config,
+               value_l2_warm=samples_per_step / (warm_ms / K / 1e3), ms_per_step_l2_warm=warm_ms / K,
+               e2e=dict(value=samples_per_step * K / e2e_s, unit='samples/s', steps_per_sec=K / e2e_s, h2d_bytes_per_step=h2d,
+                        d2h_bytes_per_step=13 * 4 * args.seeds, api='FQLAgent.update(host numpy batch)'),
+               gpu_launches=launches, gpu_launches_per_step=launches / K, roofline=roof, clocks=clk, last_critic_loss=last_loss)
+    if not args.no_cpu_baseline and n == 1:
+        r = cpu_reference_arm(wl, args.batch, 50, 1, budget_s=15.0)
+        cv = args.batch * 1e3 / r['ms_per_step']
+        out['cpu_baseline'] = dict(value=cv, unit='samples/s', steps_per_sec=1e3 / r['ms_per_step'], cores=r['cores'], kind='port',
+                                   sample=f"{r['steps_measured']} full updates at batch {args.batch}, 1 seed (median), fp32 torch-CPU "
+                                          f"restatement of the reference (JAX not installable)")
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

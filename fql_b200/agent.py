@@ -147,6 +147,11 @@ class FQLAgent:
         self._grads = torch.zeros_like(self._params)
         self._count = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._shadow = None
+        if self._precision == _lib.PRECISION_BF16_TC:
+            nb = int(self._lib.fql_shadow_bytes(C.byref(d)))
+            if nb == 0:
+                raise _lib.FqlError('fql_shadow_bytes: ' + self._lib.fql_last_error().decode())
+            self._shadow = torch.zeros(nb, dtype=torch.uint8, device=self.device)
         self._bufs = {}
         self._ring, self._ring_i = [], 0
         self._init_params(seed)
@@ -183,6 +188,15 @@ class FQLAgent:
                 host[:, sl] = 1.0
         self._params.copy_(torch.from_numpy(host))
         self._copy_critic_to_target()
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        """Rebuild the bf16 tensor-core operand copies from the fp32 master parameters (no-op in fp32 mode)."""
+        if self._shadow is not None:
+            d = self._dims(int(self.config.get('batch_size', 256)))
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.fql_refresh_shadow(C.byref(d), _ptr(self._params), _ptr(self._shadow), self._stream()),
+                           'fql_refresh_shadow')
 
     def _net_range(self, net):
         offs = [lf['offset'] for lf in self._leaves if lf['net'] == net]
@@ -227,6 +241,7 @@ class FQLAgent:
             rec(src, views)
         if count is not None:
             self._count.fill_(int(count))
+        self.refresh_shadow()
         return self
 
     def export_tree(self, which='params'):

@@ -211,8 +211,9 @@ __global__ void __launch_bounds__(256) act_ln_bwd_kernel(ActLnBwdArgs a) {
   }
 }
 
-// out[c] = sum_r X[r,c] * (Z ? xhat(Z)[r,c] : 1); block = 32 columns x 8 row lanes; deterministic tree
-__global__ void __launch_bounds__(256) colsum_kernel(ColSumArgs a) {
+// out[c] = sum_r X[r,c] * (Z ? xhat(Z)[r,c] : 1); block = 32 columns x 32 row lanes, 4 independent accumulators per
+// thread (the loop is latency-bound otherwise); deterministic tree
+__global__ void __launch_bounds__(1024) colsum_kernel(ColSumArgs a) {
   const int g = blockIdx.y;
   const int e = g % a.E, s = (g / a.E) % a.S, p = g / (a.E * a.S);
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -221,21 +222,33 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColSumArgs a) {
   const float* __restrict__ Z = a.Z.base[p] ? a.Z.at(p, s, e) : nullptr;
   const float* __restrict__ mu = Z ? a.mu.at(p, s, e) : nullptr;
   const float* __restrict__ rstd = Z ? a.rstd.at(p, s, e) : nullptr;
-  float acc = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < a.N) {
-    for (int r = ry; r < a.M; r += 8) {
-      float v = X[(int64_t)r * a.ld + c];
-      if (Z) v *= (gelu_tanh_f(Z[(int64_t)r * a.ld + c]) - mu[r]) * rstd[r];
-      acc += v;
+    if (!Z) {
+      for (int r0 = ry; r0 < a.M; r0 += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int r = r0 + u * 32;
+          if (r < a.M) acc[u] += X[(int64_t)r * a.ld + c];
+        }
+      }
+    } else {
+      for (int r0 = ry; r0 < a.M; r0 += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int r = r0 + u * 32;
+          if (r < a.M) acc[u] += X[(int64_t)r * a.ld + c] * ((gelu_tanh_f(Z[(int64_t)r * a.ld + c]) - mu[r]) * rstd[r]);
+        }
+      }
     }
   }
-  __shared__ float red[8][33];
-  red[ry][cx] = acc;
+  __shared__ float red[32][33];
+  red[ry][cx] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   __syncthreads();
   if (ry == 0 && c < a.N) {
     float v = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; q++) v += red[q][cx];
+    for (int q = 0; q < 32; q++) v += red[q][cx];
     a.out.at(p, s, e)[c] = v;
   }
 }
@@ -275,7 +288,7 @@ int launch_act_ln_bwd(const ActLnBwdArgs& a, cudaStream_t st) {
 
 int launch_colsum(const ColSumArgs& a, cudaStream_t st) {
   dim3 grid((a.N + 31) / 32, a.P * a.S * a.E);
-  colsum_kernel<<<grid, 256, 0, st>>>(a);
+  colsum_kernel<<<grid, 1024, 0, st>>>(a);
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -58,6 +58,7 @@ __global__ void prep_kernel(StepShape sh, FqlBatch b, WsPtrs w) {
     xf1[F + c] = z[c];
     xc1[F + c] = a;
     w.vel[(int64_t)row * A + c] = a - x;
+    if (w.euler_a) w.euler_a[(int64_t)row * A + c] = z[c];
   }
   if (threadIdx.x == 0) {
     xf0[F + A] = t;

@@ -83,35 +83,36 @@ __global__ void __launch_bounds__(256) adam_polyak_stats_kernel(Layout L, FqlHpa
   }
 }
 
-// one CTA per seed: per-leaf L2 norms from the block partials, then the three scalars of flax_utils.py:147-149
-__global__ void __launch_bounds__(128) grad_stats_final_kernel(Layout L, const float* __restrict__ partials,
-                                                               float* __restrict__ gstats, int32_t* count_inc) {
+// one CTA per seed, one WARP per leaf (lanes stride over the leaf's block partials): per-leaf L2 norms, then the three
+// scalars of flax_utils.py:147-149
+__global__ void __launch_bounds__(1024) grad_stats_final_kernel(Layout L, const float* __restrict__ partials,
+                                                                float* __restrict__ gstats, int32_t* count_inc) {
   const int s = blockIdx.x;
   const int nblk = L.leaf_blk[L.n_leaves];
   const float* part = partials + (int64_t)s * nblk * 4;
-  float mx = 0.f, mn = 0.f, norm = 0.f;  // the target critic's zero gradients are leaves too
-  const int leaf = threadIdx.x;
-  if (leaf < L.n_leaves && L.leaf_net[leaf] != FQL_NET_TARGET_CRITIC) {
-    float sq = 0.f;
-    mx = -INFINITY;
-    mn = INFINITY;
-    for (int b = L.leaf_blk[leaf]; b < L.leaf_blk[leaf + 1]; b++) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __shared__ float smx[32], smn[32], snorm[32];
+  float wmx = 0.f, wmn = 0.f, wnorm = 0.f;  // the target critic's zero gradients are leaves too
+  for (int leaf = w; leaf < L.n_leaves; leaf += 32) {
+    if (L.leaf_net[leaf] == FQL_NET_TARGET_CRITIC) continue;
+    float mx = -INFINITY, mn = INFINITY, sq = 0.f;
+    for (int b = L.leaf_blk[leaf] + lane; b < L.leaf_blk[leaf + 1]; b += 32) {
       mx = fmaxf(mx, part[b * 4 + 0]);
       mn = fminf(mn, part[b * 4 + 1]);
       sq += part[b * 4 + 2];
     }
-    norm = sqrtf(sq);
+    mx = warp_max(mx);
+    mn = warp_min(mn);
+    sq = warp_sum(sq);
+    wmx = fmaxf(wmx, mx);
+    wmn = fminf(wmn, mn);
+    wnorm += sqrtf(sq);
   }
-  __shared__ float smx[4], smn[4], ssum[4];
-  mx = warp_max(mx);
-  mn = warp_min(mn);
-  norm = warp_sum(norm);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { smx[w] = mx; smn[w] = mn; ssum[w] = norm; }
+  if (lane == 0) { smx[w] = wmx; smn[w] = wmn; snorm[w] = wnorm; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float a = smx[0], b = smn[0], c = ssum[0];
-    for (int i = 1; i < 4; i++) { a = fmaxf(a, smx[i]); b = fminf(b, smn[i]); c += ssum[i]; }
+    float a = smx[0], b = smn[0], c = snorm[0];
+    for (int i = 1; i < 32; i++) { a = fmaxf(a, smx[i]); b = fminf(b, smn[i]); c += snorm[i]; }
     gstats[s * 4 + 0] = a;
     gstats[s * 4 + 1] = b;
     gstats[s * 4 + 2] = c;
@@ -136,8 +137,7 @@ int launch_adam_polyak_stats(const Layout& L, const FqlHparams& hp, int S, float
 }
 
 int launch_grad_stats_final(const Layout& L, int S, const float* partials, float* gstats, int32_t* count_inc, cudaStream_t st) {
-  static_assert(FQL_MAX_LEAVES <= 128, "one thread per leaf");
-  grad_stats_final_kernel<<<S, 128, 0, st>>>(L, partials, gstats, count_inc);
+  grad_stats_final_kernel<<<S, 1024, 0, st>>>(L, partials, gstats, count_inc);
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -9,6 +9,7 @@
 //   S0: join -> grad stats + Adam + Polyak (optim.cu) -> info
 #include "step.cuh"
 
+#include <cuda_bf16.h>
 #include <stdarg.h>
 
 #include <vector>
@@ -145,6 +146,30 @@ size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w)
   w->raw_local = c.take(S * FQL_NUM_RAW);
   w->gstats = c.take(S * 4);
   w->partials = c.take(S * (int64_t)L.leaf_blk[L.n_leaves] * 4);
+  if (d->precision == FQL_PRECISION_BF16_TC) {
+    const int64_t kO = round_up64(F + A, 64), kF = round_up64(F + A + 1, 64);
+    w->XOb = c.take((S * 3 * B * kO + 1) / 2);
+    w->XFb = c.take((S * 2 * B * kF + 1) / 2);
+    w->XCb = c.take((3 * S * B * kO + 1) / 2);
+    for (int l = 0; l < NH; l++) {
+      w->O_Hb[l] = c.take(S * 3 * B * H / 2);
+      w->O_Zb[l] = c.take(S * 3 * B * H / 2);
+      w->F_Hb[l] = c.take(S * 2 * B * H / 2);
+      w->F_Zb[l] = c.take(S * 2 * B * H / 2);
+      w->C_Hb[l] = c.take(3 * S * 2 * B * H / 2);
+    }
+    for (int i = 0; i < 2; i++) {
+      w->O_dZb[i] = c.take(S * B * H / 2);
+      w->F_dZb[i] = c.take(S * B * H / 2);
+    }
+    w->O_dOutb = c.take(S * B * 64 / 2);
+    w->F_dOutb = c.take(S * B * 64 / 2);
+    w->C1_dZb = c.take(S * 2 * B * H / 2);
+    w->C2_dZb = c.take(S * 2 * B * H / 2);
+    w->C1_dOutb = c.take(S * 2 * B * 64 / 2);
+    w->C2_dOutb = c.take(S * 2 * B * 64 / 2);
+    w->euler_a = c.take(S * B * A);
+  }
   for (int i = 0; i < 2; i++) {
     w->dC[i] = c.take(S * 2 * B * H);
     w->dCp[i] = c.take(S * 2 * B * H);
@@ -395,18 +420,120 @@ int check_common(const FqlDims* d, const void* ws, size_t ws_bytes, Layout* L, W
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// FQL_PRECISION_BF16_TC schedule of the loss/gradient half of the step: every contraction on tcgen05.
+//   S1: Euler integration, layer by layer (each layer = 16 CTAs of tc_gemm at B=256)              <- longest chain
+//   S2: bc-flow forward on the BC rows, BC loss, bc-flow backward; then the critic backward
+//   S0: one-step actor forward, grouped critic forward (fused chain kernel, LayerNorm in the epilogue), TD/Q post,
+//       critic input gradient, [join Euler] distillation, one-step actor backward
+// ---------------------------------------------------------------------------------------------------------
+int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs& w, const StepShape& sh, const FqlHparams& hp,
+                     float* raw, cudaStream_t S0) {
+  const FqlBatch& b = *c.b;
+  const FqlDims* d = c.d;
+  const int S = sh.S, B = sh.B, H = sh.H, NH = sh.NH;
+  const float* P = c.st->params;
+  const void* shadow = c.st->shadow;
+  typedef __nv_bfloat16 bf16;
+  cudaStream_t S1 = ctx->s1, S2 = ctx->s2;
+  cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4], ev_pad = ctx->ev[5];
+  const int kO = (int)round_up64(sh.F + sh.A, 64), kF = (int)round_up64(sh.F + sh.A + 1, 64);
+  FQL_TRY(launch_zero(raw, (int64_t)S * FQL_NUM_RAW, S0));
+  FQL_TRY(launch_prep(sh, b, w, S0));
+  FQL_CHECK_CUDA(cudaEventRecord(ev_prep, S0));
+  FQL_CHECK_CUDA(cudaStreamWaitEvent(S1, ev_prep, 0));
+
+  auto actor = [&](int net, const void* X0b, int K0pad, int rows_cap, int r0, int M, void* const* Hb, void* const* Zb, bool with_z) {
+    TcActor t;
+    memset(&t, 0, sizeof(t));
+    t.d = d; t.L = &L; t.net = net; t.params = P; t.shadow = shadow; t.grads = c.st->grads; t.M = M;
+    t.X0b = reinterpret_cast<const bf16*>(X0b) + (int64_t)r0 * K0pad; t.K0pad = K0pad; t.x_ss = (long long)rows_cap * K0pad;
+    for (int l = 0; l < NH; l++) {
+      t.Hb[l] = reinterpret_cast<bf16*>(Hb[l]) + (int64_t)r0 * H;
+      t.Zb[l] = with_z ? reinterpret_cast<bf16*>(Zb[l]) + (int64_t)r0 * H : nullptr;
+    }
+    t.h_ss = (long long)rows_cap * H;
+    return t;
+  };
+
+  // ---- S1: Euler (agents/fql.py:155-171) on rows [B, 2B) of the bc-flow buffers
+  FQL_TRY(tc_pad_bf16(w.XF, w.XFb, (int64_t)S * 2 * B, sh.F + sh.A + 1, kF, S1));
+  FQL_CHECK_CUDA(cudaEventRecord(ev_pad, S1));
+  {
+    TcActor e = actor(FQL_NET_ACTOR_BC_FLOW, w.XFb, kF, 2 * B, B, B, w.F_Hb, w.F_Zb, false);
+    for (int i = 0; i < sh.flow_steps; i++) {
+      TcEuler eu{w.euler_a, w.target, i, sh.flow_steps};
+      FQL_TRY(tc_actor_forward(e, nullptr, 0, 0, &eu, S1));
+    }
+  }
+  FQL_CHECK_CUDA(cudaEventRecord(ev_euler, S1));
+
+  // ---- S2: bc-flow on the BC rows [0, B), BC loss, backward
+  FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_pad, 0));
+  TcActor fbc = actor(FQL_NET_ACTOR_BC_FLOW, w.XFb, kF, 2 * B, 0, B, w.F_Hb, w.F_Zb, true);
+  FQL_TRY(tc_actor_forward(fbc, w.F_out, (long long)2 * B * sh.A, 0, nullptr, S2));
+  FQL_TRY(launch_bc_post(sh, w, raw, S2));
+  if (c.do_backward) FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.dF, S2));
+  (void)ev_f0;
+
+  // ---- S0: one-step actor on {(s',z_next), (s,z), (s,z')}, grouped critic pass
+  FQL_TRY(tc_pad_bf16(w.XO, w.XOb, (int64_t)S * 3 * B, sh.F + sh.A, kO, S0));
+  TcActor fo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, true);
+  FQL_TRY(tc_actor_forward(fo, w.O_out, (long long)3 * B * sh.A, 0, nullptr, S0));
+  FQL_TRY(launch_post_onestep(sh, b, w, raw, S0));
+  FQL_TRY(tc_pad_bf16(w.XC, w.XCb, (int64_t)3 * S * B, sh.F + sh.A, kO, S0));
+  {
+    TcChainSpec t;
+    memset(&t, 0, sizeof(t));
+    t.d = d; t.L = &L; t.P = 3; t.net[0] = FQL_NET_TARGET_CRITIC; t.net[1] = FQL_NET_CRITIC; t.net[2] = FQL_NET_CRITIC;
+    t.params = P; t.shadow = shadow; t.M = B; t.X0b = w.XCb; t.Mcap0 = B; t.buf = &w.pC; t.save = 1; t.n_steps = 1; t.Hb = w.C_Hb;
+    FQL_TRY(tc_mlp_chain(t, S0));
+  }
+  FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0));
+  FQL_CHECK_CUDA(cudaEventRecord(ev_cpost, S0));
+
+  if (c.do_backward) {
+    // critic backward (fql.py:36-37) on S2, after the bc-flow backward
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_cpost, 0));
+    TcCritic t;
+    memset(&t, 0, sizeof(t));
+    t.d = d; t.L = &L; t.params = P; t.shadow = shadow; t.grads = c.st->grads; t.M = B; t.p = 1;
+    t.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)1 * S * B * kO; t.K0pad = kO; t.x_ss = (long long)B * kO;
+    t.buf = &w.pC; t.Hb = w.C_Hb; t.dOut = w.dq; t.dOutb = w.C1_dOutb; t.dZb = w.C1_dZb; t.dZf = w.dC[0]; t.dHf = w.dC[1];
+    FQL_TRY(tc_critic_backward(t, S2));
+    // critic input gradient with stored params (fql.py:70) on S0
+    TcCritic q = t;
+    q.grads = nullptr; q.p = 2; q.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)2 * S * B * kO;
+    q.dOut = w.dqs; q.dOutb = w.C2_dOutb; q.dZb = w.C2_dZb; q.dZf = w.dCp[0]; q.dHf = w.dCp[1]; q.dX0 = w.dX0;
+    FQL_TRY(tc_critic_backward(q, S0));
+  }
+  FQL_CHECK_CUDA(cudaEventRecord(ev_s2, S2));
+  FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_euler, 0));
+  FQL_TRY(launch_actor_grad(sh, hp, w, raw, S0));
+  if (c.do_backward) {
+    TcActor bo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, B, B, w.O_Hb, w.O_Zb, true);
+    FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.dO, S0));
+  }
+  FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
+  return 0;
+}
+
 int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
   Layout L;
   WsPtrs w;
   FQL_TRY(check_common(c.d, c.ws, c.ws_bytes, &L, &w));
-  FQL_REQUIRE(c.d->precision == FQL_PRECISION_FP32, "FQL_PRECISION_BF16_TC step is not built into this library version");
+  const bool tcm = c.d->precision == FQL_PRECISION_BF16_TC;
+  if (tcm) {
+    FQL_TRY(tc_supported(c.d));
+    FQL_REQUIRE(c.st->shadow != nullptr, "FQL_PRECISION_BF16_TC needs FqlState.shadow (fql_shadow_bytes() bytes, kept by fql_refresh_shadow)");
+  }
   const StepShape sh = make_shape(c.d);
   const FqlHparams hp = *c.hp;
   const int S = sh.S, B = sh.B, H = sh.H;
   float* raw = c.raw ? c.raw : w.raw_local;
   const float* P = c.st->params;
 
-  if (c.do_grads) {
+  if (c.do_grads && !tcm) {
     const FqlBatch& b = *c.b;
     cudaStream_t S1 = ctx->s1, S2 = ctx->s2;
     cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4];
@@ -422,12 +549,14 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     fF.P = 1; fF.nv[0] = &L.net[FQL_NET_ACTOR_BC_FLOW]; fF.params = P; fF.arena = L.arena;
     fF.S = S; fF.E = 1; fF.M = 2 * B; fF.H = H; fF.X0 = w.XF; fF.Mcap0 = 2 * B; fF.r0_in = 0;
     fF.buf = &w.pF; fF.r0 = 0; fF.save_z = 1;
-    FQL_TRY(mlp_forward(fF, S1));
-    FQL_CHECK_CUDA(cudaEventRecord(ev_f0, S1));
-    fF.M = B; fF.r0_in = B; fF.r0 = B; fF.save_z = 0;
-    for (int i = 0; i < sh.flow_steps; i++) {
-      FQL_TRY(launch_euler_update(sh, w, i, S1));
-      if (i + 1 < sh.flow_steps) FQL_TRY(mlp_forward(fF, S1));
+    {
+      FQL_TRY(mlp_forward(fF, S1));
+      FQL_CHECK_CUDA(cudaEventRecord(ev_f0, S1));
+      fF.M = B; fF.r0_in = B; fF.r0 = B; fF.save_z = 0;
+      for (int i = 0; i < sh.flow_steps; i++) {
+        FQL_TRY(launch_euler_update(sh, w, i, S1));
+        if (i + 1 < sh.flow_steps) FQL_TRY(mlp_forward(fF, S1));
+      }
     }
     FQL_CHECK_CUDA(cudaEventRecord(ev_euler, S1));
 
@@ -490,10 +619,12 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
   }
 
+  if (c.do_grads && tcm) FQL_TRY(enqueue_grads_tc(ctx, c, L, w, sh, hp, raw, S0));
   if (c.do_apply) {
     FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, c.st->count, w.partials,
                                      c.st->shadow, S0));
     FQL_TRY(launch_grad_stats_final(L, S, w.partials, w.gstats, c.st->count, S0));
+    if (tcm) FQL_TRY(tc_refresh_shadow(c.d, L, c.st->params, c.st->shadow, S0));
   }
   if (c.info) FQL_TRY(launch_finalize_info(sh, hp, raw, w.gstats, c.info, c.do_apply, S0));
   return 0;
@@ -548,7 +679,10 @@ int run_step_on(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     Layout L;
     WsPtrs w;
     FQL_TRY(check_common(c.d, c.ws, c.ws_bytes, &L, &w));
-    FQL_REQUIRE(c.d->precision == FQL_PRECISION_FP32, "FQL_PRECISION_BF16_TC step is not built into this library version");
+    if (c.d->precision == FQL_PRECISION_BF16_TC) {
+      FQL_TRY(tc_supported(c.d));
+      FQL_REQUIRE(c.st->shadow != nullptr, "FQL_PRECISION_BF16_TC needs FqlState.shadow");
+    }
   }
   FQL_CHECK_CUDA(cudaStreamBeginCapture(S0, cudaStreamCaptureModeThreadLocal));
   const long long before = g_fql_launches;
@@ -621,9 +755,12 @@ extern "C" int fql_total_loss(FqlContext* ctx, const FqlDims* d, const FqlHparam
 // standalone forward entry points
 // ---------------------------------------------------------------------------------------------------------
 namespace {
-size_t carve_forward(const FqlDims* d, int rows, int ens, int in_dim, int out_dim, bool ln, void* base, float** X, PassBuf* pb) {
+size_t carve_forward(const FqlDims* d, int rows, int ens, int in_dim, int out_dim, bool ln, void* base, float** X, PassBuf* pb,
+                     void** Xb = nullptr) {
   Carver c{reinterpret_cast<char*>(base)};
   *X = c.take((int64_t)d->num_seeds * rows * in_dim);
+  void* xb = c.take((int64_t)d->num_seeds * rows * 128 / 2 + 4);
+  if (Xb) *Xb = xb;
   carve_pass(c, pb, d->num_seeds * ens, rows, d->hidden, d->num_hidden, out_dim, ln, false);
   return c.off + 256;
 }
@@ -664,43 +801,63 @@ extern "C" int fql_mlp_forward(FqlContext*, const FqlDims* d, int32_t net, const
   return 0;
 }
 
-extern "C" int fql_sample_actions(FqlContext*, const FqlDims* d, const float* params, const void*, const float* obs,
+extern "C" int fql_sample_actions(FqlContext*, const FqlDims* d, const float* params, const void* shadow, const float* obs,
                                   const float* noise, float* actions_out, int32_t rows, void* workspace, size_t ws_bytes,
                                   void* stream) {
   Layout L;
   FQL_TRY(fql_build_layout(d, &L));
   FQL_REQUIRE(rows >= 1, "rows=%d", rows);
-  FQL_REQUIRE(d->precision == FQL_PRECISION_FP32, "fql_sample_actions: FP32 only in this library version");
   const NetView& nv = L.net[FQL_NET_ACTOR_ONESTEP_FLOW];
   float* X;
+  void* Xb;
   PassBuf pb;
   const size_t need = carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, nullptr, &X, &pb);
   FQL_REQUIRE(workspace && ws_bytes >= need, "workspace too small: have %zu need %zu", ws_bytes, need);
-  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb);
+  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb, &Xb);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t R = (int64_t)d->num_seeds * rows;
   FQL_TRY(launch_concat(obs, d->obs_dim, noise, d->action_dim, 0.f, 0, X, R, st));
+  if (d->precision == FQL_PRECISION_BF16_TC) {
+    FQL_REQUIRE(shadow != nullptr, "FQL_PRECISION_BF16_TC needs the bf16 shadow");
+    const int kp = (int)round_up64(nv.in_dim, 64);
+    FQL_TRY(tc_pad_bf16(X, Xb, R, nv.in_dim, kp, st));
+    TcChainSpec t;
+    memset(&t, 0, sizeof(t));
+    t.d = d; t.L = &L; t.P = 1; t.net[0] = FQL_NET_ACTOR_ONESTEP_FLOW; t.params = params; t.shadow = shadow;
+    t.M = rows; t.X0b = Xb; t.Mcap0 = rows; t.n_steps = 1; t.out_override = actions_out; t.clip_out = 1;
+    return tc_mlp_chain(t, st);
+  }
   FQL_TRY(forward_net(d, L, FQL_NET_ACTOR_ONESTEP_FLOW, params, X, &pb, rows, st));
   FQL_TRY(launch_clip(pb.out, actions_out, R * d->action_dim, st));
   return 0;
 }
 
-extern "C" int fql_compute_flow_actions(FqlContext*, const FqlDims* d, const float* params, const void*, const float* obs,
+extern "C" int fql_compute_flow_actions(FqlContext*, const FqlDims* d, const float* params, const void* shadow, const float* obs,
                                         const float* noise, float* actions_out, int32_t rows, void* workspace, size_t ws_bytes,
                                         void* stream) {
   Layout L;
   FQL_TRY(fql_build_layout(d, &L));
   FQL_REQUIRE(rows >= 1, "rows=%d", rows);
-  FQL_REQUIRE(d->precision == FQL_PRECISION_FP32, "fql_compute_flow_actions: FP32 only in this library version");
   const NetView& nv = L.net[FQL_NET_ACTOR_BC_FLOW];
   float* X;
+  void* Xb;
   PassBuf pb;
   const size_t need = carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, nullptr, &X, &pb);
   FQL_REQUIRE(workspace && ws_bytes >= need, "workspace too small: have %zu need %zu", ws_bytes, need);
-  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb);
+  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb, &Xb);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t R = (int64_t)d->num_seeds * rows;
   FQL_TRY(launch_concat(obs, d->obs_dim, noise, d->action_dim, 0.f, 1, X, R, st));
+  if (d->precision == FQL_PRECISION_BF16_TC) {
+    FQL_REQUIRE(shadow != nullptr, "FQL_PRECISION_BF16_TC needs the bf16 shadow");
+    const int kp = (int)round_up64(nv.in_dim, 64);
+    FQL_TRY(tc_pad_bf16(X, Xb, R, nv.in_dim, kp, st));
+    TcChainSpec t;
+    memset(&t, 0, sizeof(t));
+    t.d = d; t.L = &L; t.P = 1; t.net[0] = FQL_NET_ACTOR_BC_FLOW; t.params = params; t.shadow = shadow;
+    t.M = rows; t.X0b = Xb; t.Mcap0 = rows; t.n_steps = d->flow_steps; t.a0 = noise; t.target = actions_out;
+    return tc_mlp_chain(t, st);
+  }
   for (int i = 0; i < d->flow_steps; i++) {
     FQL_TRY(forward_net(d, L, FQL_NET_ACTOR_BC_FLOW, params, X, &pb, rows, st));
     FQL_TRY(launch_euler_inplace(X, pb.out, d->obs_dim, d->action_dim, R, i, d->flow_steps, actions_out, st));
@@ -731,10 +888,17 @@ extern "C" size_t fql_workspace_bytes(const FqlDims* d) {
   return carve_workspace(d, L, nullptr, &w);
 }
 extern "C" size_t fql_shadow_bytes(const FqlDims* d) {
-  (void)d;
-  return 0;
+  Layout L;
+  if (fql_build_layout(d, &L)) return 0;
+  if (d->precision != FQL_PRECISION_BF16_TC) return 0;
+  return (size_t)d->num_seeds * (size_t)tc_shadow_seed_elems(d, L) * 2;
 }
-extern "C" int fql_refresh_shadow(const FqlDims*, const float*, void*, void*) { return 0; }
+extern "C" int fql_refresh_shadow(const FqlDims* d, const float* params, void* shadow, void* stream) {
+  Layout L;
+  FQL_TRY(fql_build_layout(d, &L));
+  if (d->precision != FQL_PRECISION_BF16_TC) return 0;
+  return tc_refresh_shadow(d, L, params, shadow, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int fql_layout(const FqlDims* d, FqlLeaf* leaves, int32_t cap, int32_t* n_leaves) {
   Layout L;

@@ -30,6 +30,13 @@ struct WsPtrs {
   float *partials;             // [S][blocks][4] per 1024-float arena block: max, min, sumsq
   PassBuf pO, pF, pC;
   float *dC[2], *dCp[2], *dF[2], *dO[2];  // backward ping-pong [S][E][B][H]
+  void *XOb, *XFb, *XCb;       // bf16 zero-padded copies of the first-layer inputs (FQL_PRECISION_BF16_TC)
+  // per-layer tensor-core path (actor networks): bf16 activations / pre-activations, backward ping-pong, Euler state
+  void *O_Hb[FQL_MAXL], *O_Zb[FQL_MAXL], *F_Hb[FQL_MAXL], *F_Zb[FQL_MAXL], *E_Hb[FQL_MAXL];
+  void *C_Hb[FQL_MAXL];        // bf16 post-LN activations of the grouped critic pass [3][S][2][B][H]
+  void *O_dZb[2], *F_dZb[2], *O_dOutb, *F_dOutb;
+  void *C1_dZb, *C1_dOutb, *C2_dZb, *C2_dOutb;
+  float *euler_a;
 };
 
 StepShape make_shape(const FqlDims* d);
@@ -52,3 +59,97 @@ int launch_adam_polyak_stats(const Layout& L, const FqlHparams& hp, int S, float
                              const float* grads, const int32_t* count, float* partials, void* shadow, cudaStream_t st);
 int launch_grad_stats_final(const Layout& L, int S, const float* partials, float* gstats, int32_t* count_inc, cudaStream_t st);
 int launch_zero(float* p, int64_t n, cudaStream_t st);
+
+// mlp_tc.cu -- tensor-core forward path
+struct TcChainSpec {
+  const FqlDims* d;
+  const Layout* L;
+  int P;
+  int net[FQL_MAXP];
+  const float* params;
+  const void* shadow;
+  int M;             // valid rows per group
+  const void* X0b;   // bf16 [P][S][Mcap0][K0pad]
+  int Mcap0, r0_in;
+  PassBuf* buf;      // fp32 saves / output (optional)
+  int r0, save;
+  float* out_override;
+  void* const* Hb;   // optional bf16 copies of the hidden activations [G][Mcap][H] per layer (tensor-core backward operands)
+  int n_steps;       // > 1: Euler integration of compute_flow_actions
+  const float* a0;
+  float* target;
+  int clip_out;
+};
+int tc_supported(const FqlDims* d);
+int64_t tc_shadow_seed_elems(const FqlDims* d, const Layout& L);
+int tc_refresh_shadow(const FqlDims* d, const Layout& L, const float* params, void* shadow, cudaStream_t st);
+int tc_pad_bf16(const float* x, void* y, int64_t rows, int K0, int K0pad, cudaStream_t st);
+int tc_mlp_chain(const TcChainSpec& f, cudaStream_t st);
+
+// tc_gemm.cu -- generic tcgen05 GEMM (one Dense layer: forward / dgrad / wgrad)
+enum { TC_MODE_STORE_F32 = 0, TC_MODE_FWD_HIDDEN = 1, TC_MODE_DGRAD_GELU = 2, TC_MODE_EULER = 3 };
+struct TcOperand {   // bf16 tensor [g1][g0][rows][inner] with pitches ld / s0 / s1 (elements)
+  const void* ptr;
+  int inner, rows;
+  long long ld;
+  int g0;
+  long long s0;
+  int g1;
+  long long s1;
+};
+struct TcPtr {       // epilogue operand addressed as base + g0*s0 + g1*s1 (elements of its own type), row pitch ld
+  void* base;
+  long long s0, s1;
+  int ld;
+};
+struct TcGemmSpec {
+  int M, N, K, G0, G1;
+  int a_mn, b_mn;    // operand is MN-major ([K][rows] row-major) instead of K-major ([rows][K])
+  TcOperand A, B;
+  int mode;
+  TcPtr bias, out_f, out_h, out_z, zin, act, xb, target;
+  int F, Adim, step, n_steps, clip;
+};
+int tc_gemm(const TcGemmSpec& s, cudaStream_t st);
+
+// tc_path.cu -- layer-by-layer tensor-core schedules
+struct TcActor {
+  const FqlDims* d;
+  const Layout* L;
+  int net;
+  const float* params;
+  const void* shadow;
+  float* grads;
+  int M;                 // valid rows per seed
+  const void* X0b;       // bf16 [S][..][K0pad], already offset to the first row
+  int K0pad;
+  long long x_ss;        // seed pitch (elements)
+  void* Hb[FQL_MAXL];    // bf16 [S][..][H] per hidden layer, already offset to the first row
+  void* Zb[FQL_MAXL];
+  long long h_ss;
+};
+struct TcEuler {
+  float* act;
+  float* target;
+  int step, n_steps;
+};
+struct TcCritic {
+  const FqlDims* d;
+  const Layout* L;
+  const float* params;
+  const void* shadow;
+  float* grads;          // NULL: input gradient only
+  int M, p;
+  const void* X0b;       // bf16 [S][M][K0pad] of problem p
+  int K0pad;
+  long long x_ss;
+  const PassBuf* buf;    // fp32 Z / mu / rstd of the grouped pass
+  void* const* Hb;       // bf16 H per layer [P][S][E][Mcap][H]
+  const float* dOut;     // [S][2][M]
+  void* dOutb;
+  void* dZb;
+  float *dZf, *dHf, *dX0;
+};
+int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, const TcEuler* eu, cudaStream_t st);
+int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[2], float* const dZf[2], cudaStream_t st);
+int tc_critic_backward(const TcCritic& t, cudaStream_t st);

@@ -1,0 +1,302 @@
+// tc_gemm.cu -- generic tcgen05 GEMM for one Dense layer (forward, dgrad or wgrad) with fused epilogues.
+//
+//   D[M,N] = A[M,K] * B[K,N]   bf16 operands from HBM/L2 via TMA (4-D tensor maps: inner, rows, head, seed), fp32 accumulate
+//   in TMEM, 128x64 output tile per CTA, 64-deep K blocks, 9-stage mbarrier pipeline (216 KB in flight per SM).
+//
+// Both operands may be K-major ([rows][K] row-major) or MN-major ([K][rows] row-major); with SWIZZLE_128B TMA boxes of
+// 64 inner elements both land in smem as the canonical UMMA atoms, so every GEMM of the MLP reads the SAME row-major bf16
+// tensors with no transposed copies:
+//   forward  Y = X W        A = X  [batch][in]  K-major     B = W  [in][out]   MN-major   (utils/networks.py:54)
+//   dgrad    dX = dY W^T    A = dY [batch][out] K-major     B = W  [in][out]   K-major    (n = in, k = out)
+//   wgrad    dW = X^T dY    A = X  [batch][in]  MN-major    B = dY [batch][out] MN-major  (k = batch)
+// A B=256 layer becomes 2 x 8 = 16 CTAs on 16 SMs: at small batch the step is latency-bound and spreading one layer over
+// many SMs beats keeping it on the 2 SMs a row-tile-persistent kernel would use.
+#include "step.cuh"
+#include "tc_prims.cuh"
+
+#include <cudaTypedefs.h>
+
+using namespace tc;
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 64;
+constexpr int A_STAGE = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE = BN * BK * 2;  //  8 KB
+constexpr int STAGE = A_STAGE + B_STAGE;
+constexpr int NSTAGE = 9;
+constexpr int SMEM_BYTES = NSTAGE * STAGE + 1024 + 256;
+
+struct GPtrB {
+  void* base;
+  long long s0, s1;
+  int ld;
+  template <typename T>
+  __device__ __forceinline__ T* at(int g0, int g1) const {
+    return base ? reinterpret_cast<T*>(base) + g0 * s0 + g1 * s1 : nullptr;
+  }
+};
+
+struct TcGemmArgs {
+  int M, N, K;
+  int G0, G1;
+  int a_mn, b_mn, a_bcast0, b_bcast0;
+  int mode;
+  GPtrB bias;    // fp32 [N]
+  GPtrB out_f;   // fp32 [M][ld]
+  GPtrB out_h;   // bf16 [M][ld]
+  GPtrB out_z;   // bf16 [M][ld]   pre-activation copy (forward) for the backward's gelu'
+  GPtrB zin;     // bf16 [M][ld]   pre-activation of the layer below (dgrad)
+  GPtrB act;     // fp32 [M][A]    Euler state (in/out)
+  GPtrB xb;      // bf16 [M][ld]   first-layer operand whose action/time columns the Euler step rewrites
+  GPtrB target;  // fp32 [M][A]
+  int F, A, step, n_steps, clip;
+};
+
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float u = FQL_GELU_C * (x + FQL_GELU_A * x * x * x);
+  return 0.5f * x * (1.0f + tanh_approx(u));
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float x2 = x * x;
+  const float u = FQL_GELU_C * (x + FQL_GELU_A * x2 * x);
+  const float th = tanh_approx(u);
+  const float du = FQL_GELU_C * (1.0f + 3.0f * FQL_GELU_A * x2);
+  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * du;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                         const __grid_constant__ CUtensorMap mapB, const TcGemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NSTAGE;
+  uint64_t* acc_full = bars + 2 * NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int g0 = blockIdx.z % a.G0, g1 = blockIdx.z / a.G0;
+  const int nkb = (a.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int i = 0; i < NSTAGE; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int ga0 = a.a_bcast0 ? 0 : g0, gb0 = a.b_bcast0 ? 0 : g0;
+      for (int kb = 0; kb < nkb; kb++) {
+        const int st = kb % NSTAGE;
+        if (kb >= NSTAGE) mbar_wait(&empty[st], ((kb / NSTAGE) - 1) & 1);
+        uint8_t* sa = smem + st * STAGE;
+        uint8_t* sb = sa + A_STAGE;
+        mbar_expect_tx(&full[st], STAGE);
+        if (!a.a_mn) {
+          tma_load_4d(sa, &mapA, &full[st], kb * BK, m0, ga0, g1);
+        } else {
+          tma_load_4d(sa, &mapA, &full[st], m0, kb * BK, ga0, g1);
+          tma_load_4d(sa + A_STAGE / 2, &mapA, &full[st], m0 + 64, kb * BK, ga0, g1);
+        }
+        if (!a.b_mn) tma_load_4d(sb, &mapB, &full[st], kb * BK, n0, gb0, g1);
+        else tma_load_4d(sb, &mapB, &full[st], n0, kb * BK, gb0, g1);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN, a.a_mn != 0, a.b_mn != 0);
+      for (int kb = 0; kb < nkb; kb++) {
+        const int st = kb % NSTAGE;
+        mbar_wait(&full[st], (kb / NSTAGE) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + st * STAGE), sb = sa + A_STAGE;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ks++) {
+          const uint64_t ad = a.a_mn ? make_smem_desc(sa + ks * 2048, A_STAGE / 2, 1024) : make_smem_desc(sa + ks * 32, 16, 1024);
+          const uint64_t bd = a.b_mn ? make_smem_desc(sb + ks * 2048, B_STAGE, 1024) : make_smem_desc(sb + ks * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (kb | ks) != 0);
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ---------------- epilogue: thread per row, 64 accumulator columns ----------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool valid = m < a.M;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float* bias = a.bias.at<const float>(g0, g1);
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    uint32_t rr[2][32];
+    tmem_ld32(t_lane, rr[0]);
+    tmem_ld32(t_lane + 32, rr[1]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const uint32_t(&r)[32] = rr[j];
+      const int nb = n0 + j * 32;
+      if (!valid || nb >= a.N) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]) + ((bias && nb + i < a.N) ? bias[nb + i] : 0.f);
+      if (a.mode == TC_MODE_STORE_F32) {
+        float* o = a.out_f.at<float>(g0, g1) + (int64_t)m * a.out_f.ld + nb;
+        if (nb + 32 <= a.N && (a.out_f.ld & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 w4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (a.clip) {
+              w4.x = fminf(fmaxf(w4.x, -1.0f), 1.0f); w4.y = fminf(fmaxf(w4.y, -1.0f), 1.0f);
+              w4.z = fminf(fmaxf(w4.z, -1.0f), 1.0f); w4.w = fminf(fmaxf(w4.w, -1.0f), 1.0f);
+            }
+            *reinterpret_cast<float4*>(o + i) = w4;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (nb + i < a.N) o[i] = a.clip ? fminf(fmaxf(v[i], -1.0f), 1.0f) : v[i];
+        }
+      } else if (a.mode == TC_MODE_FWD_HIDDEN) {
+        // utils/networks.py:54-56: z = xW + b ; h = gelu(z).  N is a multiple of 64 on this path.
+        uint4* oz = a.out_z.base ? reinterpret_cast<uint4*>(a.out_z.at<__nv_bfloat16>(g0, g1) + (int64_t)m * a.out_z.ld + nb) : nullptr;
+        uint4* oh = reinterpret_cast<uint4*>(a.out_h.at<__nv_bfloat16>(g0, g1) + (int64_t)m * a.out_h.ld + nb);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (oz) oz[c] = make_uint4(pack2(v[c * 8], v[c * 8 + 1]), pack2(v[c * 8 + 2], v[c * 8 + 3]), pack2(v[c * 8 + 4], v[c * 8 + 5]),
+                                     pack2(v[c * 8 + 6], v[c * 8 + 7]));
+          float h[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) h[i] = gelu_fast(v[c * 8 + i]);
+          oh[c] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+        }
+      } else if (a.mode == TC_MODE_DGRAD_GELU) {
+        // dZ_{l-1} = (dZ_l W_l^T) * gelu'(Z_{l-1})
+        const uint4* zi = reinterpret_cast<const uint4*>(a.zin.at<const __nv_bfloat16>(g0, g1) + (int64_t)m * a.zin.ld + nb);
+        uint4* oh = reinterpret_cast<uint4*>(a.out_h.at<__nv_bfloat16>(g0, g1) + (int64_t)m * a.out_h.ld + nb);
+        float* of = a.out_f.base ? a.out_f.at<float>(g0, g1) + (int64_t)m * a.out_f.ld + nb : nullptr;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const uint4 zz = zi[c];
+          const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+          float d[8];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const __nv_bfloat162 zb = *reinterpret_cast<const __nv_bfloat162*>(&zw[i]);
+            d[2 * i] = v[c * 8 + 2 * i] * gelu_grad_fast(__low2float(zb));
+            d[2 * i + 1] = v[c * 8 + 2 * i + 1] * gelu_grad_fast(__high2float(zb));
+          }
+          oh[c] = make_uint4(pack2(d[0], d[1]), pack2(d[2], d[3]), pack2(d[4], d[5]), pack2(d[6], d[7]));
+          if (of) {
+            *reinterpret_cast<float4*>(of + c * 8) = make_float4(d[0], d[1], d[2], d[3]);
+            *reinterpret_cast<float4*>(of + c * 8 + 4) = make_float4(d[4], d[5], d[6], d[7]);
+          }
+        }
+      } else if (a.mode == TC_MODE_EULER) {
+        // agents/fql.py:166-170: a += v / flow_steps; next t; after the last step target = clip(a)
+        float* act = a.act.at<float>(g0, g1) + (int64_t)m * a.A;
+        __nv_bfloat16* xb = a.xb.at<__nv_bfloat16>(g0, g1) + (int64_t)m * a.xb.ld;
+        float* tg = a.target.at<float>(g0, g1) + (int64_t)m * a.A;
+        const float inv = (float)a.n_steps;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const int n = nb + i;
+          if (n < a.A) {
+            const float an = act[n] + v[i] / inv;
+            act[n] = an;
+            xb[a.F + n] = __float2bfloat16(an);
+            if (a.step == a.n_steps - 1) tg[n] = fminf(fmaxf(an, -1.0f), 1.0f);
+          }
+        }
+        if (j == 0) xb[a.F + a.A] = __float2bfloat16((float)((double)(a.step + 1) / (double)a.n_steps));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+int make_map_4d(CUtensorMap* m, const TcOperand& o, uint32_t box_rows) {
+  auto enc = get_encode();
+  FQL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const int g0 = o.g0 > 0 ? o.g0 : 1, g1 = o.g1 > 0 ? o.g1 : 1;
+  cuuint64_t dims[4] = {(cuuint64_t)o.inner, (cuuint64_t)o.rows, (cuuint64_t)g0, (cuuint64_t)g1};
+  const long long s0 = (g0 > 1) ? o.s0 : (long long)o.ld * o.rows, s1 = (g1 > 1) ? o.s1 : s0 * g0;
+  cuuint64_t strides[3] = {(cuuint64_t)o.ld * 2, (cuuint64_t)s0 * 2, (cuuint64_t)s1 * 2};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  FQL_REQUIRE(((uintptr_t)o.ptr & 15) == 0 && (strides[0] & 15) == 0 && (strides[1] & 15) == 0 && (strides[2] & 15) == 0,
+              "TMA operand not 16-byte aligned (ptr %p ld %lld s0 %lld s1 %lld)", o.ptr, (long long)o.ld, s0, s1);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(o.ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FQL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed (%d): inner %d rows %d ld %lld g0 %d s0 %lld g1 %d s1 %lld", (int)r,
+              o.inner, o.rows, (long long)o.ld, g0, s0, g1, s1);
+  return 0;
+}
+
+GPtrB gp(const TcPtr& p) { return GPtrB{p.base, p.s0, p.s1, p.ld}; }
+
+}  // namespace
+
+int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
+  if (s.M <= 0 || s.N <= 0 || s.K <= 0) return 0;
+  TcGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = s.M; a.N = s.N; a.K = s.K; a.G0 = s.G0 > 0 ? s.G0 : 1; a.G1 = s.G1 > 0 ? s.G1 : 1;
+  a.a_mn = s.a_mn; a.b_mn = s.b_mn; a.a_bcast0 = (s.A.g0 <= 1); a.b_bcast0 = (s.B.g0 <= 1);
+  a.mode = s.mode;
+  a.bias = gp(s.bias); a.out_f = gp(s.out_f); a.out_h = gp(s.out_h); a.out_z = gp(s.out_z); a.zin = gp(s.zin);
+  a.act = gp(s.act); a.xb = gp(s.xb); a.target = gp(s.target);
+  a.F = s.F; a.A = s.Adim; a.step = s.step; a.n_steps = s.n_steps; a.clip = s.clip;
+  if (s.mode == TC_MODE_FWD_HIDDEN || s.mode == TC_MODE_DGRAD_GELU)
+    FQL_REQUIRE(s.N % 64 == 0 && s.out_h.base, "tc_gemm: hidden/dgrad epilogues need N %% 64 == 0 and a bf16 output");
+  CUtensorMap mapA, mapB;
+  FQL_TRY(make_map_4d(&mapA, s.A, s.a_mn ? 64 : BM));
+  FQL_TRY(make_map_4d(&mapB, s.B, 64));
+  static bool attr_set = false;
+  if (!attr_set) {
+    FQL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((s.N + BN - 1) / BN, (s.M + BM - 1) / BM, a.G0 * a.G1);
+  tc_gemm_kernel<<<grid, 192, SMEM_BYTES, st>>>(mapA, mapB, a);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,287 @@
+// tc_path.cu -- layer-by-layer tensor-core schedules built from tc_gemm (+ the SIMT row/column kernels):
+//   actor networks (no LayerNorm by default): forward incl. the Euler integration, backward (dgrad chain + wgrads)
+//   critic (LayerNorm): backward; its forward is the fused chain kernel of mlp_tc.cu
+// Reference: utils/networks.py:34-61 (layer arithmetic), agents/fql.py:155-171 (Euler), utils/flax_utils.py:137 (jax.grad).
+#include "step.cuh"
+
+#include <cuda_bf16.h>
+
+namespace {
+typedef __nv_bfloat16 bf16;
+
+TcOperand op(const void* ptr, int inner, int rows, long long ld, int g0, long long s0, int g1, long long s1) {
+  TcOperand o;
+  o.ptr = ptr; o.inner = inner; o.rows = rows; o.ld = ld; o.g0 = g0; o.s0 = s0; o.g1 = g1; o.s1 = s1;
+  return o;
+}
+TcPtr tp(const void* base, long long s0, long long s1, int ld) {
+  TcPtr p;
+  p.base = const_cast<void*>(base); p.s0 = s0; p.s1 = s1; p.ld = ld;
+  return p;
+}
+int64_t wl_offset(const FqlDims* d, const Layout& L, int net) {
+  int64_t o = L.arena;
+  for (int t = 0; t < net; t++) o += (int64_t)L.net[t].ens * d->hidden * 64;
+  return o;
+}
+
+// dZ rows kernel for LayerNorm nets with an extra bf16 copy: dZ = LNbwd(dH; Z) * gelu'(Z)
+__global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const float* __restrict__ dH, const float* __restrict__ Z,
+                                                          const float* __restrict__ scale_base, int64_t scale_s, int64_t scale_e,
+                                                          float* __restrict__ dZ, bf16* __restrict__ dZb, int M, int N, int S, int E,
+                                                          int64_t z_rows_e, int64_t z_rows_s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  if (row >= (int64_t)S * E * M) return;
+  const int r = (int)(row % M), g = (int)(row / M), e = g % E, s = g / E;
+  const float* z = Z + ((int64_t)s * z_rows_s + (int64_t)e * z_rows_e + r) * N;
+  const float* dh = dH + row * N;
+  float* dz = dZ + row * N;
+  bf16* dzb = dZb + row * N;
+  const float* sc = scale_base + s * scale_s + e * scale_e;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < N; c += 32) {
+    const float gv = gelu_tanh_f(z[c]);
+    s1 += gv;
+    s2 += gv * gv;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const float inv_n = 1.0f / (float)N;
+  const float mu = s1 * inv_n;
+  const float var = fmaxf(0.f, s2 * inv_n - mu * mu);
+  const float rstd = rsqrtf(var + FQL_LN_EPS);
+  float m1 = 0.f, m2 = 0.f;
+  for (int c = lane; c < N; c += 32) {
+    const float xh = (gelu_tanh_f(z[c]) - mu) * rstd;
+    const float dx = dh[c] * sc[c];
+    m1 += dx;
+    m2 += dx * xh;
+  }
+  m1 = warp_sum(m1) * inv_n;
+  m2 = warp_sum(m2) * inv_n;
+  for (int c = lane; c < N; c += 32) {
+    const float zc = z[c];
+    const float xh = (gelu_tanh_f(zc) - mu) * rstd;
+    const float dx = dh[c] * sc[c];
+    const float v = rstd * (dx - m1 - xh * m2) * gelu_tanh_grad_f(zc);
+    dz[c] = v;
+    dzb[c] = __float2bfloat16(v);
+  }
+}
+
+// dZ = dH * gelu'(Z) (no LayerNorm) with a bf16 copy
+__global__ void gelu_bwd_bf16_kernel(const float* __restrict__ dH, const float* __restrict__ Z, float* __restrict__ dZ,
+                                     bf16* __restrict__ dZb, int M, int N, int S, int E, int64_t z_rows_e, int64_t z_rows_s) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)S * E * M * N) return;
+  const int c = (int)(i % N);
+  const int64_t row = i / N;
+  const int r = (int)(row % M), g = (int)(row / M), e = g % E, s = g / E;
+  const float v = dH[i] * gelu_tanh_grad_f(Z[((int64_t)s * z_rows_s + (int64_t)e * z_rows_e + r) * N + c]);
+  dZ[i] = v;
+  dZb[i] = __float2bfloat16(v);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// actor forward (optionally one Euler step: the last layer's epilogue applies a += v/n and rewrites the operand tile)
+// ---------------------------------------------------------------------------------------------------------------
+int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, const TcEuler* eu, cudaStream_t st) {
+  const FqlDims* d = t.d;
+  const Layout& L = *t.L;
+  const NetView& nv = L.net[t.net];
+  const int H = d->hidden, NL = nv.n_layers, S = d->num_seeds;
+  const int64_t seed_elems = tc_shadow_seed_elems(d, L);
+  const bf16* sh = reinterpret_cast<const bf16*>(t.shadow);
+  FQL_REQUIRE(!nv.ln && nv.ens == 1, "tc_actor_forward: LayerNorm / ensemble networks use the fused chain kernel");
+  for (int l = 0; l < NL; l++) {
+    const bool last = (l == NL - 1);
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.M = t.M; g.K = nv.k_of(l); g.G0 = 1; g.G1 = S; g.a_mn = 0; g.b_mn = 1;
+    if (l == 0) g.A = op(t.X0b, t.K0pad, t.M, t.K0pad, 1, 0, S, t.x_ss);
+    else g.A = op(t.Hb[l - 1], H, t.M, H, 1, 0, S, t.h_ss);
+    g.bias = tp(t.params + nv.off_b[l], 0, L.arena, 0);
+    if (!last) {
+      g.N = H;
+      g.B = op(sh + nv.off_w[l], H, g.K, H, 1, 0, S, seed_elems);
+      g.mode = TC_MODE_FWD_HIDDEN;
+      g.out_h = tp(t.Hb[l], 0, t.h_ss, H);
+      if (t.Zb[l]) g.out_z = tp(t.Zb[l], 0, t.h_ss, H);
+    } else {
+      g.N = nv.out_dim;
+      g.B = op(sh + wl_offset(d, L, t.net), 64, H, 64, 1, 0, S, seed_elems);
+      if (!eu) {
+        g.mode = TC_MODE_STORE_F32;
+        g.out_f = tp(out, 0, out_ss, nv.out_dim);
+        g.clip = clip;
+      } else {
+        g.mode = TC_MODE_EULER;
+        g.act = tp(eu->act, 0, (long long)t.M * nv.out_dim, nv.out_dim);
+        g.xb = tp(t.X0b, 0, t.x_ss, t.K0pad);
+        g.target = tp(eu->target, 0, (long long)t.M * nv.out_dim, nv.out_dim);
+        g.F = d->obs_dim; g.Adim = d->action_dim; g.step = eu->step; g.n_steps = eu->n_steps;
+      }
+    }
+    FQL_TRY(tc_gemm(g, st));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// actor backward: dOut fp32 [S][M][A] -> parameter gradients (fp32, into the arena)
+// ---------------------------------------------------------------------------------------------------------------
+int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[2], float* const dZf[2], cudaStream_t st) {
+  const FqlDims* d = t.d;
+  const Layout& L = *t.L;
+  const NetView& nv = L.net[t.net];
+  const int H = d->hidden, NL = nv.n_layers, S = d->num_seeds, A = nv.out_dim;
+  const int64_t seed_elems = tc_shadow_seed_elems(d, L);
+  const bf16* sh = reinterpret_cast<const bf16*>(t.shadow);
+  const long long dz_ss = (long long)t.M * H;
+  auto colsum = [&](const float* X, int N, int ld, long long ss, int64_t goff) {
+    ColSumArgs c;
+    memset(&c, 0, sizeof(c));
+    c.P = 1; c.S = S; c.E = 1; c.M = t.M; c.N = N; c.ld = ld;
+    c.X.base[0] = X; c.X.stride_s = ss;
+    c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena;
+    return launch_colsum(c, st);
+  };
+  FQL_TRY(tc_pad_bf16(dOut, dOutb, (int64_t)S * t.M, A, 64, st));
+  FQL_TRY(colsum(dOut, A, A, (long long)t.M * A, nv.off_b[NL - 1]));
+  {  // last layer: dW = H^T dOut ; dZ_{NL-2} = (dOut W^T) * gelu'(Z)
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.M = H; g.N = A; g.K = t.M; g.G0 = 1; g.G1 = S; g.a_mn = 1; g.b_mn = 1;
+    g.A = op(t.Hb[NL - 2], H, t.M, H, 1, 0, S, t.h_ss);
+    g.B = op(dOutb, 64, t.M, 64, 1, 0, S, (long long)t.M * 64);
+    g.mode = TC_MODE_STORE_F32;
+    g.out_f = tp(t.grads + nv.off_w[NL - 1], 0, L.arena, A);
+    FQL_TRY(tc_gemm(g, st));
+    memset(&g, 0, sizeof(g));
+    g.M = t.M; g.N = H; g.K = 64; g.G0 = 1; g.G1 = S; g.a_mn = 0; g.b_mn = 0;
+    g.A = op(dOutb, 64, t.M, 64, 1, 0, S, (long long)t.M * 64);
+    g.B = op(sh + wl_offset(d, L, t.net), 64, H, 64, 1, 0, S, seed_elems);
+    g.mode = TC_MODE_DGRAD_GELU;
+    g.zin = tp(t.Zb[NL - 2], 0, t.h_ss, H);
+    g.out_h = tp(dZb[0], 0, dz_ss, H);
+    g.out_f = tp(dZf[0], 0, dz_ss, H);
+    FQL_TRY(tc_gemm(g, st));
+  }
+  int cur = 0;
+  for (int l = NL - 2; l >= 0; l--) {
+    FQL_TRY(colsum(dZf[cur], H, H, dz_ss, nv.off_b[l]));
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.M = nv.k_of(l); g.N = H; g.K = t.M; g.G0 = 1; g.G1 = S; g.a_mn = 1; g.b_mn = 1;
+    if (l == 0) g.A = op(t.X0b, t.K0pad, t.M, t.K0pad, 1, 0, S, t.x_ss);
+    else g.A = op(t.Hb[l - 1], H, t.M, H, 1, 0, S, t.h_ss);
+    g.B = op(dZb[cur], H, t.M, H, 1, 0, S, dz_ss);
+    g.mode = TC_MODE_STORE_F32;
+    g.out_f = tp(t.grads + nv.off_w[l], 0, L.arena, H);
+    FQL_TRY(tc_gemm(g, st));
+    if (l == 0) break;
+    memset(&g, 0, sizeof(g));
+    g.M = t.M; g.N = H; g.K = H; g.G0 = 1; g.G1 = S; g.a_mn = 0; g.b_mn = 0;
+    g.A = op(dZb[cur], H, t.M, H, 1, 0, S, dz_ss);
+    g.B = op(sh + nv.off_w[l], H, nv.k_of(l), H, 1, 0, S, seed_elems);
+    g.mode = TC_MODE_DGRAD_GELU;
+    g.zin = tp(t.Zb[l - 1], 0, t.h_ss, H);
+    g.out_h = tp(dZb[cur ^ 1], 0, dz_ss, H);
+    g.out_f = tp(dZf[cur ^ 1], 0, dz_ss, H);
+    FQL_TRY(tc_gemm(g, st));
+    cur ^= 1;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// critic backward (2 heads, optional LayerNorm) on saved fp32 Z / mu / rstd and bf16 H of one problem of the grouped pass
+//   grads != NULL : full backward (critic loss, fql.py:36-37)
+//   grads == NULL : input gradient only, stored params (actor Q loss, fql.py:70) -> dX0 [S][2][M][K0]
+// ---------------------------------------------------------------------------------------------------------------
+int tc_critic_backward(const TcCritic& t, cudaStream_t st) {
+  const FqlDims* d = t.d;
+  const Layout& L = *t.L;
+  const NetView& nv = L.net[FQL_NET_CRITIC];
+  const int H = d->hidden, NL = nv.n_layers, S = d->num_seeds, E = 2, M = t.M, K0 = nv.in_dim;
+  const int64_t seed_elems = tc_shadow_seed_elems(d, L);
+  const bf16* sh = reinterpret_cast<const bf16*>(t.shadow);
+  const long long dz_se = (long long)M * H, dz_ss = (long long)E * M * H;
+  // saved activations of problem p inside the grouped pass buffers [P][S][E][Mcap][H]
+  const int64_t Mcap = t.buf->Mcap;
+  const int64_t prow = (int64_t)t.p * S * E * Mcap;  // first row of the problem
+  const long long z_se = Mcap * H, z_ss = (long long)E * Mcap * H;
+  auto colsum = [&](const float* X, int N, int ld, long long se, long long ss, int64_t goff, const float* Z, const float* mu,
+                    const float* rstd) {
+    ColSumArgs c;
+    memset(&c, 0, sizeof(c));
+    c.P = 1; c.S = S; c.E = E; c.M = M; c.N = N; c.ld = ld;
+    c.X.base[0] = X; c.X.stride_s = ss; c.X.stride_e = se;
+    if (Z) {
+      c.Z.base[0] = Z; c.Z.stride_s = z_ss; c.Z.stride_e = z_se;
+      c.mu.base[0] = mu; c.mu.stride_s = (long long)E * Mcap; c.mu.stride_e = Mcap;
+      c.rstd.base[0] = rstd; c.rstd.stride_s = c.mu.stride_s; c.rstd.stride_e = Mcap;
+    }
+    c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena; c.out.stride_e = N;
+    return launch_colsum(c, st);
+  };
+  // dOut [S][2][M] (out_dim 1) -> bf16 [S][2][M][64]
+  FQL_TRY(tc_pad_bf16(t.dOut, t.dOutb, (int64_t)S * E * M, 1, 64, st));
+  if (t.grads) FQL_TRY(colsum(t.dOut, 1, 1, M, (long long)E * M, nv.off_b[NL - 1], nullptr, nullptr, nullptr));
+  const bf16* Hb_prev = nullptr;
+  for (int l = NL - 1; l >= 0; l--) {
+    // here: dZ_l is available as bf16 (dZb) [S][E][M][N_l] (for l = NL-1: dOutb with N padded to 64)
+    const bool last = (l == NL - 1);
+    const void* dzb = last ? t.dOutb : t.dZb;
+    const int dz_inner = last ? 64 : H;
+    const long long dzb_se = (long long)M * dz_inner, dzb_ss = (long long)E * M * dz_inner;
+    if (t.grads) {
+      if (!last) FQL_TRY(colsum(t.dZf, H, H, dz_se, dz_ss, nv.off_b[l], nullptr, nullptr, nullptr));
+      TcGemmSpec g;  // dW_l [K_l][N_l] = A_l^T dZ_l
+      memset(&g, 0, sizeof(g));
+      g.M = nv.k_of(l); g.N = nv.n_of(l); g.K = M; g.G0 = E; g.G1 = S; g.a_mn = 1; g.b_mn = 1;
+      if (l == 0) g.A = op(t.X0b, t.K0pad, M, t.K0pad, 1, 0, S, t.x_ss);  // input shared by both heads
+      else g.A = op(reinterpret_cast<const bf16*>(t.Hb[l - 1]) + prow * H, H, M, H, E, z_se, S, z_ss);
+      g.B = op(dzb, dz_inner, M, dz_inner, E, dzb_se, S, dzb_ss);
+      g.mode = TC_MODE_STORE_F32;
+      g.out_f = tp(t.grads + nv.off_w[l], (long long)nv.k_of(l) * nv.n_of(l), L.arena, nv.n_of(l));
+      FQL_TRY(tc_gemm(g, st));
+    }
+    if (l == 0 && !t.dX0) break;
+    TcGemmSpec g;  // dH_{l-1} [M][K_l] = dZ_l W_l^T   (raw, fp32)
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.N = nv.k_of(l); g.K = last ? 64 : H; g.G0 = E; g.G1 = S; g.a_mn = 0; g.b_mn = 0;
+    g.A = op(dzb, dz_inner, M, dz_inner, E, dzb_se, S, dzb_ss);
+    if (last) g.B = op(sh + wl_offset(d, L, FQL_NET_CRITIC), 64, H, 64, E, (long long)H * 64, S, seed_elems);
+    else g.B = op(sh + nv.off_w[l], H, nv.k_of(l), H, E, (long long)nv.k_of(l) * H, S, seed_elems);
+    g.mode = TC_MODE_STORE_F32;
+    if (l == 0) {
+      g.out_f = tp(t.dX0, (long long)M * K0, (long long)E * M * K0, K0);
+      FQL_TRY(tc_gemm(g, st));
+      break;
+    }
+    g.out_f = tp(t.dHf, dz_se, dz_ss, H);
+    FQL_TRY(tc_gemm(g, st));
+    const float* Zp = t.buf->Z[l - 1] + prow * H;
+    if (nv.ln) {
+      if (t.grads) {
+        FQL_TRY(colsum(t.dHf, H, H, dz_se, dz_ss, nv.off_lnb[l - 1], nullptr, nullptr, nullptr));
+        FQL_TRY(colsum(t.dHf, H, H, dz_se, dz_ss, nv.off_lns[l - 1], Zp, t.buf->mu[l - 1] + prow, t.buf->rstd[l - 1] + prow));
+      }
+      const int64_t rows = (int64_t)S * E * M;
+      ln_bwd_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(t.dHf, Zp, t.params + nv.off_lns[l - 1], L.arena, H, t.dZf,
+                                                                     reinterpret_cast<bf16*>(t.dZb), M, H, S, E, Mcap, (int64_t)E * Mcap);
+      FQL_CHECK_LAUNCH();
+    } else {
+      const int64_t n = (int64_t)S * E * M * H;
+      gelu_bwd_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.dHf, Zp, t.dZf, reinterpret_cast<bf16*>(t.dZb), M, H, S, E, Mcap,
+                                                                        (int64_t)E * Mcap);
+      FQL_CHECK_LAUNCH();
+    }
+    (void)Hb_prev;
+  }
+  return 0;
+}

@@ -225,3 +225,23 @@ def test_fp32_vs_fp64_gap():
         if path[0] == 'modules_target_critic':
             continue
         assert np.abs(a - b).max() / np.abs(a).max() < 2e-5, path
+
+
+def test_torch_cpu_restatement_matches_numpy_oracle():
+    """oracle/fql_torch_cpu.py (the timed CPU baseline) is the same algorithm as oracle/fql_oracle.py: one whole update in
+    fp64 from identical state -> identical info, grads, params, mu, nu."""
+    from oracle.fql_torch_cpu import TorchCpuAgent
+    for kw in (dict(q_agg='min', alpha=10.0), dict(normalize_q_loss=True, alpha=1000.0)):
+        cfg = small_cfg(**kw)
+        params, batch, noise = setup(cfg, B=12, F=6, A=3, seed=6)
+        state = O.init_state(params, warm=True)
+        ta = TorchCpuAgent(state['params'], cfg, state['mu'], state['nu'], state['count'], dtype=torch.float64)
+        new_state, info, grads = O.update(copy.deepcopy(state), cfg, batch, noise)
+        tinfo, tgrads = ta.update(batch, noise)
+        for k in O.INFO_KEYS:
+            np.testing.assert_allclose(tinfo[k], float(info[k]), rtol=1e-9, atol=1e-12, err_msg=k)
+        for which, ref in (('p', new_state['params']), ('m', new_state['mu']), ('v', new_state['nu'])):
+            for (path, r), (_, g) in zip(O.tree_leaves(ref), O.tree_leaves(ta.tree(which))):
+                np.testing.assert_allclose(g, r, rtol=1e-9, atol=1e-13, err_msg=f'{which} {path}')
+        for (path, r), (_, g) in zip(O.tree_leaves(grads), O.tree_leaves(tgrads)):
+            np.testing.assert_allclose(g, r, rtol=1e-8, atol=1e-12, err_msg=str(path))
