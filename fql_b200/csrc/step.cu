@@ -158,9 +158,11 @@ size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w)
       w->F_Zb[l] = c.take(S * 2 * B * H / 2);
       w->C_Hb[l] = c.take(3 * S * 2 * B * H / 2);
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NH; i++) {
       w->O_dZb[i] = c.take(S * B * H / 2);
       w->F_dZb[i] = c.take(S * B * H / 2);
+      w->O_dZf[i] = c.take(S * B * H);
+      w->F_dZf[i] = c.take(S * B * H);
     }
     w->O_dOutb = c.take(S * B * 64 / 2);
     w->F_dOutb = c.take(S * B * 64 / 2);
@@ -361,8 +363,8 @@ struct GraphEntry {
   long long kernels;  // kernel nodes in the captured graph
 };
 struct FqlContext {
-  cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr;  // s0 stands in for the caller's stream when that is the legacy default
-  cudaEvent_t ev[8] = {};
+  cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr, s3 = nullptr, s4 = nullptr;  // s0 stands in for the caller's stream when that is the legacy default
+  cudaEvent_t ev[32] = {};
   std::vector<GraphEntry> graphs;
   int use_graph = 1;
   long long launches = 0;  // kernels enqueued through this context
@@ -376,6 +378,8 @@ extern "C" int fql_context_create(FqlContext** out) {
   FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking));
   FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s1, cudaStreamNonBlocking));
   FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking));
+  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s3, cudaStreamNonBlocking));
+  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s4, cudaStreamNonBlocking));
   for (auto& e : c->ev) FQL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const char* g = getenv("FQL_B200_GRAPH");
   if (g && g[0] == '0') c->use_graph = 0;
@@ -390,6 +394,8 @@ extern "C" int fql_context_destroy(FqlContext* c) {
   if (c->s0) cudaStreamDestroy(c->s0);
   if (c->s1) cudaStreamDestroy(c->s1);
   if (c->s2) cudaStreamDestroy(c->s2);
+  if (c->s3) cudaStreamDestroy(c->s3);
+  if (c->s4) cudaStreamDestroy(c->s4);
   delete c;
   return 0;
 }
@@ -473,7 +479,10 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   TcActor fbc = actor(FQL_NET_ACTOR_BC_FLOW, w.XFb, kF, 2 * B, 0, B, w.F_Hb, w.F_Zb, true);
   FQL_TRY(tc_actor_forward(fbc, w.F_out, (long long)2 * B * sh.A, 0, nullptr, S2));
   FQL_TRY(launch_bc_post(sh, w, raw, S2));
-  if (c.do_backward) FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.dF, S2));
+  if (c.do_backward) {
+    FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.F_dZf, S2, ctx->s3, &ctx->ev[8]));
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], ctx->s3));
+  }
   (void)ev_f0;
 
   // ---- S0: one-step actor on {(s',z_next), (s,z), (s,z')}, grouped critic pass
@@ -512,7 +521,10 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   FQL_TRY(launch_actor_grad(sh, hp, w, raw, S0));
   if (c.do_backward) {
     TcActor bo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, B, B, w.O_Hb, w.O_Zb, true);
-    FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.dO, S0));
+    FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, &ctx->ev[18]));
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[26], ctx->s4));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[26], 0));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[16], 0));
   }
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
   return 0;

@@ -34,7 +34,8 @@ struct WsPtrs {
   // per-layer tensor-core path (actor networks): bf16 activations / pre-activations, backward ping-pong, Euler state
   void *O_Hb[FQL_MAXL], *O_Zb[FQL_MAXL], *F_Hb[FQL_MAXL], *F_Zb[FQL_MAXL], *E_Hb[FQL_MAXL];
   void *C_Hb[FQL_MAXL];        // bf16 post-LN activations of the grouped critic pass [3][S][2][B][H]
-  void *O_dZb[2], *F_dZb[2], *O_dOutb, *F_dOutb;
+  void *O_dZb[FQL_MAXL], *F_dZb[FQL_MAXL], *O_dOutb, *F_dOutb;
+  float *O_dZf[FQL_MAXL], *F_dZf[FQL_MAXL];
   void *C1_dZb, *C1_dOutb, *C2_dZb, *C2_dOutb;
   float *euler_a;
 };
@@ -109,6 +110,7 @@ struct TcGemmSpec {
   int mode;
   TcPtr bias, out_f, out_h, out_z, zin, act, xb, target;
   int F, Adim, step, n_steps, clip;
+  void* dbg;  // optional device buffer for per-CTA timestamps
 };
 int tc_gemm(const TcGemmSpec& s, cudaStream_t st);
 
@@ -151,5 +153,6 @@ struct TcCritic {
   float *dZf, *dHf, *dX0;
 };
 int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, const TcEuler* eu, cudaStream_t st);
-int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[2], float* const dZf[2], cudaStream_t st);
+int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
+                      cudaStream_t st, cudaStream_t side, cudaEvent_t* ev);
 int tc_critic_backward(const TcCritic& t, cudaStream_t st);

@@ -15,6 +15,7 @@
 #include "tc_prims.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 using namespace tc;
 
@@ -51,7 +52,14 @@ struct TcGemmArgs {
   GPtrB xb;      // bf16 [M][ld]   first-layer operand whose action/time columns the Euler step rewrites
   GPtrB target;  // fp32 [M][A]
   int F, A, step, n_steps, clip;
+  unsigned long long* dbg;  // optional [CTA][8] globaltimer stamps (diagnostics)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ float gelu_fast(float x) {
   const float u = FQL_GELU_C * (x + FQL_GELU_A * x * x * x);
@@ -89,6 +97,8 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int g0 = blockIdx.z % a.G0, g1 = blockIdx.z / a.G0;
   const int nkb = (a.K + BK - 1) / BK;
+  unsigned long long* dbg = a.dbg ? a.dbg + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = gtime();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -105,6 +115,11 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = gtime();
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on we read what it
+  // wrote.  Let the next kernel in the stream start its own prologue right away.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -132,6 +147,8 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__
         const int st = kb % NSTAGE;
         mbar_wait(&full[st], (kb / NSTAGE) & 1);
         tc_fence_after();
+        if (dbg && kb == 0) dbg[2] = gtime();
+        if (dbg && kb == nkb - 1) dbg[3] = gtime();
         const uint32_t sa = smem_u32(smem + st * STAGE), sb = sa + A_STAGE;
 #pragma unroll
         for (int ks = 0; ks < BK / 16; ks++) {
@@ -153,6 +170,7 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__
     const float* bias = a.bias.at<const float>(g0, g1);
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[4] = gtime();
     uint32_t rr[2][32];
     tmem_ld32(t_lane, rr[0]);
     tmem_ld32(t_lane + 32, rr[1]);
@@ -237,9 +255,11 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__
       }
     }
   }
+  if (dbg && threadIdx.x == 64) dbg[5] = gtime();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 64);
+  if (dbg && threadIdx.x == 32) dbg[6] = gtime();
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -273,6 +293,11 @@ int make_map_4d(CUtensorMap* m, const TcOperand& o, uint32_t box_rows) {
 
 GPtrB gp(const TcPtr& p) { return GPtrB{p.base, p.s0, p.s1, p.ld}; }
 
+const int g_tc_pdl = []() {
+  const char* e = getenv("FQL_B200_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+
 }  // namespace
 
 int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
@@ -285,6 +310,7 @@ int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
   a.bias = gp(s.bias); a.out_f = gp(s.out_f); a.out_h = gp(s.out_h); a.out_z = gp(s.out_z); a.zin = gp(s.zin);
   a.act = gp(s.act); a.xb = gp(s.xb); a.target = gp(s.target);
   a.F = s.F; a.A = s.Adim; a.step = s.step; a.n_steps = s.n_steps; a.clip = s.clip;
+  a.dbg = reinterpret_cast<unsigned long long*>(s.dbg);
   if (s.mode == TC_MODE_FWD_HIDDEN || s.mode == TC_MODE_DGRAD_GELU)
     FQL_REQUIRE(s.N % 64 == 0 && s.out_h.base, "tc_gemm: hidden/dgrad epilogues need N %% 64 == 0 and a bf16 output");
   CUtensorMap mapA, mapB;
@@ -296,7 +322,18 @@ int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((s.N + BN - 1) / BN, (s.M + BM - 1) / BM, a.G0 * a.G1);
-  tc_gemm_kernel<<<grid, 192, SMEM_BYTES, st>>>(mapA, mapB, a);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_tc_pdl ? 1 : 0;
+  FQL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mapA, mapB, a));
   FQL_CHECK_LAUNCH();
   return 0;
 }

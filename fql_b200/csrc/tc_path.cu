@@ -133,7 +133,10 @@ int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, c
 // ---------------------------------------------------------------------------------------------------------------
 // actor backward: dOut fp32 [S][M][A] -> parameter gradients (fp32, into the arena)
 // ---------------------------------------------------------------------------------------------------------------
-int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[2], float* const dZf[2], cudaStream_t st) {
+int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
+                      cudaStream_t st, cudaStream_t side, cudaEvent_t* ev) {
+  // st carries the dependent dgrad chain dZ_4 -> dZ_3 -> ... -> dZ_0; the weight/bias gradients of layer l only need dZ_l,
+  // so they go to `side` behind an event (every layer has its own dZ buffer, nothing is overwritten).
   const FqlDims* d = t.d;
   const Layout& L = *t.L;
   const NetView& nv = L.net[t.net];
@@ -147,11 +150,40 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
     c.P = 1; c.S = S; c.E = 1; c.M = t.M; c.N = N; c.ld = ld;
     c.X.base[0] = X; c.X.stride_s = ss;
     c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena;
-    return launch_colsum(c, st);
+    return launch_colsum(c, side);
   };
   FQL_TRY(tc_pad_bf16(dOut, dOutb, (int64_t)S * t.M, A, 64, st));
+  FQL_CHECK_CUDA(cudaEventRecord(ev[0], st));
+  {  // dZ_{NL-2} = (dOut W^T) * gelu'(Z)
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.M = t.M; g.N = H; g.K = 64; g.G0 = 1; g.G1 = S; g.a_mn = 0; g.b_mn = 0;
+    g.A = op(dOutb, 64, t.M, 64, 1, 0, S, (long long)t.M * 64);
+    g.B = op(sh + wl_offset(d, L, t.net), 64, H, 64, 1, 0, S, seed_elems);
+    g.mode = TC_MODE_DGRAD_GELU;
+    g.zin = tp(t.Zb[NL - 2], 0, t.h_ss, H);
+    g.out_h = tp(dZb[NL - 2], 0, dz_ss, H);
+    g.out_f = tp(dZf[NL - 2], 0, dz_ss, H);
+    FQL_TRY(tc_gemm(g, st));
+    FQL_CHECK_CUDA(cudaEventRecord(ev[1], st));
+  }
+  for (int l = NL - 2; l >= 1; l--) {  // dZ_{l-1} = (dZ_l W_l^T) * gelu'(Z_{l-1})
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.M = t.M; g.N = H; g.K = H; g.G0 = 1; g.G1 = S; g.a_mn = 0; g.b_mn = 0;
+    g.A = op(dZb[l], H, t.M, H, 1, 0, S, dz_ss);
+    g.B = op(sh + nv.off_w[l], H, nv.k_of(l), H, 1, 0, S, seed_elems);
+    g.mode = TC_MODE_DGRAD_GELU;
+    g.zin = tp(t.Zb[l - 1], 0, t.h_ss, H);
+    g.out_h = tp(dZb[l - 1], 0, dz_ss, H);
+    g.out_f = tp(dZf[l - 1], 0, dz_ss, H);
+    FQL_TRY(tc_gemm(g, st));
+    FQL_CHECK_CUDA(cudaEventRecord(ev[2 + (NL - 2 - l)], st));
+  }
+  // ---- side stream: parameter gradients
+  FQL_CHECK_CUDA(cudaStreamWaitEvent(side, ev[0], 0));
   FQL_TRY(colsum(dOut, A, A, (long long)t.M * A, nv.off_b[NL - 1]));
-  {  // last layer: dW = H^T dOut ; dZ_{NL-2} = (dOut W^T) * gelu'(Z)
+  {  // dW_last = H^T dOut
     TcGemmSpec g;
     memset(&g, 0, sizeof(g));
     g.M = H; g.N = A; g.K = t.M; g.G0 = 1; g.G1 = S; g.a_mn = 1; g.b_mn = 1;
@@ -159,40 +191,20 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
     g.B = op(dOutb, 64, t.M, 64, 1, 0, S, (long long)t.M * 64);
     g.mode = TC_MODE_STORE_F32;
     g.out_f = tp(t.grads + nv.off_w[NL - 1], 0, L.arena, A);
-    FQL_TRY(tc_gemm(g, st));
-    memset(&g, 0, sizeof(g));
-    g.M = t.M; g.N = H; g.K = 64; g.G0 = 1; g.G1 = S; g.a_mn = 0; g.b_mn = 0;
-    g.A = op(dOutb, 64, t.M, 64, 1, 0, S, (long long)t.M * 64);
-    g.B = op(sh + wl_offset(d, L, t.net), 64, H, 64, 1, 0, S, seed_elems);
-    g.mode = TC_MODE_DGRAD_GELU;
-    g.zin = tp(t.Zb[NL - 2], 0, t.h_ss, H);
-    g.out_h = tp(dZb[0], 0, dz_ss, H);
-    g.out_f = tp(dZf[0], 0, dz_ss, H);
-    FQL_TRY(tc_gemm(g, st));
+    FQL_TRY(tc_gemm(g, side));
   }
-  int cur = 0;
   for (int l = NL - 2; l >= 0; l--) {
-    FQL_TRY(colsum(dZf[cur], H, H, dz_ss, nv.off_b[l]));
-    TcGemmSpec g;
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(side, ev[1 + (NL - 2 - l)], 0));
+    FQL_TRY(colsum(dZf[l], H, H, dz_ss, nv.off_b[l]));
+    TcGemmSpec g;  // dW_l = A_l^T dZ_l
     memset(&g, 0, sizeof(g));
     g.M = nv.k_of(l); g.N = H; g.K = t.M; g.G0 = 1; g.G1 = S; g.a_mn = 1; g.b_mn = 1;
     if (l == 0) g.A = op(t.X0b, t.K0pad, t.M, t.K0pad, 1, 0, S, t.x_ss);
     else g.A = op(t.Hb[l - 1], H, t.M, H, 1, 0, S, t.h_ss);
-    g.B = op(dZb[cur], H, t.M, H, 1, 0, S, dz_ss);
+    g.B = op(dZb[l], H, t.M, H, 1, 0, S, dz_ss);
     g.mode = TC_MODE_STORE_F32;
     g.out_f = tp(t.grads + nv.off_w[l], 0, L.arena, H);
-    FQL_TRY(tc_gemm(g, st));
-    if (l == 0) break;
-    memset(&g, 0, sizeof(g));
-    g.M = t.M; g.N = H; g.K = H; g.G0 = 1; g.G1 = S; g.a_mn = 0; g.b_mn = 0;
-    g.A = op(dZb[cur], H, t.M, H, 1, 0, S, dz_ss);
-    g.B = op(sh + nv.off_w[l], H, nv.k_of(l), H, 1, 0, S, seed_elems);
-    g.mode = TC_MODE_DGRAD_GELU;
-    g.zin = tp(t.Zb[l - 1], 0, t.h_ss, H);
-    g.out_h = tp(dZb[cur ^ 1], 0, dz_ss, H);
-    g.out_f = tp(dZf[cur ^ 1], 0, dz_ss, H);
-    FQL_TRY(tc_gemm(g, st));
-    cur ^= 1;
+    FQL_TRY(tc_gemm(g, side));
   }
   return 0;
 }
@@ -284,4 +296,18 @@ int tc_critic_backward(const TcCritic& t, cudaStream_t st) {
     (void)Hb_prev;
   }
   return 0;
+}
+
+// Diagnostics (not part of the product ABI surface used by the agent): one hidden-layer forward GEMM on caller buffers.
+extern "C" int fql_debug_tc_gemm(const void* X, const void* W, const float* bias, void* Hout, int M, int N, int K, void* dbg, void* stream) {
+  TcGemmSpec g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.G0 = 1; g.G1 = 1; g.a_mn = 0; g.b_mn = 1;
+  g.A = op(X, K, M, K, 1, 0, 1, 0);
+  g.B = op(W, N, K, N, 1, 0, 1, 0);
+  g.mode = TC_MODE_FWD_HIDDEN;
+  g.bias = tp(bias, 0, 0, 0);
+  g.out_h = tp(Hout, 0, 0, N);
+  g.dbg = dbg;
+  return tc_gemm(g, reinterpret_cast<cudaStream_t>(stream));
 }
