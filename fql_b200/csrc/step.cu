@@ -166,11 +166,18 @@ size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w)
     }
     w->O_dOutb = c.take(S * B * 64 / 2);
     w->F_dOutb = c.take(S * B * 64 / 2);
-    w->C1_dZb = c.take(S * 2 * B * H / 2);
-    w->C2_dZb = c.take(S * 2 * B * H / 2);
+    for (int i = 0; i < NH; i++) {
+      w->C1_dZb[i] = c.take(S * 2 * B * H / 2);
+      w->C2_dZb[i] = c.take(S * 2 * B * H / 2);
+      w->C1_dZf[i] = c.take(S * 2 * B * H);
+      w->C1_dHf[i] = c.take(S * 2 * B * H);
+      w->C2_dZf[i] = c.take(S * 2 * B * H);
+      w->C2_dHf[i] = c.take(S * 2 * B * H);
+    }
     w->C1_dOutb = c.take(S * 2 * B * 64 / 2);
     w->C2_dOutb = c.take(S * 2 * B * 64 / 2);
     w->euler_a = c.take(S * B * A);
+    w->euler_hx = c.take((int64_t)(tc_euler_scratch_elems(d, (int)B) / 2 + 4));
   }
   for (int i = 0; i < 2; i++) {
     w->dC[i] = c.take(S * 2 * B * H);
@@ -363,10 +370,12 @@ struct GraphEntry {
   long long kernels;  // kernel nodes in the captured graph
 };
 struct FqlContext {
-  cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr, s3 = nullptr, s4 = nullptr;  // s0 stands in for the caller's stream when that is the legacy default
-  cudaEvent_t ev[32] = {};
+  cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr, s3 = nullptr, s4 = nullptr, s5 = nullptr, s6 = nullptr;  // s0 stands in for the caller's stream when that is the legacy default
+  cudaEvent_t ev[64] = {};
   std::vector<GraphEntry> graphs;
   int use_graph = 1;
+  int use_euler_cluster = 1;
+  int use_critic_chain = 0;
   long long launches = 0;  // kernels enqueued through this context
 };
 
@@ -380,9 +389,15 @@ extern "C" int fql_context_create(FqlContext** out) {
   FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking));
   FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s3, cudaStreamNonBlocking));
   FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s4, cudaStreamNonBlocking));
+  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s5, cudaStreamNonBlocking));
+  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s6, cudaStreamNonBlocking));
   for (auto& e : c->ev) FQL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const char* g = getenv("FQL_B200_GRAPH");
   if (g && g[0] == '0') c->use_graph = 0;
+  const char* ec = getenv("FQL_B200_EULER_CLUSTER");
+  if (ec && ec[0] == '0') c->use_euler_cluster = 0;
+  const char* cc = getenv("FQL_B200_CRITIC_CHAIN");
+  if (cc && cc[0] == '1') c->use_critic_chain = 1;
   *out = c;
   return 0;
 }
@@ -396,6 +411,8 @@ extern "C" int fql_context_destroy(FqlContext* c) {
   if (c->s2) cudaStreamDestroy(c->s2);
   if (c->s3) cudaStreamDestroy(c->s3);
   if (c->s4) cudaStreamDestroy(c->s4);
+  if (c->s5) cudaStreamDestroy(c->s5);
+  if (c->s6) cudaStreamDestroy(c->s6);
   delete c;
   return 0;
 }
@@ -465,7 +482,13 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   // ---- S1: Euler (agents/fql.py:155-171) on rows [B, 2B) of the bc-flow buffers
   FQL_TRY(tc_pad_bf16(w.XF, w.XFb, (int64_t)S * 2 * B, sh.F + sh.A + 1, kF, S1));
   FQL_CHECK_CUDA(cudaEventRecord(ev_pad, S1));
-  {
+  if (H == 512 && ctx->use_euler_cluster) {
+    TcEulerSpec e;
+    memset(&e, 0, sizeof(e));
+    e.d = d; e.L = &L; e.params = P; e.shadow = shadow; e.X0b = w.XFb; e.Mcap0 = 2 * B; e.r0_in = B; e.M = B;
+    e.a0 = b.z; e.target = w.target; e.scratch = w.euler_hx;
+    FQL_TRY(tc_euler_cluster(e, S1));
+  } else {
     TcActor e = actor(FQL_NET_ACTOR_BC_FLOW, w.XFb, kF, 2 * B, B, B, w.F_Hb, w.F_Zb, false);
     for (int i = 0; i < sh.flow_steps; i++) {
       TcEuler eu{w.euler_a, w.target, i, sh.flow_steps};
@@ -491,12 +514,30 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   FQL_TRY(tc_actor_forward(fo, w.O_out, (long long)3 * B * sh.A, 0, nullptr, S0));
   FQL_TRY(launch_post_onestep(sh, b, w, raw, S0));
   FQL_TRY(tc_pad_bf16(w.XC, w.XCb, (int64_t)3 * S * B, sh.F + sh.A, kO, S0));
-  {
+  TcCritic cr;
+  memset(&cr, 0, sizeof(cr));
+  cr.d = d; cr.L = &L; cr.params = P; cr.shadow = shadow; cr.M = B; cr.K0pad = kO; cr.x_ss = (long long)B * kO; cr.buf = &w.pC; cr.Hb = w.C_Hb;
+  if (ctx->use_critic_chain) {
     TcChainSpec t;
     memset(&t, 0, sizeof(t));
     t.d = d; t.L = &L; t.P = 3; t.net[0] = FQL_NET_TARGET_CRITIC; t.net[1] = FQL_NET_CRITIC; t.net[2] = FQL_NET_CRITIC;
     t.params = P; t.shadow = shadow; t.M = B; t.X0b = w.XCb; t.Mcap0 = B; t.buf = &w.pC; t.save = 1; t.n_steps = 1; t.Hb = w.C_Hb;
     FQL_TRY(tc_mlp_chain(t, S0));
+  } else {
+    // three independent chains {target critic(s',a'), critic(s,a), critic(s,clip a_pi)}: S0 + two forked streams
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[40], S0));
+    cudaStream_t cs[3] = {S0, ctx->s5, ctx->s6};
+    const int nets[3] = {FQL_NET_TARGET_CRITIC, FQL_NET_CRITIC, FQL_NET_CRITIC};
+    for (int p = 0; p < 3; p++) {
+      if (p) FQL_CHECK_CUDA(cudaStreamWaitEvent(cs[p], ctx->ev[40], 0));
+      TcCritic f = cr;
+      f.p = p; f.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)p * S * B * kO;
+      FQL_TRY(tc_critic_forward(f, nets[p], w.C_out, cs[p]));
+      if (p) {
+        FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[40 + p], cs[p]));
+        FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[40 + p], 0));
+      }
+    }
   }
   FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0));
   FQL_CHECK_CUDA(cudaEventRecord(ev_cpost, S0));
@@ -504,17 +545,19 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   if (c.do_backward) {
     // critic backward (fql.py:36-37) on S2, after the bc-flow backward
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_cpost, 0));
-    TcCritic t;
-    memset(&t, 0, sizeof(t));
-    t.d = d; t.L = &L; t.params = P; t.shadow = shadow; t.grads = c.st->grads; t.M = B; t.p = 1;
-    t.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)1 * S * B * kO; t.K0pad = kO; t.x_ss = (long long)B * kO;
-    t.buf = &w.pC; t.Hb = w.C_Hb; t.dOut = w.dq; t.dOutb = w.C1_dOutb; t.dZb = w.C1_dZb; t.dZf = w.dC[0]; t.dHf = w.dC[1];
-    FQL_TRY(tc_critic_backward(t, S2));
+    TcCritic t = cr;
+    t.grads = c.st->grads; t.p = 1; t.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)1 * S * B * kO;
+    t.dOut = w.dq; t.dOutb = w.C1_dOutb;
+    for (int l = 0; l < NH; l++) { t.dZb[l] = w.C1_dZb[l]; t.dZf[l] = w.C1_dZf[l]; t.dHf[l] = w.C1_dHf[l]; }
+    FQL_TRY(tc_critic_backward(t, S2, ctx->s5, &ctx->ev[28]));
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], ctx->s5));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[36], 0));
     // critic input gradient with stored params (fql.py:70) on S0
-    TcCritic q = t;
+    TcCritic q = cr;
     q.grads = nullptr; q.p = 2; q.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)2 * S * B * kO;
-    q.dOut = w.dqs; q.dOutb = w.C2_dOutb; q.dZb = w.C2_dZb; q.dZf = w.dCp[0]; q.dHf = w.dCp[1]; q.dX0 = w.dX0;
-    FQL_TRY(tc_critic_backward(q, S0));
+    q.dOut = w.dqs; q.dOutb = w.C2_dOutb; q.dX0 = w.dX0;
+    for (int l = 0; l < NH; l++) { q.dZb[l] = w.C2_dZb[l]; q.dZf[l] = w.C2_dZf[l]; q.dHf[l] = w.C2_dHf[l]; }
+    FQL_TRY(tc_critic_backward(q, S0, nullptr, &ctx->ev[44]));
   }
   FQL_CHECK_CUDA(cudaEventRecord(ev_s2, S2));
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_euler, 0));
@@ -768,11 +811,13 @@ extern "C" int fql_total_loss(FqlContext* ctx, const FqlDims* d, const FqlHparam
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 size_t carve_forward(const FqlDims* d, int rows, int ens, int in_dim, int out_dim, bool ln, void* base, float** X, PassBuf* pb,
-                     void** Xb = nullptr) {
+                     void** Xb = nullptr, void** Hx = nullptr) {
   Carver c{reinterpret_cast<char*>(base)};
   *X = c.take((int64_t)d->num_seeds * rows * in_dim);
   void* xb = c.take((int64_t)d->num_seeds * rows * 128 / 2 + 4);
   if (Xb) *Xb = xb;
+  void* hx = (d->precision == FQL_PRECISION_BF16_TC && d->hidden == 512) ? c.take((int64_t)(tc_euler_scratch_elems(d, rows) / 2 + 4)) : nullptr;
+  if (Hx) *Hx = hx;
   carve_pass(c, pb, d->num_seeds * ens, rows, d->hidden, d->num_hidden, out_dim, ln, false);
   return c.off + 256;
 }
@@ -853,10 +898,11 @@ extern "C" int fql_compute_flow_actions(FqlContext*, const FqlDims* d, const flo
   const NetView& nv = L.net[FQL_NET_ACTOR_BC_FLOW];
   float* X;
   void* Xb;
+  void* Hx = nullptr;
   PassBuf pb;
   const size_t need = carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, nullptr, &X, &pb);
   FQL_REQUIRE(workspace && ws_bytes >= need, "workspace too small: have %zu need %zu", ws_bytes, need);
-  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb, &Xb);
+  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb, &Xb, &Hx);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t R = (int64_t)d->num_seeds * rows;
   FQL_TRY(launch_concat(obs, d->obs_dim, noise, d->action_dim, 0.f, 1, X, R, st));
@@ -864,6 +910,17 @@ extern "C" int fql_compute_flow_actions(FqlContext*, const FqlDims* d, const flo
     FQL_REQUIRE(shadow != nullptr, "FQL_PRECISION_BF16_TC needs the bf16 shadow");
     const int kp = (int)round_up64(nv.in_dim, 64);
     FQL_TRY(tc_pad_bf16(X, Xb, R, nv.in_dim, kp, st));
+    if (d->hidden == 512 && Hx) {
+      TcEulerSpec e;
+      memset(&e, 0, sizeof(e));
+      e.d = d; e.L = &L; e.params = params; e.shadow = shadow; e.X0b = Xb; e.Mcap0 = rows; e.r0_in = 0; e.M = rows;
+      e.a0 = noise; e.target = actions_out; e.scratch = Hx;
+      {
+        const char* dp = getenv("FQL_B200_EULER_DBG");
+        if (dp) e.dbg = reinterpret_cast<void*>(strtoull(dp, nullptr, 0));
+      }
+      return tc_euler_cluster(e, st);
+    }
     TcChainSpec t;
     memset(&t, 0, sizeof(t));
     t.d = d; t.L = &L; t.P = 1; t.net[0] = FQL_NET_ACTOR_BC_FLOW; t.params = params; t.shadow = shadow;

@@ -36,8 +36,10 @@ struct WsPtrs {
   void *C_Hb[FQL_MAXL];        // bf16 post-LN activations of the grouped critic pass [3][S][2][B][H]
   void *O_dZb[FQL_MAXL], *F_dZb[FQL_MAXL], *O_dOutb, *F_dOutb;
   float *O_dZf[FQL_MAXL], *F_dZf[FQL_MAXL];
-  void *C1_dZb, *C1_dOutb, *C2_dZb, *C2_dOutb;
+  void *C1_dZb[FQL_MAXL], *C1_dOutb, *C2_dZb[FQL_MAXL], *C2_dOutb;
+  float *C1_dZf[FQL_MAXL], *C1_dHf[FQL_MAXL], *C2_dZf[FQL_MAXL], *C2_dHf[FQL_MAXL];
   float *euler_a;
+  void *euler_hx;              // exchange scratch of the cluster Euler kernel
 };
 
 StepShape make_shape(const FqlDims* d);
@@ -149,10 +151,29 @@ struct TcCritic {
   void* const* Hb;       // bf16 H per layer [P][S][E][Mcap][H]
   const float* dOut;     // [S][2][M]
   void* dOutb;
-  void* dZb;
-  float *dZf, *dHf, *dX0;
+  void* dZb[FQL_MAXL];     // per hidden layer: bf16 dZ_l  [S][2][M][H]
+  float* dZf[FQL_MAXL];    //                   fp32 dZ_l
+  float* dHf[FQL_MAXL];    //                   fp32 dH_l (before the LayerNorm/GELU backward)
+  float* dX0;
 };
 int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, const TcEuler* eu, cudaStream_t st);
 int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
                       cudaStream_t st, cudaStream_t side, cudaEvent_t* ev);
-int tc_critic_backward(const TcCritic& t, cudaStream_t st);
+int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cudaEvent_t* ev);
+int tc_critic_forward(const TcCritic& t, int net, float* out, cudaStream_t st);
+
+// euler_cluster.cu -- compute_flow_actions as one persistent thread-block-cluster kernel (hidden = 512)
+struct TcEulerSpec {
+  const FqlDims* d;
+  const Layout* L;
+  const float* params;
+  const void* shadow;
+  const void* X0b;     // bf16 [S][Mcap0][K0pad] first-layer operand (obs | noise | t = 0)
+  int Mcap0, r0_in, M;
+  const float* a0;     // [S][M][A]
+  float* target;       // [S][M][A]
+  void* scratch;       // tc_euler_scratch_elems() bf16 elements
+  void* dbg;           // optional timestamp buffer (diagnostics)
+};
+size_t tc_euler_scratch_elems(const FqlDims* d, int M);
+int tc_euler_cluster(const TcEulerSpec& f, cudaStream_t st);

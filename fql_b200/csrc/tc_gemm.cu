@@ -26,6 +26,8 @@ constexpr int A_STAGE = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE = BN * BK * 2;  //  8 KB
 constexpr int STAGE = A_STAGE + B_STAGE;
 constexpr int NSTAGE = 9;
+constexpr int NACC = 4;                // MMA-issuer warps = independent TMEM accumulators (k-step ks of every block -> warp ks)
+constexpr int NTHREADS = 32 * (1 + NACC + 4);  // TMA warp, NACC MMA warps, 4 epilogue warps
 constexpr int SMEM_BYTES = NSTAGE * STAGE + 1024 + 256;
 
 struct GPtrB {
@@ -83,7 +85,7 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                          const __grid_constant__ CUtensorMap mapB, const TcGemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -105,12 +107,12 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__
     tma_prefetch_desc(&mapB);
     for (int i = 0; i < NSTAGE; i++) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], NACC);
     }
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full, NACC);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  if (warp == 1) tmem_alloc(tmem_slot, 64 * NACC);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -140,23 +142,28 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__
         else tma_load_4d(sb, &mapB, &full[st], n0, kb * BK, gb0, g1);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= NACC) {
+    // ---------------- MMA issuers ----------------
+    // A tcgen05.mma costs its issuing warp ~80 ns whatever N is (measured, profiles/micro/mma_bench.cu: 81 ns at N=16..256),
+    // and the cost is per warp: four warps issue at ~3x the rate of one.  Warp w therefore owns k-step w of every 64-wide K
+    // block and accumulates into its own 64 TMEM columns; the epilogue adds the four partial accumulators.
     if (lane == 0) {
+      const int mw = warp - 1;
       const uint32_t idesc = make_idesc_bf16(BM, BN, a.a_mn != 0, a.b_mn != 0);
+      const uint64_t a_t = (a.a_mn ? make_smem_desc(0, A_STAGE / 2, 1024) : make_smem_desc(0, 16, 1024)) + (uint64_t)(mw * (a.a_mn ? (2048 >> 4) : (32 >> 4)));
+      const uint64_t b_t = (a.b_mn ? make_smem_desc(0, B_STAGE, 1024) : make_smem_desc(0, 16, 1024)) + (uint64_t)(mw * (a.b_mn ? (2048 >> 4) : (32 >> 4)));
+      const uint32_t s0 = smem_u32(smem) >> 4;
+      const uint32_t tacc = tmem_base + mw * 64;
+      int st = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < nkb; kb++) {
-        const int st = kb % NSTAGE;
-        mbar_wait(&full[st], (kb / NSTAGE) & 1);
+        mbar_wait(&full[st], ph);
         tc_fence_after();
-        if (dbg && kb == 0) dbg[2] = gtime();
-        if (dbg && kb == nkb - 1) dbg[3] = gtime();
-        const uint32_t sa = smem_u32(smem + st * STAGE), sb = sa + A_STAGE;
-#pragma unroll
-        for (int ks = 0; ks < BK / 16; ks++) {
-          const uint64_t ad = a.a_mn ? make_smem_desc(sa + ks * 2048, A_STAGE / 2, 1024) : make_smem_desc(sa + ks * 32, 16, 1024);
-          const uint64_t bd = a.b_mn ? make_smem_desc(sb + ks * 2048, B_STAGE, 1024) : make_smem_desc(sb + ks * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (kb | ks) != 0);
-        }
+        if (dbg && mw == 0 && kb == 0) dbg[2] = gtime();
+        if (dbg && mw == 0 && kb == nkb - 1) dbg[3] = gtime();
+        umma_bf16(tacc, a_t + (uint64_t)(s0 + st * (STAGE >> 4)), b_t + (uint64_t)(s0 + st * (STAGE >> 4) + (A_STAGE >> 4)), idesc, kb != 0);
         umma_commit(&empty[st]);
+        if (++st == NSTAGE) { st = 0; ph ^= 1; }
       }
       umma_commit(acc_full);
     }
@@ -170,14 +177,21 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__
     const float* bias = a.bias.at<const float>(g0, g1);
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    if (dbg && threadIdx.x == 64) dbg[4] = gtime();
-    uint32_t rr[2][32];
-    tmem_ld32(t_lane, rr[0]);
-    tmem_ld32(t_lane + 32, rr[1]);
-    tmem_wait_ld();
-#pragma unroll
+    if (dbg && threadIdx.x == 32 * (1 + NACC)) dbg[4] = gtime();
+#pragma unroll 1
     for (int j = 0; j < 2; j++) {
-      const uint32_t(&r)[32] = rr[j];
+      // one 32-column half at a time keeps the live set at 64 registers: partial accumulators of the NACC MMA warps are added
+      uint32_t r[32];
+      tmem_ld32(t_lane + j * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int acc = 1; acc < NACC; acc++) {
+        uint32_t t[32];
+        tmem_ld32(t_lane + acc * 64 + j * 32, t);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t[i]));
+      }
       const int nb = n0 + j * 32;
       if (!valid || nb >= a.N) continue;
       float v[32];
@@ -255,10 +269,10 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_kernel(const __grid_constant__
       }
     }
   }
-  if (dbg && threadIdx.x == 64) dbg[5] = gtime();
+  if (dbg && threadIdx.x == 32 * (1 + NACC)) dbg[5] = gtime();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 64);
+  if (warp == 1) tmem_dealloc(tmem_base, 64 * NACC);
   if (dbg && threadIdx.x == 32) dbg[6] = gtime();
 }
 
@@ -325,7 +339,7 @@ int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -25,6 +25,51 @@ int64_t wl_offset(const FqlDims* d, const Layout& L, int net) {
   return o;
 }
 
+// H = [LayerNorm](gelu(Z)) -> bf16 (+ row statistics); one warp per row.  Z: fp32 [rows][N] contiguous; scale/bias per (s, e).
+__global__ void __launch_bounds__(256) act_ln_bf16_kernel(const float* __restrict__ Z, const float* __restrict__ scale_base,
+                                                          const float* __restrict__ bias_base, int64_t par_s, int64_t par_e,
+                                                          bf16* __restrict__ Hb, float* __restrict__ mu_out, float* __restrict__ rstd_out,
+                                                          int M, int N, int S, int E, int ln) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  if (row >= (int64_t)S * E * M) return;
+  const int g = (int)(row / M), e = g % E, s = g / E;
+  const float* z = Z + row * N;
+  bf16* h = Hb + row * N;
+  if (!ln) {
+    for (int c = lane * 2; c < N; c += 64) {
+      const float2 zz = *reinterpret_cast<const float2*>(z + c);
+      *reinterpret_cast<__nv_bfloat162*>(h + c) = __floats2bfloat162_rn(gelu_tanh_f(zz.x), gelu_tanh_f(zz.y));
+    }
+    return;
+  }
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane * 2; c < N; c += 64) {
+    const float2 zz = *reinterpret_cast<const float2*>(z + c);
+    const float g0 = gelu_tanh_f(zz.x), g1 = gelu_tanh_f(zz.y);
+    s1 += g0 + g1;
+    s2 += g0 * g0 + g1 * g1;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const float inv_n = 1.0f / (float)N;
+  const float mu = s1 * inv_n;
+  const float var = fmaxf(0.f, s2 * inv_n - mu * mu);
+  const float rstd = rsqrtf(var + FQL_LN_EPS);
+  const float* sc = scale_base + s * par_s + e * par_e;
+  const float* bi = bias_base + s * par_s + e * par_e;
+  for (int c = lane * 2; c < N; c += 64) {
+    const float2 zz = *reinterpret_cast<const float2*>(z + c);
+    const float h0 = (gelu_tanh_f(zz.x) - mu) * rstd * sc[c] + bi[c];
+    const float h1 = (gelu_tanh_f(zz.y) - mu) * rstd * sc[c + 1] + bi[c + 1];
+    *reinterpret_cast<__nv_bfloat162*>(h + c) = __floats2bfloat162_rn(h0, h1);
+  }
+  if (lane == 0 && mu_out) {
+    mu_out[row] = mu;
+    rstd_out[row] = rstd;
+  }
+}
+
 // dZ rows kernel for LayerNorm nets with an extra bf16 copy: dZ = LNbwd(dH; Z) * gelu'(Z)
 __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const float* __restrict__ dH, const float* __restrict__ Z,
                                                           const float* __restrict__ scale_base, int64_t scale_s, int64_t scale_e,
@@ -214,7 +259,9 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
 //   grads != NULL : full backward (critic loss, fql.py:36-37)
 //   grads == NULL : input gradient only, stored params (actor Q loss, fql.py:70) -> dX0 [S][2][M][K0]
 // ---------------------------------------------------------------------------------------------------------------
-int tc_critic_backward(const TcCritic& t, cudaStream_t st) {
+int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cudaEvent_t* ev) {
+  // st: the dependent chain  dZ_4 -> dgrad -> [LN/GELU bwd] -> dZ_3 -> ...   side: everything that only CONSUMES dZ_l / dH_l
+  // (weight, bias and LayerNorm-parameter gradients).  Every layer has its own dH / dZ buffers, nothing is overwritten.
   const FqlDims* d = t.d;
   const Layout& L = *t.L;
   const NetView& nv = L.net[FQL_NET_CRITIC];
@@ -222,9 +269,8 @@ int tc_critic_backward(const TcCritic& t, cudaStream_t st) {
   const int64_t seed_elems = tc_shadow_seed_elems(d, L);
   const bf16* sh = reinterpret_cast<const bf16*>(t.shadow);
   const long long dz_se = (long long)M * H, dz_ss = (long long)E * M * H;
-  // saved activations of problem p inside the grouped pass buffers [P][S][E][Mcap][H]
   const int64_t Mcap = t.buf->Mcap;
-  const int64_t prow = (int64_t)t.p * S * E * Mcap;  // first row of the problem
+  const int64_t prow = (int64_t)t.p * S * E * Mcap;  // first row of the problem inside the grouped pass buffers
   const long long z_se = Mcap * H, z_ss = (long long)E * Mcap * H;
   auto colsum = [&](const float* X, int N, int ld, long long se, long long ss, int64_t goff, const float* Z, const float* mu,
                     const float* rstd) {
@@ -238,31 +284,17 @@ int tc_critic_backward(const TcCritic& t, cudaStream_t st) {
       c.rstd.base[0] = rstd; c.rstd.stride_s = c.mu.stride_s; c.rstd.stride_e = Mcap;
     }
     c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena; c.out.stride_e = N;
-    return launch_colsum(c, st);
+    return launch_colsum(c, side);
   };
-  // dOut [S][2][M] (out_dim 1) -> bf16 [S][2][M][64]
+  // ---- chain
   FQL_TRY(tc_pad_bf16(t.dOut, t.dOutb, (int64_t)S * E * M, 1, 64, st));
-  if (t.grads) FQL_TRY(colsum(t.dOut, 1, 1, M, (long long)E * M, nv.off_b[NL - 1], nullptr, nullptr, nullptr));
-  const bf16* Hb_prev = nullptr;
+  FQL_CHECK_CUDA(cudaEventRecord(ev[0], st));
   for (int l = NL - 1; l >= 0; l--) {
-    // here: dZ_l is available as bf16 (dZb) [S][E][M][N_l] (for l = NL-1: dOutb with N padded to 64)
     const bool last = (l == NL - 1);
-    const void* dzb = last ? t.dOutb : t.dZb;
+    if (l == 0 && !t.dX0) break;
+    const void* dzb = last ? t.dOutb : t.dZb[l];
     const int dz_inner = last ? 64 : H;
     const long long dzb_se = (long long)M * dz_inner, dzb_ss = (long long)E * M * dz_inner;
-    if (t.grads) {
-      if (!last) FQL_TRY(colsum(t.dZf, H, H, dz_se, dz_ss, nv.off_b[l], nullptr, nullptr, nullptr));
-      TcGemmSpec g;  // dW_l [K_l][N_l] = A_l^T dZ_l
-      memset(&g, 0, sizeof(g));
-      g.M = nv.k_of(l); g.N = nv.n_of(l); g.K = M; g.G0 = E; g.G1 = S; g.a_mn = 1; g.b_mn = 1;
-      if (l == 0) g.A = op(t.X0b, t.K0pad, M, t.K0pad, 1, 0, S, t.x_ss);  // input shared by both heads
-      else g.A = op(reinterpret_cast<const bf16*>(t.Hb[l - 1]) + prow * H, H, M, H, E, z_se, S, z_ss);
-      g.B = op(dzb, dz_inner, M, dz_inner, E, dzb_se, S, dzb_ss);
-      g.mode = TC_MODE_STORE_F32;
-      g.out_f = tp(t.grads + nv.off_w[l], (long long)nv.k_of(l) * nv.n_of(l), L.arena, nv.n_of(l));
-      FQL_TRY(tc_gemm(g, st));
-    }
-    if (l == 0 && !t.dX0) break;
     TcGemmSpec g;  // dH_{l-1} [M][K_l] = dZ_l W_l^T   (raw, fp32)
     memset(&g, 0, sizeof(g));
     g.M = M; g.N = nv.k_of(l); g.K = last ? 64 : H; g.G0 = E; g.G1 = S; g.a_mn = 0; g.b_mn = 0;
@@ -275,36 +307,108 @@ int tc_critic_backward(const TcCritic& t, cudaStream_t st) {
       FQL_TRY(tc_gemm(g, st));
       break;
     }
-    g.out_f = tp(t.dHf, dz_se, dz_ss, H);
+    g.out_f = tp(t.dHf[l - 1], dz_se, dz_ss, H);
     FQL_TRY(tc_gemm(g, st));
     const float* Zp = t.buf->Z[l - 1] + prow * H;
     if (nv.ln) {
-      if (t.grads) {
-        FQL_TRY(colsum(t.dHf, H, H, dz_se, dz_ss, nv.off_lnb[l - 1], nullptr, nullptr, nullptr));
-        FQL_TRY(colsum(t.dHf, H, H, dz_se, dz_ss, nv.off_lns[l - 1], Zp, t.buf->mu[l - 1] + prow, t.buf->rstd[l - 1] + prow));
-      }
       const int64_t rows = (int64_t)S * E * M;
-      ln_bwd_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(t.dHf, Zp, t.params + nv.off_lns[l - 1], L.arena, H, t.dZf,
-                                                                     reinterpret_cast<bf16*>(t.dZb), M, H, S, E, Mcap, (int64_t)E * Mcap);
+      ln_bwd_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(t.dHf[l - 1], Zp, t.params + nv.off_lns[l - 1], L.arena, H, t.dZf[l - 1],
+                                                                     reinterpret_cast<bf16*>(t.dZb[l - 1]), M, H, S, E, Mcap, (int64_t)E * Mcap);
       FQL_CHECK_LAUNCH();
     } else {
       const int64_t n = (int64_t)S * E * M * H;
-      gelu_bwd_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.dHf, Zp, t.dZf, reinterpret_cast<bf16*>(t.dZb), M, H, S, E, Mcap,
-                                                                        (int64_t)E * Mcap);
+      gelu_bwd_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.dHf[l - 1], Zp, t.dZf[l - 1], reinterpret_cast<bf16*>(t.dZb[l - 1]), M, H,
+                                                                        S, E, Mcap, (int64_t)E * Mcap);
       FQL_CHECK_LAUNCH();
     }
-    (void)Hb_prev;
+    FQL_CHECK_CUDA(cudaEventRecord(ev[1 + (NL - 1 - l)], st));  // dZ_{l-1} (and dH_{l-1}) ready
+  }
+  if (!t.grads) return 0;
+  // ---- side: parameter gradients
+  FQL_CHECK_CUDA(cudaStreamWaitEvent(side, ev[0], 0));
+  FQL_TRY(colsum(t.dOut, 1, 1, M, (long long)E * M, nv.off_b[NL - 1], nullptr, nullptr, nullptr));
+  for (int l = NL - 1; l >= 0; l--) {
+    const bool last = (l == NL - 1);
+    if (!last) {
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(side, ev[1 + (NL - 2 - l)], 0));  // dZ_l
+      FQL_TRY(colsum(t.dZf[l], H, H, dz_se, dz_ss, nv.off_b[l], nullptr, nullptr, nullptr));
+      if (nv.ln) {
+        const float* Zl = t.buf->Z[l] + prow * H;
+        FQL_TRY(colsum(t.dHf[l], H, H, dz_se, dz_ss, nv.off_lnb[l], nullptr, nullptr, nullptr));
+        FQL_TRY(colsum(t.dHf[l], H, H, dz_se, dz_ss, nv.off_lns[l], Zl, t.buf->mu[l] + prow, t.buf->rstd[l] + prow));
+      }
+    }
+    const void* dzb = last ? t.dOutb : t.dZb[l];
+    const int dz_inner = last ? 64 : H;
+    const long long dzb_se = (long long)M * dz_inner, dzb_ss = (long long)E * M * dz_inner;
+    TcGemmSpec g;  // dW_l [K_l][N_l] = A_l^T dZ_l
+    memset(&g, 0, sizeof(g));
+    g.M = nv.k_of(l); g.N = nv.n_of(l); g.K = M; g.G0 = E; g.G1 = S; g.a_mn = 1; g.b_mn = 1;
+    if (l == 0) g.A = op(t.X0b, t.K0pad, M, t.K0pad, 1, 0, S, t.x_ss);  // input shared by both heads
+    else g.A = op(reinterpret_cast<const bf16*>(t.Hb[l - 1]) + prow * H, H, M, H, E, z_se, S, z_ss);
+    g.B = op(dzb, dz_inner, M, dz_inner, E, dzb_se, S, dzb_ss);
+    g.mode = TC_MODE_STORE_F32;
+    g.out_f = tp(t.grads + nv.off_w[l], (long long)nv.k_of(l) * nv.n_of(l), L.arena, nv.n_of(l));
+    FQL_TRY(tc_gemm(g, side));
   }
   return 0;
 }
 
-// Diagnostics (not part of the product ABI surface used by the agent): one hidden-layer forward GEMM on caller buffers.
-extern "C" int fql_debug_tc_gemm(const void* X, const void* W, const float* bias, void* Hout, int M, int N, int K, void* dbg, void* stream) {
+// ---------------------------------------------------------------------------------------------------------------
+// critic forward of ONE problem of the grouped pass (2 heads), layer by layer: tc_gemm (+bias, fp32 Z) -> fused GELU+LayerNorm
+// row kernel (bf16 H, fp32 row statistics).  The three problems {target(s',a'), critic(s,a), critic(s,a_pi)} are independent
+// chains and run on three streams.
+// ---------------------------------------------------------------------------------------------------------------
+int tc_critic_forward(const TcCritic& t, int net, float* out, cudaStream_t st) {
+  const FqlDims* d = t.d;
+  const Layout& L = *t.L;
+  const NetView& nv = L.net[net];
+  const int H = d->hidden, NL = nv.n_layers, S = d->num_seeds, E = 2, M = t.M;
+  const int64_t seed_elems = tc_shadow_seed_elems(d, L);
+  const bf16* sh = reinterpret_cast<const bf16*>(t.shadow);
+  const int64_t Mcap = t.buf->Mcap;
+  FQL_REQUIRE(Mcap == M, "tc_critic_forward: the grouped pass buffers must be dense (Mcap == M)");
+  const int64_t prow = (int64_t)t.p * S * E * Mcap;
+  const long long z_se = Mcap * H, z_ss = (long long)E * Mcap * H;
+  for (int l = 0; l < NL; l++) {
+    const bool last = (l == NL - 1);
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.K = nv.k_of(l); g.G0 = E; g.G1 = S; g.a_mn = 0; g.b_mn = 1;
+    if (l == 0) g.A = op(t.X0b, t.K0pad, M, t.K0pad, 1, 0, S, t.x_ss);
+    else g.A = op(reinterpret_cast<const bf16*>(t.Hb[l - 1]) + prow * H, H, M, H, E, z_se, S, z_ss);
+    g.mode = TC_MODE_STORE_F32;
+    g.bias = tp(t.params + nv.off_b[l], nv.n_of(l), L.arena, 0);
+    if (!last) {
+      g.N = H;
+      g.B = op(sh + nv.off_w[l], H, g.K, H, E, (long long)g.K * H, S, seed_elems);
+      g.out_f = tp(t.buf->Z[l] + prow * H, z_se, z_ss, H);
+      FQL_TRY(tc_gemm(g, st));
+      const int64_t rows = (int64_t)S * E * M;
+      act_ln_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+          t.buf->Z[l] + prow * H, nv.ln ? t.params + nv.off_lns[l] : nullptr, nv.ln ? t.params + nv.off_lnb[l] : nullptr, L.arena, H,
+          reinterpret_cast<bf16*>(t.Hb[l]) + prow * H, nv.ln ? t.buf->mu[l] + prow : nullptr, nv.ln ? t.buf->rstd[l] + prow : nullptr, M, H, S, E,
+          nv.ln);
+      FQL_CHECK_LAUNCH();
+    } else {
+      g.N = 1;
+      g.B = op(sh + wl_offset(d, L, net), 64, H, 64, E, (long long)H * 64, S, seed_elems);
+      g.out_f = tp(out + prow, Mcap, (long long)E * Mcap, 1);
+      FQL_TRY(tc_gemm(g, st));
+    }
+  }
+  return 0;
+}
+
+// Diagnostics (not part of the product ABI surface used by the agent): one GEMM on caller buffers with chosen operand
+// majorness (timing only: the buffers are interpreted as whatever layout the flags say).
+extern "C" int fql_debug_tc_gemm(const void* X, const void* W, const float* bias, void* Hout, int M, int N, int K, void* dbg, void* stream,
+                                 int a_mn, int b_mn) {
   TcGemmSpec g;
   memset(&g, 0, sizeof(g));
-  g.M = M; g.N = N; g.K = K; g.G0 = 1; g.G1 = 1; g.a_mn = 0; g.b_mn = 1;
-  g.A = op(X, K, M, K, 1, 0, 1, 0);
-  g.B = op(W, N, K, N, 1, 0, 1, 0);
+  g.M = M; g.N = N; g.K = K; g.G0 = 1; g.G1 = 1; g.a_mn = a_mn; g.b_mn = b_mn;
+  g.A = a_mn ? op(X, M, K, M, 1, 0, 1, 0) : op(X, K, M, K, 1, 0, 1, 0);
+  g.B = b_mn ? op(W, N, K, N, 1, 0, 1, 0) : op(W, K, N, K, 1, 0, 1, 0);
   g.mode = TC_MODE_FWD_HIDDEN;
   g.bias = tp(bias, 0, 0, 0);
   g.out_h = tp(Hout, 0, 0, N);

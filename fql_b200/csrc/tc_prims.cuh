@@ -79,6 +79,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Four consecutive k-steps (one 64-wide K block) from ONE asm block: the descriptors advance by constant adds inside PTX, so
+// ptxas materialises the uniform-register operands once instead of an R2UR round trip before every UTCHMMA.
+__device__ __forceinline__ void umma_bf16_x4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint64_t a_step, uint64_t b_step,
+                                             uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "add.u64 a1, %1, %5;\n\tadd.u64 b1, %2, %6;\n\t"
+      "add.u64 a2, a1, %5;\n\tadd.u64 b2, b1, %6;\n\t"
+      "add.u64 a3, a2, %5;\n\tadd.u64 b3, b2, %6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, q;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "l"(a_step), "l"(b_step)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed (implies fence::before)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -1,13 +1,14 @@
-"""Diagnostics: per-phase globaltimer stamps of tc_gemm_kernel (one hidden-layer forward GEMM, M=256 N=512 K=512)."""
+"""Diagnostics: per-phase globaltimer stamps of tc_gemm_kernel for the four operand-majorness combinations (M=256 N=512 K=512)."""
 import ctypes as C
+import os
 import sys
-import numpy as np
+os.environ['FQL_B200_PDL'] = '0'
 import torch
 sys.path.insert(0, '.')
 from fql_b200 import _lib
 lib = C.CDLL(_lib.LIB_PATH)
-lib.fql_debug_tc_gemm.argtypes = [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 2
-M, N, K = 256, 512, int(sys.argv[1]) if len(sys.argv) > 1 else 512
+lib.fql_debug_tc_gemm.argtypes = [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p] * 2 + [C.c_int] * 2
+M, N, K = 256, 512, 512
 X = torch.randn(M, K, device='cuda').bfloat16()
 W = (torch.randn(K, N, device='cuda') / K ** 0.5).bfloat16()
 b = torch.zeros(N, device='cuda')
@@ -16,22 +17,12 @@ nct = (N // 64) * ((M + 127) // 128)
 dbg = torch.zeros(nct * 8, dtype=torch.int64, device='cuda')
 st = torch.cuda.Stream()
 with torch.cuda.stream(st):
-    for it in range(5):
-        rc = lib.fql_debug_tc_gemm(X.data_ptr(), W.data_ptr(), b.data_ptr(), H.data_ptr(), M, N, K, dbg.data_ptr(), st.cuda_stream)
-        assert rc == 0
-    torch.cuda.synchronize()
-    ref = torch.nn.functional.gelu(X.float() @ W.float(), approximate='tanh')
-    print('max err', (H.float() - ref).abs().max().item())
-    d = dbg.cpu().numpy().reshape(nct, 8)
-    t0 = d[:, 0].min()
-    print('per-CTA ns since first CTA start: start, setup_done, first_full, last_full, acc_full, epi_done, end')
-    for r in d[:4]:
-        print([int(x - t0) for x in r[:7]])
-    print('mean', [float((d[:, i] - d[:, 0]).mean()) for i in range(7)])
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for it in range(100):
-        lib.fql_debug_tc_gemm(X.data_ptr(), W.data_ptr(), b.data_ptr(), H.data_ptr(), M, N, K, None, st.cuda_stream)
-    e1.record()
-    torch.cuda.synchronize()
-    print('back-to-back launches: us per GEMM', e0.elapsed_time(e1) * 10)
+    for a_mn in (0, 1):
+        for b_mn in (0, 1):
+            for it in range(4):
+                assert lib.fql_debug_tc_gemm(X.data_ptr(), W.data_ptr(), b.data_ptr(), H.data_ptr(), M, N, K, dbg.data_ptr(), st.cuda_stream, a_mn, b_mn) == 0
+            torch.cuda.synchronize()
+            d = dbg.cpu().numpy().reshape(nct, 8)
+            m = [float((d[:, i] - d[:, 0]).mean()) for i in range(7)]
+            print(f'a_mn={a_mn} b_mn={b_mn}: setup {m[1]:.0f}  first block seen {m[2]:.0f}  last block seen {m[3]:.0f}  acc_full {m[4]:.0f}  epilogue done {m[5]:.0f}  end {m[6]:.0f} ns'
+                  f'   => MMA phase per k-block {(m[3] - m[2]) / 7:.0f} ns')
