@@ -107,7 +107,7 @@ class FQLAgent:
     # ------------------------------------------------------------------ construction (agents/fql.py:173-246)
     @classmethod
     def create(cls, seed, ex_observations, ex_actions, config, *, num_seeds=1, device=None, precision='fp32',
-               process_group=None):
+               process_group=None, world_size=None):
         self = cls.__new__(cls)
         cfg = dict(config)
         if cfg.get('encoder') is not None:
@@ -129,6 +129,8 @@ class FQLAgent:
         if process_group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
+        if world_size is not None:
+            self.world = int(world_size)  # explicit override: the caller drives grads_phase / apply_phase itself
         self._precision = {'fp32': _lib.PRECISION_FP32, 'bf16': _lib.PRECISION_BF16_TC}[precision]
         self._hidden, self._num_hidden = ah[0], len(ah)
         self._lib = _lib.lib()
@@ -336,21 +338,28 @@ class FQLAgent:
             if fill_noise:
                 self._fill_noise(bufs, self._host_step)
             self._host_step += 1
-            a = (self._ctx, C.byref(bufs['d']), C.byref(self._hp))
             if self.world == 1:
+                a = (self._ctx, C.byref(bufs['d']), C.byref(self._hp))
                 _lib.check(self._lib.fql_update_step(*a, C.byref(bufs['fb']), C.byref(bufs['st']), _ptr(bufs['info']),
                                                      _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_update_step')
             else:
-                import torch.distributed as dist
-                _lib.check(self._lib.fql_step_grads(*a, C.byref(bufs['fb']), C.byref(bufs['st']), _ptr(bufs['raw']),
-                                                    _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_step_grads')
+                from . import dist as fdist
+                self.grads_phase(bufs)
                 t0, _ = self._net_range('target_critic')
-                dist.all_reduce(self._grads[:, :t0], op=dist.ReduceOp.SUM, group=self.pg)
-                dist.all_reduce(bufs['raw'][:, :9], op=dist.ReduceOp.SUM, group=self.pg)
-                dist.all_reduce(bufs['raw'][:, 9:11], op=dist.ReduceOp.MAX, group=self.pg)
-                _lib.check(self._lib.fql_step_apply(*a, C.byref(bufs['st']), _ptr(bufs['raw']), _ptr(bufs['info']),
-                                                    _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_step_apply')
+                fdist.allreduce_step(self._grads[:, :t0], bufs['raw'], group=self.pg)
+                self.apply_phase(bufs)
             return self._info_out(bufs['info'])
+
+    def grads_phase(self, bufs):
+        """Data-parallel half 1 (fql_step_grads): this rank's gradient contribution (already divided by the global batch) into
+        the gradient arena and the raw metric accumulators into bufs['raw']."""
+        _lib.check(self._lib.fql_step_grads(self._ctx, C.byref(bufs['d']), C.byref(self._hp), C.byref(bufs['fb']), C.byref(bufs['st']),
+                                            _ptr(bufs['raw']), _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_step_grads')
+
+    def apply_phase(self, bufs):
+        """Data-parallel half 2 (fql_step_apply) on the all-reduced gradients / accumulators: stats + Adam + Polyak + info."""
+        _lib.check(self._lib.fql_step_apply(self._ctx, C.byref(bufs['d']), C.byref(self._hp), C.byref(bufs['st']), _ptr(bufs['raw']),
+                                            _ptr(bufs['info']), _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_step_apply')
 
     def _fill_noise(self, bufs, step_for_noise):
         dev = bufs['dev']

@@ -1,0 +1,76 @@
+"""Data-parallel plumbing of FQLAgent.update: the batch shards by rows, every rank runs the loss/gradient half
+of the step on its rows with loss denominators of the GLOBAL batch (FqlDims.global_batch), the flat gradient arena and
+the raw metric accumulators are all-reduced, and every rank applies the identical Adam/Polyak step (no parameter
+broadcast).  Nothing here touches CUDA directly, so the same functions run under gloo on CPU in the tests.
+
+The reference itself is single-device (no pmap/shard_map anywhere): this module is new capability, not a port.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+RAW_SUM = slice(0, 9)    # include/fql_b200.h: raw[0..8] are sums
+RAW_MAX = slice(9, 11)   # raw[9] = max q, raw[10] = -min q
+
+
+def shard_rows(batch: dict, rank: int, world: int) -> dict:
+    """Rank r takes rows [r*B/R, (r+1)*B/R) of every array of the GLOBAL batch / noise dict (same global index draw on every
+    rank, so R ranks reproduce the 1-rank step on the concatenated batch)."""
+    out = {}
+    for k, v in batch.items():
+        n = v.shape[0]
+        if n % world:
+            raise ValueError(f'batch rows ({n}) must divide evenly over {world} ranks')
+        per = n // world
+        out[k] = v[rank * per:(rank + 1) * per]
+    return out
+
+
+def allreduce_step(grads: torch.Tensor, raw: torch.Tensor, group=None) -> None:
+    """In-place all-reduce of the gradient arena (SUM) and the raw accumulators (SUM for sums, MAX for max / -min)."""
+    dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)
+    s = raw[..., RAW_SUM].contiguous()
+    m = raw[..., RAW_MAX].contiguous()
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    raw[..., RAW_SUM] = s
+    raw[..., RAW_MAX] = m
+
+
+def shard_seeds(num_seeds: int, rank: int, world: int) -> range:
+    """Multi-seed runs (BASELINE config 4) shard by agent: no collective on the step."""
+    if num_seeds % world:
+        raise ValueError(f'{num_seeds} seeds do not divide over {world} ranks')
+    per = num_seeds // world
+    return range(rank * per, (rank + 1) * per)
+
+
+def raw_from_losses(info: dict, q: np.ndarray, q_pi: np.ndarray, local_rows: int, action_dim: int) -> np.ndarray:
+    """Raw accumulators a rank would produce, reconstructed from per-rank MEAN metrics (used by the CPU tests to exercise the
+    reduction semantics against the oracle)."""
+    raw = np.zeros(16, np.float64)
+    B, A = local_rows, action_dim
+    raw[0] = info['critic/critic_loss'] * 2 * B
+    raw[1] = info['critic/q_mean'] * 2 * B
+    raw[2] = info['actor/bc_flow_loss'] * B * A
+    raw[3] = info['actor/distill_loss'] * B * A
+    raw[4] = info['actor/q'] * B
+    raw[5] = np.abs(q_pi).sum()
+    raw[6] = info['actor/mse'] * B * A
+    raw[9] = info['critic/q_max']
+    raw[10] = -info['critic/q_min']
+    return raw
+
+
+def info_from_raw(raw: np.ndarray, global_rows: int, action_dim: int, alpha: float, normalize_q_loss: bool) -> dict:
+    """finalize_info_kernel in NumPy (losses.cu): the 10 loss metrics from the reduced accumulators."""
+    gb, A = float(global_rows), float(action_dim)
+    bc, distill, q = raw[2] / (gb * A), raw[3] / (gb * A), raw[4] / gb
+    q_loss = -q
+    if normalize_q_loss:
+        q_loss = q_loss / (raw[5] / gb)
+    return {'critic/critic_loss': raw[0] / (2 * gb), 'critic/q_mean': raw[1] / (2 * gb), 'critic/q_max': raw[9], 'critic/q_min': -raw[10],
+            'actor/actor_loss': bc + alpha * distill + q_loss, 'actor/bc_flow_loss': bc, 'actor/distill_loss': distill, 'actor/q_loss': q_loss,
+            'actor/q': q, 'actor/mse': raw[6] / (gb * A)}

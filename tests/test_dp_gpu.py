@@ -1,0 +1,97 @@
+"""Data-parallel decomposition on the GPU: (a) two ranks emulated on ONE device through the C ABI's fql_step_grads /
+fql_step_apply split reproduce the single-rank oracle step; (b) with >= 2 GPUs, two NCCL processes do the same."""
+import copy
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fql_oracle as O
+from tests.helpers import cuda_agent_from_state, f32, info_close, make_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(cfg, B, F, A, world, precision):
+    from fql_b200 import FQLAgent
+    c = dict(cfg)
+    c['batch_size'] = B // world
+    return FQLAgent.create(0, np.zeros((1, F), np.float32), np.zeros((1, A), np.float32), c, precision=precision, world_size=world)
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-5), ('bf16', 8e-2)])
+def test_two_emulated_ranks_match_single_rank_oracle(precision, tol):
+    from fql_b200 import dist as fdist
+    B, F, A, H = 128, 29, 8, 512
+    cfg, state, batch, noise = make_case(dict(q_agg='min', alpha=10.0), B, F, A, seed=5, hidden=H)
+    new_state, ref_info, ref_grads = O.update(copy.deepcopy(state), cfg, batch, noise)
+    agents, bufs = [], []
+    for r in range(2):
+        a = _mk(cfg, B, F, A, 2, precision)
+        a.load_tree(f32(state['params']), f32(state['mu']), f32(state['nu']), state['count'])
+        b = a.stage(f32(fdist.shard_rows(batch, r, 2)), f32(fdist.shard_rows(noise, r, 2)))
+        a.grads_phase(b)
+        agents.append(a)
+        bufs.append(b)
+    torch.cuda.synchronize()
+    g = agents[0]._grads + agents[1]._grads
+    raw = bufs[0]['raw'].clone()
+    raw[:, :9] = bufs[0]['raw'][:, :9] + bufs[1]['raw'][:, :9]
+    raw[:, 9:11] = torch.maximum(bufs[0]['raw'][:, 9:11], bufs[1]['raw'][:, 9:11])
+    for a, b in zip(agents, bufs):
+        a._grads.copy_(g)
+        b['raw'].copy_(raw)
+        a.apply_phase(b)
+    info = agents[0]._info_out(bufs[0]['info'])
+    for k in O.INFO_KEYS:
+        if k.startswith('grad/') and precision == 'bf16':
+            continue
+        info_close(k, info[k], ref_info, 3 * tol if precision == 'fp32' else 5e-2)
+    for which, ref, t in (('grads', ref_grads, tol), ('params', new_state['params'], tol if precision == 'fp32' else 3e-3)):
+        got = agents[0].export_tree(which)
+        for (path, r), (_, gg) in zip(O.tree_leaves(ref), O.tree_leaves(got)):
+            assert rel_err(gg, r) <= t, (which, path, rel_err(gg, r))
+    p0, p1 = agents[0].export_tree('params'), agents[1].export_tree('params')
+    for (_, x), (_, y) in zip(O.tree_leaves(p0), O.tree_leaves(p1)):
+        assert np.array_equal(x, y)                      # replicas stay bit-identical without a parameter broadcast
+
+
+def _nccl_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(f'cuda:{rank}'))
+    from fql_b200 import FQLAgent, dist as fdist
+    B, F, A, H = 256, 29, 8, 512
+    cfg, state, batch, noise = make_case(dict(q_agg='min', alpha=10.0), B, F, A, seed=6, hidden=H)
+    c = dict(cfg)
+    c['batch_size'] = B // world
+    agent = FQLAgent.create(0, np.zeros((1, F), np.float32), np.zeros((1, A), np.float32), c, process_group=dist.group.WORLD)
+    agent.load_tree(f32(state['params']), f32(state['mu']), f32(state['nu']), state['count'])
+    _, info = agent.update(f32(fdist.shard_rows(batch, rank, world)), noise=f32(fdist.shard_rows(noise, rank, world)))
+    new_state, ref_info, _ = O.update(copy.deepcopy(state), cfg, batch, noise)
+    for k in O.INFO_KEYS:
+        info_close(k, info[k], ref_info, 3e-5)
+    got = agent.export_tree('params')
+    worst = max(rel_err(g, r) for (_, r), (_, g) in zip(O.tree_leaves(new_state['params']), O.tree_leaves(got)))
+    assert worst <= 1e-5, worst
+    if rank == 0:
+        ret.put(worst)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_two_nccl_ranks_match_single_rank_oracle():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) <= 1e-5

@@ -66,7 +66,7 @@ def check_update(agent, cfg, state, batch, noise, seeds=None):
 
 @pytest.mark.parametrize('name,over,B,F,A,hidden', CASES, ids=[c[0] for c in CASES])
 def test_update_step_parity(name, over, B, F, A, hidden):
-    cfg, state, batch, noise = make_case(over, B, F, A, seed=hash(name) % 1000, hidden=hidden)
+    cfg, state, batch, noise = make_case(over, B, F, A, seed=sum(map(ord, name)) % 1000, hidden=hidden)
     agent = cuda_agent_from_state(cfg, state, B, F, A)
     worst = check_update(agent, cfg, state, batch, noise)
     print(name, {k: f'{v:.2e}' for k, v in worst.items()})
