@@ -63,7 +63,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -142,8 +142,10 @@ def main():
     ap.add_argument('--workload', default='antmaze-large', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=256, help='rows per GPU (per seed)')
     ap.add_argument('--seeds', type=int, default=1, help='independent agents vectorised on each GPU')
-    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default='bf16', choices=['fp32', 'bf16'],
+                    help='bf16: tcgen05 operands, fp32 accumulate/master weights (default); fp32: FFMA parity mode')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-fp32-leg', action='store_true')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     F, A = wl['F'], wl['A']
@@ -177,6 +179,7 @@ def main():
     from fql_b200 import FQLAgent, get_config
 
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    os.environ['NCCL_DEBUG'] = os.environ.get('FQL_BENCH_NCCL_DEBUG', 'WARN')  # keep stdout to the one JSON line
     torch.cuda.set_device(local_rank)
     pg = None
     if world > 1:
@@ -200,11 +203,14 @@ def main():
     with torch.cuda.stream(stream):
         # ---------------- device-resident leg: `value`
         bufs = agent.stage(batches[0])
+        clocks = ClockSampler(local_rank) if rank == 0 else None
+        t_load = time.perf_counter()
         for _ in range(W):
+            agent.step(bufs)
+        while time.perf_counter() - t_load < 0.5:  # keep the GPU under the same load until nvidia-smi is sampling
             agent.step(bufs)
         barrier()
         l0 = agent.launch_count()
-        clocks = ClockSampler(local_rank) if rank == 0 else None
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         barrier()
         for i in range(K):
@@ -213,7 +219,6 @@ def main():
             info = agent.step(bufs)
             ev[i][1].record()
         barrier()
-        clk = clocks.stop() if clocks else None
         launches = agent.launch_count() - l0
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
         last_loss = float(np.ravel(info['critic/critic_loss'])[0])
@@ -226,6 +231,7 @@ def main():
         e1.record()
         barrier()
         warm_ms = e0.elapsed_time(e1)
+        clk = clocks.stop() if clocks else None
 
         # ---------------- end-to-end leg: public API, host batches, pinned H2D + D2H of the metrics every step
         for i in range(W):
@@ -274,10 +280,29 @@ def main():
     out = dict(metric='fql_update_samples_per_sec', value=value, unit='samples/s', steps_per_sec=1e3 / ms_per_step, n_gpus=n,
                steps=K, warmup=W, ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None,
                dtype='f32' if args.precision == 'fp32' else 'bf16', data='synthetic', config=config,
-               value_l2_warm=samples_per_step / (warm_ms / K / 1e3), ms_per_step_l2_warm=warm_ms / K,
+               value_l2_warm=(samples_per_step / (warm_ms / K / 1e3)) if n == 1 else None,
+               ms_per_step_l2_warm=(warm_ms / K) if n == 1 else None,
                e2e=dict(value=samples_per_step * K / e2e_s, unit='samples/s', steps_per_sec=K / e2e_s, h2d_bytes_per_step=h2d,
                         d2h_bytes_per_step=13 * 4 * args.seeds, api='FQLAgent.update(host numpy batch)'),
                gpu_launches=launches, gpu_launches_per_step=launches / K, roofline=roof, clocks=clk, last_critic_loss=last_loss)
+    if n == 1 and args.precision == 'bf16' and not args.no_fp32_leg:
+        with torch.cuda.stream(stream):
+            a32 = FQLAgent.create(0, np.zeros((1, F), np.float32), np.zeros((1, A), np.float32), cfg, num_seeds=args.seeds, precision='fp32')
+            b32 = a32.stage(batches[0])
+            for _ in range(5):
+                a32.step(b32)
+            torch.cuda.synchronize()
+            k32 = min(K, 50)
+            e32 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k32)]
+            for i in range(k32):
+                flush.zero_()
+                e32[i][0].record()
+                a32.step(b32)
+                e32[i][1].record()
+            torch.cuda.synchronize()
+            ms32 = sum(x.elapsed_time(y) for x, y in e32) / k32
+        out['fp32_parity_mode'] = dict(ms_per_step=ms32, steps_per_sec=1e3 / ms32, value=samples_per_step / (ms32 / 1e3), unit='samples/s',
+                                       note='FQL_PRECISION_FP32 (FFMA everywhere, 1e-5 parity vs the fp64 oracle), same workload')
     if not args.no_cpu_baseline and n == 1:
         r = cpu_reference_arm(wl, args.batch, 50, 1, budget_s=15.0)
         cv = args.batch * 1e3 / r['ms_per_step']

@@ -450,6 +450,14 @@ int tc_refresh_shadow(const FqlDims* d, const Layout& L, const float* params, vo
   return 0;
 }
 
+int tc_refresh_shadow_lastlayer(const FqlDims* d, const Layout& L, const float* params, void* shadow, cudaStream_t st) {
+  const int64_t seed = tc_shadow_seed_elems(d, L);
+  dim3 g2((unsigned)((2 * d->hidden * 64 + 255) / 256), FQL_NUM_NETS, d->num_seeds);
+  shadow_lastlayer_kernel<<<g2, 256, 0, st>>>(params, reinterpret_cast<__nv_bfloat16*>(shadow), L, seed, d->hidden);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+
 int tc_pad_bf16(const float* x, void* y, int64_t rows, int K0, int K0pad, cudaStream_t st) {
   const int64_t n = rows * K0pad;
   if (n == 0) return 0;

@@ -7,13 +7,16 @@
 // identity on them; they are only written by the Polyak half.  HBM-bound: 28 B/param (+8 B/critic param).
 #include "step.cuh"
 
+#include <cuda_bf16.h>
+
 namespace {
 
 __global__ void __launch_bounds__(256) adam_polyak_stats_kernel(Layout L, FqlHparams hp, float* __restrict__ params,
                                                                 float* __restrict__ mu, float* __restrict__ nu,
                                                                 const float* __restrict__ grads,
                                                                 const int32_t* __restrict__ count,
-                                                                float* __restrict__ partials) {
+                                                                float* __restrict__ partials, __nv_bfloat16* __restrict__ shadow,
+                                                                int64_t shadow_seed) {
   const int blk = blockIdx.x, s = blockIdx.y;
   const int nblk = gridDim.x;
   const int64_t off = (int64_t)blk * FQL_LEAF_PAD + threadIdx.x * 4;
@@ -55,6 +58,10 @@ __global__ void __launch_bounds__(256) adam_polyak_stats_kernel(Layout L, FqlHpa
     pn[i] = pr[i] + (-hp.lr * (mhat / (sqrtf(vhat) + hp.eps)));
   }
   *reinterpret_cast<float4*>(params + base + off) = make_float4(pn[0], pn[1], pn[2], pn[3]);
+  if (shadow) {  // bf16 tensor-core operand copy of the fresh parameters (same [in,out] layout)
+    __nv_bfloat162 lo = __floats2bfloat162_rn(pn[0], pn[1]), hi = __floats2bfloat162_rn(pn[2], pn[3]);
+    *reinterpret_cast<uint2*>(shadow + (int64_t)s * shadow_seed + off) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
   *reinterpret_cast<float4*>(mu + base + off) = make_float4(mr[0], mr[1], mr[2], mr[3]);
   *reinterpret_cast<float4*>(nu + base + off) = make_float4(vr[0], vr[1], vr[2], vr[3]);
   if (off >= cri.begin && off < cri.end) {  // Polyak with the pre-step critic values still in registers
@@ -66,6 +73,10 @@ __global__ void __launch_bounds__(256) adam_polyak_stats_kernel(Layout L, FqlHpa
     tp.z = pr[2] * hp.tau + tp.z * omt;
     tp.w = pr[3] * hp.tau + tp.w * omt;
     *reinterpret_cast<float4*>(params + toff) = tp;
+    if (shadow) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(tp.x, tp.y), hi = __floats2bfloat162_rn(tp.z, tp.w);
+      *reinterpret_cast<uint2*>(shadow + (int64_t)s * shadow_seed + (toff - base)) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
   }
   // block reduce of the statistics
   __shared__ float smx[8], smn[8], ssq[8];
@@ -128,10 +139,9 @@ __global__ void zero_kernel(float4* p, int64_t n4) {
 }  // namespace
 
 int launch_adam_polyak_stats(const Layout& L, const FqlHparams& hp, int S, float* params, float* mu, float* nu,
-                             const float* grads, const int32_t* count, float* partials, void* shadow, cudaStream_t st) {
-  (void)shadow;
+                             const float* grads, const int32_t* count, float* partials, void* shadow, int64_t shadow_seed, cudaStream_t st) {
   dim3 grid(L.leaf_blk[L.n_leaves], S);
-  adam_polyak_stats_kernel<<<grid, 256, 0, st>>>(L, hp, params, mu, nu, grads, count, partials);
+  adam_polyak_stats_kernel<<<grid, 256, 0, st>>>(L, hp, params, mu, nu, grads, count, partials, reinterpret_cast<__nv_bfloat16*>(shadow), shadow_seed);
   FQL_CHECK_LAUNCH();
   return 0;
 }

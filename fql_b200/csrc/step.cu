@@ -676,10 +676,17 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
 
   if (c.do_grads && tcm) FQL_TRY(enqueue_grads_tc(ctx, c, L, w, sh, hp, raw, S0));
   if (c.do_apply) {
+    // Adam + Polyak + gradient statistics (+ the bf16 operand shadow of the new parameters) in one pass over the arenas
     FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, c.st->count, w.partials,
-                                     c.st->shadow, S0));
+                                     tcm ? c.st->shadow : nullptr, tcm ? tc_shadow_seed_elems(c.d, L) : 0, S0));
+    if (tcm) {  // the zero-padded narrow last-layer copies, beside the statistics tail
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[50], S0));
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s1, ctx->ev[50], 0));
+      FQL_TRY(tc_refresh_shadow_lastlayer(c.d, L, c.st->params, c.st->shadow, ctx->s1));
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[51], ctx->s1));
+    }
     FQL_TRY(launch_grad_stats_final(L, S, w.partials, w.gstats, c.st->count, S0));
-    if (tcm) FQL_TRY(tc_refresh_shadow(c.d, L, c.st->params, c.st->shadow, S0));
+    if (tcm) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[51], 0));
   }
   if (c.info) FQL_TRY(launch_finalize_info(sh, hp, raw, w.gstats, c.info, c.do_apply, S0));
   return 0;

@@ -59,7 +59,7 @@ int launch_euler_inplace(float* X, const float* v, int F, int A, int64_t rows, i
 
 // optim.cu
 int launch_adam_polyak_stats(const Layout& L, const FqlHparams& hp, int S, float* params, float* mu, float* nu,
-                             const float* grads, const int32_t* count, float* partials, void* shadow, cudaStream_t st);
+                             const float* grads, const int32_t* count, float* partials, void* shadow, int64_t shadow_seed, cudaStream_t st);
 int launch_grad_stats_final(const Layout& L, int S, const float* partials, float* gstats, int32_t* count_inc, cudaStream_t st);
 int launch_zero(float* p, int64_t n, cudaStream_t st);
 
@@ -86,6 +86,7 @@ struct TcChainSpec {
 int tc_supported(const FqlDims* d);
 int64_t tc_shadow_seed_elems(const FqlDims* d, const Layout& L);
 int tc_refresh_shadow(const FqlDims* d, const Layout& L, const float* params, void* shadow, cudaStream_t st);
+int tc_refresh_shadow_lastlayer(const FqlDims* d, const Layout& L, const float* params, void* shadow, cudaStream_t st);
 int tc_pad_bf16(const float* x, void* y, int64_t rows, int K0, int K0pad, cudaStream_t st);
 int tc_mlp_chain(const TcChainSpec& f, cudaStream_t st);
 

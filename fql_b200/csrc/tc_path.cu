@@ -9,6 +9,22 @@
 namespace {
 typedef __nv_bfloat16 bf16;
 
+// bf16 mode: MUFU tanh (2^-11 abs error) instead of the ~25-instruction tanhf; these kernels sit on the critic chain
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  return 0.5f * x * (1.0f + tanh_fast(FQL_GELU_C * (x + FQL_GELU_A * x * x * x)));
+}
+__device__ __forceinline__ void gelu_and_grad_fast(float x, float* g, float* dg) {
+  const float x2 = x * x;
+  const float th = tanh_fast(FQL_GELU_C * (x + FQL_GELU_A * x2 * x));
+  *g = 0.5f * x * (1.0f + th);
+  *dg = 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * (FQL_GELU_C * (1.0f + 3.0f * FQL_GELU_A * x2));
+}
+
 TcOperand op(const void* ptr, int inner, int rows, long long ld, int g0, long long s0, int g1, long long s1) {
   TcOperand o;
   o.ptr = ptr; o.inner = inner; o.rows = rows; o.ld = ld; o.g0 = g0; o.s0 = s0; o.g1 = g1; o.s1 = s1;
@@ -39,14 +55,14 @@ __global__ void __launch_bounds__(256) act_ln_bf16_kernel(const float* __restric
   if (!ln) {
     for (int c = lane * 2; c < N; c += 64) {
       const float2 zz = *reinterpret_cast<const float2*>(z + c);
-      *reinterpret_cast<__nv_bfloat162*>(h + c) = __floats2bfloat162_rn(gelu_tanh_f(zz.x), gelu_tanh_f(zz.y));
+      *reinterpret_cast<__nv_bfloat162*>(h + c) = __floats2bfloat162_rn(gelu_fast(zz.x), gelu_fast(zz.y));
     }
     return;
   }
   float s1 = 0.f, s2 = 0.f;
   for (int c = lane * 2; c < N; c += 64) {
     const float2 zz = *reinterpret_cast<const float2*>(z + c);
-    const float g0 = gelu_tanh_f(zz.x), g1 = gelu_tanh_f(zz.y);
+    const float g0 = gelu_fast(zz.x), g1 = gelu_fast(zz.y);
     s1 += g0 + g1;
     s2 += g0 * g0 + g1 * g1;
   }
@@ -60,8 +76,8 @@ __global__ void __launch_bounds__(256) act_ln_bf16_kernel(const float* __restric
   const float* bi = bias_base + s * par_s + e * par_e;
   for (int c = lane * 2; c < N; c += 64) {
     const float2 zz = *reinterpret_cast<const float2*>(z + c);
-    const float h0 = (gelu_tanh_f(zz.x) - mu) * rstd * sc[c] + bi[c];
-    const float h1 = (gelu_tanh_f(zz.y) - mu) * rstd * sc[c + 1] + bi[c + 1];
+    const float h0 = (gelu_fast(zz.x) - mu) * rstd * sc[c] + bi[c];
+    const float h1 = (gelu_fast(zz.y) - mu) * rstd * sc[c + 1] + bi[c + 1];
     *reinterpret_cast<__nv_bfloat162*>(h + c) = __floats2bfloat162_rn(h0, h1);
   }
   if (lane == 0 && mu_out) {
@@ -75,6 +91,8 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const float* __restric
                                                           const float* __restrict__ scale_base, int64_t scale_s, int64_t scale_e,
                                                           float* __restrict__ dZ, bf16* __restrict__ dZb, int M, int N, int S, int E,
                                                           int64_t z_rows_e, int64_t z_rows_s) {
+  // one warp per row; every element's gelu / gelu' is evaluated once and kept in registers (N <= 512 -> 16 per lane)
+  constexpr int MAXC = 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + warp;
   if (row >= (int64_t)S * E * M) return;
@@ -84,34 +102,43 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const float* __restric
   float* dz = dZ + row * N;
   bf16* dzb = dZb + row * N;
   const float* sc = scale_base + s * scale_s + e * scale_e;
-  float s1 = 0.f, s2 = 0.f;
-  for (int c = lane; c < N; c += 32) {
-    const float gv = gelu_tanh_f(z[c]);
-    s1 += gv;
-    s2 += gv * gv;
+  float gv[MAXC], dg[MAXC], dx[MAXC];
+  float s1 = 0.f, s2 = 0.f, m1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; i++) {
+    const int c = lane + 32 * i;
+    gv[i] = dg[i] = dx[i] = 0.f;
+    if (c < N) {
+      gelu_and_grad_fast(z[c], &gv[i], &dg[i]);
+      dx[i] = dh[c] * sc[c];
+      s1 += gv[i];
+      s2 += gv[i] * gv[i];
+      m1 += dx[i];
+    }
   }
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
+  m1 = warp_sum(m1);
   const float inv_n = 1.0f / (float)N;
   const float mu = s1 * inv_n;
   const float var = fmaxf(0.f, s2 * inv_n - mu * mu);
   const float rstd = rsqrtf(var + FQL_LN_EPS);
-  float m1 = 0.f, m2 = 0.f;
-  for (int c = lane; c < N; c += 32) {
-    const float xh = (gelu_tanh_f(z[c]) - mu) * rstd;
-    const float dx = dh[c] * sc[c];
-    m1 += dx;
-    m2 += dx * xh;
+  float m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; i++) {
+    gv[i] = (gv[i] - mu) * rstd;  // xhat
+    if (lane + 32 * i < N) m2 += dx[i] * gv[i];
   }
-  m1 = warp_sum(m1) * inv_n;
+  m1 *= inv_n;
   m2 = warp_sum(m2) * inv_n;
-  for (int c = lane; c < N; c += 32) {
-    const float zc = z[c];
-    const float xh = (gelu_tanh_f(zc) - mu) * rstd;
-    const float dx = dh[c] * sc[c];
-    const float v = rstd * (dx - m1 - xh * m2) * gelu_tanh_grad_f(zc);
-    dz[c] = v;
-    dzb[c] = __float2bfloat16(v);
+#pragma unroll
+  for (int i = 0; i < MAXC; i++) {
+    const int c = lane + 32 * i;
+    if (c < N) {
+      const float v = rstd * (dx[i] - m1 - gv[i] * m2) * dg[i];
+      dz[c] = v;
+      dzb[c] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -123,7 +150,9 @@ __global__ void gelu_bwd_bf16_kernel(const float* __restrict__ dH, const float* 
   const int c = (int)(i % N);
   const int64_t row = i / N;
   const int r = (int)(row % M), g = (int)(row / M), e = g % E, s = g / E;
-  const float v = dH[i] * gelu_tanh_grad_f(Z[((int64_t)s * z_rows_s + (int64_t)e * z_rows_e + r) * N + c]);
+  float gg, dgg;
+  gelu_and_grad_fast(Z[((int64_t)s * z_rows_s + (int64_t)e * z_rows_e + r) * N + c], &gg, &dgg);
+  const float v = dH[i] * dgg;
   dZ[i] = v;
   dZb[i] = __float2bfloat16(v);
 }

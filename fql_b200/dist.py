@@ -29,14 +29,16 @@ def shard_rows(batch: dict, rank: int, world: int) -> dict:
 
 
 def allreduce_step(grads: torch.Tensor, raw: torch.Tensor, group=None) -> None:
-    """In-place all-reduce of the gradient arena (SUM) and the raw accumulators (SUM for sums, MAX for max / -min)."""
+    """In-place reduction of the gradient arena (all-reduce SUM) and of the raw accumulators (one all-gather of the 16 floats per
+    seed, reduced locally: SUM for the sums, MAX for max q / -min q) -- two collectives per step."""
     dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)
-    s = raw[..., RAW_SUM].contiguous()
-    m = raw[..., RAW_MAX].contiguous()
-    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
-    raw[..., RAW_SUM] = s
-    raw[..., RAW_MAX] = m
+    world = dist.get_world_size(group)
+    flat = raw.contiguous().reshape(-1)
+    gathered = torch.empty(world * flat.numel(), dtype=raw.dtype, device=raw.device)
+    dist.all_gather_into_tensor(gathered, flat, group=group)
+    gathered = gathered.reshape((world,) + tuple(raw.shape))
+    raw[..., RAW_SUM] = gathered[..., RAW_SUM].sum(dim=0)
+    raw[..., RAW_MAX] = gathered[..., RAW_MAX].max(dim=0).values
 
 
 def shard_seeds(num_seeds: int, rank: int, world: int) -> range:
