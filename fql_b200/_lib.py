@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libfql_b200.so')
 NUM_INFO = 13
 NUM_RAW = 16
 NET_NAMES = ('actor_bc_flow', 'actor_onestep_flow', 'critic', 'target_critic')
-LEAF_KINDS = ('kernel', 'bias', 'scale', 'bias')
+LEAF_KINDS = ('kernel', 'bias', 'scale', 'bias', 'kernel', 'bias', 'kernel', 'bias')
 PRECISION_FP32, PRECISION_BF16_TC = 0, 1
 
 
@@ -106,13 +106,16 @@ def check(rc, what=''):
 
 
 def make_dims(batch, obs_dim, action_dim, *, global_batch=None, hidden=512, num_hidden=4, critic_layer_norm=True,
-              actor_layer_norm=False, q_agg='mean', normalize_q_loss=False, flow_steps=10, num_seeds=1, precision=PRECISION_FP32):
+              actor_layer_norm=False, q_agg='mean', normalize_q_loss=False, flow_steps=10, num_seeds=1, precision=PRECISION_FP32,
+              image=None):
     d = FqlDims()
     d.batch, d.global_batch = int(batch), int(global_batch if global_batch is not None else batch)
     d.obs_dim, d.action_dim, d.hidden, d.num_hidden = int(obs_dim), int(action_dim), int(hidden), int(num_hidden)
     d.critic_layer_norm, d.actor_layer_norm = int(bool(critic_layer_norm)), int(bool(actor_layer_norm))
     d.q_agg_min, d.normalize_q_loss = int(q_agg == 'min'), int(bool(normalize_q_loss))
     d.flow_steps, d.num_seeds, d.precision = int(flow_steps), int(num_seeds), int(precision)
+    if image is not None:  # (H, W, C) uint8 observations through impala_small; obs_dim is then the encoder width 512
+        d.reserved[0], d.reserved[1], d.reserved[2] = int(image[0]), int(image[1]), int(image[2])
     return d
 
 
@@ -132,7 +135,15 @@ def layout(dims):
     check(l.fql_layout(C.byref(dims), arr, n.value, C.byref(n)), 'fql_layout')
     out = []
     for lf in arr:
-        mod = ('LayerNorm' if lf.kind >= 2 else 'Dense') + f'_{lf.layer}'
-        out.append(dict(net=NET_NAMES[lf.net], module=mod, name=LEAF_KINDS[lf.kind], ens=lf.ens, rows=lf.rows, cols=lf.cols,
-                        offset=lf.offset, is_kernel=lf.kind == 0))
+        if lf.kind < 4:
+            path = (('LayerNorm' if lf.kind >= 2 else 'Dense') + f'_{lf.layer}',)
+        elif lf.kind < 6:     # encoder convolution: stack_blocks_<i>/Conv_<j>  (utils/encoders.py:17-57)
+            path = ('encoder', f'stack_blocks_{lf.layer // 3}', f'Conv_{lf.layer % 3}')
+        else:                 # encoder head: MLP_0/Dense_0 (utils/encoders.py:98)
+            path = ('encoder', 'MLP_0', 'Dense_0')
+        shape = None
+        if lf.kind == 4:      # HWIO [3,3,cin,cout]
+            shape = (3, 3, lf.rows // 9, lf.cols)
+        out.append(dict(net=NET_NAMES[lf.net], module=path[-1], path=path, name=LEAF_KINDS[lf.kind], ens=lf.ens, rows=lf.rows, cols=lf.cols,
+                        offset=lf.offset, is_kernel=lf.kind in (0, 4, 6), shape=shape, kind=lf.kind))
     return out, int(l.fql_arena_floats(C.byref(dims)))

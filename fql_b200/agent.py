@@ -110,13 +110,16 @@ class FQLAgent:
                process_group=None, world_size=None):
         self = cls.__new__(cls)
         cfg = dict(config)
-        if cfg.get('encoder') is not None:
-            raise NotImplementedError('visual encoders (config 5, impala_small) are not built yet: see DESIGN.md scope table')
         ex_observations = np.asarray(ex_observations)
         ex_actions = np.asarray(ex_actions)
         ob_dims = tuple(ex_observations.shape[1:])
-        if len(ob_dims) != 1:
-            raise NotImplementedError(f'state observations only (got ob_dims={ob_dims})')
+        if cfg.get('encoder') is not None:
+            if cfg['encoder'] != 'impala_small':
+                raise NotImplementedError(f"encoder {cfg['encoder']!r}: only 'impala_small' (BASELINE config 5) is built")
+            if len(ob_dims) != 3:
+                raise ValueError(f'pixel observations must be [H,W,C] (got ob_dims={ob_dims})')
+        elif len(ob_dims) != 1:
+            raise ValueError(f'state observations must be vectors (got ob_dims={ob_dims}); set config["encoder"] for pixels')
         ah, vh = tuple(cfg['actor_hidden_dims']), tuple(cfg['value_hidden_dims'])
         if len(set(ah + vh)) != 1 or len(ah) != len(vh):
             raise NotImplementedError('actor/value hidden dims must be one common width and depth')
@@ -133,6 +136,8 @@ class FQLAgent:
             self.world = int(world_size)  # explicit override: the caller drives grads_phase / apply_phase itself
         self._precision = {'fp32': _lib.PRECISION_FP32, 'bf16': _lib.PRECISION_BF16_TC}[precision]
         self._hidden, self._num_hidden = ah[0], len(ah)
+        self._image = ob_dims if cfg.get('encoder') is not None else None
+        self._feat = 512 if self._image else ob_dims[0]
         self._lib = _lib.lib()
         ctx = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -167,10 +172,10 @@ class FQLAgent:
         if batch not in self._dims_cache:
             c = self.config
             self._dims_cache[batch] = _lib.make_dims(
-                batch, c['ob_dims'][0], c['action_dim'], global_batch=batch * self.world, hidden=self._hidden,
+                batch, self._feat, c['action_dim'], global_batch=batch * self.world, hidden=self._hidden,
                 num_hidden=self._num_hidden, critic_layer_norm=c['layer_norm'], actor_layer_norm=c['actor_layer_norm'],
                 q_agg=c['q_agg'], normalize_q_loss=c['normalize_q_loss'], flow_steps=c['flow_steps'],
-                num_seeds=self.num_seeds, precision=self._precision)
+                num_seeds=self.num_seeds, precision=self._precision, image=self._image)
         return self._dims_cache[batch]
 
     def _init_params(self, seed):
@@ -184,7 +189,9 @@ class FQLAgent:
             n = lf['ens'] * lf['rows'] * lf['cols']
             sl = slice(lf['offset'], lf['offset'] + n)
             if lf['is_kernel']:
-                lim = np.sqrt(6.0 / (lf['rows'] + lf['cols']))
+                # Dense: variance_scaling(1,'fan_avg','uniform'); conv (rows = 9*cin): xavier_uniform with fans 9*cin / 9*cout
+                fan_out = lf['cols'] * (9 if lf.get('kind') == 4 else 1)
+                lim = np.sqrt(6.0 / (lf['rows'] + fan_out))
                 host[:, sl] = rng.uniform(-lim, lim, (self.num_seeds, n)).astype(np.float32)
             elif lf['name'] == 'scale':
                 host[:, sl] = 1.0
@@ -215,15 +222,22 @@ class FQLAgent:
         out = {}
         S = self.num_seeds
         for lf in self._leaves:
-            net = out.setdefault('modules_' + lf['net'], {})
-            sub = net.setdefault('value_net' if 'critic' in lf['net'] else 'mlp', {})
-            mod = sub.setdefault(lf['module'], {})
+            path = lf.get('path', (lf['module'],))
+            if path[0] == 'encoder' and lf['net'] == 'actor_bc_flow':
+                node = out.setdefault('modules_actor_bc_flow_encoder', {})   # fql.py:230-232
+                path = path[1:]
+            else:
+                node = out.setdefault('modules_' + lf['net'], {})
+                if path[0] != 'encoder':
+                    node = node.setdefault('value_net' if 'critic' in lf['net'] else 'mlp', {})
+            for k in path:
+                node = node.setdefault(k, {})
             n = lf['ens'] * lf['rows'] * lf['cols']
-            shape = ((lf['rows'], lf['cols']) if lf['is_kernel'] else (lf['cols'],))
+            shape = lf.get('shape') or ((lf['rows'], lf['cols']) if lf['is_kernel'] else (lf['cols'],))
             if lf['ens'] > 1:
                 shape = (lf['ens'],) + shape
             v = arena[:, lf['offset']:lf['offset'] + n]
-            mod[lf['name']] = v.view((S,) + shape) if S > 1 else v.view(shape)
+            node[lf['name']] = v.view((S,) + shape) if S > 1 else v.view(shape)
         return out
 
     # ------------------------------------------------------------------ state import/export
@@ -271,11 +285,13 @@ class FQLAgent:
         if B in self._bufs:
             return self._bufs[B]
         d = self._dims(B)
-        S, F, A = self.num_seeds, self.config['ob_dims'][0], self.config['action_dim']
-        shapes = dict(observations=(S, B, F), actions=(S, B, A), next_observations=(S, B, F), rewards=(S, B), masks=(S, B),
+        S, A = self.num_seeds, self.config['action_dim']
+        ob = tuple(self.config['ob_dims'])
+        shapes = dict(observations=(S, B) + ob, actions=(S, B, A), next_observations=(S, B) + ob, rewards=(S, B), masks=(S, B),
                       z_next=(S, B, A), x0=(S, B, A), t=(S, B, 1), z=(S, B, A), z_metric=(S, B, A))
-        dev = {k: torch.empty(s, dtype=torch.float32, device=self.device) for k, s in shapes.items()}
-        pin = {k: torch.empty(s, dtype=torch.float32).pin_memory() for k, s in shapes.items()}
+        dt = lambda k: torch.uint8 if (self._image and k in ('observations', 'next_observations')) else torch.float32
+        dev = {k: torch.empty(s, dtype=dt(k), device=self.device) for k, s in shapes.items()}
+        pin = {k: torch.empty(s, dtype=dt(k)).pin_memory() for k, s in shapes.items()}
         ws_bytes = int(self._lib.fql_workspace_bytes(C.byref(d)))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         fb = _lib.FqlBatch(*[dev[k].data_ptr() for k in _BATCH_KEYS + NOISE_KEYS])
@@ -291,11 +307,12 @@ class FQLAgent:
         if isinstance(src, torch.Tensor) and src.is_cuda:
             dst.copy_(src.reshape(dst.shape), non_blocking=True)
             return 0
-        t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32))
+        npdt = np.uint8 if dst.dtype == torch.uint8 else np.float32
+        t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src, dtype=npdt))
         pin = bufs['pin'][k]
         pin.copy_(t.reshape(pin.shape))
         dst.copy_(pin, non_blocking=True)
-        return pin.numel() * 4
+        return pin.numel() * pin.element_size()
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -390,10 +407,12 @@ class FQLAgent:
 
     # ------------------------------------------------------------------ agents/fql.py:135-171
     def _fwd_call(self, fn, observations, noises):
-        obs = torch.as_tensor(np.asarray(observations, dtype=np.float32) if not isinstance(observations, torch.Tensor) else observations)
-        F, A, S = self.config['ob_dims'][0], self.config['action_dim'], self.num_seeds
-        lead = tuple(obs.shape[:-1])
-        obs = obs.to(self.device, torch.float32).reshape(S, -1, F).contiguous()
+        nob = len(self.config['ob_dims'])
+        odt, onp = (torch.uint8, np.uint8) if self._image else (torch.float32, np.float32)
+        obs = torch.as_tensor(np.asarray(observations, dtype=onp) if not isinstance(observations, torch.Tensor) else observations)
+        A, S = self.config['action_dim'], self.num_seeds
+        lead = tuple(obs.shape[:-nob])
+        obs = obs.to(self.device, odt).reshape((S, -1) + tuple(self.config['ob_dims'])).contiguous()
         rows = obs.shape[1]
         nz = torch.as_tensor(noises).to(self.device, torch.float32).reshape(S, rows, A).contiguous()
         d = self._dims(int(self.config.get('batch_size', 256)))
@@ -408,7 +427,7 @@ class FQLAgent:
     def sample_actions(self, observations, seed=None, temperature=1.0, noise=None):
         """clip(actor_onestep_flow(obs, z)), z ~ N(0, I) of shape obs.shape[:-1] + (A,).  `temperature` is accepted and
         ignored exactly like the reference (fql.py:140).  Returns a host numpy array (np.array-able, evaluation.py:150)."""
-        lead = tuple(np.shape(observations)[:-1])
+        lead = tuple(np.shape(observations)[:-len(self.config['ob_dims'])])
         A = self.config['action_dim']
         if noise is None:
             key = np.ravel(np.asarray(seed if seed is not None else self.rng)).astype(np.uint64)

@@ -42,6 +42,10 @@ extern thread_local long long g_fql_launches;  // kernels enqueued by this threa
 // ---------------------------------------------------------------------------------------------------------
 // arena layout
 // ---------------------------------------------------------------------------------------------------------
+struct EncView {            // ImpalaEncoder('impala_small') leaves of one network (utils/encoders.py)
+  int64_t off_cw[3][3], off_cb[3][3];  // stack_blocks_i / Conv_j kernel [3,3,cin,cout] and bias
+  int64_t off_dw, off_db;              // MLP_0 / Dense_0 kernel [flat,512] and bias
+};
 struct NetView {
   int n_layers;           // Dense layers
   int in_dim, out_dim;    // first-layer fan-in, last-layer fan-out
@@ -49,12 +53,14 @@ struct NetView {
   int ens;                // 1 or 2
   int ln;                 // LayerNorm after each hidden activation
   int64_t off_w[FQL_MAXL], off_b[FQL_MAXL], off_lns[FQL_MAXL], off_lnb[FQL_MAXL];
+  int has_enc;
+  EncView enc;
   int64_t begin, end;     // float range of this network inside one seed's arena
   __host__ __device__ int k_of(int l) const { return l == 0 ? in_dim : hidden; }
   __host__ __device__ int n_of(int l) const { return l == n_layers - 1 ? out_dim : hidden; }
 };
 #define FQL_LEAF_PAD 1024  // every leaf is padded to a multiple of this many floats: one optimizer CTA = one leaf
-#define FQL_MAX_LEAVES 80
+#define FQL_MAX_LEAVES 160
 struct Layout {
   NetView net[FQL_NUM_NETS];
   int64_t arena;                       // floats per seed

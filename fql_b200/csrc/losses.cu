@@ -29,8 +29,12 @@ __global__ void prep_kernel(StepShape sh, FqlBatch b, WsPtrs w) {
   const int s = row / sh.B, r = row % sh.B;
   const int F = sh.F, A = sh.A, B = sh.B;
   const int KO = F + A, KF = F + A + 1, KC = F + A;
-  const float* obs = b.observations + (int64_t)row * F;
-  const float* nobs = b.next_observations + (int64_t)row * F;
+  // what each call site sees as its observation: the batch itself, or (pixel configs) that network's encoder output
+  const float* sOn = w.src[0] + (int64_t)row * F;   // onestep(next_obs)        fql.py:25
+  const float* sO = w.src[1] + (int64_t)row * F;    // onestep(obs)             fql.py:65,82
+  const float* sTn = w.src[2] + (int64_t)row * F;   // target critic(next_obs)  fql.py:28
+  const float* sC = w.src[3] + (int64_t)row * F;    // critic(obs)              fql.py:36,70
+  const float* sF = w.src[4] + (int64_t)row * F;    // bc flow(obs)             fql.py:58,64
   const float* act = b.actions + (int64_t)row * A;
   const float* zn = b.z_next + (int64_t)row * A;
   const float* x0 = b.x0 + (int64_t)row * A;
@@ -46,10 +50,10 @@ __global__ void prep_kernel(StepShape sh, FqlBatch b, WsPtrs w) {
   float* xc1 = w.XC + ((int64_t)(1 * sh.S + s) * B + r) * KC;
   float* xc2 = w.XC + ((int64_t)(2 * sh.S + s) * B + r) * KC;
   for (int c = threadIdx.x; c < F; c += blockDim.x) {
-    float o = obs[c], no = nobs[c];
-    xo0[c] = no; xo1[c] = o; xo2[c] = o;
-    xf0[c] = o; xf1[c] = o;
-    xc0[c] = no; xc1[c] = o; xc2[c] = o;
+    const float o = sO[c], f = sF[c], cc = sC[c];
+    xo0[c] = sOn[c]; xo1[c] = o; xo2[c] = o;
+    xf0[c] = f; xf1[c] = f;
+    xc0[c] = sTn[c]; xc1[c] = cc; xc2[c] = cc;
   }
   for (int c = threadIdx.x; c < A; c += blockDim.x) {
     float a = act[c], x = x0[c];

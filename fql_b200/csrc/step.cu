@@ -37,6 +37,12 @@ int fql_validate_dims(const FqlDims* d) {
   FQL_REQUIRE(d->num_seeds >= 1, "num_seeds=%d", d->num_seeds);
   FQL_REQUIRE(d->flow_steps >= 1, "flow_steps=%d", d->flow_steps);
   FQL_REQUIRE(d->precision == FQL_PRECISION_FP32 || d->precision == FQL_PRECISION_BF16_TC, "precision=%d", d->precision);
+  if (d->reserved[0] > 0) {  // pixel observations through ImpalaEncoder('impala_small')
+    FQL_REQUIRE(d->reserved[1] > 0 && d->reserved[2] > 0 && d->reserved[2] <= 32, "image dims %dx%dx%d", d->reserved[0], d->reserved[1], d->reserved[2]);
+    FQL_REQUIRE(d->obs_dim == 512, "pixel configs: obs_dim is the encoder output width and must be 512 (got %d)", d->obs_dim);
+    FQL_REQUIRE(d->num_seeds == 1, "pixel configs are built for num_seeds == 1");
+    FQL_REQUIRE(d->precision == FQL_PRECISION_FP32, "pixel configs run in FQL_PRECISION_FP32 in this version (encoders are fp32 CUDA-core kernels)");
+  }
   FQL_REQUIRE(!(d->normalize_q_loss && d->global_batch != d->batch),
               "normalize_q_loss with a data-parallel split needs a global |q| exchange inside the step: not supported; "
               "shard seeds instead (SURVEY 8e)");
@@ -68,7 +74,7 @@ int fql_build_layout(const FqlDims* d, Layout* L) {
     v.out_dim = critic ? 1 : A;
     v.begin = off;
     const int extra = v.ln ? 4 : 2;
-    FQL_REQUIRE(nl + NL * extra <= FQL_MAX_LEAVES, "too many leaves");
+    FQL_REQUIRE(nl + NL * extra + 20 <= FQL_MAX_LEAVES, "too many leaves");
     for (int l = 0; l < NL; l++) {
       const int64_t K = v.k_of(l), N = v.n_of(l);
       v.off_w[l] = add_leaf(n, v.ens * K * N);
@@ -77,6 +83,22 @@ int fql_build_layout(const FqlDims* d, Layout* L) {
         v.off_lns[l] = add_leaf(n, v.ens * N);
         v.off_lnb[l] = add_leaf(n, v.ens * N);
       }
+    }
+    if (d->reserved[0] > 0) {  // encoder of this network (the bc-flow one is the separate `actor_bc_flow_encoder` module, fql.py:230-232)
+      v.has_enc = 1;
+      static const int stacks[3] = {16, 32, 32};
+      int c = d->reserved[2], h = d->reserved[0], w = d->reserved[1];
+      for (int i = 0; i < 3; i++) {
+        const int f = stacks[i];
+        const int cin[3] = {c, f, f};
+        for (int j = 0; j < 3; j++) {
+          v.enc.off_cw[i][j] = add_leaf(n, 9 * cin[j] * f);
+          v.enc.off_cb[i][j] = add_leaf(n, f);
+        }
+        c = f; h = (h + 1) / 2; w = (w + 1) / 2;
+      }
+      v.enc.off_dw = add_leaf(n, (int64_t)h * w * c * d->obs_dim);  // MLP((512,)): the encoder output width is obs_dim
+      v.enc.off_db = add_leaf(n, d->obs_dim);
     }
     v.end = off;
   }
@@ -146,6 +168,18 @@ size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w)
   w->raw_local = c.take(S * FQL_NUM_RAW);
   w->gstats = c.take(S * 4);
   w->partials = c.take(S * (int64_t)L.leaf_blk[L.n_leaves] * 4);
+  if (d->reserved[0] > 0) {
+    for (int i = 0; i < 5; i++) w->feat[i] = c.take(S * B * F);
+    for (int i = 0; i < 3; i++) w->dfeat[i] = c.take(S * B * F);
+    w->dX0F = c.take(S * B * (F + A + 1));
+    w->dX0O = c.take(S * B * (F + A));
+    w->dX0C = c.take(S * 2 * B * (F + A));
+    const bool bwd[5] = {false, true, false, true, true};
+    for (int i = 0; i < 5; i++) {
+      c.off = (c.off + 255) & ~(size_t)255;
+      c.off += enc_carve(d, B, base ? c.base + c.off : nullptr, &w->enc[i], bwd[i]);
+    }
+  }
   if (d->precision == FQL_PRECISION_BF16_TC) {
     const int64_t kO = round_up64(F + A, 64), kF = round_up64(F + A + 1, 64);
     w->XOb = c.take((S * 3 * B * kO + 1) / 2);
@@ -443,6 +477,37 @@ int check_common(const FqlDims* d, const void* ws, size_t ws_bytes, Layout* L, W
   return 0;
 }
 
+// What every call site reads as "observations": the batch itself (state configs) or the output of that network's encoder.
+// Five unique encoder forwards per step: onestep(next_obs), onestep(obs), target critic(next_obs), critic(obs), bc flow(obs).
+int encode_observations(const StepCall& c, const Layout& L, WsPtrs& w, cudaStream_t st) {
+  const FqlBatch& b = *c.b;
+  if (c.d->reserved[0] == 0) {
+    w.src[0] = w.src[2] = b.next_observations;
+    w.src[1] = w.src[3] = w.src[4] = b.observations;
+    return 0;
+  }
+  const uint8_t* obs = reinterpret_cast<const uint8_t*>(b.observations);
+  const uint8_t* nobs = reinterpret_cast<const uint8_t*>(b.next_observations);
+  const float* P = c.st->params;
+  const int64_t B = c.d->batch;
+  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_ACTOR_ONESTEP_FLOW].enc, P, nobs, B, w.enc[0], w.feat[0], st));
+  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_ACTOR_ONESTEP_FLOW].enc, P, obs, B, w.enc[1], w.feat[1], st));
+  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_TARGET_CRITIC].enc, P, nobs, B, w.enc[2], w.feat[2], st));
+  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_CRITIC].enc, P, obs, B, w.enc[3], w.feat[3], st));
+  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_ACTOR_BC_FLOW].enc, P, obs, B, w.enc[4], w.feat[4], st));
+  for (int i = 0; i < 5; i++) w.src[i] = w.feat[i];
+  return 0;
+}
+
+// Encoder backward of one trainable network from its MLP's first-layer input gradient dX0 [E][B][K0] (feature columns first).
+int encoder_grads(const StepCall& c, const Layout& L, const WsPtrs& w, int net, const float* dX0, int E, int K0, float* dfeat, int enc_idx,
+                  cudaStream_t st) {
+  const int64_t B = c.d->batch;
+  FQL_TRY(launch_extract_feat_grad(dX0, dfeat, E, B, K0, c.d->obs_dim, st));
+  return enc_backward(c.d, L.net[net].enc, c.st->params, c.st->grads, reinterpret_cast<const uint8_t*>(c.b->observations), B, w.enc[enc_idx],
+                      dfeat, st);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // FQL_PRECISION_BF16_TC schedule of the loss/gradient half of the step: every contraction on tcgen05.
 //   S1: Euler integration, layer by layer (each layer = 16 CTAs of tc_gemm at B=256)              <- longest chain
@@ -462,6 +527,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4], ev_pad = ctx->ev[5];
   const int kO = (int)round_up64(sh.F + sh.A, 64), kF = (int)round_up64(sh.F + sh.A + 1, 64);
   FQL_TRY(launch_zero(raw, (int64_t)S * FQL_NUM_RAW, S0));
+  FQL_TRY(encode_observations(c, L, w, S0));
   FQL_TRY(launch_prep(sh, b, w, S0));
   FQL_CHECK_CUDA(cudaEventRecord(ev_prep, S0));
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S1, ev_prep, 0));
@@ -593,7 +659,9 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     cudaStream_t S1 = ctx->s1, S2 = ctx->s2;
     cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4];
     FQL_TRY(launch_zero(raw, (int64_t)S * FQL_NUM_RAW, S0));
+    FQL_TRY(encode_observations(c, L, w, S0));
     FQL_TRY(launch_prep(sh, b, w, S0));
+    const bool pix = c.d->reserved[0] > 0;
     FQL_CHECK_CUDA(cudaEventRecord(ev_prep, S0));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S1, ev_prep, 0));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_prep, 0));
@@ -641,14 +709,18 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
       bF.nv = &L.net[FQL_NET_ACTOR_BC_FLOW]; bF.params = P; bF.grads = c.st->grads; bF.arena = L.arena;
       bF.S = S; bF.E = 1; bF.M = B; bF.H = H; bF.X0 = w.XF; bF.Mcap0 = 2 * B; bF.buf = &w.pF; bF.p = 0; bF.r0 = 0;
       bF.dOut = w.dpred; bF.dpp[0] = w.dF[0]; bF.dpp[1] = w.dF[1];
+      if (pix) bF.dX0 = w.dX0F;
       FQL_TRY(mlp_backward(bF, S2));
+      if (pix) FQL_TRY(encoder_grads(c, L, w, FQL_NET_ACTOR_BC_FLOW, w.dX0F, 1, sh.F + sh.A + 1, w.dfeat[1], 4, S2));
       FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_cpost, 0));
       BwdSpec bC;
       memset(&bC, 0, sizeof(bC));
       bC.nv = &L.net[FQL_NET_CRITIC]; bC.params = P; bC.grads = c.st->grads; bC.arena = L.arena;
       bC.S = S; bC.E = 2; bC.M = B; bC.H = H; bC.X0 = w.XC + (int64_t)1 * S * B * (sh.F + sh.A); bC.Mcap0 = B;
       bC.buf = &w.pC; bC.p = 1; bC.r0 = 0; bC.dOut = w.dq; bC.dpp[0] = w.dC[0]; bC.dpp[1] = w.dC[1];
+      if (pix) bC.dX0 = w.dX0C;
       FQL_TRY(mlp_backward(bC, S2));
+      if (pix) FQL_TRY(encoder_grads(c, L, w, FQL_NET_CRITIC, w.dX0C, 2, sh.F + sh.A, w.dfeat[0], 3, S2));
     }
     FQL_CHECK_CUDA(cudaEventRecord(ev_s2, S2));
 
@@ -669,7 +741,9 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
       bO.nv = &L.net[FQL_NET_ACTOR_ONESTEP_FLOW]; bO.params = P; bO.grads = c.st->grads; bO.arena = L.arena;
       bO.S = S; bO.E = 1; bO.M = B; bO.H = H; bO.X0 = w.XO + (int64_t)B * (sh.F + sh.A); bO.Mcap0 = 3 * B;
       bO.buf = &w.pO; bO.p = 0; bO.r0 = B; bO.dOut = w.dapi; bO.dpp[0] = w.dO[0]; bO.dpp[1] = w.dO[1];
+      if (pix) bO.dX0 = w.dX0O;
       FQL_TRY(mlp_backward(bO, S0));
+      if (pix) FQL_TRY(encoder_grads(c, L, w, FQL_NET_ACTOR_ONESTEP_FLOW, w.dX0O, 1, sh.F + sh.A, w.dfeat[2], 1, S0));
     }
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
   }
@@ -818,13 +892,20 @@ extern "C" int fql_total_loss(FqlContext* ctx, const FqlDims* d, const FqlHparam
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 size_t carve_forward(const FqlDims* d, int rows, int ens, int in_dim, int out_dim, bool ln, void* base, float** X, PassBuf* pb,
-                     void** Xb = nullptr, void** Hx = nullptr) {
+                     void** Xb = nullptr, void** Hx = nullptr, float** feat = nullptr, EncBuf* eb = nullptr) {
   Carver c{reinterpret_cast<char*>(base)};
   *X = c.take((int64_t)d->num_seeds * rows * in_dim);
   void* xb = c.take((int64_t)d->num_seeds * rows * 128 / 2 + 4);
   if (Xb) *Xb = xb;
   void* hx = (d->precision == FQL_PRECISION_BF16_TC && d->hidden == 512) ? c.take((int64_t)(tc_euler_scratch_elems(d, rows) / 2 + 4)) : nullptr;
   if (Hx) *Hx = hx;
+  if (d->reserved[0] > 0) {  // pixel observations: encoder pass buffers + its output
+    float* ft = c.take((int64_t)rows * d->obs_dim);
+    if (feat) *feat = ft;
+    c.off = (c.off + 255) & ~(size_t)255;
+    EncBuf tmp;
+    c.off += enc_carve(d, rows, base ? c.base + c.off : nullptr, eb ? eb : &tmp, false);
+  }
   carve_pass(c, pb, d->num_seeds * ens, rows, d->hidden, d->num_hidden, out_dim, ln, false);
   return c.off + 256;
 }
@@ -877,9 +958,15 @@ extern "C" int fql_sample_actions(FqlContext*, const FqlDims* d, const float* pa
   PassBuf pb;
   const size_t need = carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, nullptr, &X, &pb);
   FQL_REQUIRE(workspace && ws_bytes >= need, "workspace too small: have %zu need %zu", ws_bytes, need);
-  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb, &Xb);
+  float* feat = nullptr;
+  EncBuf eb;
+  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb, &Xb, nullptr, &feat, &eb);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t R = (int64_t)d->num_seeds * rows;
+  if (d->reserved[0] > 0) {  // obs is uint8 [rows,H,W,C]: encode with the one-step actor's encoder (networks.py:226-227)
+    FQL_TRY(enc_forward(d, nv.enc, params, reinterpret_cast<const uint8_t*>(obs), rows, eb, feat, st));
+    obs = feat;
+  }
   FQL_TRY(launch_concat(obs, d->obs_dim, noise, d->action_dim, 0.f, 0, X, R, st));
   if (d->precision == FQL_PRECISION_BF16_TC) {
     FQL_REQUIRE(shadow != nullptr, "FQL_PRECISION_BF16_TC needs the bf16 shadow");
@@ -909,9 +996,15 @@ extern "C" int fql_compute_flow_actions(FqlContext*, const FqlDims* d, const flo
   PassBuf pb;
   const size_t need = carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, nullptr, &X, &pb);
   FQL_REQUIRE(workspace && ws_bytes >= need, "workspace too small: have %zu need %zu", ws_bytes, need);
-  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb, &Xb, &Hx);
+  float* feat = nullptr;
+  EncBuf eb;
+  carve_forward(d, rows, 1, nv.in_dim, nv.out_dim, nv.ln, workspace, &X, &pb, &Xb, &Hx, &feat, &eb);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t R = (int64_t)d->num_seeds * rows;
+  if (d->reserved[0] > 0) {  // fql.py:162-163: encode once with actor_bc_flow_encoder, then is_encoded=True
+    FQL_TRY(enc_forward(d, nv.enc, params, reinterpret_cast<const uint8_t*>(obs), rows, eb, feat, st));
+    obs = feat;
+  }
   FQL_TRY(launch_concat(obs, d->obs_dim, noise, d->action_dim, 0.f, 1, X, R, st));
   if (d->precision == FQL_PRECISION_BF16_TC) {
     FQL_REQUIRE(shadow != nullptr, "FQL_PRECISION_BF16_TC needs the bf16 shadow");
@@ -993,6 +1086,21 @@ extern "C" int fql_layout(const FqlDims* d, FqlLeaf* leaves, int32_t cap, int32_
         put(t, l, FQL_LEAF_LN_SCALE, v.ens, 1, v.n_of(l), v.off_lns[l]);
         put(t, l, FQL_LEAF_LN_BIAS, v.ens, 1, v.n_of(l), v.off_lnb[l]);
       }
+    }
+    if (v.has_enc) {
+      static const int stacks[3] = {16, 32, 32};
+      int c = d->reserved[2], h = d->reserved[0], w = d->reserved[1];
+      for (int i = 0; i < 3; i++) {
+        const int f = stacks[i];
+        const int cin[3] = {c, f, f};
+        for (int j = 0; j < 3; j++) {
+          put(t, 3 * i + j, FQL_LEAF_CONV_KERNEL, 1, 9 * cin[j], f, v.enc.off_cw[i][j]);
+          put(t, 3 * i + j, FQL_LEAF_CONV_BIAS, 1, 1, f, v.enc.off_cb[i][j]);
+        }
+        c = f; h = (h + 1) / 2; w = (w + 1) / 2;
+      }
+      put(t, 0, FQL_LEAF_ENC_DENSE_KERNEL, 1, h * w * c, d->obs_dim, v.enc.off_dw);
+      put(t, 0, FQL_LEAF_ENC_DENSE_BIAS, 1, 1, d->obs_dim, v.enc.off_db);
     }
   }
   if (n_leaves) *n_leaves = n;

@@ -21,6 +21,14 @@ struct PassBuf {               // activations of one grouped MLP pass: [G][Mcap]
   int G, Mcap;
 };
 
+struct EncBuf {               // activations of one encoder pass over B images (encoder.cu)
+  float *pl[3], *c1[3], *x[3];
+  uint8_t* arg[3];
+  float *flat, *z, *scratch;
+  float *dz, *dflat, *da, *db, *dc, *partial;
+  int flat_dim;
+};
+
 struct WsPtrs {
   float *XO, *XF, *XC, *vel;   // first-layer inputs [S][3B][F+A], [S][2B][F+A+1], [3][S][B][F+A]; vel [S][B][A]
   float *O_out, *F_out, *C_out;
@@ -39,6 +47,12 @@ struct WsPtrs {
   void *C1_dZb[FQL_MAXL], *C1_dOutb, *C2_dZb[FQL_MAXL], *C2_dOutb;
   float *C1_dZf[FQL_MAXL], *C1_dHf[FQL_MAXL], *C2_dZf[FQL_MAXL], *C2_dHf[FQL_MAXL];
   float *euler_a;
+  // pixel configs: encoder outputs that replace the observations per call site, encoder pass buffers, feature gradients
+  float *feat[5];              // [S][B][512]: onestep(next_obs), onestep(obs), target critic(next_obs), critic(obs), bc_flow(obs)
+  float *dfeat[3];             // gradients w.r.t. feat[3] (critic), feat[4] (bc flow), feat[1] (onestep)
+  float *dX0F, *dX0O, *dX0C;   // first-layer input gradients of the three trainable MLPs
+  EncBuf enc[5];
+  const float *src[5];         // what prep reads as `observations` for the 5 call sites (features, or the batch itself)
   void *euler_hx;              // exchange scratch of the cluster Euler kernel
 };
 
@@ -178,3 +192,11 @@ struct TcEulerSpec {
 };
 size_t tc_euler_scratch_elems(const FqlDims* d, int M);
 int tc_euler_cluster(const TcEulerSpec& f, cudaStream_t st);
+
+// encoder.cu
+size_t enc_carve(const FqlDims* d, int64_t B, void* base, EncBuf* e, bool for_backward);
+int enc_forward(const FqlDims* d, const EncView& v, const float* params, const uint8_t* obs, int64_t B, const EncBuf& e, float* feat,
+                cudaStream_t st);
+int enc_backward(const FqlDims* d, const EncView& v, const float* params, float* grads, const uint8_t* obs, int64_t B, const EncBuf& e,
+                 const float* dfeat, cudaStream_t st);
+int launch_extract_feat_grad(const float* dX0, float* out, int E, int64_t M, int K0, int F, cudaStream_t st);

@@ -32,7 +32,9 @@ extern "C" {
 /* Networks inside an arena, in arena order.  Names follow agents/fql.py:224-229 (`modules_<name>`). */
 enum { FQL_NET_ACTOR_BC_FLOW = 0, FQL_NET_ACTOR_ONESTEP_FLOW = 1, FQL_NET_CRITIC = 2, FQL_NET_TARGET_CRITIC = 3, FQL_NUM_NETS = 4 };
 /* Leaf kinds inside a network (utils/networks.py:54,58). */
-enum { FQL_LEAF_KERNEL = 0, FQL_LEAF_BIAS = 1, FQL_LEAF_LN_SCALE = 2, FQL_LEAF_LN_BIAS = 3 };
+enum { FQL_LEAF_KERNEL = 0, FQL_LEAF_BIAS = 1, FQL_LEAF_LN_SCALE = 2, FQL_LEAF_LN_BIAS = 3,
+       /* encoder leaves (utils/encoders.py): layer = 3*stack + conv for the convolutions */
+       FQL_LEAF_CONV_KERNEL = 4, FQL_LEAF_CONV_BIAS = 5, FQL_LEAF_ENC_DENSE_KERNEL = 6, FQL_LEAF_ENC_DENSE_BIAS = 7 };
 /* Arithmetic mode of the contractions. */
 enum { FQL_PRECISION_FP32 = 0,      /* fp32 FFMA everywhere: parity mode (1e-5 vs the fp32/fp64 oracle)          */
        FQL_PRECISION_BF16_TC = 1 }; /* bf16 operands on tcgen05, fp32 accumulate/epilogue, fp32 master weights   */
@@ -52,7 +54,9 @@ typedef struct FqlDims {
   int32_t flow_steps;        /* config['flow_steps']                                                         */
   int32_t num_seeds;         /* independent agents vectorised on the leading axis (1 = the reference)        */
   int32_t precision;         /* FQL_PRECISION_*                                                              */
-  int32_t reserved[3];
+  int32_t reserved[3];       /* pixel configs (config['encoder']=='impala_small'): {img_h, img_w, img_c}, observations are
+                              * uint8 [S,B,img_h,img_w,img_c] (passed through the float* fields) and obs_dim must be 512;
+                              * {0,0,0} = state-based */
 } FqlDims;
 
 /* Hyper-parameters that are runtime scalars. agents/fql.py:255-264, optax.adam defaults. */

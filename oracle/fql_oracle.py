@@ -207,17 +207,28 @@ def _zeros_like_tree(t):
     return np.zeros_like(t)
 
 
-def total_loss(params, cfg, batch, noise, with_grads=True):
+def total_loss(params, cfg, batch, noise, with_grads=True, feats=None):
     """Returns (loss, info[10 keys], grads-or-None).  grads has the full tree of `params`
-    (target critic gradients are exactly zero)."""
-    obs, act, nobs = batch['observations'], batch['actions'], batch['next_observations']
+    (target critic gradients are exactly zero).
+
+    feats (pixel configs, oracle/fql_pixel_oracle.py): encoder outputs that stand in for the observations, per call site:
+    {'O_next','O','T_next','C','F'} = onestep(next_obs), onestep(obs), target_critic(next_obs), critic(obs), bc_flow(obs).
+    With feats the function returns a 4th value: the gradients w.r.t. feats['C'], feats['F'], feats['O']."""
+    act = batch['actions']
+    if feats is None:
+        obs_C = obs_F = obs_O = batch['observations']
+        nobs_O = nobs_T = batch['next_observations']
+    else:
+        obs_C, obs_F, obs_O, nobs_O, nobs_T = feats['C'], feats['F'], feats['O'], feats['O_next'], feats['T_next']
+    obs, nobs = obs_C, nobs_T
     rew, masks = batch['rewards'], batch['masks']
-    dt = obs.dtype.type
+    dt = act.dtype.type
     B, A = act.shape
+    Fdim = obs.shape[-1]
     info = {}
 
     # ---- critic loss (fql.py:22-44)
-    next_a = sample_actions_given_noise(params, cfg, nobs, noise['z_next'])
+    next_a = sample_actions_given_noise(params, cfg, nobs_O, noise['z_next'])
     next_a = np.clip(next_a, -1, 1)
     next_qs = critic_forward(params['modules_target_critic'], cfg, nobs, next_a)
     next_q = next_qs.min(axis=0) if cfg['q_agg'] == 'min' else next_qs.mean(axis=0)
@@ -235,13 +246,13 @@ def total_loss(params, cfg, batch, noise, with_grads=True):
     x1 = act
     x_t = (dt(1) - t) * x0 + t * x1
     vel = x1 - x0
-    pred, f_cache = actor_forward(params['modules_actor_bc_flow'], cfg, obs, x_t, t, save=True)
+    pred, f_cache = actor_forward(params['modules_actor_bc_flow'], cfg, obs_F, x_t, t, save=True)
     bc_diff = pred - vel
     bc_flow_loss = (bc_diff * bc_diff).mean()
 
     z = noise['z']
-    target_flow = compute_flow_actions(params, cfg, obs, z)
-    a_pi, o_cache = actor_forward(params['modules_actor_onestep_flow'], cfg, obs, z, save=True)
+    target_flow = compute_flow_actions(params, cfg, obs_F, z)
+    a_pi, o_cache = actor_forward(params['modules_actor_onestep_flow'], cfg, obs_O, z, save=True)
     d_diff = a_pi - target_flow
     distill_loss = (d_diff * d_diff).mean()
 
@@ -255,7 +266,7 @@ def total_loss(params, cfg, batch, noise, with_grads=True):
         q_loss = lam * q_loss
     actor_loss = bc_flow_loss + dt(cfg['alpha']) * distill_loss + q_loss
 
-    metric_a = sample_actions_given_noise(params, cfg, obs, noise['z_metric'])
+    metric_a = sample_actions_given_noise(params, cfg, obs_O, noise['z_metric'])
     mse = ((metric_a - act) ** 2).mean()
     info['actor/actor_loss'] = actor_loss
     info['actor/bc_flow_loss'] = bc_flow_loss
@@ -265,17 +276,18 @@ def total_loss(params, cfg, batch, noise, with_grads=True):
     info['actor/mse'] = mse
     loss = critic_loss + actor_loss
     if not with_grads:
-        return loss, info, None
+        return (loss, info, None) if feats is None else (loss, info, None, None)
 
+    need_dx = feats is not None
     grads = _zeros_like_tree(params)
     # critic <- critic_loss only
     dq = (dt(2.0) / dt(q.size)) * diff                              # [2,B]
-    g_c, _ = mlp_backward(params['modules_critic']['value_net'], c_cache, dq[..., None], cfg['layer_norm'], need_dx=False)
-    grads['modules_critic'] = {'value_net': g_c}
+    g_c, dx_C = mlp_backward(params['modules_critic']['value_net'], c_cache, dq[..., None], cfg['layer_norm'], need_dx=need_dx)
+    grads['modules_critic']['value_net'] = g_c
     # bc flow <- bc_flow_loss only
     dpred = (dt(2.0) / dt(B * A)) * bc_diff
-    g_f, _ = mlp_backward(params['modules_actor_bc_flow']['mlp'], f_cache, dpred, cfg['actor_layer_norm'], need_dx=False)
-    grads['modules_actor_bc_flow'] = {'mlp': g_f}
+    g_f, dx_F = mlp_backward(params['modules_actor_bc_flow']['mlp'], f_cache, dpred, cfg['actor_layer_norm'], need_dx=need_dx)
+    grads['modules_actor_bc_flow']['mlp'] = g_f
     # onestep <- alpha*distill + q_loss (through clip and the critic's input gradient; critic weights get nothing)
     dqs = np.full_like(qs_pi, -lam / dt(2 * B))
     _, dx_c = mlp_backward(params['modules_critic']['value_net'], cpi_cache, dqs[..., None], cfg['layer_norm'],
@@ -283,9 +295,12 @@ def total_loss(params, cfg, batch, noise, with_grads=True):
     da_clip = dx_c.sum(axis=0)[:, -A:]                               # sum over the 2 heads (input was broadcast)
     inside = ((a_pi >= -1) & (a_pi <= 1)).astype(obs.dtype)
     da_pi = dt(cfg['alpha']) * (dt(2.0) / dt(B * A)) * d_diff + da_clip * inside
-    g_o, _ = mlp_backward(params['modules_actor_onestep_flow']['mlp'], o_cache, da_pi, cfg['actor_layer_norm'], need_dx=False)
-    grads['modules_actor_onestep_flow'] = {'mlp': g_o}
-    return loss, info, grads
+    g_o, dx_O = mlp_backward(params['modules_actor_onestep_flow']['mlp'], o_cache, da_pi, cfg['actor_layer_norm'], need_dx=need_dx)
+    grads['modules_actor_onestep_flow']['mlp'] = g_o
+    if feats is None:
+        return loss, info, grads
+    dfeat = {'C': dx_C.sum(axis=0)[:, :Fdim], 'F': dx_F[:, :Fdim], 'O': dx_O[:, :Fdim]}   # critic input is broadcast to both heads
+    return loss, info, grads, dfeat
 
 
 # --------------------------------------------------------------------------------------

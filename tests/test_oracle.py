@@ -245,3 +245,91 @@ def test_torch_cpu_restatement_matches_numpy_oracle():
                 np.testing.assert_allclose(g, r, rtol=1e-9, atol=1e-13, err_msg=f'{which} {path}')
         for (path, r), (_, g) in zip(O.tree_leaves(grads), O.tree_leaves(tgrads)):
             np.testing.assert_allclose(g, r, rtol=1e-8, atol=1e-12, err_msg=str(path))
+
+
+def test_encoder_oracle_against_torch_autograd():
+    """oracle/encoder_oracle.py (impala_small restatement, manual backward) vs torch conv2d / max_pool2d autograd in fp64."""
+    import torch.nn.functional as Fn
+    from oracle import encoder_oracle as E
+    rng = np.random.default_rng(3)
+    p = E.init_encoder(rng, 6, dtype=np.float64, hw=16, jitter=0.1)
+    obs = rng.integers(0, 256, (3, 16, 16, 6), dtype=np.uint8)
+    out, saved = E.encoder_forward(p, obs, save=True)
+    dout = rng.standard_normal(out.shape)
+    g = E.encoder_backward(p, saved, dout)
+    tp = _to_torch(p, True)
+    x = torch.tensor(obs.astype(np.float64) / 255.0).permute(0, 3, 1, 2)
+    conv = lambda x, q: Fn.conv2d(x, q['kernel'].permute(3, 2, 0, 1), q['bias'], padding=1)
+    for i in range(3):
+        b = tp[f'stack_blocks_{i}']
+        x = conv(x, b['Conv_0'])
+        x = Fn.max_pool2d(Fn.pad(x, (0, 1, 0, 1), value=float('-inf')), 3, 2)
+        y = conv(torch.relu(x), b['Conv_1'])
+        y = conv(torch.relu(y), b['Conv_2'])
+        x = y + x
+    flat = torch.relu(x).permute(0, 2, 3, 1).reshape(x.shape[0], -1)          # NHWC flatten (encoders.py:96)
+    tout = Fn.gelu(flat @ tp['MLP_0']['Dense_0']['kernel'] + tp['MLP_0']['Dense_0']['bias'], approximate='tanh')
+    np.testing.assert_allclose(out, tout.detach().numpy(), rtol=1e-10, atol=1e-12)
+    (tout * torch.tensor(dout)).sum().backward()
+    for (path, a), (_, t) in zip(O.tree_leaves(g), O.tree_leaves(tp)):
+        np.testing.assert_allclose(a, t.grad.numpy(), rtol=1e-9, atol=1e-11, err_msg=str(path))
+    # 64x64x9 (frame_stack 3) geometry of BASELINE config 5: 64 -> 32 -> 16 -> 8, flatten 8*8*32 = 2048, 1,105,920 parameters
+    p64 = E.init_encoder(rng, 9, hw=64)
+    assert p64['MLP_0']['Dense_0']['kernel'].shape == (2048, 512)
+    assert sum(v.size for _, v in O.tree_leaves(p64)) == 1105920
+
+
+def test_pixel_oracle_finite_differences_and_state_oracle_unchanged():
+    """FD check of the pixel-config total gradient (encoders included) with separated grad/stored params, fp64, 16x16 images."""
+    from oracle import fql_pixel_oracle as PO
+    cfg = small_cfg(alpha=10.0, encoder='impala_small')
+    B, A = 3, 2
+    params = PO.init_params(0, 6, A, cfg, dtype=np.float64, hw=16, jitter=0.1, target_equals_critic=False)
+    batch = PO.make_pixel_batch(1, B, A, hw=16, ch=6, dtype=np.float64)
+    noise = O.make_noise(2, B, A, np.float64)
+    loss, info, grads = PO.total_loss(params, cfg, batch, noise)
+    stored = copy.deepcopy(params)
+
+    def routed(gp):  # only the three gradient-carrying call sites see gp (fql.py:36,58,65); everything else sees stored
+        mix = copy.deepcopy(stored)
+        fC = PO.E.encoder_forward(gp['modules_critic']['encoder'], batch['observations'])
+        fF = PO.E.encoder_forward(gp['modules_actor_bc_flow_encoder'], batch['observations'])
+        fO = PO.E.encoder_forward(gp['modules_actor_onestep_flow']['encoder'], batch['observations'])
+        sfC = PO.E.encoder_forward(stored['modules_critic']['encoder'], batch['observations'])
+        sfF = PO.E.encoder_forward(stored['modules_actor_bc_flow_encoder'], batch['observations'])
+        sfO = PO.E.encoder_forward(stored['modules_actor_onestep_flow']['encoder'], batch['observations'])
+        fOn = PO.E.encoder_forward(stored['modules_actor_onestep_flow']['encoder'], batch['next_observations'])
+        fTn = PO.E.encoder_forward(stored['modules_target_critic']['encoder'], batch['next_observations'])
+        b = dict(batch)
+        na = np.clip(O.actor_forward(stored['modules_actor_onestep_flow'], cfg, fOn, noise['z_next']), -1, 1)
+        tq = b['rewards'] + cfg['discount'] * b['masks'] * O.critic_forward(stored['modules_target_critic'], cfg, fTn, na).mean(0)
+        q = O.critic_forward(gp['modules_critic'], cfg, fC, b['actions'])
+        cl = ((q - tq) ** 2).mean()
+        x0, t = noise['x0'], noise['t']
+        pred = O.actor_forward(gp['modules_actor_bc_flow'], cfg, fF, (1 - t) * x0 + t * b['actions'], t)
+        bc = ((pred - (b['actions'] - x0)) ** 2).mean()
+        tgt = O.compute_flow_actions(stored, cfg, sfF, noise['z'])
+        api = O.actor_forward(gp['modules_actor_onestep_flow'], cfg, fO, noise['z'])
+        dl = ((api - tgt) ** 2).mean()
+        ql = -O.critic_forward(stored['modules_critic'], cfg, sfC, np.clip(api, -1, 1)).mean(0).mean()
+        return cl + bc + cfg['alpha'] * dl + ql
+
+    assert abs(routed(copy.deepcopy(params)) - loss) < 1e-10
+    rng = np.random.default_rng(4)
+    gl = dict(O.tree_leaves(grads))
+    gp = copy.deepcopy(params)
+    eps = 1e-6
+    for path, arr in O.tree_leaves(gp):
+        if path[0] == 'modules_target_critic':
+            assert not gl[path].any()
+            continue
+        for _ in range(2):
+            idx = tuple(rng.integers(0, s) for s in arr.shape)
+            old = arr[idx]
+            arr[idx] = old + eps
+            lp = routed(gp)
+            arr[idx] = old - eps
+            lm = routed(gp)
+            arr[idx] = old
+            fd = (lp - lm) / (2 * eps)
+            assert abs(fd - gl[path][idx]) <= 2e-6 * max(1.0, abs(fd)) + 1e-8, (path, idx, fd, gl[path][idx])

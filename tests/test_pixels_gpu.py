@@ -1,0 +1,83 @@
+"""BASELINE config 5 (visual observations through ImpalaEncoder('impala_small'), utils/encoders.py): the CUDA step against the
+pixel oracle (oracle/fql_pixel_oracle.py) in FP32 mode on every leaf incl. the three encoders.
+
+Tolerance: 1e-5 tensor-norm-relative against the **fp32** oracle (the reference's own arithmetic), 1e-2 against the fp64 oracle.
+Unlike the state-based MLPs this network is not smooth: ReLU masks and max-pool argmaxes on near-ties come out differently in fp32
+and fp64, which moves a few convolution gradients by ~1e-3 (measured: the fp32 NumPy oracle differs from the fp64 oracle by
+exactly the amounts the CUDA path does, e.g. 1.33e-3 on critic/encoder/stack_blocks_0/Conv_0/bias at the config-5 geometry)."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import fql_oracle as O
+from oracle import fql_pixel_oracle as PO
+from tests.helpers import f32, info_close, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_agent(cfg, B, hw, ch, A):
+    from fql_b200 import FQLAgent
+    c = dict(cfg)
+    c['batch_size'] = B
+    return FQLAgent.create(0, np.zeros((1, hw, hw, ch), np.uint8), np.zeros((1, A), np.float32), c)
+
+
+@pytest.mark.parametrize('name,B,hw,ch,A,hidden,over', [
+    ('small-16px', 6, 16, 6, 3, 64, dict(alpha=10.0)),
+    ('odd-20px', 5, 20, 3, 2, 64, dict(q_agg='min', alpha=10.0)),
+    ('visual-cube-single', 8, 64, 9, 5, 512, dict(alpha=300.0)),          # BASELINE config 5 geometry (frame_stack 3 x RGB), small batch
+])
+def test_pixel_update_parity(name, B, hw, ch, A, hidden, over):
+    cfg = dict(O.DEFAULT_CONFIG)
+    cfg.update(over)
+    cfg.update(actor_hidden_dims=(hidden,) * 4, value_hidden_dims=(hidden,) * 4, encoder='impala_small')
+    params = PO.init_params(3, ch, A, cfg, dtype=np.float64, hw=hw, jitter=0.05, target_equals_critic=False)
+    params['modules_actor_onestep_flow']['mlp']['Dense_4']['bias'][0] += 1.1
+    state = O.init_state(params, warm=True, seed=3)
+    batch = PO.make_pixel_batch(4, B, A, hw=hw, ch=ch, dtype=np.float64)
+    noise = O.make_noise(5, B, A, np.float64)
+    st64, info64, grads64 = PO.update(copy.deepcopy(state), cfg, batch, noise)
+    b32o = {k: (v if v.dtype == np.uint8 else v.astype(np.float32)) for k, v in batch.items()}
+    st32 = dict(params=f32(state['params']), mu=f32(state['mu']), nu=f32(state['nu']), count=state['count'], step=state['step'])
+    new_state, ref_info, ref_grads = PO.update(st32, cfg, b32o, f32(noise))          # the reference's arithmetic: fp32
+    agent = make_agent(cfg, B, hw, ch, A)
+    agent.load_tree(f32(state['params']), f32(state['mu']), f32(state['nu']), state['count'])
+    b32 = {k: (v if v.dtype == np.uint8 else v.astype(np.float32)) for k, v in batch.items()}
+    _, info = agent.update(b32, noise=f32(noise))
+    for k in O.INFO_KEYS:
+        info_close(k, info[k], ref_info, 3e-5)
+    worst, bad = {}, []
+    for which, ref in (('grads', ref_grads), ('params', new_state['params']), ('mu', new_state['mu']), ('nu', new_state['nu'])):
+        got = agent.export_tree(which)
+        lr, lg = O.tree_leaves(ref), O.tree_leaves(got)
+        assert [p for p, _ in lr] == [p for p, _ in lg], 'parameter tree of the pixel config differs from the reference layout'
+        for (path, r), (_, g) in zip(lr, lg):
+            assert g.shape == r.shape, (path, g.shape, r.shape)
+            e = rel_err(g, r)
+            worst[which] = max(worst.get(which, 0), e)
+            if e > 1e-5:
+                bad.append((which, '/'.join(path), f'{e:.2e}'))
+    print(name, {k: f'{v:.2e}' for k, v in worst.items()})
+    assert not bad, bad[:12]
+    for (path, r), (_, g) in zip(O.tree_leaves(grads64), O.tree_leaves(agent.export_tree('grads'))):
+        assert rel_err(g, r) <= 1e-2, ('fp64', path, rel_err(g, r))
+    # forward entry points on pixels
+    a = agent.sample_actions(batch['observations'], noise=noise['z'].astype(np.float32))
+    p64 = O.cast_tree(new_state['params'], np.float64)
+    feats = PO.E.encoder_forward(p64['modules_actor_onestep_flow']['encoder'], batch['observations'], dtype=np.dtype(np.float64))
+    assert rel_err(a, O.sample_actions_given_noise(O.cast_tree(new_state['params'], np.float64), cfg, feats, noise['z'])) <= 2e-5
+    fa = agent.compute_flow_actions(batch['observations'], noise['z'].astype(np.float32))
+    ff = PO.E.encoder_forward(p64['modules_actor_bc_flow_encoder'], batch['observations'], dtype=np.dtype(np.float64))
+    assert rel_err(fa, O.compute_flow_actions(p64, cfg, ff, noise['z'])) <= 2e-5
+
+
+def test_pixel_param_count_matches_survey():
+    """config 5 has 7,545,356 trainable + 3,221,506 target parameters (A=5)."""
+    from fql_b200 import _lib
+    d = _lib.make_dims(256, 512, 5, image=(64, 64, 9))
+    leaves, _ = _lib.layout(d)
+    n = lambda l: l['ens'] * l['rows'] * l['cols']
+    assert sum(n(l) for l in leaves if l['net'] != 'target_critic') == 7545356
+    assert sum(n(l) for l in leaves if l['net'] == 'target_critic') == 3221506
