@@ -27,11 +27,20 @@ WORKLOADS = {  # BASELINE.json configs 1-4 (state-based); SURVEY 8d hyper-parame
     'antmaze-large': dict(F=29, A=8, cfg=dict(q_agg='min', alpha=10.0)),
     'humanoidmaze-medium': dict(F=69, A=21, cfg=dict(discount=0.995, alpha=30.0)),
     'puzzle-4x4': dict(F=83, A=5, cfg=dict(normalize_q_loss=True, alpha=1000.0)),  # F=83 assumed (unverified)
+    # BASELINE config 5: 64x64x3 pixels, frame_stack 3 -> 64x64x9 uint8, impala_small encoders (fp32 CUDA-core kernels this round)
+    'visual-cube-single': dict(F=512, A=5, image=(64, 64, 9), cfg=dict(alpha=300.0, encoder='impala_small')),
 }
 
 
-def flops_per_sample(F, A, H=512):
-    """Algorithmic FLOPs of one update per sample: MACs x2 of the Dense layers only."""
+ENC_FWD_FLOPS = 48.10e6          # impala_small forward per 64x64x9 image
+ENC_FIRST_DGRAD = 10.62e6        # the pixel-input gradient of the first convolution that is never needed
+
+
+def flops_per_sample(F, A, H=512, pixels=False):
+    """Algorithmic FLOPs of one update per sample: MACs x2 of the Dense/Conv layers only.  Pixels: + 5 encoder
+    forwards, 3 encoder backwards (2x forward minus the first conv's input gradient) and the first-layer dgrad into the features."""
+    if pixels:
+        return flops_per_sample(F, A, H) + 3 * 2 * F * H + 5 * ENC_FWD_FLOPS + 3 * (2 * ENC_FWD_FLOPS - ENC_FIRST_DGRAD)
     G = lambda d, o: 2 * (d * H + 3 * H * H + H * o)
     d_bc, d_os, d_c = F + A + 1, F + A, F + A
     fwd = 11 * G(d_bc, A) + 3 * G(d_os, A) + 6 * G(d_c, 1)
@@ -90,17 +99,18 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(rows[0][1]), reasons=reasons, samples=len(rows))
 
 
-def make_host_batches(n, B, F, A, seeds, seed0=0):
+def make_host_batches(n, B, F, A, seeds, seed0=0, image=None):
     import numpy as np
     out = []
     for i in range(n):
         rng = np.random.default_rng(seed0 + i)
         shp = (seeds, B) if seeds > 1 else (B,)
         rew = -(rng.random(shp) >= 0.01).astype(np.float32)
+        mk = (lambda: rng.integers(0, 256, shp + tuple(image), dtype=np.uint8)) if image else (lambda: rng.standard_normal(shp + (F,), dtype=np.float32))
         out.append(dict(
-            observations=rng.standard_normal(shp + (F,), dtype=np.float32),
+            observations=mk(),
             actions=np.clip(rng.uniform(-1, 1, shp + (A,)), -1 + 1e-5, 1 - 1e-5).astype(np.float32),
-            next_observations=rng.standard_normal(shp + (F,), dtype=np.float32),
+            next_observations=mk(),
             rewards=rew, masks=(rew != 0).astype(np.float32), terminals=np.zeros(shp, np.float32)))
     return out
 
@@ -115,8 +125,13 @@ def cpu_reference_arm(wl, B, steps, warmup, budget_s=20.0):
     cfg = dict(O.DEFAULT_CONFIG)
     cfg.update(wl['cfg'])
     F, A = wl['F'], wl['A']
-    agent = TorchCpuAgent(O.init_params(1, F, A, cfg, dtype=np.float32), cfg)
-    batches = make_host_batches(4, B, F, A, 1)
+    if wl.get('image'):
+        from oracle import fql_pixel_oracle as PO
+        params = PO.init_params(1, wl['image'][2], A, cfg, dtype=np.float32, hw=wl['image'][0])
+    else:
+        params = O.init_params(1, F, A, cfg, dtype=np.float32)
+    agent = TorchCpuAgent(params, cfg)
+    batches = make_host_batches(4, B, F, A, 1, image=wl.get('image'))
     noises = [O.make_noise(i, B, A, np.float32) for i in range(4)]
     for i in range(max(1, min(warmup, 3))):
         agent.update(batches[i % 4], noises[i % 4])
@@ -148,6 +163,8 @@ def main():
     ap.add_argument('--no-fp32-leg', action='store_true')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if wl.get('image'):
+        args.precision = 'fp32'  # the pixel path is fp32 this round
     F, A = wl['F'], wl['A']
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -188,9 +205,10 @@ def main():
     cfg = get_config()
     cfg.update(wl['cfg'])
     cfg['batch_size'] = args.batch
-    agent = FQLAgent.create(0, np.zeros((1, F), np.float32), np.zeros((1, A), np.float32), cfg, num_seeds=args.seeds,
+    ex_obs = np.zeros((1,) + tuple(wl['image']), np.uint8) if wl.get('image') else np.zeros((1, F), np.float32)
+    agent = FQLAgent.create(0, ex_obs, np.zeros((1, A), np.float32), cfg, num_seeds=args.seeds,
                             precision=args.precision, process_group=pg)
-    batches = make_host_batches(8, args.batch, F, A, args.seeds, seed0=1000 * rank)
+    batches = make_host_batches(8, args.batch, F, A, args.seeds, seed0=1000 * rank, image=wl.get('image'))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     stream = torch.cuda.Stream()  # a real (non-legacy) stream: the library captures its step graph on it
     K, W = args.steps, max(args.warmup, 3)
@@ -263,8 +281,10 @@ def main():
     leaves = agent._leaves
     cnt = lambda pred: sum(l['ens'] * l['rows'] * l['cols'] for l in leaves if pred(l))
     p_train, p_target = cnt(lambda l: l['net'] != 'target_critic'), cnt(lambda l: l['net'] == 'target_critic')
-    flops_gpu = flops_per_sample(F, A) * args.batch * args.seeds               # per GPU per step
+    flops_gpu = flops_per_sample(F, A, pixels=bool(wl.get('image'))) * args.batch * args.seeds   # per GPU per step
     bytes_gpu = (hbm_bytes_per_step(p_train, p_target, args.batch, F, A)) * args.seeds
+    if wl.get('image'):
+        bytes_gpu += args.batch * 2 * int(np.prod(wl['image'])) - args.batch * 2 * F * 4   # the batch is uint8 frames, not features
     t_s = ms_per_step / 1e3
     t_tc, t_hbm = flops_gpu / (peaks['tc'] * 1e12), bytes_gpu / (peaks['hbm'] * 1e9)
     if t_hbm >= t_tc:

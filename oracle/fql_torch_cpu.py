@@ -44,39 +44,69 @@ def mlp(p, x, ln):
     return x
 
 
+def encoder(p, obs_u8):
+    """ImpalaEncoder('impala_small') (utils/encoders.py:60-100) with torch ops; obs uint8 [B,H,W,C] -> [B,512]."""
+    x = obs_u8.to(p['MLP_0']['Dense_0']['kernel'].dtype).permute(0, 3, 1, 2) / 255.0
+    conv = lambda x, q: Fn.conv2d(x, q['kernel'].permute(3, 2, 0, 1), q['bias'], padding=1)
+    for i in range(3):
+        blk = p[f'stack_blocks_{i}']
+        x = conv(x, blk['Conv_0'])
+        ph, pw = x.shape[2] % 2, x.shape[3] % 2   # SAME 3x3/2: pad (0,1) for even sizes, (1,1) for odd
+        x = Fn.max_pool2d(Fn.pad(x, (pw, 1, ph, 1), value=float('-inf')), 3, 2)
+        y = conv(torch.relu(x), blk['Conv_1'])
+        y = conv(torch.relu(y), blk['Conv_2'])
+        x = y + x
+    flat = torch.relu(x).permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+    return Fn.gelu(flat @ p['MLP_0']['Dense_0']['kernel'] + p['MLP_0']['Dense_0']['bias'], approximate='tanh')
+
+
 def total_loss(gp, sp, cfg, b, nz):
     """agents/fql.py:22-111.  gp: params that receive gradients (`params=grad_params`), sp: stored params (stop-gradient)."""
     cat = lambda *a: torch.cat(a, -1)
     aln, cln = cfg['actor_layer_norm'], cfg['layer_norm']
     obs, act, nobs = b['observations'], b['actions'], b['next_observations']
     info = {}
+    pix = cfg.get('encoder') is not None
+    if pix:  # agents/fql.py with encoders: per call site features (see oracle/fql_pixel_oracle.py for the routing)
+        with torch.no_grad():
+            nobs_O = encoder(sp['modules_actor_onestep_flow']['encoder'], nobs)
+            nobs_T = encoder(sp['modules_target_critic']['encoder'], nobs)
+            s_fC = encoder(sp['modules_critic']['encoder'], obs)
+            s_fF = encoder(sp['modules_actor_bc_flow_encoder'], obs)
+            s_fO = encoder(sp['modules_actor_onestep_flow']['encoder'], obs)
+        g_fC = encoder(gp['modules_critic']['encoder'], obs)
+        g_fF = encoder(gp['modules_actor_bc_flow_encoder'], obs)
+        g_fO = encoder(gp['modules_actor_onestep_flow']['encoder'], obs)
+    else:
+        nobs_O = nobs_T = nobs
+        s_fC = s_fF = s_fO = g_fC = g_fF = g_fO = obs
     with torch.no_grad():
-        na = mlp(sp['modules_actor_onestep_flow']['mlp'], cat(nobs, nz['z_next']), aln).clamp(-1, 1)
-        nq = mlp(sp['modules_target_critic']['value_net'], cat(nobs, na), cln)[..., 0]
+        na = mlp(sp['modules_actor_onestep_flow']['mlp'], cat(nobs_O, nz['z_next']), aln).clamp(-1, 1)
+        nq = mlp(sp['modules_target_critic']['value_net'], cat(nobs_T, na), cln)[..., 0]
         nq = nq.min(0).values if cfg['q_agg'] == 'min' else nq.mean(0)
         tq = b['rewards'] + cfg['discount'] * b['masks'] * nq
-    q = mlp(gp['modules_critic']['value_net'], cat(obs, act), cln)[..., 0]
+    q = mlp(gp['modules_critic']['value_net'], cat(g_fC, act), cln)[..., 0]
     cl = ((q - tq) ** 2).mean()
     info.update({'critic/critic_loss': cl, 'critic/q_mean': q.mean(), 'critic/q_max': q.max(), 'critic/q_min': q.min()})
     x0, t = nz['x0'], nz['t']
-    pred = mlp(gp['modules_actor_bc_flow']['mlp'], cat(obs, (1 - t) * x0 + t * act, t), aln)
+    pred = mlp(gp['modules_actor_bc_flow']['mlp'], cat(g_fF, (1 - t) * x0 + t * act, t), aln)
     bc = ((pred - (act - x0)) ** 2).mean()
     with torch.no_grad():
         a = nz['z']
         n = cfg['flow_steps']
         for i in range(n):
-            tt = torch.full((obs.shape[0], 1), i / n, dtype=obs.dtype)
-            a = a + mlp(sp['modules_actor_bc_flow']['mlp'], cat(obs, a, tt), aln) / n
+            tt = torch.full((act.shape[0], 1), i / n, dtype=act.dtype)
+            a = a + mlp(sp['modules_actor_bc_flow']['mlp'], cat(s_fF, a, tt), aln) / n
         tgt = a.clamp(-1, 1)
-    api = mlp(gp['modules_actor_onestep_flow']['mlp'], cat(obs, nz['z']), aln)
+    api = mlp(gp['modules_actor_onestep_flow']['mlp'], cat(g_fO, nz['z']), aln)
     dl = ((api - tgt) ** 2).mean()
-    qm = mlp(sp['modules_critic']['value_net'], cat(obs, api.clamp(-1, 1)), cln)[..., 0].mean(0)
+    qm = mlp(sp['modules_critic']['value_net'], cat(s_fC, api.clamp(-1, 1)), cln)[..., 0].mean(0)
     ql = -qm.mean()
     if cfg['normalize_q_loss']:
         ql = ql * (1 / qm.abs().mean()).detach()
     al = bc + cfg['alpha'] * dl + ql
     with torch.no_grad():
-        ma = mlp(sp['modules_actor_onestep_flow']['mlp'], cat(obs, nz['z_metric']), aln).clamp(-1, 1)
+        ma = mlp(sp['modules_actor_onestep_flow']['mlp'], cat(s_fO, nz['z_metric']), aln).clamp(-1, 1)
         mse = ((ma - act) ** 2).mean()
     info.update({'actor/actor_loss': al, 'actor/bc_flow_loss': bc, 'actor/distill_loss': dl, 'actor/q_loss': ql,
                  'actor/q': qm.mean(), 'actor/mse': mse})
@@ -108,7 +138,7 @@ class TorchCpuAgent:
 
     def update(self, batch, noise):
         cfg = self.cfg
-        b = {k: torch.as_tensor(v, dtype=self.dtype) for k, v in batch.items()}
+        b = {k: (torch.as_tensor(v) if np.asarray(v).dtype == np.uint8 else torch.as_tensor(v, dtype=self.dtype)) for k, v in batch.items()}
         nz = {k: torch.as_tensor(v, dtype=self.dtype) for k, v in noise.items()}
         gp_flat = [t.detach().requires_grad_(True) for t in self.p]
         loss, info = total_loss(self._tree(gp_flat), self._tree(self.p), cfg, b, nz)
@@ -125,7 +155,7 @@ class TorchCpuAgent:
         with torch.no_grad():
             for i, (pth, p, g) in enumerate(zip(self.paths, self.p, grads)):
                 if pth[0] == 'modules_target_critic':
-                    src = self.p[self.paths.index(('modules_critic',) + pth[1:])]
+                    src = self.p[self.paths.index(('modules_critic',) + pth[1:])]  # incl. the encoder (deepcopy of the critic def)
                     new_p.append(src * tau + p * (1 - tau))                         # pre-step critic (fql.py:113-120)
                     continue
                 self.m[i] = 0.9 * self.m[i] + (1 - 0.9) * g

@@ -333,3 +333,24 @@ def test_pixel_oracle_finite_differences_and_state_oracle_unchanged():
             arr[idx] = old
             fd = (lp - lm) / (2 * eps)
             assert abs(fd - gl[path][idx]) <= 2e-6 * max(1.0, abs(fd)) + 1e-8, (path, idx, fd, gl[path][idx])
+
+
+def test_torch_cpu_restatement_matches_pixel_oracle():
+    """The timed CPU baseline with encoders == the pixel oracle (one whole update, fp64, 16x16 images)."""
+    from oracle import fql_pixel_oracle as PO
+    from oracle.fql_torch_cpu import TorchCpuAgent
+    cfg = small_cfg(alpha=10.0, encoder='impala_small', q_agg='min')
+    B, A = 4, 3
+    params = PO.init_params(0, 6, A, cfg, dtype=np.float64, hw=16, jitter=0.1, target_equals_critic=False)
+    state = O.init_state(params, warm=True)
+    batch = PO.make_pixel_batch(1, B, A, hw=16, ch=6, dtype=np.float64)
+    noise = O.make_noise(2, B, A, np.float64)
+    new_state, info, grads = PO.update(copy.deepcopy(state), cfg, batch, noise)
+    ta = TorchCpuAgent(state['params'], cfg, state['mu'], state['nu'], state['count'], dtype=torch.float64)
+    tinfo, tgrads = ta.update(batch, noise)
+    for k in O.INFO_KEYS:
+        np.testing.assert_allclose(tinfo[k], float(info[k]), rtol=1e-8, atol=1e-11, err_msg=k)
+    for (path, r), (_, g) in zip(O.tree_leaves(grads), O.tree_leaves(tgrads)):
+        np.testing.assert_allclose(g, r, rtol=1e-7, atol=1e-11, err_msg=str(path))
+    for (path, r), (_, g) in zip(O.tree_leaves(new_state['params']), O.tree_leaves(ta.tree('p'))):
+        np.testing.assert_allclose(g, r, rtol=1e-8, atol=1e-12, err_msg=str(path))
