@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(128) conv3x3_kernel(const float* __restrict__ 
                                                       const float* __restrict__ skip, const float* __restrict__ mask_src,
                                                       float* __restrict__ out, int B, int H, int W, int CIN, int relu_in, int flip,
                                                       int accumulate) {
+  // each thread computes PX horizontally adjacent output pixels x all COUT channels: every weight fetched from smem feeds PX FMAs
+  constexpr int PX = 4;
   extern __shared__ float ws[];  // [9][CIN][COUT]
   for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) {
     const int co = i % COUT, ci = (i / COUT) % CIN, tap = i / (COUT * CIN);
@@ -26,43 +28,65 @@ __global__ void __launch_bounds__(128) conv3x3_kernel(const float* __restrict__ 
     ws[i] = flip ? Wg[((8 - tap) * COUT + co) * CIN + ci] : Wg[i];
   }
   __syncthreads();
-  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (int64_t)B * H * W) return;
-  const int x = (int)(pix % W), y = (int)((pix / W) % H);
-  const int64_t b = pix / ((int64_t)W * H);
-  float acc[COUT];
+  const int WQ = (W + PX - 1) / PX;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (int64_t)B * H * WQ) return;
+  const int x0 = (int)(q % WQ) * PX, y = (int)((q / WQ) % H);
+  const int64_t b = q / ((int64_t)WQ * H);
+  float acc[PX][COUT];
 #pragma unroll
-  for (int co = 0; co < COUT; co++) acc[co] = bias ? bias[co] : 0.f;
+  for (int p = 0; p < PX; p++)
+#pragma unroll
+    for (int co = 0; co < COUT; co++) acc[p][co] = bias ? bias[co] : 0.f;
   for (int ky = 0; ky < 3; ky++) {
     const int iy = y + ky - 1;
     if (iy < 0 || iy >= H) continue;
-    for (int kx = 0; kx < 3; kx++) {
-      const int ix = x + kx - 1;
-      if (ix < 0 || ix >= W) continue;
-      const int64_t ioff = ((b * H + iy) * W + ix) * CIN;
-      const float* wt = ws + (ky * 3 + kx) * CIN * COUT;
-      for (int ci = 0; ci < CIN; ci++) {
-        float v = in_u8 ? (float)in_u8[ioff + ci] / 255.0f : in_f[ioff + ci];
-        if (relu_in) v = fmaxf(v, 0.f);
-        const float4* w4 = reinterpret_cast<const float4*>(wt + ci * COUT);
+    const int64_t rowoff = (b * H + iy) * W;
+    for (int ci = 0; ci < CIN; ci++) {
+      // the PX+2 input values of this row / channel that the PX outputs touch
+      float v[PX + 2];
+#pragma unroll
+      for (int j = 0; j < PX + 2; j++) {
+        const int ix = x0 + j - 1;
+        float t = 0.f;
+        if (ix >= 0 && ix < W) {
+          const int64_t o = (rowoff + ix) * CIN + ci;
+          t = in_u8 ? (float)in_u8[o] / 255.0f : in_f[o];
+          if (relu_in) t = fmaxf(t, 0.f);
+        }
+        v[j] = t;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const float4* w4 = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * CIN + ci) * COUT);
 #pragma unroll
         for (int c4 = 0; c4 < COUT / 4; c4++) {
           const float4 w = w4[c4];
-          acc[c4 * 4 + 0] = fmaf(v, w.x, acc[c4 * 4 + 0]);
-          acc[c4 * 4 + 1] = fmaf(v, w.y, acc[c4 * 4 + 1]);
-          acc[c4 * 4 + 2] = fmaf(v, w.z, acc[c4 * 4 + 2]);
-          acc[c4 * 4 + 3] = fmaf(v, w.w, acc[c4 * 4 + 3]);
+#pragma unroll
+          for (int p = 0; p < PX; p++) {
+            const float a = v[p + kx];
+            acc[p][c4 * 4 + 0] = fmaf(a, w.x, acc[p][c4 * 4 + 0]);
+            acc[p][c4 * 4 + 1] = fmaf(a, w.y, acc[p][c4 * 4 + 1]);
+            acc[p][c4 * 4 + 2] = fmaf(a, w.z, acc[p][c4 * 4 + 2]);
+            acc[p][c4 * 4 + 3] = fmaf(a, w.w, acc[p][c4 * 4 + 3]);
+          }
         }
       }
     }
   }
-  float* o = out + pix * COUT;
 #pragma unroll
-  for (int co = 0; co < COUT; co++) {
-    float v = acc[co];
-    if (skip) v += skip[pix * COUT + co];
-    if (mask_src) v = mask_src[pix * COUT + co] > 0.f ? v : 0.f;
-    o[co] = accumulate ? o[co] + v : v;
+  for (int p = 0; p < PX; p++) {
+    const int x = x0 + p;
+    if (x >= W) break;
+    const int64_t pix = (b * H + y) * W + x;
+    float* o = out + pix * COUT;
+#pragma unroll
+    for (int co = 0; co < COUT; co++) {
+      float t = acc[p][co];
+      if (skip) t += skip[pix * COUT + co];
+      if (mask_src) t = mask_src[pix * COUT + co] > 0.f ? t : 0.f;
+      o[co] = accumulate ? o[co] + t : t;
+    }
   }
 }
 
@@ -96,11 +120,11 @@ __global__ void __launch_bounds__(128) conv3x3_dgrad_generic_kernel(const float*
 // Weight + bias gradient: one CTA per image, partial sums [B][9*CIN*COUT + COUT]; rows of the image staged in smem.
 __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const float* __restrict__ in_f, const uint8_t* __restrict__ in_u8,
                                                             const float* __restrict__ dout, float* __restrict__ partial, int H, int W,
-                                                            int CIN, int COUT, int relu_in) {
+                                                            int CIN, int COUT, int relu_in, int rows_per_cta) {
   extern __shared__ float sm[];
   float* s_in = sm;                              // [3][W+2][CIN]
   float* s_do = sm + 3 * (W + 2) * CIN;          // [W][COUT]
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, y_begin = blockIdx.y * rows_per_cta, y_end = min(H, y_begin + rows_per_cta);
   const int nout = 9 * CIN * COUT;
   constexpr int MAXO = 36;                       // ceil(9*32*32 / 256)
   // a row's 64-term dot product runs in fp32; rows are accumulated in double: these are sums of up to B*H*W signed terms with
@@ -109,7 +133,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const float* __restr
 #pragma unroll
   for (int k = 0; k < MAXO; k++) acc[k] = 0.0;
   double bacc = 0.0;
-  for (int y = 0; y < H; y++) {
+  for (int y = y_begin; y < y_end; y++) {
     __syncthreads();
     for (int i = threadIdx.x; i < 3 * (W + 2) * CIN; i += blockDim.x) {
       const int ci = i % CIN, xx = (i / CIN) % (W + 2), r = i / (CIN * (W + 2));
@@ -142,7 +166,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const float* __restr
       bacc += (double)r;
     }
   }
-  float* p = partial + (int64_t)b * (nout + COUT);
+  float* p = partial + ((int64_t)b * gridDim.y + blockIdx.y) * (nout + COUT);
 #pragma unroll
   for (int k = 0; k < MAXO; k++) {
     const int o = threadIdx.x + k * 256;
@@ -245,9 +269,9 @@ int launch1d(K kern, int64_t n, cudaStream_t st, Args... args) {
 
 int conv_fwd(const float* in_f, const uint8_t* in_u8, const float* Wg, const float* bias, const float* skip, const float* mask,
              float* out, int B, int H, int W, int CIN, int COUT, int relu_in, int flip, int accumulate, cudaStream_t st) {
-  const int64_t npix = (int64_t)B * H * W;
+  const int64_t nq = (int64_t)B * H * ((W + 3) / 4);
   const size_t smem = (size_t)9 * CIN * COUT * sizeof(float);
-  const unsigned grid = (unsigned)((npix + 127) / 128);
+  const unsigned grid = (unsigned)((nq + 127) / 128);
   if (COUT == 16) conv3x3_kernel<16><<<grid, 128, smem, st>>>(in_f, in_u8, Wg, bias, skip, mask, out, B, H, W, CIN, relu_in, flip, accumulate);
   else if (COUT == 32) conv3x3_kernel<32><<<grid, 128, smem, st>>>(in_f, in_u8, Wg, bias, skip, mask, out, B, H, W, CIN, relu_in, flip, accumulate);
   else FQL_REQUIRE(false, "conv3x3: unsupported channel count %d", COUT);
@@ -259,10 +283,13 @@ int conv_wgrad(const float* in_f, const uint8_t* in_u8, const float* dout, float
                int COUT, int relu_in, cudaStream_t st) {
   FQL_REQUIRE(9 * CIN * COUT <= 36 * 256, "conv3x3 wgrad: too many weights");
   const size_t smem = ((size_t)3 * (W + 2) * CIN + (size_t)W * COUT) * sizeof(float);
-  conv3x3_wgrad_kernel<<<B, 256, smem, st>>>(in_f, in_u8, dout, partial, H, W, CIN, COUT, relu_in);
+  // one CTA per (image, chunk of rows): enough CTAs to fill the GPU at small batch, partials reduced deterministically afterwards
+  const int chunks = (B >= 512 || H < 16) ? 1 : (H >= 32 ? 4 : 2);
+  const int rows = (H + chunks - 1) / chunks;
+  conv3x3_wgrad_kernel<<<dim3(B, chunks), 256, smem, st>>>(in_f, in_u8, dout, partial, H, W, CIN, COUT, relu_in, rows);
   FQL_CHECK_LAUNCH();
   const int n_w = 9 * CIN * COUT;
-  reduce_partials_kernel<<<(n_w + COUT + 255) / 256, 256, 0, st>>>(partial, B, n_w, COUT, gw, gb);
+  reduce_partials_kernel<<<(n_w + COUT + 255) / 256, 256, 0, st>>>(partial, B * chunks, n_w, COUT, gw, gb);
   FQL_CHECK_LAUNCH();
   return 0;
 }
@@ -312,7 +339,7 @@ size_t enc_carve(const FqlDims* d, int64_t B, void* base, EncBuf* e, bool for_ba
     e->db = take(big2);
     e->dc = take(big2);
     int wmax = 9 * 32 * 32 + 32;
-    e->partial = take(B * (int64_t)wmax);
+    e->partial = take(4 * B * (int64_t)wmax);
   }
   return off + 256;
 }
@@ -394,11 +421,8 @@ int enc_backward(const FqlDims* d, const EncView& v, const float* params, float*
     // conv0: input x[i-1] (or the pixels), output gradient dc0
     FQL_TRY(conv_wgrad(i ? e.x[i - 1] : nullptr, i ? nullptr : obs, e.scratch, e.partial, grads + v.off_cw[i][0], grads + v.off_cb[i][0], (int)B, H, W, C,
                        f, 0, st));
-    if (i > 0) {  // gradient w.r.t. the previous stack's output (no relu between stacks)
-      const size_t smem = (size_t)9 * C * f * sizeof(float);
-      const int64_t npix = B * H * W;
-      conv3x3_dgrad_generic_kernel<<<(unsigned)((npix + 127) / 128), 128, smem, st>>>(e.scratch, params + v.off_cw[i][0], other, (int)B, H, W, C, f);
-      FQL_CHECK_LAUNCH();
+    if (i > 0) {  // gradient w.r.t. the previous stack's output (no relu between stacks): C = 16 or 32 output channels
+      FQL_TRY(conv_fwd(e.scratch, nullptr, params + v.off_cw[i][0], nullptr, nullptr, nullptr, other, (int)B, H, W, f, C, 0, 1, 0, st));
       float* t = dx; dx = other; other = t;
     }
     (void)n;
