@@ -222,10 +222,19 @@ def main():
         # ---------------- device-resident leg: `value`
         bufs = agent.stage(batches[0])
         clocks = ClockSampler(local_rank) if rank == 0 else None
-        t_load = time.perf_counter()
         for _ in range(W):
             agent.step(bufs)
-        while time.perf_counter() - t_load < 0.5:  # keep the GPU under the same load until nvidia-smi is sampling
+        # keep the GPU under the same load until nvidia-smi is sampling (~0.5 s): the step count must be IDENTICAL on every rank
+        # (each step contains collectives), so it is derived from a max-reduced timing, never from a per-rank clock
+        torch.cuda.synchronize()
+        t_probe = time.perf_counter()
+        for _ in range(5):
+            agent.step(bufs)
+        torch.cuda.synchronize()
+        per = torch.tensor([(time.perf_counter() - t_probe) / 5], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(per, op=dist.ReduceOp.MAX)
+        for _ in range(int(min(3000, max(0, 0.5 / max(float(per.item()), 1e-6))))):
             agent.step(bufs)
         barrier()
         l0 = agent.launch_count()

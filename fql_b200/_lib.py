@@ -67,6 +67,10 @@ _SIGS = {
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'fql_step_apply': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlHparams), C.POINTER(FqlState), C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'fql_step_apply_gathered': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlHparams), C.POINTER(FqlState), C.c_void_p, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'fql_set_early_grads_event': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'fql_early_grads_floats': (C.c_int64, [C.POINTER(FqlDims)]),
     'fql_total_loss': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlHparams), C.POINTER(FqlBatch), C.POINTER(FqlState),
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'fql_sample_actions': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -13,6 +13,7 @@ There is no CPU path: everything below calls CUDA through fql_b200._lib.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -360,12 +361,43 @@ class FQLAgent:
                 _lib.check(self._lib.fql_update_step(*a, C.byref(bufs['fb']), C.byref(bufs['st']), _ptr(bufs['info']),
                                                      _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_update_step')
             else:
-                from . import dist as fdist
-                self.grads_phase(bufs)
-                t0, _ = self._net_range('target_critic')
-                fdist.allreduce_step(self._grads[:, :t0], bufs['raw'], group=self.pg)
-                self.apply_phase(bufs)
+                self._dp_step(bufs)
             return self._info_out(bufs['info'])
+
+    def _dp_step(self, bufs):
+        """Data-parallel step: gradients -> all-reduce (the bc-flow + critic prefix of the arena starts on a side stream as soon as
+        the library's early event fires, while the one-step actor's backward is still running) -> all-gather of the 64-byte metric
+        accumulators -> identical Adam/Polyak step on every rank."""
+        import torch.distributed as dist
+        from . import dist as fdist
+        main = torch.cuda.current_stream(self.device)
+        if self._dp_side is None:
+            self._dp_side = torch.cuda.Stream(device=self.device)
+            self._dp_early = torch.cuda.Event()
+            self._dp_early.record(main)                 # materialise the cudaEvent_t
+            self._n_early = int(self._lib.fql_early_grads_floats(C.byref(bufs['d'])))
+            if self._dp_overlap:
+                _lib.check(self._lib.fql_set_early_grads_event(self._ctx, C.c_void_p(self._dp_early.cuda_event)), 'fql_set_early_grads_event')
+        self.grads_phase(bufs)
+        t0, _ = self._net_range('target_critic')
+        if self._dp_overlap:
+            with torch.cuda.stream(self._dp_side):
+                self._dp_side.wait_event(self._dp_early)
+                w1 = dist.all_reduce(self._grads[:, :self._n_early], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            w2 = dist.all_reduce(self._grads[:, self._n_early:t0], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            raw_all = fdist.gather_raw(bufs['raw'], group=self.pg)
+            w1.wait()
+            w2.wait()
+        else:
+            dist.all_reduce(self._grads[:, :t0], op=dist.ReduceOp.SUM, group=self.pg)
+            raw_all = fdist.gather_raw(bufs['raw'], group=self.pg)
+        _lib.check(self._lib.fql_step_apply_gathered(self._ctx, C.byref(bufs['d']), C.byref(self._hp), C.byref(bufs['st']), _ptr(raw_all),
+                                                     self.world, _ptr(bufs['info']), _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()),
+                   'fql_step_apply_gathered')
+        self._raw_all = raw_all                         # keep alive until the stream has consumed it
+
+    _dp_side = None
+    _dp_overlap = os.environ.get('FQL_DP_OVERLAP', '1') != '0'
 
     def grads_phase(self, bufs):
         """Data-parallel half 1 (fql_step_grads): this rank's gradient contribution (already divided by the global batch) into

@@ -194,11 +194,19 @@ __global__ void actor_grad_kernel(StepShape sh, FqlHparams hp, WsPtrs w, float* 
 }
 
 // info[13] from the (all-reduced) raw accumulators + gradient statistics.
-__global__ void finalize_info_kernel(StepShape sh, FqlHparams hp, const float* raw, const float* gstats, float* info,
+__global__ void finalize_info_kernel(StepShape sh, FqlHparams hp, const float* raw, int ranks, const float* gstats, float* info,
                                      int with_grad_stats) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= sh.S) return;
-  const float* rw = raw + s * FQL_NUM_RAW;
+  // data parallel: `raw` is the all-gather of every rank's accumulators [ranks][S][FQL_NUM_RAW]: sums add, max / -min take the max
+  float rw[FQL_NUM_RAW];
+  for (int i = 0; i < FQL_NUM_RAW; i++) rw[i] = raw[s * FQL_NUM_RAW + i];
+  for (int r = 1; r < ranks; r++) {
+    const float* o = raw + ((int64_t)r * sh.S + s) * FQL_NUM_RAW;
+    for (int i = 0; i < 9; i++) rw[i] += o[i];
+    rw[RAW_Q_MAX] = fmaxf(rw[RAW_Q_MAX], o[RAW_Q_MAX]);
+    rw[RAW_Q_NEGMIN] = fmaxf(rw[RAW_Q_NEGMIN], o[RAW_Q_NEGMIN]);
+  }
   float* o = info + s * FQL_NUM_INFO;
   const float gb = (float)sh.GB, A = (float)sh.A;
   const float critic_loss = rw[RAW_CRITIC_SQ] / (2.0f * gb);
@@ -288,9 +296,9 @@ int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w
   FQL_CHECK_LAUNCH();
   return 0;
 }
-int launch_finalize_info(const StepShape& sh, const FqlHparams& hp, const float* raw, const float* gstats, float* info,
+int launch_finalize_info(const StepShape& sh, const FqlHparams& hp, const float* raw, int ranks, const float* gstats, float* info,
                          int with_grad_stats, cudaStream_t st) {
-  finalize_info_kernel<<<(sh.S + 63) / 64, 64, 0, st>>>(sh, hp, raw, gstats, info, with_grad_stats);
+  finalize_info_kernel<<<(sh.S + 63) / 64, 64, 0, st>>>(sh, hp, raw, ranks, gstats, info, with_grad_stats);
   FQL_CHECK_LAUNCH();
   return 0;
 }

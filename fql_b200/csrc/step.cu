@@ -63,7 +63,12 @@ int fql_build_layout(const FqlDims* d, Layout* L) {
     off += round_up64(n, FQL_LEAF_PAD);
     return o;
   };
-  for (int n = 0; n < FQL_NUM_NETS; n++) {
+  // arena order: bc_flow | critic | onestep | target.  The first two networks' gradients are complete long before the one-step
+  // actor's (which waits for the Euler target), so a data-parallel run all-reduces [0, onestep.begin) early; the target critic
+  // (zero gradients) stays last.
+  static const int kOrder[FQL_NUM_NETS] = {FQL_NET_ACTOR_BC_FLOW, FQL_NET_CRITIC, FQL_NET_ACTOR_ONESTEP_FLOW, FQL_NET_TARGET_CRITIC};
+  for (int oi = 0; oi < FQL_NUM_NETS; oi++) {
+    const int n = kOrder[oi];
     NetView& v = L->net[n];
     v.n_layers = NL;
     v.hidden = H;
@@ -410,10 +415,30 @@ struct FqlContext {
   int use_graph = 1;
   int use_euler_cluster = 1;
   int use_critic_chain = 0;
+  cudaEvent_t early_event = nullptr;  // optional: recorded when the bc-flow and critic gradients of fql_step_grads are complete
   long long launches = 0;  // kernels enqueued through this context
 };
 
 extern "C" long long fql_launch_count(FqlContext* c) { return c ? c->launches : -1; }
+extern "C" int fql_set_early_grads_event(FqlContext* c, void* event) {
+  FQL_REQUIRE(c != nullptr, "context is NULL");
+  c->early_event = reinterpret_cast<cudaEvent_t>(event);
+  for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  c->graphs.clear();  // the event is baked into captured graphs
+  return 0;
+}
+extern "C" int64_t fql_early_grads_floats(const FqlDims* d) {
+  Layout L;
+  if (fql_build_layout(d, &L)) return -1;
+  return L.net[FQL_NET_ACTOR_ONESTEP_FLOW].begin;
+}
+static int record_early(FqlContext* ctx, cudaStream_t st) {
+  if (!ctx->early_event) return 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  FQL_CHECK_CUDA(cudaStreamIsCapturing(st, &cap));
+  FQL_CHECK_CUDA(cudaEventRecordWithFlags(ctx->early_event, st, cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+  return 0;
+}
 
 extern "C" int fql_context_create(FqlContext** out) {
   FQL_REQUIRE(out != nullptr, "out is NULL");
@@ -466,6 +491,7 @@ struct StepCall {
   void* ws;
   size_t ws_bytes;
   int do_grads, do_backward, do_apply;
+  int raw_ranks;  // fql_step_apply: `raw` holds the all-gathered accumulators of this many ranks [ranks][S][FQL_NUM_RAW]
 };
 
 int check_common(const FqlDims* d, const void* ws, size_t ws_bytes, Layout* L, WsPtrs* w) {
@@ -618,6 +644,8 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     FQL_TRY(tc_critic_backward(t, S2, ctx->s5, &ctx->ev[28]));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], ctx->s5));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[36], 0));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[16], 0));  // bc-flow weight gradients (side stream s3)
+    FQL_TRY(record_early(ctx, S2));
     // critic input gradient with stored params (fql.py:70) on S0
     TcCritic q = cr;
     q.grads = nullptr; q.p = 2; q.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)2 * S * B * kO;
@@ -721,6 +749,7 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
       if (pix) bC.dX0 = w.dX0C;
       FQL_TRY(mlp_backward(bC, S2));
       if (pix) FQL_TRY(encoder_grads(c, L, w, FQL_NET_CRITIC, w.dX0C, 2, sh.F + sh.A, w.dfeat[0], 3, S2));
+      FQL_TRY(record_early(ctx, S2));
     }
     FQL_CHECK_CUDA(cudaEventRecord(ev_s2, S2));
 
@@ -762,7 +791,7 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     FQL_TRY(launch_grad_stats_final(L, S, w.partials, w.gstats, c.st->count, S0));
     if (tcm) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[51], 0));
   }
-  if (c.info) FQL_TRY(launch_finalize_info(sh, hp, raw, w.gstats, c.info, c.do_apply, S0));
+  if (c.info) FQL_TRY(launch_finalize_info(sh, hp, raw, c.raw_ranks > 1 ? c.raw_ranks : 1, w.gstats, c.info, c.do_apply, S0));
   return 0;
 }
 
@@ -784,7 +813,7 @@ int run_step_on(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
   if (c.b) push(c.b, sizeof(FqlBatch));
   push(c.st, sizeof(FqlState));
   push(&c.raw, sizeof(void*)); push(&c.info, sizeof(void*)); push(&c.ws, sizeof(void*)); push(&c.ws_bytes, sizeof(size_t));
-  int flags[3] = {c.do_grads, c.do_backward, c.do_apply};
+  int flags[4] = {c.do_grads, c.do_backward, c.do_apply, c.raw_ranks};
   push(flags, sizeof(flags));
   push(&S0, sizeof(S0));
   GraphEntry* seen = nullptr;
@@ -862,28 +891,35 @@ int run_step(FqlContext* ctx, const StepCall& c, void* stream) {
 extern "C" int fql_update_step(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlBatch* batch,
                                const FqlState* st, float* info, void* workspace, size_t ws_bytes, void* stream) {
   FQL_REQUIRE(batch != nullptr, "batch is NULL");
-  StepCall c{d, hp, batch, st, nullptr, info, workspace, ws_bytes, 1, 1, 1};
+  StepCall c{d, hp, batch, st, nullptr, info, workspace, ws_bytes, 1, 1, 1, 1};
   return run_step(ctx, c, stream);
 }
 
 extern "C" int fql_step_grads(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlBatch* batch,
                               const FqlState* st, float* raw, void* workspace, size_t ws_bytes, void* stream) {
   FQL_REQUIRE(batch != nullptr && raw != nullptr, "batch/raw is NULL");
-  StepCall c{d, hp, batch, st, raw, nullptr, workspace, ws_bytes, 1, 1, 0};
+  StepCall c{d, hp, batch, st, raw, nullptr, workspace, ws_bytes, 1, 1, 0, 1};
   return run_step(ctx, c, stream);
 }
 
 extern "C" int fql_step_apply(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlState* st, const float* raw,
                               float* info, void* workspace, size_t ws_bytes, void* stream) {
   FQL_REQUIRE(raw != nullptr, "raw is NULL");
-  StepCall c{d, hp, nullptr, st, const_cast<float*>(raw), info, workspace, ws_bytes, 0, 0, 1};
+  StepCall c{d, hp, nullptr, st, const_cast<float*>(raw), info, workspace, ws_bytes, 0, 0, 1, 1};
+  return run_step(ctx, c, stream);
+}
+
+extern "C" int fql_step_apply_gathered(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlState* st, const float* raw_all,
+                                       int32_t ranks, float* info, void* workspace, size_t ws_bytes, void* stream) {
+  FQL_REQUIRE(raw_all != nullptr && ranks >= 1, "raw_all is NULL / ranks < 1");
+  StepCall c{d, hp, nullptr, st, const_cast<float*>(raw_all), info, workspace, ws_bytes, 0, 0, 1, ranks};
   return run_step(ctx, c, stream);
 }
 
 extern "C" int fql_total_loss(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlBatch* batch,
                               const FqlState* st, float* info, void* workspace, size_t ws_bytes, void* stream) {
   FQL_REQUIRE(batch != nullptr && info != nullptr, "batch/info is NULL");
-  StepCall c{d, hp, batch, st, nullptr, info, workspace, ws_bytes, 1, 0, 0};
+  StepCall c{d, hp, batch, st, nullptr, info, workspace, ws_bytes, 1, 0, 0, 1};
   return run_step(ctx, c, stream);
 }
 
@@ -1077,7 +1113,9 @@ extern "C" int fql_layout(const FqlDims* d, FqlLeaf* leaves, int32_t cap, int32_
     if (leaves && n < cap) leaves[n] = FqlLeaf{net, layer, kind, ens, rows, cols, off};
     n++;
   };
-  for (int t = 0; t < FQL_NUM_NETS; t++) {
+  static const int kOrder[FQL_NUM_NETS] = {FQL_NET_ACTOR_BC_FLOW, FQL_NET_CRITIC, FQL_NET_ACTOR_ONESTEP_FLOW, FQL_NET_TARGET_CRITIC};
+  for (int oi = 0; oi < FQL_NUM_NETS; oi++) {  // arena order
+    const int t = kOrder[oi];
     const NetView& v = L.net[t];
     for (int l = 0; l < v.n_layers; l++) {
       put(t, l, FQL_LEAF_KERNEL, v.ens, v.k_of(l), v.n_of(l), v.off_w[l]);

@@ -65,7 +65,7 @@ int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch
 int launch_bc_post(const StepShape& sh, const WsPtrs& w, float* raw, cudaStream_t st);
 int launch_euler_update(const StepShape& sh, const WsPtrs& w, int step, cudaStream_t st);
 int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w, float* raw, cudaStream_t st);
-int launch_finalize_info(const StepShape& sh, const FqlHparams& hp, const float* raw, const float* gstats, float* info,
+int launch_finalize_info(const StepShape& sh, const FqlHparams& hp, const float* raw, int ranks, const float* gstats, float* info,
                          int with_grad_stats, cudaStream_t st);
 int launch_clip(const float* in, float* out, int64_t n, cudaStream_t st);
 int launch_concat(const float* x0, int k0, const float* x1, int k1, float c2, int k2, float* out, int64_t rows, cudaStream_t st);

@@ -41,6 +41,16 @@ def allreduce_step(grads: torch.Tensor, raw: torch.Tensor, group=None) -> None:
     raw[..., RAW_MAX] = gathered[..., RAW_MAX].max(dim=0).values
 
 
+def gather_raw(raw: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather of the per-rank accumulators -> [world, S, 16]; the SUM / MAX reduction over ranks happens inside
+    fql_step_apply_gathered (one collective, no host-side reduction kernels)."""
+    world = dist.get_world_size(group)
+    flat = raw.contiguous().reshape(-1)
+    out = torch.empty(world * flat.numel(), dtype=raw.dtype, device=raw.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.reshape((world,) + tuple(raw.shape))
+
+
 def shard_seeds(num_seeds: int, rank: int, world: int) -> range:
     """Multi-seed runs (BASELINE config 4) shard by agent: no collective on the step."""
     if num_seeds % world:

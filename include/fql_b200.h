@@ -136,6 +136,15 @@ int fql_step_grads(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, cons
                    const FqlState* st, float* raw, void* workspace, size_t ws_bytes, void* stream);
 int fql_step_apply(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlState* st, const float* raw,
                    float* info, void* workspace, size_t ws_bytes, void* stream);
+/* Same as fql_step_apply on the ALL-GATHERED accumulators [ranks][S][FQL_NUM_RAW]: the SUM / MAX reduction over ranks happens in
+ * the info kernel (no extra collectives or host-side reductions). */
+int fql_step_apply_gathered(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlState* st, const float* raw_all,
+                            int32_t ranks, float* info, void* workspace, size_t ws_bytes, void* stream);
+/* Overlap hook for data parallelism: `event` (a cudaEvent_t, or NULL to disable) is recorded by fql_step_grads as soon as the
+ * gradients of the first fql_early_grads_floats() floats of the arena (bc-flow actor + critic) are final, i.e. while the one-step
+ * actor's backward is still running; the caller may start all-reducing that prefix on another stream behind the event. */
+int fql_set_early_grads_event(FqlContext* ctx, void* event);
+int64_t fql_early_grads_floats(const FqlDims* d);
 /* Forward-only total_loss(grad_params=None) (agents/fql.py:94-111 as called from main.py:284): 10 info floats
  * [0..9] and the scalar loss in info[FQL_NUM_INFO-3] slot order documented in fql_info_name. */
 int fql_total_loss(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlBatch* batch,
