@@ -34,7 +34,9 @@ constexpr int A_BLK = TILE_M * 128;   // 16 KB: [128][64] bf16
 constexpr int B_BLK = KB * 128;       //  8 KB: [64 k][64 n] bf16
 constexpr int MAX_A = 32;
 constexpr int NMMA = 4;                // MMA-issuer warps (k-step w of every K block -> warp w, own TMEM accumulator)
-constexpr int NTHREADS = 32 * (1 + NMMA + 4);
+constexpr int NEPI = 4;                // epilogue warps (4: one thread per row, both 32-column halves; 8 was measured slower:
+                                       // the 416-thread CTA caps registers at 128 and the epilogue spills)
+constexpr int NTHREADS = 32 * (1 + NMMA + NEPI);
 constexpr int EPI0 = 32 * (1 + NMMA);  // first epilogue thread
 
 struct EulerArgs {
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     mbar_init(full_b, 1);
     mbar_init(acc_full, NMMA);
     mbar_init(free_a, NC * NMMA);
-    mbar_init(a_ready, 4);
+    mbar_init(a_ready, NEPI);
     mbar_init(x_full, 1);
     fence_barrier_init();
   }
@@ -192,7 +194,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     if (lane == 0) {
       const int mw = warp - 1;
       const uint32_t idesc = make_idesc_bf16(TILE_M, 64, false, true);
-      const uint64_t a_t = make_smem_desc(0, 16, 1024) + (uint64_t)(mw * 2), b_t = make_smem_desc(0, B_BLK, 1024) + (uint64_t)(mw * 128);
+      const uint64_t a_t0 = make_smem_desc(0, 16, 1024), b_t0 = make_smem_desc(0, B_BLK, 1024);
+      const uint64_t a_t = a_t0 + (uint64_t)(mw * 2), b_t = b_t0 + (uint64_t)(mw * 128);
       const uint32_t sa0 = smem_u32(sA) >> 4, sx0 = smem_u32(sX) >> 4, sb0 = smem_u32(sB) >> 4;
       const uint32_t tacc = tmem_base + mw * 64;
       int n_a = 0;  // uses of the full_a barriers
@@ -209,15 +212,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
         mbar_wait(full_b, it & 1);
         tc_fence_after();
         const uint32_t a0d = (l == 0 ? sx0 : sa0);
-        for (int kb = 0; kb < kblocks; kb++) {
-          if (l >= 1) {
+        if (l >= 1) {
+          // hidden / last layers (K = H = 8 blocks): warp w takes K-blocks 2w and 2w+1 entirely -> two barrier waits per layer
+          for (int i = 0; i < 2; i++) {
+            const int kb = mw * 2 + i;
             mbar_wait(&full_a[kb], n_a & 1);
             tc_fence_after();
-            if (dbg && mw == 0 && it == DBG_IT && kb == 0) dbg[5] = gtime();
-            if (dbg && mw == 0 && it == DBG_IT && kb == kblocks - 1) dbg[6] = gtime();
+            if (dbg && mw == 0 && it == DBG_IT && i == 0) dbg[5] = gtime();
+            if (dbg && mw == NMMA - 1 && it == DBG_IT && i == 1) dbg[6] = gtime();
+            umma_bf16_x4(tacc, a_t0 + (uint64_t)(a0d + kb * (A_BLK >> 4)), b_t0 + (uint64_t)(sb0 + kb * (B_BLK >> 4)), 2, 128, idesc, i != 0);
           }
-          if (l != 0 || mw < (a.K0 - kb * KB + 15) / 16)
-            umma_bf16(tacc, a_t + (uint64_t)(a0d + kb * (A_BLK >> 4)), b_t + (uint64_t)(sb0 + kb * (B_BLK >> 4)), idesc, kb != 0);
+        } else {
+          // first layer (K0 <= 128): k-step w of every block -> warp w
+          for (int kb = 0; kb < kblocks; kb++)
+            if (mw < (a.K0 - kb * KB + 15) / 16)
+              umma_bf16(tacc, a_t + (uint64_t)(a0d + kb * (A_BLK >> 4)), b_t + (uint64_t)(sb0 + kb * (B_BLK >> 4)), idesc, kb != 0);
         }
         if (l >= 1) n_a++;
         umma_commit(acc_full);
@@ -227,17 +236,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
       }
     }
   } else {
-    // ================= epilogue: one thread per row, 64 columns =================
-    const int q = warp & 3;
+    // ================= epilogue: one thread per (row, 32-column half) =================
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int half0 = (warp - (1 + NMMA)) >> 2;      // first 32-column half this warp handles (stride NEPI/4)
     const int row = q * 32 + lane;
     const int grow = tile * TILE_M + row;
     const bool valid = grow < a.M;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_lane0 = tmem_base + ((uint32_t)(q * 32) << 16);
     const int et = threadIdx.x - EPI0;
     float act[MAX_A];
 #pragma unroll
     for (int c = 0; c < MAX_A; c++) act[c] = 0.f;
-    if (valid) {
+    if (valid && half0 == 0) {
 #pragma unroll
       for (int c = 0; c < MAX_A; c++)
         if (c < a.A) act[c] = a.a0[((int64_t)s * a.M + grow) * a.A + c];
@@ -251,66 +261,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
         const int N = last ? a.A : a.H;
         const int col = last ? et : (int)j * 64 + et;
         if (et < 64) sb[et] = (col < N) ? a.params[(int64_t)s * a.arena + a.off_b[l] + col] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI) : "memory");
       }
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
       if (dbg && et == 0 && it == DBG_IT - 1) dbg[0] = gtime();
       if (dbg && et == 0 && it == DBG_IT) dbg[7] = gtime();
-      // partial accumulators of the NMMA issuer warps are added one 32-column half at a time (a first layer with K0 < 64 only
-      // has ceil(K0/16) live accumulators)
+      // partial accumulators of the NMMA issuer warps, loads issued in pairs (a first layer with K0 < 64 has ceil(K0/16) of them)
       const int live = (l == 0 && a.K0 < KB) ? (a.K0 + 15) / 16 : NMMA;
-      uint32_t r0[32], r1[32];
-      tmem_ld32(t_lane, r0);
-      tmem_wait_ld();
-      for (int acc = 1; acc < live; acc++) {
-        uint32_t t[32];
-        tmem_ld32(t_lane + acc * 64, t);
+      const int buf = n_exch & 1;
+      if (!last) n_exch++;
+#pragma unroll 1
+      for (int half = half0; half < 2; half += NEPI / 4) {
+      const uint32_t t_lane = t_lane0 + half * 32;
+      uint32_t r0[32];
+      if (!last || half == 0) {
+        uint32_t t1[32];
+        tmem_ld32(t_lane, r0);
+        if (live > 1) tmem_ld32(t_lane + 64, t1);
         tmem_wait_ld();
+        if (live > 1) {
 #pragma unroll
-        for (int i = 0; i < 32; i++) r0[i] = __float_as_uint(__uint_as_float(r0[i]) + __uint_as_float(t[i]));
-      }
-      if (!last) {
-        tmem_ld32(t_lane + 32, r1);
-        tmem_wait_ld();
-        for (int acc = 1; acc < live; acc++) {
-          uint32_t t[32];
-          tmem_ld32(t_lane + acc * 64 + 32, t);
+          for (int i = 0; i < 32; i++) r0[i] = __float_as_uint(__uint_as_float(r0[i]) + __uint_as_float(t1[i]));
+        }
+        if (live > 2) {
+          uint32_t t2[32];
+          tmem_ld32(t_lane + 128, t1);
+          if (live > 3) tmem_ld32(t_lane + 192, t2);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; i++) r1[i] = __float_as_uint(__uint_as_float(r1[i]) + __uint_as_float(t[i]));
+          for (int i = 0; i < 32; i++) {
+            float v = __uint_as_float(r0[i]) + __uint_as_float(t1[i]);
+            if (live > 3) v += __uint_as_float(t2[i]);
+            r0[i] = __float_as_uint(v);
+          }
         }
       }
       if (!last) {
-        const int buf = n_exch & 1;
-        n_exch++;
-        uint4* dst = reinterpret_cast<uint4*>(a.hx + (int64_t)buf * a.hx_buf_elems + (int64_t)(hx_row + row) * a.H + j * 64);
+        uint4* dst = reinterpret_cast<uint4*>(a.hx + (int64_t)buf * a.hx_buf_elems + (int64_t)(hx_row + row) * a.H + j * 64 + half * 32);
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-          const uint32_t(&r)[32] = half ? r1 : r0;
+        for (int c = 0; c < 4; c++) {
+          float h[8];
 #pragma unroll
-          for (int c = 0; c < 4; c++) {
-            float h[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) h[i] = gelu_fast(__uint_as_float(r[c * 8 + i]) + sb[half * 32 + c * 8 + i]);
-            dst[half * 4 + c] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-          }
+          for (int i = 0; i < 8; i++) h[i] = gelu_fast(__uint_as_float(r0[c * 8 + i]) + sb[half * 32 + c * 8 + i]);
+          dst[c] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
         }
-        // publish: my slice is in the scratch -> (CTA barrier) -> one thread multicasts it into all 8 CTAs' sA[j]
-        tc_fence_before();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (dbg && et == 0 && it == DBG_IT - 1) dbg[2] = gtime();
-        if (et == 0) {
-          asm volatile("fence.proxy.async.global;" ::: "memory");  // this CTA's st.global (ordered by the bar.sync) -> its own TMA read
-          mbar_wait_cluster(free_a, it & 1);  // every CTA finished reading sA for this layer
-          if (dbg && it == DBG_IT - 1) dbg[3] = gtime();
-          asm volatile(
-              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-              ::"r"(smem_u32(sA + j * A_BLK)), "l"(reinterpret_cast<uint64_t>(&mapHx)), "r"(smem_u32(&full_a[j])), "r"((int)j * KB),
-              "r"(buf * (a.S * a.tiles * TILE_M) + hx_row), "h"((uint16_t)0xFF)
-              : "memory");
-        }
-      } else {
+      } else if (half == 0) {
         // Euler step on this CTA's resident copy of the first-layer operand (every CTA computes the same last layer)
         const float inv = (float)a.n_steps;
 #pragma unroll
@@ -331,6 +327,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
           for (int c = 0; c < MAX_A; c++)
             if (c < a.A) a.target[((int64_t)s * a.M + grow) * a.A + c] = fminf(fmaxf(act[c], -1.0f), 1.0f);
         }
+      }
+      }  // halves
+      if (!last) {
+        if (dbg && et == 0 && it == DBG_IT - 1) dbg[1] = gtime();
+        // publish: my slice is in the scratch -> (CTA barrier) -> one thread multicasts it into all 8 CTAs' sA[j]
+        tc_fence_before();
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * NEPI) : "memory");
+        if (dbg && et == 0 && it == DBG_IT - 1) dbg[2] = gtime();
+        if (et == 0) {
+          asm volatile("fence.proxy.async.global;" ::: "memory");  // this CTA's st.global (ordered by the bar.sync) -> its own TMA read
+          mbar_wait_cluster(free_a, it & 1);  // every CTA finished reading sA for this layer
+          if (dbg && it == DBG_IT - 1) dbg[3] = gtime();
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+              ::"r"(smem_u32(sA + j * A_BLK)), "l"(reinterpret_cast<uint64_t>(&mapHx)), "r"(smem_u32(&full_a[j])), "r"((int)j * KB),
+              "r"(buf * (a.S * a.tiles * TILE_M) + hx_row), "h"((uint16_t)0xFF)
+              : "memory");
+        }
+      } else {
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
