@@ -129,7 +129,7 @@ struct ColSumArgs {
   int M, N, ld;
   int P, S, E;
 };
-int launch_colsum(const ColSumArgs& a, cudaStream_t st);
+int launch_colsum(const ColSumArgs& a, cudaStream_t st, float* scratch = nullptr, size_t scratch_floats = 0);
 
 // ---------------------------------------------------------------------------------------------------------
 // device math shared by every kernel (must match oracle/fql_oracle.py gelu_tanh / gelu_tanh_grad)

@@ -213,8 +213,9 @@ __global__ void __launch_bounds__(256) act_ln_bwd_kernel(ActLnBwdArgs a) {
 
 // out[c] = sum_r X[r,c] * (Z ? xhat(Z)[r,c] : 1); block = 32 columns x 32 row lanes, 4 independent accumulators per
 // thread (the loop is latency-bound otherwise); deterministic tree
-__global__ void __launch_bounds__(1024) colsum_kernel(ColSumArgs a) {
+__global__ void __launch_bounds__(1024) colsum_kernel(ColSumArgs a, int rows_per_chunk, float* __restrict__ partial) {
   const int g = blockIdx.y;
+  const int r_begin = blockIdx.z * rows_per_chunk, r_end = min(a.M, r_begin + rows_per_chunk);
   const int e = g % a.E, s = (g / a.E) % a.S, p = g / (a.E * a.S);
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -225,19 +226,19 @@ __global__ void __launch_bounds__(1024) colsum_kernel(ColSumArgs a) {
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < a.N) {
     if (!Z) {
-      for (int r0 = ry; r0 < a.M; r0 += 128) {
+      for (int r0 = r_begin + ry; r0 < r_end; r0 += 128) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int r = r0 + u * 32;
-          if (r < a.M) acc[u] += X[(int64_t)r * a.ld + c];
+          if (r < r_end) acc[u] += X[(int64_t)r * a.ld + c];
         }
       }
     } else {
-      for (int r0 = ry; r0 < a.M; r0 += 128) {
+      for (int r0 = r_begin + ry; r0 < r_end; r0 += 128) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int r = r0 + u * 32;
-          if (r < a.M) acc[u] += X[(int64_t)r * a.ld + c] * ((gelu_tanh_f(Z[(int64_t)r * a.ld + c]) - mu[r]) * rstd[r]);
+          if (r < r_end) acc[u] += X[(int64_t)r * a.ld + c] * ((gelu_tanh_f(Z[(int64_t)r * a.ld + c]) - mu[r]) * rstd[r]);
         }
       }
     }
@@ -249,8 +250,19 @@ __global__ void __launch_bounds__(1024) colsum_kernel(ColSumArgs a) {
     float v = 0.f;
 #pragma unroll
     for (int q = 0; q < 32; q++) v += red[q][cx];
-    a.out.at(p, s, e)[c] = v;
+    if (partial) partial[((int64_t)blockIdx.z * gridDim.y + g) * a.N + c] = v;
+    else a.out.at(p, s, e)[c] = v;
   }
+}
+
+// second stage: out[g][c] = sum over chunks (fixed order)
+__global__ void colsum_final_kernel(ColSumArgs a, const float* __restrict__ partial, int chunks) {
+  const int g = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.N) return;
+  const int e = g % a.E, s = (g / a.E) % a.S, p = g / (a.E * a.S);
+  float v = 0.f;
+  for (int k = 0; k < chunks; k++) v += partial[((int64_t)k * gridDim.y + g) * a.N + c];
+  a.out.at(p, s, e)[c] = v;
 }
 
 }  // namespace
@@ -286,9 +298,25 @@ int launch_act_ln_bwd(const ActLnBwdArgs& a, cudaStream_t st) {
   return 0;
 }
 
-int launch_colsum(const ColSumArgs& a, cudaStream_t st) {
-  dim3 grid((a.N + 31) / 32, a.P * a.S * a.E);
-  colsum_kernel<<<grid, 1024, 0, st>>>(a);
+int launch_colsum(const ColSumArgs& a, cudaStream_t st, float* scratch, size_t scratch_floats) {
+  const int G = a.P * a.S * a.E;
+  const int col_blocks = (a.N + 31) / 32;
+  // few rows: one pass.  Many rows: split the rows over enough CTAs to fill the GPU, then a deterministic second stage.
+  int chunks = 1;
+  if (scratch && a.M >= 1024) {
+    chunks = (a.M + 511) / 512;
+    while (chunks > 1 && (int64_t)chunks * G * col_blocks > 1184) chunks = (chunks + 1) / 2;
+    if ((size_t)chunks * G * a.N > scratch_floats) chunks = 1;
+  }
+  if (chunks == 1) {
+    colsum_kernel<<<dim3(col_blocks, G, 1), 1024, 0, st>>>(a, a.M, nullptr);
+    FQL_CHECK_LAUNCH();
+    return 0;
+  }
+  const int rows = (a.M + chunks - 1) / chunks;
+  colsum_kernel<<<dim3(col_blocks, G, chunks), 1024, 0, st>>>(a, rows, scratch);
+  FQL_CHECK_LAUNCH();
+  colsum_final_kernel<<<dim3((a.N + 127) / 128, G), 128, 0, st>>>(a, scratch, chunks);
   FQL_CHECK_LAUNCH();
   return 0;
 }

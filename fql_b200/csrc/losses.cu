@@ -78,7 +78,7 @@ __global__ void post_onestep_kernel(StepShape sh, FqlBatch b, WsPtrs w, float* r
   const int F = sh.F, A = sh.A, B = sh.B, KC = F + A;
   const float* out = w.O_out + (int64_t)s * 3 * B * A;
   float mse = 0.f;
-  for (int i = threadIdx.x; i < B * A; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < B * A; i += gridDim.y * blockDim.x) {
     const int r = i / A, c = i % A;
     w.XC[((int64_t)(0 * sh.S + s) * B + r) * KC + F + c] = clip1(out[i]);
     w.XC[((int64_t)(2 * sh.S + s) * B + r) * KC + F + c] = clip1(out[(int64_t)B * A + i]);
@@ -86,7 +86,7 @@ __global__ void post_onestep_kernel(StepShape sh, FqlBatch b, WsPtrs w, float* r
     mse += d * d;
   }
   mse = block_reduce<0>(mse, red);
-  if (threadIdx.x == 0) raw[s * FQL_NUM_RAW + RAW_MSE] = mse;
+  if (threadIdx.x == 0) atomicAdd(&raw[s * FQL_NUM_RAW + RAW_MSE], mse);  // raw is zeroed at the start of the step
 }
 
 // TD target + critic loss gradient (fql.py:28-44) and the actor's Q statistics / dQ seed (fql.py:70-76).
@@ -144,13 +144,13 @@ __global__ void bc_post_kernel(StepShape sh, WsPtrs w, float* raw) {
   const float* pred = w.F_out + (int64_t)s * 2 * B * A;
   const float scale = 2.0f / ((float)sh.GB * (float)A);
   float sq = 0.f;
-  for (int i = threadIdx.x; i < B * A; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < B * A; i += gridDim.y * blockDim.x) {
     float d = pred[i] - w.vel[(int64_t)s * B * A + i];
     sq += d * d;
     w.dpred[(int64_t)s * B * A + i] = scale * d;
   }
   sq = block_reduce<0>(sq, red);
-  if (threadIdx.x == 0) raw[s * FQL_NUM_RAW + RAW_BC_SQ] = sq;
+  if (threadIdx.x == 0) atomicAdd(&raw[s * FQL_NUM_RAW + RAW_BC_SQ], sq);
 }
 
 // One Euler step (fql.py:166-169): a += v / flow_steps on the Euler rows of XF; t column <- (i+1)/flow_steps;
@@ -179,7 +179,7 @@ __global__ void actor_grad_kernel(StepShape sh, FqlHparams hp, WsPtrs w, float* 
   const float* api = w.O_out + ((int64_t)s * 3 * B + B) * A;
   const float scale = hp.alpha * 2.0f / ((float)sh.GB * (float)A);
   float sq = 0.f;
-  for (int i = threadIdx.x; i < B * A; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < B * A; i += gridDim.y * blockDim.x) {
     const int r = i / A, c = i % A;
     const float a = api[i];
     const float d = a - w.target[(int64_t)s * B * A + i];
@@ -190,7 +190,7 @@ __global__ void actor_grad_kernel(StepShape sh, FqlHparams hp, WsPtrs w, float* 
     w.dapi[(int64_t)s * B * A + i] = scale * d + (g0 + g1) * inside;
   }
   sq = block_reduce<0>(sq, red);
-  if (threadIdx.x == 0) raw[s * FQL_NUM_RAW + RAW_DISTILL_SQ] = sq;
+  if (threadIdx.x == 0) atomicAdd(&raw[s * FQL_NUM_RAW + RAW_DISTILL_SQ], sq);
 }
 
 // info[13] from the (all-reduced) raw accumulators + gradient statistics.
@@ -265,13 +265,21 @@ __global__ void euler_inplace_kernel(float* X, const float* v, int F, int A, int
 
 }  // namespace
 
+// CTAs per seed of the elementwise loss kernels: one per 8192 (row, action) elements; a single CTA (deterministic sum order)
+// for small batches, several + one float atomicAdd each for large ones
+static int loss_ctas(const StepShape& sh) {
+  const int64_t n = (int64_t)sh.B * sh.A;
+  int c = (int)((n + 8191) / 8192);
+  return c < 1 ? 1 : (c > 64 ? 64 : c);
+}
+
 int launch_prep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, cudaStream_t st) {
   prep_kernel<<<sh.S * sh.B, 64, 0, st>>>(sh, b, w);
   FQL_CHECK_LAUNCH();
   return 0;
 }
 int launch_post_onestep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st) {
-  post_onestep_kernel<<<sh.S, 1024, 0, st>>>(sh, b, w, raw);
+  post_onestep_kernel<<<dim3(sh.S, loss_ctas(sh)), 1024, 0, st>>>(sh, b, w, raw);
   FQL_CHECK_LAUNCH();
   return 0;
 }
@@ -281,7 +289,7 @@ int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch
   return 0;
 }
 int launch_bc_post(const StepShape& sh, const WsPtrs& w, float* raw, cudaStream_t st) {
-  bc_post_kernel<<<sh.S, 1024, 0, st>>>(sh, w, raw);
+  bc_post_kernel<<<dim3(sh.S, loss_ctas(sh)), 1024, 0, st>>>(sh, w, raw);
   FQL_CHECK_LAUNCH();
   return 0;
 }
@@ -292,7 +300,7 @@ int launch_euler_update(const StepShape& sh, const WsPtrs& w, int step, cudaStre
   return 0;
 }
 int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w, float* raw, cudaStream_t st) {
-  actor_grad_kernel<<<sh.S, 1024, 0, st>>>(sh, hp, w, raw);
+  actor_grad_kernel<<<dim3(sh.S, loss_ctas(sh)), 1024, 0, st>>>(sh, hp, w, raw);
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -43,6 +43,7 @@ struct ChainArgs {
   float* mu[FQL_MAXL];
   float* rstd[FQL_MAXL];
   void* Hb[FQL_MAXL];  // bf16 copies of H (operands of the tensor-core backward)
+  void* Zb[FQL_MAXL];  // bf16 copies of Z (gelu' in the tensor-core backward; non-LayerNorm networks)
   int Mcap, r0;
   int n_steps, F, A;   // Euler: n_steps > 1
   const float* a0;     // [S][M][A] initial actions (noise) for the Euler chain
@@ -60,7 +61,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(192, 1) mlp_chain_tc_kernel(const __grid_constant__ CUtensorMap mapX,
+constexpr int CH_NMMA = 2;   // MMA-issuer warps: one per 256-column half of the accumulator (a tcgen05.mma costs its issuing warp ~80 ns)
+constexpr int CH_THREADS = 32 * (1 + CH_NMMA + 4);
+constexpr int CH_EPI0 = 32 * (1 + CH_NMMA);
+
+__global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const __grid_constant__ CUtensorMap mapX,
                                                               const __grid_constant__ CUtensorMap mapW,
                                                               const __grid_constant__ CUtensorMap mapWL, const ChainArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -84,6 +89,7 @@ __global__ void __launch_bounds__(192, 1) mlp_chain_tc_kernel(const __grid_const
   const int e = g % a.E, s = (g / a.E) % a.S, p = g / (a.E * a.S);
   const int NL = a.n_layers;
   const int total_iters = a.n_steps * NL;
+  const int n_issuers = (a.H > 256) ? CH_NMMA : 1;  // hidden layers: issuer h owns N-half h; the narrow last layer: issuer 0
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
@@ -91,10 +97,10 @@ __global__ void __launch_bounds__(192, 1) mlp_chain_tc_kernel(const __grid_const
     tma_prefetch_desc(&mapWL);
     for (int i = 0; i < a.nstage; i++) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], n_issuers);
     }
     mbar_init(x_full, 1);
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full, n_issuers);
     mbar_init(a_ready, 4);
     fence_barrier_init();
   }
@@ -133,15 +139,17 @@ __global__ void __launch_bounds__(192, 1) mlp_chain_tc_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+  } else if (warp <= CH_NMMA) {
+    // ================= MMA issuers =================
+    const int mw = warp - 1;
+    if (lane == 0 && mw < n_issuers) {
       int stage = 0;
       uint32_t phase = 0;
       const int n_mma = (a.H > 256) ? 256 : a.H;          // N per instruction for hidden layers
-      const int n_halves = a.H / n_mma;
       const uint32_t idesc_h = make_idesc_bf16(128, n_mma, false, true);
       const uint32_t idesc_l = make_idesc_bf16(128, 64, false, true);
+      const uint64_t a_t = make_smem_desc(0, 16, 1024), b_t = make_smem_desc(0, CHUNK_BYTES, 1024);
+      const uint32_t sa0 = smem_u32(sA) >> 4, sx0 = smem_u32(sX) >> 4, sb0 = smem_u32(sB) >> 4;
       for (int it = 0; it < total_iters; it++) {
         const int l = it % NL;
         const bool last = (l == NL - 1);
@@ -150,21 +158,16 @@ __global__ void __launch_bounds__(192, 1) mlp_chain_tc_kernel(const __grid_const
         tc_fence_after();
         const int K = (l == 0) ? a.K0 : a.H;
         const int ksteps = (K + STAGE_K - 1) / STAGE_K;
-        const uint8_t* Abase = (l == 0) ? sX : sA;
+        const uint32_t a0 = (l == 0) ? sx0 : sa0;
         for (int ks = 0; ks < ksteps; ks++) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(Abase + (ks >> 2) * KB_BYTES) + (ks & 3) * 32;
-          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-          const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
+          const uint64_t adesc = a_t + (uint64_t)(a0 + (ks >> 2) * (KB_BYTES >> 4) + (ks & 3) * 2);
+          const uint32_t b0 = sb0 + stage * (stage_bytes >> 4);
           if (!last) {
-            for (int h = 0; h < n_halves; h++) {
-              const uint64_t bdesc = make_smem_desc(b_addr + h * (n_mma / 64) * CHUNK_BYTES, CHUNK_BYTES, 1024);
-              umma_bf16(tmem_base + h * n_mma, adesc, bdesc, idesc_h, ks > 0);
-            }
-          } else {
-            const uint64_t bdesc = make_smem_desc(b_addr, CHUNK_BYTES, 1024);
-            umma_bf16(tmem_base, adesc, bdesc, idesc_l, ks > 0);
+            umma_bf16(tmem_base + mw * n_mma, adesc, b_t + (uint64_t)(b0 + mw * (n_mma / 64) * (CHUNK_BYTES >> 4)), idesc_h, ks > 0);
+          } else if (mw == 0) {
+            umma_bf16(tmem_base, adesc, b_t + (uint64_t)b0, idesc_l, ks > 0);
           }
           umma_commit(&empty[stage]);
           if (++stage == a.nstage) { stage = 0; phase ^= 1; }
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(192, 1) mlp_chain_tc_kernel(const __grid_const
     const int grow = tile * TILE_M + row;         // row inside the group
     const bool valid = grow < a.M;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int et = threadIdx.x - 64;              // 0..127
+    const int et = threadIdx.x - CH_EPI0;         // 0..127
     const int64_t gidx = (int64_t)((p * a.S + s) * a.E + e) * a.Mcap + a.r0 + grow;  // row index into [G][Mcap][*] buffers
     const float* bias_g[FQL_MAXL];
     float act[MAX_A];
@@ -235,6 +238,15 @@ __global__ void __launch_bounds__(192, 1) mlp_chain_tc_kernel(const __grid_const
             if (valid && Hs) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(Hs + j * 32 + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+            }
+            if (valid && a.Zb[l]) {
+#pragma unroll
+              for (int c = 0; c < 4; c++)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.Zb[l]) + gidx * a.H + j * 32 + c * 8) =
+                    make_uint4(pack_bf16(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1])),
+                               pack_bf16(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3])),
+                               pack_bf16(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5])),
+                               pack_bf16(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7])));
             }
             uint8_t* blk = sA + ((j * 32) >> 6) * KB_BYTES;
             const int c0 = ((j * 32) & 63) >> 3;
@@ -506,6 +518,13 @@ int tc_mlp_chain(const TcChainSpec& f, cudaStream_t st) {
       a.Hb[l] = f.Hb ? f.Hb[l] : nullptr;
     }
   }
+  if (!f.buf) {
+    for (int l = 0; l + 1 < n0.n_layers; l++) {
+      a.Hb[l] = f.Hb ? f.Hb[l] : nullptr;
+      a.Zb[l] = f.Zb ? f.Zb[l] : nullptr;
+    }
+    if (f.Mcap_override > 0) a.Mcap = f.Mcap_override;
+  }
   if (f.out_override) a.out = f.out_override;
   a.n_steps = f.n_steps > 0 ? f.n_steps : 1; a.F = d->obs_dim; a.A = d->action_dim; a.a0 = f.a0; a.target = f.target;
   a.clip_out = f.clip_out;
@@ -529,7 +548,7 @@ int tc_mlp_chain(const TcChainSpec& f, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = a.tiles * a.P * a.S * a.E;
-  mlp_chain_tc_kernel<<<grid, 192, smem, st>>>(mapX, mapW, mapWL, a);
+  mlp_chain_tc_kernel<<<grid, CH_THREADS, smem, st>>>(mapX, mapW, mapWL, a);
   FQL_CHECK_LAUNCH();
   return 0;
 }

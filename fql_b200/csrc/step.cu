@@ -216,6 +216,7 @@ size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w)
     w->C1_dOutb = c.take(S * 2 * B * 64 / 2);
     w->C2_dOutb = c.take(S * 2 * B * 64 / 2);
     w->euler_a = c.take(S * B * A);
+    for (int i = 0; i < 3; i++) w->cs_scratch[i] = c.take(65536);
     w->euler_hx = c.take((int64_t)(tc_euler_scratch_elems(d, (int)B) / 2 + 4));
   }
   for (int i = 0; i < 2; i++) {
@@ -415,6 +416,7 @@ struct FqlContext {
   int use_graph = 1;
   int use_euler_cluster = 1;
   int use_critic_chain = 0;
+  int chain_min_tiles = 48;  // row tiles (x seeds) from which the fused per-tile chain kernels replace the per-layer GEMMs
   cudaEvent_t early_event = nullptr;  // optional: recorded when the bc-flow and critic gradients of fql_step_grads are complete
   long long launches = 0;  // kernels enqueued through this context
 };
@@ -455,6 +457,8 @@ extern "C" int fql_context_create(FqlContext** out) {
   if (g && g[0] == '0') c->use_graph = 0;
   const char* ec = getenv("FQL_B200_EULER_CLUSTER");
   if (ec && ec[0] == '0') c->use_euler_cluster = 0;
+  const char* cm = getenv("FQL_B200_CHAIN_MIN_TILES");
+  if (cm) c->chain_min_tiles = atoi(cm);
   const char* cc = getenv("FQL_B200_CRITIC_CHAIN");
   if (cc && cc[0] == '1') c->use_critic_chain = 1;
   *out = c;
@@ -568,13 +572,27 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
       t.Zb[l] = with_z ? reinterpret_cast<bf16*>(Zb[l]) + (int64_t)r0 * H : nullptr;
     }
     t.h_ss = (long long)rows_cap * H;
+    t.cs_scratch = (net == FQL_NET_ACTOR_BC_FLOW) ? w.cs_scratch[0] : w.cs_scratch[1];
     return t;
   };
 
   // ---- S1: Euler (agents/fql.py:155-171) on rows [B, 2B) of the bc-flow buffers
   FQL_TRY(tc_pad_bf16(w.XF, w.XFb, (int64_t)S * 2 * B, sh.F + sh.A + 1, kF, S1));
   FQL_CHECK_CUDA(cudaEventRecord(ev_pad, S1));
-  if (H == 512 && ctx->use_euler_cluster) {
+  const int row_tiles = S * ((B + 127) / 128);
+  const bool many_tiles = row_tiles >= ctx->chain_min_tiles;  // enough 128-row tiles to fill the GPU: fused per-tile chain kernels
+  auto chain = [&](int net, const void* X0b, int rows_cap, int r0_in, int M, void* const* Hb, void* const* Zb, float* out, int n_steps,
+                   cudaStream_t st) {
+    TcChainSpec t;
+    memset(&t, 0, sizeof(t));
+    t.d = d; t.L = &L; t.P = 1; t.net[0] = net; t.params = P; t.shadow = shadow; t.M = M; t.X0b = X0b; t.Mcap0 = rows_cap; t.r0_in = r0_in;
+    t.r0 = r0_in; t.Hb = Hb; t.Zb = Zb; t.Mcap_override = rows_cap; t.out_override = out; t.n_steps = n_steps;
+    if (n_steps > 1) { t.a0 = b.z; t.target = w.target; }
+    return tc_mlp_chain(t, st);
+  };
+  if (many_tiles) {
+    FQL_TRY(chain(FQL_NET_ACTOR_BC_FLOW, w.XFb, 2 * B, B, B, nullptr, nullptr, nullptr, sh.flow_steps, S1));
+  } else if (H == 512 && ctx->use_euler_cluster) {
     TcEulerSpec e;
     memset(&e, 0, sizeof(e));
     e.d = d; e.L = &L; e.params = P; e.shadow = shadow; e.X0b = w.XFb; e.Mcap0 = 2 * B; e.r0_in = B; e.M = B;
@@ -592,7 +610,8 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   // ---- S2: bc-flow on the BC rows [0, B), BC loss, backward
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_pad, 0));
   TcActor fbc = actor(FQL_NET_ACTOR_BC_FLOW, w.XFb, kF, 2 * B, 0, B, w.F_Hb, w.F_Zb, true);
-  FQL_TRY(tc_actor_forward(fbc, w.F_out, (long long)2 * B * sh.A, 0, nullptr, S2));
+  if (many_tiles) FQL_TRY(chain(FQL_NET_ACTOR_BC_FLOW, w.XFb, 2 * B, 0, B, w.F_Hb, w.F_Zb, w.F_out, 1, S2));
+  else FQL_TRY(tc_actor_forward(fbc, w.F_out, (long long)2 * B * sh.A, 0, nullptr, S2));
   FQL_TRY(launch_bc_post(sh, w, raw, S2));
   if (c.do_backward) {
     FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.F_dZf, S2, ctx->s3, &ctx->ev[8]));
@@ -603,12 +622,14 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   // ---- S0: one-step actor on {(s',z_next), (s,z), (s,z')}, grouped critic pass
   FQL_TRY(tc_pad_bf16(w.XO, w.XOb, (int64_t)S * 3 * B, sh.F + sh.A, kO, S0));
   TcActor fo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, true);
-  FQL_TRY(tc_actor_forward(fo, w.O_out, (long long)3 * B * sh.A, 0, nullptr, S0));
+  if (many_tiles) FQL_TRY(chain(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, w.O_out, 1, S0));
+  else FQL_TRY(tc_actor_forward(fo, w.O_out, (long long)3 * B * sh.A, 0, nullptr, S0));
   FQL_TRY(launch_post_onestep(sh, b, w, raw, S0));
   FQL_TRY(tc_pad_bf16(w.XC, w.XCb, (int64_t)3 * S * B, sh.F + sh.A, kO, S0));
   TcCritic cr;
   memset(&cr, 0, sizeof(cr));
   cr.d = d; cr.L = &L; cr.params = P; cr.shadow = shadow; cr.M = B; cr.K0pad = kO; cr.x_ss = (long long)B * kO; cr.buf = &w.pC; cr.Hb = w.C_Hb;
+  cr.cs_scratch = w.cs_scratch[2];
   if (ctx->use_critic_chain) {
     TcChainSpec t;
     memset(&t, 0, sizeof(t));

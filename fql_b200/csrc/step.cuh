@@ -47,6 +47,7 @@ struct WsPtrs {
   void *C1_dZb[FQL_MAXL], *C1_dOutb, *C2_dZb[FQL_MAXL], *C2_dOutb;
   float *C1_dZf[FQL_MAXL], *C1_dHf[FQL_MAXL], *C2_dZf[FQL_MAXL], *C2_dHf[FQL_MAXL];
   float *euler_a;
+  float *cs_scratch[3];        // column-sum scratch per backward side stream
   // pixel configs: encoder outputs that replace the observations per call site, encoder pass buffers, feature gradients
   float *feat[5];              // [S][B][512]: onestep(next_obs), onestep(obs), target critic(next_obs), critic(obs), bc_flow(obs)
   float *dfeat[3];             // gradients w.r.t. feat[3] (critic), feat[4] (bc flow), feat[1] (onestep)
@@ -92,6 +93,8 @@ struct TcChainSpec {
   int r0, save;
   float* out_override;
   void* const* Hb;   // optional bf16 copies of the hidden activations [G][Mcap][H] per layer (tensor-core backward operands)
+  void* const* Zb;   // optional bf16 copies of the pre-activations (buf == NULL only)
+  int Mcap_override; // row capacity of the Hb/Zb/out buffers when buf == NULL
   int n_steps;       // > 1: Euler integration of compute_flow_actions
   const float* a0;
   float* target;
@@ -146,6 +149,7 @@ struct TcActor {
   void* Hb[FQL_MAXL];    // bf16 [S][..][H] per hidden layer, already offset to the first row
   void* Zb[FQL_MAXL];
   long long h_ss;
+  float* cs_scratch;     // scratch of the two-stage column sums (65536 floats)
 };
 struct TcEuler {
   float* act;
@@ -170,6 +174,7 @@ struct TcCritic {
   float* dZf[FQL_MAXL];    //                   fp32 dZ_l
   float* dHf[FQL_MAXL];    //                   fp32 dH_l (before the LayerNorm/GELU backward)
   float* dX0;
+  float* cs_scratch;
 };
 int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, const TcEuler* eu, cudaStream_t st);
 int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],

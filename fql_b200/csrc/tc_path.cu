@@ -224,7 +224,7 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
     c.P = 1; c.S = S; c.E = 1; c.M = t.M; c.N = N; c.ld = ld;
     c.X.base[0] = X; c.X.stride_s = ss;
     c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena;
-    return launch_colsum(c, side);
+    return launch_colsum(c, side, t.cs_scratch, t.cs_scratch ? 65536 : 0);
   };
   FQL_TRY(tc_pad_bf16(dOut, dOutb, (int64_t)S * t.M, A, 64, st));
   FQL_CHECK_CUDA(cudaEventRecord(ev[0], st));
@@ -313,7 +313,7 @@ int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cu
       c.rstd.base[0] = rstd; c.rstd.stride_s = c.mu.stride_s; c.rstd.stride_e = Mcap;
     }
     c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena; c.out.stride_e = N;
-    return launch_colsum(c, side);
+    return launch_colsum(c, side, t.cs_scratch, t.cs_scratch ? 65536 : 0);
   };
   // ---- chain
   FQL_TRY(tc_pad_bf16(t.dOut, t.dOutb, (int64_t)S * E * M, 1, 64, st));
