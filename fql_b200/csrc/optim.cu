@@ -16,9 +16,8 @@ __global__ void __launch_bounds__(256) adam_polyak_stats_kernel(Layout L, FqlHpa
                                                                 const float* __restrict__ grads,
                                                                 const int32_t* __restrict__ count,
                                                                 float* __restrict__ partials, __nv_bfloat16* __restrict__ shadow,
-                                                                int64_t shadow_seed) {
-  const int blk = blockIdx.x, s = blockIdx.y;
-  const int nblk = gridDim.x;
+                                                                int64_t shadow_seed, int blk0, int nblk) {
+  const int blk = blk0 + blockIdx.x, s = blockIdx.y;
   const int64_t off = (int64_t)blk * FQL_LEAF_PAD + threadIdx.x * 4;
   const int64_t base = (int64_t)s * L.arena;
   float* part = partials + ((int64_t)s * nblk + blk) * 4;
@@ -139,9 +138,13 @@ __global__ void zero_kernel(float4* p, int64_t n4) {
 }  // namespace
 
 int launch_adam_polyak_stats(const Layout& L, const FqlHparams& hp, int S, float* params, float* mu, float* nu,
-                             const float* grads, const int32_t* count, float* partials, void* shadow, int64_t shadow_seed, cudaStream_t st) {
-  dim3 grid(L.leaf_blk[L.n_leaves], S);
-  adam_polyak_stats_kernel<<<grid, 256, 0, st>>>(L, hp, params, mu, nu, grads, count, partials, reinterpret_cast<__nv_bfloat16*>(shadow), shadow_seed);
+                             const float* grads, const int32_t* count, float* partials, void* shadow, int64_t shadow_seed, cudaStream_t st,
+                             int blk0, int blk1) {
+  const int nblk = L.leaf_blk[L.n_leaves];
+  if (blk1 < 0) blk1 = nblk;
+  if (blk1 <= blk0) return 0;
+  dim3 grid(blk1 - blk0, S);
+  adam_polyak_stats_kernel<<<grid, 256, 0, st>>>(L, hp, params, mu, nu, grads, count, partials, reinterpret_cast<__nv_bfloat16*>(shadow), shadow_seed, blk0, nblk);
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -415,6 +415,10 @@ struct FqlContext {
   std::vector<GraphEntry> graphs;
   int use_graph = 1;
   int use_euler_cluster = 1;
+  unsigned long long* stamps = nullptr;  // FQL_B200_STAMPS=1: %globaltimer at schedule points (diagnostics, profiles/dbg_timeline.py)
+  int split_adam = 0;        // FQL_B200_SPLIT_ADAM=1: optimizer pass over bc-flow|critic(+target) overlaps the one-step actor's backward
+                             // (measured: no gain -- its HBM traffic slows the Euler tail and the dgrad chain by what it saves)
+  int adam_done_blk = 0;     // blocks [0, adam_done_blk) were already applied by enqueue_grads_tc in this enqueue
   int use_critic_chain = 0;
   int chain_min_tiles = 48;  // row tiles (x seeds) from which the fused per-tile chain kernels replace the per-layer GEMMs
   cudaEvent_t early_event = nullptr;  // optional: recorded when the bc-flow and critic gradients of fql_step_grads are complete
@@ -434,6 +438,22 @@ extern "C" int64_t fql_early_grads_floats(const FqlDims* d) {
   if (fql_build_layout(d, &L)) return -1;
   return L.net[FQL_NET_ACTOR_ONESTEP_FLOW].begin;
 }
+__global__ void stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+static int stamp(FqlContext* ctx, int idx, cudaStream_t st) {
+  if (!ctx->stamps) return 0;
+  stamp_kernel<<<1, 1, 0, st>>>(ctx->stamps + idx);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int fql_debug_stamps(FqlContext* c, unsigned long long* host_out, int n) {
+  FQL_REQUIRE(c && c->stamps && n <= 64, "stamps are off (FQL_B200_STAMPS=1)");
+  FQL_CHECK_CUDA(cudaMemcpy(host_out, c->stamps, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
 static int record_early(FqlContext* ctx, cudaStream_t st) {
   if (!ctx->early_event) return 0;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -445,18 +465,31 @@ static int record_early(FqlContext* ctx, cudaStream_t st) {
 extern "C" int fql_context_create(FqlContext** out) {
   FQL_REQUIRE(out != nullptr, "out is NULL");
   FqlContext* c = new FqlContext();
-  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s0, cudaStreamNonBlocking));
-  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s1, cudaStreamNonBlocking));
-  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking));
-  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s3, cudaStreamNonBlocking));
-  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s4, cudaStreamNonBlocking));
-  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s5, cudaStreamNonBlocking));
-  FQL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->s6, cudaStreamNonBlocking));
+  // the dependent chains that bound a small-batch step (S0: one-step actor / critic / tail, s1: Euler) get the highest
+  // priority so that their CTAs are placed before those of the bulk side work (weight gradients, early optimizer pass)
+  int prio_lo = 0, prio_hi = 0;
+  FQL_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  const char* pr = getenv("FQL_B200_PRIO");
+  if (pr && pr[0] == '0') prio_hi = prio_lo;
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s0, cudaStreamNonBlocking, prio_hi));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s1, cudaStreamNonBlocking, prio_hi));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s2, cudaStreamNonBlocking, prio_lo));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s3, cudaStreamNonBlocking, prio_lo));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s4, cudaStreamNonBlocking, prio_lo));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s5, cudaStreamNonBlocking, prio_lo));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s6, cudaStreamNonBlocking, prio_lo));
   for (auto& e : c->ev) FQL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const char* g = getenv("FQL_B200_GRAPH");
   if (g && g[0] == '0') c->use_graph = 0;
   const char* ec = getenv("FQL_B200_EULER_CLUSTER");
   if (ec && ec[0] == '0') c->use_euler_cluster = 0;
+  const char* stp = getenv("FQL_B200_STAMPS");
+  if (stp && stp[0] == '1') {
+    FQL_CHECK_CUDA(cudaMalloc(&c->stamps, 64 * sizeof(unsigned long long)));
+    FQL_CHECK_CUDA(cudaMemset(c->stamps, 0, 64 * sizeof(unsigned long long)));
+  }
+  const char* sa = getenv("FQL_B200_SPLIT_ADAM");
+  if (sa) c->split_adam = sa[0] == '1';
   const char* cm = getenv("FQL_B200_CHAIN_MIN_TILES");
   if (cm) c->chain_min_tiles = atoi(cm);
   const char* cc = getenv("FQL_B200_CRITIC_CHAIN");
@@ -556,9 +589,11 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   cudaStream_t S1 = ctx->s1, S2 = ctx->s2;
   cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4], ev_pad = ctx->ev[5];
   const int kO = (int)round_up64(sh.F + sh.A, 64), kF = (int)round_up64(sh.F + sh.A + 1, 64);
+  FQL_TRY(stamp(ctx, 0, S0));   // step start
   FQL_TRY(launch_zero(raw, (int64_t)S * FQL_NUM_RAW, S0));
   FQL_TRY(encode_observations(c, L, w, S0));
   FQL_TRY(launch_prep(sh, b, w, S0));
+  FQL_TRY(stamp(ctx, 1, S0));   // prep done
   FQL_CHECK_CUDA(cudaEventRecord(ev_prep, S0));
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S1, ev_prep, 0));
 
@@ -605,7 +640,13 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
       FQL_TRY(tc_actor_forward(e, nullptr, 0, 0, &eu, S1));
     }
   }
+  FQL_TRY(stamp(ctx, 2, S1));   // Euler done
   FQL_CHECK_CUDA(cudaEventRecord(ev_euler, S1));
+  if (getenv("FQL_B200_EULER_ALONE")) {  // diagnostics: serialise everything else behind the Euler chain
+    const int m = atoi(getenv("FQL_B200_EULER_ALONE"));
+    if (m & 1) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_euler, 0));
+    if (m & 2) FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_euler, 0));
+  }
 
   // ---- S2: bc-flow on the BC rows [0, B), BC loss, backward
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_pad, 0));
@@ -616,6 +657,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   if (c.do_backward) {
     FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.F_dZf, S2, ctx->s3, &ctx->ev[8]));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], ctx->s3));
+    FQL_TRY(stamp(ctx, 4, S2));   // bc-flow dgrad chain done (weight gradients on s3 may still run)
   }
   (void)ev_f0;
 
@@ -624,6 +666,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   TcActor fo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, true);
   if (many_tiles) FQL_TRY(chain(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, w.O_out, 1, S0));
   else FQL_TRY(tc_actor_forward(fo, w.O_out, (long long)3 * B * sh.A, 0, nullptr, S0));
+  FQL_TRY(stamp(ctx, 3, S0));   // one-step actor forward done
   FQL_TRY(launch_post_onestep(sh, b, w, raw, S0));
   FQL_TRY(tc_pad_bf16(w.XC, w.XCb, (int64_t)3 * S * B, sh.F + sh.A, kO, S0));
   TcCritic cr;
@@ -652,6 +695,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
       }
     }
   }
+  FQL_TRY(stamp(ctx, 5, S0));   // critic forward done
   FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0));
   FQL_CHECK_CUDA(cudaEventRecord(ev_cpost, S0));
 
@@ -666,6 +710,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], ctx->s5));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[36], 0));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[16], 0));  // bc-flow weight gradients (side stream s3)
+    FQL_TRY(stamp(ctx, 8, S2));   // bc-flow + critic gradients complete
     FQL_TRY(record_early(ctx, S2));
     // critic input gradient with stored params (fql.py:70) on S0
     TcCritic q = cr;
@@ -673,16 +718,33 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     q.dOut = w.dqs; q.dOutb = w.C2_dOutb; q.dX0 = w.dX0;
     for (int l = 0; l < NH; l++) { q.dZb[l] = w.C2_dZb[l]; q.dZf[l] = w.C2_dZf[l]; q.dHf[l] = w.C2_dHf[l]; }
     FQL_TRY(tc_critic_backward(q, S0, nullptr, &ctx->ev[44]));
+    FQL_TRY(stamp(ctx, 6, S0));   // critic input-gradient chain done
+    if (c.do_apply && ctx->split_adam && d->reserved[0] == 0) {
+      // bc-flow and critic are finished with (gradients complete, last readers of their weights: the Euler chain and the critic
+      // input-gradient chain above): their optimizer pass overlaps the one-step actor's backward instead of following it
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[52], S0));
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[52], 0));
+      const int blk0 = (int)(L.net[FQL_NET_CRITIC].begin / FQL_LEAF_PAD), blk1 = (int)(L.net[FQL_NET_ACTOR_ONESTEP_FLOW].begin / FQL_LEAF_PAD);
+      FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, c.st->count, w.partials, c.st->shadow,
+                                       tc_shadow_seed_elems(d, L), S2, blk0, blk1));   // critic (+ Polyak into the target)
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_euler, 0));
+      FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, c.st->count, w.partials, c.st->shadow,
+                                       tc_shadow_seed_elems(d, L), S2, 0, blk0));      // bc-flow: the Euler chain was its last reader
+      ctx->adam_done_blk = blk1;
+      FQL_TRY(stamp(ctx, 9, S2)); // early optimizer pass done
+    }
   }
   FQL_CHECK_CUDA(cudaEventRecord(ev_s2, S2));
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_euler, 0));
   FQL_TRY(launch_actor_grad(sh, hp, w, raw, S0));
+  FQL_TRY(stamp(ctx, 7, S0));   // joined Euler, dL/da done
   if (c.do_backward) {
     TcActor bo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, B, B, w.O_Hb, w.O_Zb, true);
     FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, &ctx->ev[18]));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[26], ctx->s4));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[26], 0));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[16], 0));
+    FQL_TRY(stamp(ctx, 10, S0));  // one-step actor gradients complete
   }
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
   return 0;
@@ -798,11 +860,16 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
   }
 
+  ctx->adam_done_blk = 0;
   if (c.do_grads && tcm) FQL_TRY(enqueue_grads_tc(ctx, c, L, w, sh, hp, raw, S0));
   if (c.do_apply) {
     // Adam + Polyak + gradient statistics (+ the bf16 operand shadow of the new parameters) in one pass over the arenas
+    // (the target critic's blocks carry no gradient and are written by the critic's CTAs: skipped when the pass is split)
+    const int blk0 = ctx->adam_done_blk;
+    const int blk1 = blk0 ? (int)(L.net[FQL_NET_TARGET_CRITIC].begin / FQL_LEAF_PAD) : -1;
     FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, c.st->count, w.partials,
-                                     tcm ? c.st->shadow : nullptr, tcm ? tc_shadow_seed_elems(c.d, L) : 0, S0));
+                                     tcm ? c.st->shadow : nullptr, tcm ? tc_shadow_seed_elems(c.d, L) : 0, S0, blk0, blk1));
+    FQL_TRY(stamp(ctx, 11, S0));  // optimizer pass done
     if (tcm) {  // the zero-padded narrow last-layer copies, beside the statistics tail
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[50], S0));
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s1, ctx->ev[50], 0));
@@ -813,6 +880,7 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     if (tcm) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[51], 0));
   }
   if (c.info) FQL_TRY(launch_finalize_info(sh, hp, raw, c.raw_ranks > 1 ? c.raw_ranks : 1, w.gstats, c.info, c.do_apply, S0));
+  FQL_TRY(stamp(ctx, 12, S0));    // step end
   return 0;
 }
 

@@ -74,7 +74,8 @@ int launch_euler_inplace(float* X, const float* v, int F, int A, int64_t rows, i
 
 // optim.cu
 int launch_adam_polyak_stats(const Layout& L, const FqlHparams& hp, int S, float* params, float* mu, float* nu,
-                             const float* grads, const int32_t* count, float* partials, void* shadow, int64_t shadow_seed, cudaStream_t st);
+                             const float* grads, const int32_t* count, float* partials, void* shadow, int64_t shadow_seed, cudaStream_t st,
+                             int blk0 = 0, int blk1 = -1);  // CTA range in FQL_LEAF_PAD blocks (default: the whole arena)
 int launch_grad_stats_final(const Layout& L, int S, const float* partials, float* gstats, int32_t* count_inc, cudaStream_t st);
 int launch_zero(float* p, int64_t n, cudaStream_t st);
 
