@@ -450,7 +450,7 @@ static int stamp(FqlContext* ctx, int idx, cudaStream_t st) {
   return 0;
 }
 extern "C" int fql_debug_stamps(FqlContext* c, unsigned long long* host_out, int n) {
-  FQL_REQUIRE(c && c->stamps && n <= 64, "stamps are off (FQL_B200_STAMPS=1)");
+  FQL_REQUIRE(c && c->stamps && n <= 576, "stamps are off (FQL_B200_STAMPS=1)");
   FQL_CHECK_CUDA(cudaMemcpy(host_out, c->stamps, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -485,8 +485,8 @@ extern "C" int fql_context_create(FqlContext** out) {
   if (ec && ec[0] == '0') c->use_euler_cluster = 0;
   const char* stp = getenv("FQL_B200_STAMPS");
   if (stp && stp[0] == '1') {
-    FQL_CHECK_CUDA(cudaMalloc(&c->stamps, 64 * sizeof(unsigned long long)));
-    FQL_CHECK_CUDA(cudaMemset(c->stamps, 0, 64 * sizeof(unsigned long long)));
+    FQL_CHECK_CUDA(cudaMalloc(&c->stamps, 576 * sizeof(unsigned long long)));  // 64 schedule points + [32 CTAs][16] Euler phases
+    FQL_CHECK_CUDA(cudaMemset(c->stamps, 0, 576 * sizeof(unsigned long long)));
   }
   const char* sa = getenv("FQL_B200_SPLIT_ADAM");
   if (sa) c->split_adam = sa[0] == '1';
@@ -632,6 +632,8 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     memset(&e, 0, sizeof(e));
     e.d = d; e.L = &L; e.params = P; e.shadow = shadow; e.X0b = w.XFb; e.Mcap0 = 2 * B; e.r0_in = B; e.M = B;
     e.a0 = b.z; e.target = w.target; e.scratch = w.euler_hx;
+    e.t_start = ctx->stamps ? ctx->stamps + 13 : nullptr;
+    e.dbg = (ctx->stamps && S * ((B + 127) / 128) <= 2) ? ctx->stamps + 64 : nullptr;
     FQL_TRY(tc_euler_cluster(e, S1));
   } else {
     TcActor e = actor(FQL_NET_ACTOR_BC_FLOW, w.XFb, kF, 2 * B, B, B, w.F_Hb, w.F_Zb, false);

@@ -195,6 +195,7 @@ struct TcEulerSpec {
   float* target;       // [S][M][A]
   void* scratch;       // tc_euler_scratch_elems() bf16 elements
   void* dbg;           // optional timestamp buffer (diagnostics)
+  void* t_start;       // optional: %globaltimer when CTA 0 starts / ends (2 x u64, diagnostics)
 };
 size_t tc_euler_scratch_elems(const FqlDims* d, int M);
 int tc_euler_cluster(const TcEulerSpec& f, cudaStream_t st);

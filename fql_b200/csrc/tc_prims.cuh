@@ -37,14 +37,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a kernel bug must surface as a trap (reported by the next CUDA call), never as a hung GPU.
+// Bounded spin: a kernel bug must surface as a trap (reported by the next CUDA call), never as a hung GPU.  The report is out of
+// line: the wait is inlined at dozens of sites of latency-bound kernels whose code should stay small.
+static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+  printf("fql_b200: mbarrier timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x, (void*)bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("fql_b200: mbarrier timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x, (void*)bar, parity);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout(bar, parity);
   }
 }
 
@@ -97,6 +99,19 @@ __device__ __forceinline__ void umma_bf16_x4(uint32_t d_tmem, uint64_t a_desc, u
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "l"(a_step), "l"(b_step)
       : "memory");
 }
+// Two consecutive k-steps (one 32-wide K sub-block), same idea.
+__device__ __forceinline__ void umma_bf16_x2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint64_t a_step, uint64_t b_step,
+                                             uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 a1, b1;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "add.u64 a1, %1, %5;\n\tadd.u64 b1, %2, %6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "l"(a_step), "l"(b_step)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed (implies fence::before)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -140,6 +155,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo,
   d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // version = 1
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// Same for a K-major tile of 64-byte rows ([rows][32] bf16) in the SWIZZLE_64B layout (8-row groups sbo bytes apart).
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version = 1
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
   return d;
 }
 // Instruction descriptor for kind::f16 with bf16 operands, fp32 accumulate.  a_mn / b_mn: operand is MN-major.

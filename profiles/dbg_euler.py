@@ -2,7 +2,8 @@
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, '.')
-dbg = torch.zeros(16 * 16, dtype=torch.int64, device='cuda')
+NCTA = 32 if os.environ.get('FQL_B200_EULER_NC', '16') != '8' else 16
+dbg = torch.zeros(NCTA * 16, dtype=torch.int64, device='cuda')
 os.environ['FQL_B200_EULER_DBG'] = hex(dbg.data_ptr())
 from fql_b200 import FQLAgent, get_config
 cfg = get_config(); cfg.update(dict(q_agg='min', alpha=10.0)); cfg['batch_size'] = 256
@@ -12,13 +13,14 @@ st = torch.cuda.Stream()
 with torch.cuda.stream(st):
     for _ in range(3): ag.compute_flow_actions(obs, nz)
     torch.cuda.synchronize()
-    d = dbg.cpu().numpy().reshape(16, 16)
+    d = dbg.cpu().numpy().reshape(NCTA, 16)
     base = d[:, 0].min()
-    print('absolute ns (relative to the earliest acc_full(l-1) over all CTAs)')
-    print('cta  acc_full(l-1)  stores_done  bar  mcast_issued | true block arrival times kb0..7 | mma first/last block | acc_full(l)')
-    for cta in range(16):
+    print('ns relative to the earliest acc_full(l-1) over all CTAs')
+    print('cta  acc_full(l-1) | half0 stored, half1 stored | mcast h0, h1 issued | mma: first sub-block seen, last seen | acc_full(l)')
+    for cta in range(0, NCTA, 3):
         r = d[cta]
-        print(cta, int(r[0] - base), int(r[1] - base), int(r[2] - base), int(r[3] - base), '|', [int(x - base) for x in r[8:16]], '|', int(r[5] - base), int(r[6] - base), '|', int(r[7] - base))
+        print(cta, int(r[0] - base), '|', int(r[1] - base), int(r[2] - base), '|', int(r[3] - base), int(r[4] - base), '|', int(r[5] - base), int(r[6] - base), '|', int(r[7] - base))
+    print('median layer time (acc_full to acc_full):', float(np.median(d[:, 7] - d[:, 0])), 'ns')
     import time
     torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     obs_t = torch.tensor(obs, device='cuda'); nz_t = torch.tensor(nz, device='cuda')
