@@ -26,6 +26,34 @@ extern thread_local long long g_fql_launches;  // kernels enqueued by this threa
     g_fql_launches++;                      \
     FQL_CHECK_CUDA(cudaGetLastError());    \
   } while (0)
+// Programmatic dependent launch for the small kernels that sit between the tensor-core GEMMs of a dependent chain: the kernel may
+// be scheduled while its predecessor in the stream is still running; FQL_PDL_SYNC() (first statement that matters in the kernel)
+// blocks until the predecessor's writes are visible and lets the successor start its own prologue.  Without the launch
+// attribute both instructions are no-ops.
+#define FQL_PDL_SYNC()                                             \
+  do {                                                             \
+    asm volatile("griddepcontrol.wait;" ::: "memory");             \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+inline bool fql_pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("FQL_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t fql_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = fql_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 #define FQL_REQUIRE(cond, ...)       \
   do {                               \
     if (!(cond)) {                   \

@@ -393,6 +393,7 @@ __global__ void shadow_lastlayer_kernel(const float* __restrict__ params, __nv_b
 
 // bf16 first-layer operands [rows][K0pad] from fp32 [rows][K0] (zero padded)
 __global__ void pad_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t rows, int K0, int K0pad) {
+  FQL_PDL_SYNC();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * K0pad) return;
   const int64_t r = i / K0pad;
@@ -473,7 +474,8 @@ int tc_refresh_shadow_lastlayer(const FqlDims* d, const Layout& L, const float* 
 int tc_pad_bf16(const float* x, void* y, int64_t rows, int K0, int K0pad, cudaStream_t st) {
   const int64_t n = rows * K0pad;
   if (n == 0) return 0;
-  pad_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), rows, K0, K0pad);
+  FQL_CHECK_CUDA(fql_launch_pdl(pad_bf16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, reinterpret_cast<__nv_bfloat16*>(y), rows, K0,
+                                K0pad));
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -410,7 +410,7 @@ struct GraphEntry {
   long long kernels;  // kernel nodes in the captured graph
 };
 struct FqlContext {
-  cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr, s3 = nullptr, s4 = nullptr, s5 = nullptr, s6 = nullptr;  // s0 stands in for the caller's stream when that is the legacy default
+  cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr, s3 = nullptr, s4 = nullptr, s5 = nullptr, s6 = nullptr, s7 = nullptr, s8 = nullptr, s9 = nullptr;  // s0 stands in for the caller's stream when that is the legacy default
   cudaEvent_t ev[64] = {};
   std::vector<GraphEntry> graphs;
   int use_graph = 1;
@@ -478,6 +478,9 @@ extern "C" int fql_context_create(FqlContext** out) {
   FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s4, cudaStreamNonBlocking, prio_lo));
   FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s5, cudaStreamNonBlocking, prio_lo));
   FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s6, cudaStreamNonBlocking, prio_lo));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s7, cudaStreamNonBlocking, prio_lo));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s8, cudaStreamNonBlocking, prio_lo));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s9, cudaStreamNonBlocking, prio_lo));
   for (auto& e : c->ev) FQL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const char* g = getenv("FQL_B200_GRAPH");
   if (g && g[0] == '0') c->use_graph = 0;
@@ -509,6 +512,9 @@ extern "C" int fql_context_destroy(FqlContext* c) {
   if (c->s4) cudaStreamDestroy(c->s4);
   if (c->s5) cudaStreamDestroy(c->s5);
   if (c->s6) cudaStreamDestroy(c->s6);
+  if (c->s7) cudaStreamDestroy(c->s7);
+  if (c->s8) cudaStreamDestroy(c->s8);
+  if (c->s9) cudaStreamDestroy(c->s9);
   delete c;
   return 0;
 }
@@ -657,7 +663,9 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   else FQL_TRY(tc_actor_forward(fbc, w.F_out, (long long)2 * B * sh.A, 0, nullptr, S2));
   FQL_TRY(launch_bc_post(sh, w, raw, S2));
   if (c.do_backward) {
-    FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.F_dZf, S2, ctx->s3, &ctx->ev[8]));
+    FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.F_dZf, S2, ctx->s3, ctx->s7, &ctx->ev[8]));
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[53], ctx->s7));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s3, ctx->ev[53], 0));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], ctx->s3));
     FQL_TRY(stamp(ctx, 4, S2));   // bc-flow dgrad chain done (weight gradients on s3 may still run)
   }
@@ -708,7 +716,9 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     t.grads = c.st->grads; t.p = 1; t.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)1 * S * B * kO;
     t.dOut = w.dq; t.dOutb = w.C1_dOutb;
     for (int l = 0; l < NH; l++) { t.dZb[l] = w.C1_dZb[l]; t.dZf[l] = w.C1_dZf[l]; t.dHf[l] = w.C1_dHf[l]; }
-    FQL_TRY(tc_critic_backward(t, S2, ctx->s5, &ctx->ev[28]));
+    FQL_TRY(tc_critic_backward(t, S2, ctx->s5, ctx->s8, &ctx->ev[28]));
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[54], ctx->s8));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s5, ctx->ev[54], 0));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], ctx->s5));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[36], 0));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[16], 0));  // bc-flow weight gradients (side stream s3)
@@ -719,7 +729,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     q.grads = nullptr; q.p = 2; q.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)2 * S * B * kO;
     q.dOut = w.dqs; q.dOutb = w.C2_dOutb; q.dX0 = w.dX0;
     for (int l = 0; l < NH; l++) { q.dZb[l] = w.C2_dZb[l]; q.dZf[l] = w.C2_dZf[l]; q.dHf[l] = w.C2_dHf[l]; }
-    FQL_TRY(tc_critic_backward(q, S0, nullptr, &ctx->ev[44]));
+    FQL_TRY(tc_critic_backward(q, S0, nullptr, nullptr, &ctx->ev[44]));
     FQL_TRY(stamp(ctx, 6, S0));   // critic input-gradient chain done
     if (c.do_apply && ctx->split_adam && d->reserved[0] == 0) {
       // bc-flow and critic are finished with (gradients complete, last readers of their weights: the Euler chain and the critic
@@ -742,7 +752,9 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   FQL_TRY(stamp(ctx, 7, S0));   // joined Euler, dL/da done
   if (c.do_backward) {
     TcActor bo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, B, B, w.O_Hb, w.O_Zb, true);
-    FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, &ctx->ev[18]));
+    FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, ctx->s9, &ctx->ev[18]));
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[55], ctx->s9));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s4, ctx->ev[55], 0));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[26], ctx->s4));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[26], 0));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[16], 0));

@@ -179,8 +179,8 @@ struct TcCritic {
 };
 int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, const TcEuler* eu, cudaStream_t st);
 int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
-                      cudaStream_t st, cudaStream_t side, cudaEvent_t* ev);
-int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cudaEvent_t* ev);
+                      cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev);
+int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev);
 int tc_critic_forward(const TcCritic& t, int net, float* out, cudaStream_t st);
 
 // euler_cluster.cu -- compute_flow_actions as one persistent thread-block-cluster kernel (hidden = 512)

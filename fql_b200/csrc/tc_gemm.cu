@@ -85,6 +85,9 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// MODE (the fused epilogue) is a template parameter: one instantiation carries one epilogue, which keeps the code a short-lived
+// launch has to fetch small (the 4-epilogue kernel was 58 KB)
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                          const __grid_constant__ CUtensorMap mapB, const TcGemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]) + ((bias && nb + i < a.N) ? bias[nb + i] : 0.f);
-      if (a.mode == TC_MODE_STORE_F32) {
+      if constexpr (MODE == TC_MODE_STORE_F32) {
         float* o = a.out_f.at<float>(g0, g1) + (int64_t)m * a.out_f.ld + nb;
         if (nb + 32 <= a.N && (a.out_f.ld & 3) == 0) {
 #pragma unroll
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
           for (int i = 0; i < 32; i++)
             if (nb + i < a.N) o[i] = a.clip ? fminf(fmaxf(v[i], -1.0f), 1.0f) : v[i];
         }
-      } else if (a.mode == TC_MODE_FWD_HIDDEN) {
+      } else if constexpr (MODE == TC_MODE_FWD_HIDDEN) {
         // utils/networks.py:54-56: z = xW + b ; h = gelu(z).  N is a multiple of 64 on this path.
         uint4* oz = a.out_z.base ? reinterpret_cast<uint4*>(a.out_z.at<__nv_bfloat16>(g0, g1) + (int64_t)m * a.out_z.ld + nb) : nullptr;
         uint4* oh = reinterpret_cast<uint4*>(a.out_h.at<__nv_bfloat16>(g0, g1) + (int64_t)m * a.out_h.ld + nb);
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
           for (int i = 0; i < 8; i++) h[i] = gelu_fast(v[c * 8 + i]);
           oh[c] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
         }
-      } else if (a.mode == TC_MODE_DGRAD_GELU) {
+      } else if constexpr (MODE == TC_MODE_DGRAD_GELU) {
         // dZ_{l-1} = (dZ_l W_l^T) * gelu'(Z_{l-1})
         const uint4* zi = reinterpret_cast<const uint4*>(a.zin.at<const __nv_bfloat16>(g0, g1) + (int64_t)m * a.zin.ld + nb);
         uint4* oh = reinterpret_cast<uint4*>(a.out_h.at<__nv_bfloat16>(g0, g1) + (int64_t)m * a.out_h.ld + nb);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             *reinterpret_cast<float4*>(of + c * 8 + 4) = make_float4(d[4], d[5], d[6], d[7]);
           }
         }
-      } else if (a.mode == TC_MODE_EULER) {
+      } else if constexpr (MODE == TC_MODE_EULER) {
         // agents/fql.py:166-170: a += v / flow_steps; next t; after the last step target = clip(a)
         float* act = a.act.at<float>(g0, g1) + (int64_t)m * a.A;
         __nv_bfloat16* xb = a.xb.at<__nv_bfloat16>(g0, g1) + (int64_t)m * a.xb.ld;
@@ -330,10 +333,18 @@ int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
   CUtensorMap mapA, mapB;
   FQL_TRY(make_map_4d(&mapA, s.A, s.a_mn ? 64 : BM));
   FQL_TRY(make_map_4d(&mapB, s.B, 64));
-  static bool attr_set = false;
-  if (!attr_set) {
-    FQL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const TcGemmArgs) = nullptr;
+  switch (s.mode) {
+    case TC_MODE_STORE_F32: kern = tc_gemm_kernel<TC_MODE_STORE_F32>; break;
+    case TC_MODE_FWD_HIDDEN: kern = tc_gemm_kernel<TC_MODE_FWD_HIDDEN>; break;
+    case TC_MODE_DGRAD_GELU: kern = tc_gemm_kernel<TC_MODE_DGRAD_GELU>; break;
+    case TC_MODE_EULER: kern = tc_gemm_kernel<TC_MODE_EULER>; break;
+    default: FQL_REQUIRE(false, "tc_gemm: unknown epilogue mode %d", s.mode);
+  }
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  if (!attr_set[s.mode & 7]) {
+    FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set[s.mode & 7] = true;
   }
   dim3 grid((s.N + BN - 1) / BN, (s.M + BM - 1) / BM, a.G0 * a.G1);
   cudaLaunchConfig_t cfg;
@@ -347,7 +358,7 @@ int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_tc_pdl ? 1 : 0;
-  FQL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mapA, mapB, a));
+  FQL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, a));
   FQL_CHECK_LAUNCH();
   return 0;
 }

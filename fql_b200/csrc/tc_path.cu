@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) act_ln_bf16_kernel(const float* __restric
                                                           const float* __restrict__ bias_base, int64_t par_s, int64_t par_e,
                                                           bf16* __restrict__ Hb, float* __restrict__ mu_out, float* __restrict__ rstd_out,
                                                           int M, int N, int S, int E, int ln) {
+  FQL_PDL_SYNC();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + warp;
   if (row >= (int64_t)S * E * M) return;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const float* __restric
                                                           int64_t z_rows_e, int64_t z_rows_s) {
   // one warp per row; every element's gelu / gelu' is evaluated once and kept in registers (N <= 512 -> 16 per lane)
   constexpr int MAXC = 16;
+  FQL_PDL_SYNC();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + warp;
   if (row >= (int64_t)S * E * M) return;
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const float* __restric
 // dZ = dH * gelu'(Z) (no LayerNorm) with a bf16 copy
 __global__ void gelu_bwd_bf16_kernel(const float* __restrict__ dH, const float* __restrict__ Z, float* __restrict__ dZ,
                                      bf16* __restrict__ dZb, int M, int N, int S, int E, int64_t z_rows_e, int64_t z_rows_s) {
+  FQL_PDL_SYNC();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)S * E * M * N) return;
   const int c = (int)(i % N);
@@ -208,7 +211,10 @@ int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, c
 // actor backward: dOut fp32 [S][M][A] -> parameter gradients (fp32, into the arena)
 // ---------------------------------------------------------------------------------------------------------------
 int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
-                      cudaStream_t st, cudaStream_t side, cudaEvent_t* ev) {
+                      cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev) {
+  // side: weight-gradient GEMMs, side2: bias-gradient column sums (one stream for both was measured to be the longest chain of
+  // the backward: 8 us of side work per 5 us dgrad step)
+  if (!side2) side2 = side;
   // st carries the dependent dgrad chain dZ_4 -> dZ_3 -> ... -> dZ_0; the weight/bias gradients of layer l only need dZ_l,
   // so they go to `side` behind an event (every layer has its own dZ buffer, nothing is overwritten).
   const FqlDims* d = t.d;
@@ -224,7 +230,7 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
     c.P = 1; c.S = S; c.E = 1; c.M = t.M; c.N = N; c.ld = ld;
     c.X.base[0] = X; c.X.stride_s = ss;
     c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena;
-    return launch_colsum(c, side, t.cs_scratch, t.cs_scratch ? 65536 : 0);
+    return launch_colsum(c, side2, t.cs_scratch, t.cs_scratch ? 65536 : 0);
   };
   FQL_TRY(tc_pad_bf16(dOut, dOutb, (int64_t)S * t.M, A, 64, st));
   FQL_CHECK_CUDA(cudaEventRecord(ev[0], st));
@@ -254,8 +260,9 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
     FQL_TRY(tc_gemm(g, st));
     FQL_CHECK_CUDA(cudaEventRecord(ev[2 + (NL - 2 - l)], st));
   }
-  // ---- side stream: parameter gradients
+  // ---- side streams: parameter gradients
   FQL_CHECK_CUDA(cudaStreamWaitEvent(side, ev[0], 0));
+  if (side2 != side) FQL_CHECK_CUDA(cudaStreamWaitEvent(side2, ev[0], 0));
   FQL_TRY(colsum(dOut, A, A, (long long)t.M * A, nv.off_b[NL - 1]));
   {  // dW_last = H^T dOut
     TcGemmSpec g;
@@ -269,6 +276,7 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
   }
   for (int l = NL - 2; l >= 0; l--) {
     FQL_CHECK_CUDA(cudaStreamWaitEvent(side, ev[1 + (NL - 2 - l)], 0));
+    if (side2 != side) FQL_CHECK_CUDA(cudaStreamWaitEvent(side2, ev[1 + (NL - 2 - l)], 0));
     FQL_TRY(colsum(dZf[l], H, H, dz_ss, nv.off_b[l]));
     TcGemmSpec g;  // dW_l = A_l^T dZ_l
     memset(&g, 0, sizeof(g));
@@ -288,7 +296,8 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
 //   grads != NULL : full backward (critic loss, fql.py:36-37)
 //   grads == NULL : input gradient only, stored params (actor Q loss, fql.py:70) -> dX0 [S][2][M][K0]
 // ---------------------------------------------------------------------------------------------------------------
-int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cudaEvent_t* ev) {
+int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev) {
+  if (!side2) side2 = side;  // side: weight-gradient GEMMs, side2: bias / LayerNorm-parameter column sums
   // st: the dependent chain  dZ_4 -> dgrad -> [LN/GELU bwd] -> dZ_3 -> ...   side: everything that only CONSUMES dZ_l / dH_l
   // (weight, bias and LayerNorm-parameter gradients).  Every layer has its own dH / dZ buffers, nothing is overwritten.
   const FqlDims* d = t.d;
@@ -313,7 +322,7 @@ int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cu
       c.rstd.base[0] = rstd; c.rstd.stride_s = c.mu.stride_s; c.rstd.stride_e = Mcap;
     }
     c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena; c.out.stride_e = N;
-    return launch_colsum(c, side, t.cs_scratch, t.cs_scratch ? 65536 : 0);
+    return launch_colsum(c, side2, t.cs_scratch, t.cs_scratch ? 65536 : 0);
   };
   // ---- chain
   FQL_TRY(tc_pad_bf16(t.dOut, t.dOutb, (int64_t)S * E * M, 1, 64, st));
@@ -341,13 +350,14 @@ int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cu
     const float* Zp = t.buf->Z[l - 1] + prow * H;
     if (nv.ln) {
       const int64_t rows = (int64_t)S * E * M;
-      ln_bwd_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(t.dHf[l - 1], Zp, t.params + nv.off_lns[l - 1], L.arena, H, t.dZf[l - 1],
-                                                                     reinterpret_cast<bf16*>(t.dZb[l - 1]), M, H, S, E, Mcap, (int64_t)E * Mcap);
+      FQL_CHECK_CUDA(fql_launch_pdl(ln_bwd_bf16_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, t.dHf[l - 1], Zp,
+                                    t.params + nv.off_lns[l - 1], L.arena, H, t.dZf[l - 1], reinterpret_cast<bf16*>(t.dZb[l - 1]), M, H, S, E, Mcap,
+                                    (int64_t)E * Mcap));
       FQL_CHECK_LAUNCH();
     } else {
       const int64_t n = (int64_t)S * E * M * H;
-      gelu_bwd_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.dHf[l - 1], Zp, t.dZf[l - 1], reinterpret_cast<bf16*>(t.dZb[l - 1]), M, H,
-                                                                        S, E, Mcap, (int64_t)E * Mcap);
+      FQL_CHECK_CUDA(fql_launch_pdl(gelu_bwd_bf16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, t.dHf[l - 1], Zp, t.dZf[l - 1],
+                                    reinterpret_cast<bf16*>(t.dZb[l - 1]), M, H, S, E, Mcap, (int64_t)E * Mcap));
       FQL_CHECK_LAUNCH();
     }
     FQL_CHECK_CUDA(cudaEventRecord(ev[1 + (NL - 1 - l)], st));  // dZ_{l-1} (and dH_{l-1}) ready
@@ -355,11 +365,13 @@ int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cu
   if (!t.grads) return 0;
   // ---- side: parameter gradients
   FQL_CHECK_CUDA(cudaStreamWaitEvent(side, ev[0], 0));
+  if (side2 != side) FQL_CHECK_CUDA(cudaStreamWaitEvent(side2, ev[0], 0));
   FQL_TRY(colsum(t.dOut, 1, 1, M, (long long)E * M, nv.off_b[NL - 1], nullptr, nullptr, nullptr));
   for (int l = NL - 1; l >= 0; l--) {
     const bool last = (l == NL - 1);
     if (!last) {
       FQL_CHECK_CUDA(cudaStreamWaitEvent(side, ev[1 + (NL - 2 - l)], 0));  // dZ_l
+      if (side2 != side) FQL_CHECK_CUDA(cudaStreamWaitEvent(side2, ev[1 + (NL - 2 - l)], 0));
       FQL_TRY(colsum(t.dZf[l], H, H, dz_se, dz_ss, nv.off_b[l], nullptr, nullptr, nullptr));
       if (nv.ln) {
         const float* Zl = t.buf->Z[l] + prow * H;
@@ -414,10 +426,10 @@ int tc_critic_forward(const TcCritic& t, int net, float* out, cudaStream_t st) {
       g.out_f = tp(t.buf->Z[l] + prow * H, z_se, z_ss, H);
       FQL_TRY(tc_gemm(g, st));
       const int64_t rows = (int64_t)S * E * M;
-      act_ln_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
-          t.buf->Z[l] + prow * H, nv.ln ? t.params + nv.off_lns[l] : nullptr, nv.ln ? t.params + nv.off_lnb[l] : nullptr, L.arena, H,
-          reinterpret_cast<bf16*>(t.Hb[l]) + prow * H, nv.ln ? t.buf->mu[l] + prow : nullptr, nv.ln ? t.buf->rstd[l] + prow : nullptr, M, H, S, E,
-          nv.ln);
+      FQL_CHECK_CUDA(fql_launch_pdl(act_ln_bf16_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, t.buf->Z[l] + prow * H,
+                                    nv.ln ? t.params + nv.off_lns[l] : nullptr, nv.ln ? t.params + nv.off_lnb[l] : nullptr, L.arena, (int64_t)H,
+                                    reinterpret_cast<bf16*>(t.Hb[l]) + prow * H, nv.ln ? t.buf->mu[l] + prow : nullptr,
+                                    nv.ln ? t.buf->rstd[l] + prow : nullptr, M, H, S, E, (int)nv.ln));
       FQL_CHECK_LAUNCH();
     } else {
       g.N = 1;
