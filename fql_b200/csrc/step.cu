@@ -171,7 +171,7 @@ size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w)
   w->target = c.take(S * B * A);
   w->dX0 = c.take(S * 2 * B * (F + A));
   w->raw_local = c.take(S * FQL_NUM_RAW);
-  w->gstats = c.take(S * 4);
+  w->gstats = c.take(S * 4 + 4);  // + Adam bias corrections {1 - b1^t, 1 - b2^t} of the step in flight
   w->partials = c.take(S * (int64_t)L.leaf_blk[L.n_leaves] * 4);
   if (d->reserved[0] > 0) {
     for (int i = 0; i < 5; i++) w->feat[i] = c.take(S * B * F);
@@ -596,7 +596,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4], ev_pad = ctx->ev[5];
   const int kO = (int)round_up64(sh.F + sh.A, 64), kF = (int)round_up64(sh.F + sh.A + 1, 64);
   FQL_TRY(stamp(ctx, 0, S0));   // step start
-  FQL_TRY(launch_zero(raw, (int64_t)S * FQL_NUM_RAW, S0));
+  FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0));
   FQL_TRY(encode_observations(c, L, w, S0));
   FQL_TRY(launch_prep(sh, b, w, S0));
   FQL_TRY(stamp(ctx, 1, S0));   // prep done
@@ -737,10 +737,10 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[52], S0));
       FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[52], 0));
       const int blk0 = (int)(L.net[FQL_NET_CRITIC].begin / FQL_LEAF_PAD), blk1 = (int)(L.net[FQL_NET_ACTOR_ONESTEP_FLOW].begin / FQL_LEAF_PAD);
-      FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, c.st->count, w.partials, c.st->shadow,
+      FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, w.gstats + S * 4, w.partials, c.st->shadow,
                                        tc_shadow_seed_elems(d, L), S2, blk0, blk1));   // critic (+ Polyak into the target)
       FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ev_euler, 0));
-      FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, c.st->count, w.partials, c.st->shadow,
+      FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, w.gstats + S * 4, w.partials, c.st->shadow,
                                        tc_shadow_seed_elems(d, L), S2, 0, blk0));      // bc-flow: the Euler chain was its last reader
       ctx->adam_done_blk = blk1;
       FQL_TRY(stamp(ctx, 9, S2)); // early optimizer pass done
@@ -783,7 +783,7 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     const FqlBatch& b = *c.b;
     cudaStream_t S1 = ctx->s1, S2 = ctx->s2;
     cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4];
-    FQL_TRY(launch_zero(raw, (int64_t)S * FQL_NUM_RAW, S0));
+    FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0));
     FQL_TRY(encode_observations(c, L, w, S0));
     FQL_TRY(launch_prep(sh, b, w, S0));
     const bool pix = c.d->reserved[0] > 0;
@@ -877,11 +877,12 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
   ctx->adam_done_blk = 0;
   if (c.do_grads && tcm) FQL_TRY(enqueue_grads_tc(ctx, c, L, w, sh, hp, raw, S0));
   if (c.do_apply) {
+    if (!c.do_grads) FQL_TRY(launch_zero_bc(nullptr, 0, c.st->count, hp, w.gstats + S * 4, S0));
     // Adam + Polyak + gradient statistics (+ the bf16 operand shadow of the new parameters) in one pass over the arenas
     // (the target critic's blocks carry no gradient and are written by the critic's CTAs: skipped when the pass is split)
     const int blk0 = ctx->adam_done_blk;
     const int blk1 = blk0 ? (int)(L.net[FQL_NET_TARGET_CRITIC].begin / FQL_LEAF_PAD) : -1;
-    FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, c.st->count, w.partials,
+    FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, w.gstats + S * 4, w.partials,
                                      tcm ? c.st->shadow : nullptr, tcm ? tc_shadow_seed_elems(c.d, L) : 0, S0, blk0, blk1));
     FQL_TRY(stamp(ctx, 11, S0));  // optimizer pass done
     if (tcm) {  // the zero-padded narrow last-layer copies, beside the statistics tail
