@@ -60,10 +60,21 @@ struct EulerArgs {
   __nv_bfloat16* hx;            // exchange scratch [2][S*tiles*128][H]
   long long hx_buf_elems;
   float* state;                 // fp32 Euler state between steps, per CTA: [CTA][MAX_A][128] (keeps 32 registers out of the epilogue)
+  // MODE_FWD (one forward pass with the activations saved for the backward): bf16 [S][rows_cap][H] per hidden layer, element
+  // (s, r0 + row, col); the H buffers double as the exchange buffers.  out: fp32 [S][rows_cap][A]
+  __nv_bfloat16* Hsave[FQL_MAXL];
+  __nv_bfloat16* Zsave[FQL_MAXL];
+  float* out;
+  int rows_cap, r0;
   unsigned long long* dbg;  // optional [CTA][16] globaltimer stamps of iteration DBG_IT (diagnostics)
   unsigned long long* t_start;  // optional: kernel start / end time of CTA 0 (diagnostics)
   int dbg_it;                   // layer iteration the dbg stamps are taken at
 };
+
+struct HMaps {
+  CUtensorMap m[4];  // MODE_EULER: m[0] = exchange scratch; MODE_FWD: m[l] = H buffer of layer l
+};
+constexpr int MODE_EULER = 0, MODE_FWD = 1;
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -112,11 +123,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 
 // AMAX: compile-time bound of action_dim (the Euler update is unrolled over it; the kernel's code must stay small -- the rarely
 // executed last-layer path was measured at 3.5 us, mostly instruction fetch, when it was unrolled to 32 actions)
-template <int NC, int AMAX>
+template <int NC, int AMAX, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid_constant__ CUtensorMap mapX,
                                                                const __grid_constant__ CUtensorMap mapW,
                                                                const __grid_constant__ CUtensorMap mapWL,
-                                                               const __grid_constant__ CUtensorMap mapHx, const EulerArgs a) {
+                                                               const __grid_constant__ HMaps mapsH, const EulerArgs a) {
   constexpr int NCOL = 512 / NC;            // output columns per CTA (64 / 32)
   constexpr int HALVES = NCOL / SUB;        // 32-column exchange units per CTA (2 / 1)
   constexpr int B_ROWB = NCOL * 2;          // bytes per K row of the weight slice (128: SWIZZLE_128B, 64: SWIZZLE_64B)
@@ -155,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     tma_prefetch_desc(&mapX);
     tma_prefetch_desc(&mapW);
     tma_prefetch_desc(&mapWL);
-    tma_prefetch_desc(&mapHx);
+    for (int i = 0; i < (MODE == MODE_FWD ? NL - 1 : 1); i++) tma_prefetch_desc(&mapsH.m[i]);
     for (int i = 0; i < NSUB; i++) mbar_init(&full_a[i], 1);
     mbar_init(&half_ready[0], NEPI);
     mbar_init(&half_ready[1], NEPI);
@@ -215,8 +226,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
             const int sbk = (int)j * HALVES + h;
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-                ::"r"(smem_u32(sA + sbk * A_SUB)), "l"(reinterpret_cast<uint64_t>(&mapHx)), "r"(smem_u32(&full_a[sbk])),
-                "r"(sbk * SUB), "r"(buf * (a.S * a.tiles * TILE_M) + hx_row), "h"(MASK)
+                ::"r"(smem_u32(sA + sbk * A_SUB)), "l"(reinterpret_cast<uint64_t>(MODE == MODE_FWD ? &mapsH.m[l - 1] : &mapsH.m[0])),
+                "r"(smem_u32(&full_a[sbk])), "r"(sbk * SUB),
+                "r"(MODE == MODE_FWD ? s * a.rows_cap + a.r0 + tile * TILE_M : buf * (a.S * a.tiles * TILE_M) + hx_row), "h"(MASK)
                 : "memory");
           }
           n_pub++;
@@ -292,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
       const bool last = (l == NL - 1);
       const float* sb = sBias + l * 64;
       float ac[AMAX];  // Euler state of this row: fetched while the last layer's MMAs run (registers are free in this phase)
-      if (last) {
+      if (MODE == MODE_EULER && last) {
 #pragma unroll
         for (int c = 0; c < AMAX; c++)
           if (c < a.A) ac[c] = (step == 0) ? (valid ? __ldg(a.a0 + ((int64_t)s * a.M + grow) * a.A + c) : 0.f) : __ldcg(st_row + c * TILE_M);
@@ -332,18 +344,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
           }
         }
         if (!last) {
-          uint4* dst = reinterpret_cast<uint4*>(a.hx + (int64_t)buf * a.hx_buf_elems + (int64_t)(hx_row + row) * a.H + j * NCOL + half * 32);
+          if constexpr (MODE == MODE_EULER) {
+            uint4* dst = reinterpret_cast<uint4*>(a.hx + (int64_t)buf * a.hx_buf_elems + (int64_t)(hx_row + row) * a.H + j * NCOL + half * 32);
 #pragma unroll
-          for (int c = 0; c < 4; c++) {
-            float h[8];
+            for (int c = 0; c < 4; c++) {
+              float h[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) h[i] = gelu_fast(__uint_as_float(r0[c * 8 + i]) + sb[half * 32 + c * 8 + i]);
-            dst[c] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+              for (int i = 0; i < 8; i++) h[i] = gelu_fast(__uint_as_float(r0[c * 8 + i]) + sb[half * 32 + c * 8 + i]);
+              dst[c] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+            }
+          } else if (valid) {
+            // utils/networks.py:54-56: z = xW + b (saved for gelu' in the backward), h = gelu(z) (saved = the next layer's operand)
+            const int64_t e0 = ((int64_t)s * a.rows_cap + a.r0 + grow) * a.H + j * NCOL + half * 32;
+            uint4* dh = reinterpret_cast<uint4*>(a.Hsave[l] + e0);
+            uint4* dz = reinterpret_cast<uint4*>(a.Zsave[l] + e0);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              float z[8], h[8];
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                z[i] = __uint_as_float(r0[c * 8 + i]) + sb[half * 32 + c * 8 + i];
+                h[i] = gelu_fast(z[i]);
+              }
+              dh[c] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+              dz[c] = make_uint4(pack2(z[0], z[1]), pack2(z[2], z[3]), pack2(z[4], z[5]), pack2(z[6], z[7]));
+            }
           }
           // this warp's rows are in the scratch: the producer thread multicasts the 32 columns once all NEPI warps arrived
           __syncwarp();
           if (lane == 0) mbar_arrive(&half_ready[half]);
           if (dbg && et == 0 && it == DBG_IT - 1) dbg[1 + half] = gtime();
+        } else if (MODE == MODE_FWD) {
+          if (half == 0 && j == 0 && valid) {  // every CTA computes the narrow last layer; one writes it
+            float* o = a.out + ((int64_t)s * a.rows_cap + a.r0 + grow) * a.A;
+#pragma unroll
+            for (int c = 0; c < AMAX; c++)
+              if (c < a.A) o[c] = __uint_as_float(r0[c]) + sb[c];
+          }
         } else if (half == 0) {
           // Euler step on this CTA's resident copy of the first-layer operand (every CTA computes the same last layer)
           if (dbg && et == 0 && it == DBG_IT - 1) dbg[13] = gtime();
@@ -421,13 +458,13 @@ size_t tc_euler_scratch_elems(const FqlDims* d, int M) {
 }
 
 namespace {
-template <int NC, int AMAX>
+template <int NC, int AMAX, int MODE>
 int launch_euler(const EulerArgs& a, const TcEulerSpec& f, cudaStream_t st, bool query_only, int* max_clusters) {
   constexpr int NCOL = 512 / NC;
   const FqlDims* d = f.d;
   const int smem = NSUB * A_SUB + (a.H / KB) * (KB * NCOL * 2) + (a.K0pad / KB) * A_BLK + FQL_MAXL * 64 * 4 + 64 * 4 + 256 + 1024;
   FQL_REQUIRE(smem <= 232448, "euler_cluster_kernel: shared memory %d > 227 KB", smem);
-  auto kern = euler_cluster_kernel<NC, AMAX>;
+  auto kern = euler_cluster_kernel<NC, AMAX, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -456,29 +493,34 @@ int launch_euler(const EulerArgs& a, const TcEulerSpec& f, cudaStream_t st, bool
     return 0;
   }
   const CUtensorMapSwizzle wsw = (NC == 8) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUtensorMap mapX, mapW, mapWL, mapHx;
+  CUtensorMap mapX, mapW, mapWL;
+  HMaps mapsH;
+  memset(&mapsH, 0, sizeof(mapsH));
   FQL_TRY(make_map_2d(&mapX, f.X0b, a.K0pad, (uint64_t)a.S * f.Mcap0, 64, TILE_M));
   FQL_TRY(make_map_2d(&mapW, f.shadow, d->hidden, (uint64_t)a.S * a.w_rows_s, NCOL, KB, wsw));
   FQL_TRY(make_map_2d(&mapWL, f.shadow, 64, (uint64_t)a.S * a.wl_rows_s, NCOL, KB, wsw));  // NC = 16: the first 32 (>= action_dim) columns
-  FQL_TRY(make_map_2d(&mapHx, f.scratch, d->hidden, (uint64_t)2 * a.S * a.tiles * TILE_M, SUB, TILE_M, CU_TENSOR_MAP_SWIZZLE_64B));
-  FQL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mapX, mapW, mapWL, mapHx, a));
+  if (MODE == MODE_EULER) {
+    FQL_TRY(make_map_2d(&mapsH.m[0], f.scratch, d->hidden, (uint64_t)2 * a.S * a.tiles * TILE_M, SUB, TILE_M, CU_TENSOR_MAP_SWIZZLE_64B));
+  } else {
+    for (int l = 0; l + 1 < a.NL; l++)
+      FQL_TRY(make_map_2d(&mapsH.m[l], a.Hsave[l], d->hidden, (uint64_t)a.S * a.rows_cap, SUB, TILE_M, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
+  FQL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mapX, mapW, mapWL, mapsH, a));
   FQL_CHECK_LAUNCH();
   return 0;
 }
 }  // namespace
 
-int tc_euler_cluster(const TcEulerSpec& f, cudaStream_t st) {
-  const FqlDims* d = f.d;
-  const Layout& L = *f.L;
+namespace {
+int fill_args(EulerArgs& a, const FqlDims* d, const Layout& L, int net, const float* params, int M, int Mcap0, int r0_in) {
   FQL_TRY(tc_supported(d));
   FQL_REQUIRE(d->hidden == 512, "euler_cluster_kernel is built for hidden = 512 (16 exchange units of 32 columns)");
-  const NetView& nv = L.net[FQL_NET_ACTOR_BC_FLOW];
-  EulerArgs a;
+  const NetView& nv = L.net[net];
   memset(&a, 0, sizeof(a));
-  a.H = d->hidden; a.K0 = nv.in_dim; a.K0pad = (int)round_up64(nv.in_dim, 64); a.A = d->action_dim; a.F = d->obs_dim;
-  a.n_steps = d->flow_steps; a.NL = nv.n_layers;
-  a.S = d->num_seeds; a.M = f.M; a.tiles = (f.M + TILE_M - 1) / TILE_M;
-  a.x_rows_s = f.Mcap0; a.x_row0 = f.r0_in;
+  a.H = d->hidden; a.K0 = nv.in_dim; a.K0pad = (int)round_up64(nv.in_dim, 64); a.A = nv.out_dim; a.F = d->obs_dim;
+  a.n_steps = 1; a.NL = nv.n_layers;
+  a.S = d->num_seeds; a.M = M; a.tiles = (M + TILE_M - 1) / TILE_M;
+  a.x_rows_s = Mcap0; a.x_row0 = r0_in;
   const int64_t seed_elems = tc_shadow_seed_elems(d, L);
   a.w_rows_s = (int)(seed_elems / d->hidden);
   a.wl_rows_s = (int)(seed_elems / 64);
@@ -487,28 +529,68 @@ int tc_euler_cluster(const TcEulerSpec& f, cudaStream_t st) {
     a.off_b[l] = nv.off_b[l];
   }
   int64_t wl = L.arena;
-  for (int t = 0; t < FQL_NET_ACTOR_BC_FLOW; t++) wl += (int64_t)L.net[t].ens * d->hidden * 64;
+  for (int t = 0; t < net; t++) wl += (int64_t)L.net[t].ens * d->hidden * 64;
   a.wl_row = (int)(wl / 64);
-  a.params = f.params; a.arena = L.arena; a.a0 = f.a0; a.target = f.target;
+  a.params = params; a.arena = L.arena;
+  FQL_REQUIRE(a.A <= MAX_A, "euler_cluster_kernel: output width %d > %d", a.A, MAX_A);
+  a.dbg_it = getenv("FQL_B200_EULER_DBG_IT") ? atoi(getenv("FQL_B200_EULER_DBG_IT")) : 7;
+  return 0;
+}
+// clusters of 16 CTAs the GPU can hold at once (one per GPC); 0 when FQL_B200_EULER_NC=8 forces clusters of 8
+int max_clusters16(const EulerArgs& a, const TcEulerSpec& f) {
+  static int max16 = -1;
+  if (max16 < 0) {
+    const char* e = getenv("FQL_B200_EULER_NC");
+    if (e && atoi(e) == 8) max16 = 0;
+    else if (launch_euler<16, 8, MODE_EULER>(a, f, nullptr, true, &max16)) max16 = 0;
+    if (getenv("FQL_B200_VERBOSE")) fprintf(stderr, "fql_b200: clusters of 16 CTAs resident at once: %d\n", max16);
+  }
+  return max16;
+}
+}  // namespace
+
+int tc_euler_cluster(const TcEulerSpec& f, cudaStream_t st) {
+  const FqlDims* d = f.d;
+  EulerArgs a;
+  FQL_TRY(fill_args(a, d, *f.L, FQL_NET_ACTOR_BC_FLOW, f.params, f.M, f.Mcap0, f.r0_in));
+  a.A = d->action_dim; a.n_steps = d->flow_steps;
+  a.a0 = f.a0; a.target = f.target;
   a.hx = reinterpret_cast<__nv_bfloat16*>(f.scratch);
   a.hx_buf_elems = (long long)a.S * a.tiles * TILE_M * a.H;
   a.state = reinterpret_cast<float*>(a.hx + 2 * a.hx_buf_elems);
   a.dbg = reinterpret_cast<unsigned long long*>(f.dbg);
   a.t_start = reinterpret_cast<unsigned long long*>(f.t_start);
-  a.dbg_it = getenv("FQL_B200_EULER_DBG_IT") ? atoi(getenv("FQL_B200_EULER_DBG_IT")) : 7;
   FQL_REQUIRE(f.scratch != nullptr && f.a0 && f.target, "tc_euler_cluster: NULL argument");
-  FQL_REQUIRE(a.A <= MAX_A, "euler_cluster_kernel: action_dim %d > %d", a.A, MAX_A);
+  FQL_REQUIRE(a.n_steps < 64, "euler_cluster_kernel: flow_steps %d >= 64", a.n_steps);
   // clusters of 16 (one per GPC) halve the per-layer epilogue; fall back to clusters of 8 when there are more row tiles than the
   // GPU can hold clusters of 16 at once
-  static int max16 = -1;
-  if (max16 < 0) {
-    const char* e = getenv("FQL_B200_EULER_NC");
-    if (e && atoi(e) == 8) max16 = 0;
-    else FQL_TRY((launch_euler<16, 8>(a, f, st, true, &max16)));
+  const bool c16 = a.tiles * a.S <= max_clusters16(a, f);
+  if (a.A <= 8) return c16 ? launch_euler<16, 8, MODE_EULER>(a, f, st, false, nullptr) : launch_euler<8, 8, MODE_EULER>(a, f, st, false, nullptr);
+  if (a.A <= 16) return c16 ? launch_euler<16, 16, MODE_EULER>(a, f, st, false, nullptr) : launch_euler<8, 16, MODE_EULER>(a, f, st, false, nullptr);
+  return c16 ? launch_euler<16, 32, MODE_EULER>(a, f, st, false, nullptr) : launch_euler<8, 32, MODE_EULER>(a, f, st, false, nullptr);
+}
+
+// One forward pass of an actor network (no LayerNorm) on M rows as a cluster-of-16 chain, activations saved for the backward.
+// other_clusters: clusters of 16 that run at the same time (the Euler chain).  Returns 1 when the kernel cannot take the problem
+// (the caller then uses the layer-by-layer path), 0 on success, -1 on error.
+int tc_cluster_forward(const TcClusterFwdSpec& f, int other_clusters, cudaStream_t st) {
+  const FqlDims* d = f.d;
+  const NetView& nv = f.L->net[f.net];
+  if (d->hidden != 512 || nv.ln || nv.n_layers > 5 || nv.n_layers < 2 || nv.out_dim > MAX_A || nv.in_dim > 128) return 1;
+  EulerArgs a;
+  if (fill_args(a, d, *f.L, f.net, f.params, f.M, f.rows_cap, f.r0)) return -1;
+  TcEulerSpec e;
+  memset(&e, 0, sizeof(e));
+  e.d = d; e.L = f.L; e.params = f.params; e.shadow = f.shadow; e.X0b = f.X0b; e.Mcap0 = f.rows_cap; e.r0_in = f.r0; e.M = f.M;
+  if (a.tiles * a.S + other_clusters > max_clusters16(a, e)) return 1;
+  for (int l = 0; l + 1 < nv.n_layers; l++) {
+    a.Hsave[l] = reinterpret_cast<__nv_bfloat16*>(f.Hb[l]);
+    a.Zsave[l] = reinterpret_cast<__nv_bfloat16*>(f.Zb[l]);
+    if (!a.Hsave[l] || !a.Zsave[l]) return 1;
   }
-  FQL_REQUIRE(a.n_steps < 64, "euler_cluster_kernel: flow_steps %d >= 64", a.n_steps);
-  const bool c16 = a.tiles * a.S <= max16;
-  if (a.A <= 8) return c16 ? launch_euler<16, 8>(a, f, st, false, nullptr) : launch_euler<8, 8>(a, f, st, false, nullptr);
-  if (a.A <= 16) return c16 ? launch_euler<16, 16>(a, f, st, false, nullptr) : launch_euler<8, 16>(a, f, st, false, nullptr);
-  return c16 ? launch_euler<16, 32>(a, f, st, false, nullptr) : launch_euler<8, 32>(a, f, st, false, nullptr);
+  a.out = f.out; a.rows_cap = f.rows_cap; a.r0 = f.r0;
+  a.t_start = reinterpret_cast<unsigned long long*>(f.t_start);
+  if (a.A <= 8) return launch_euler<16, 8, MODE_FWD>(a, e, st, false, nullptr) ? -1 : 0;
+  if (a.A <= 16) return launch_euler<16, 16, MODE_FWD>(a, e, st, false, nullptr) ? -1 : 0;
+  return launch_euler<16, 32, MODE_FWD>(a, e, st, false, nullptr) ? -1 : 0;
 }

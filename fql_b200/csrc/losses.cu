@@ -72,7 +72,8 @@ __global__ void prep_kernel(StepShape sh, FqlBatch b, WsPtrs w) {
 
 // After the one-step actor pass on rows {(s',z_next), (s,z), (s,z')}: clip and scatter the actions into the critic
 // inputs (fql.py:25-26, 69-70) and reduce the logging mse (fql.py:82-83).
-__global__ void post_onestep_kernel(StepShape sh, FqlBatch b, WsPtrs w, float* raw) {
+// parts: bit 0 = the critic inputs (row groups (s',z') and (s,z)), bit 1 = the mse metric (row group (s,z''))
+__global__ void post_onestep_kernel(StepShape sh, FqlBatch b, WsPtrs w, float* raw, int parts) {
   __shared__ float red[32];
   const int s = blockIdx.x;
   const int F = sh.F, A = sh.A, B = sh.B, KC = F + A;
@@ -80,18 +81,24 @@ __global__ void post_onestep_kernel(StepShape sh, FqlBatch b, WsPtrs w, float* r
   float mse = 0.f;
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < B * A; i += gridDim.y * blockDim.x) {
     const int r = i / A, c = i % A;
-    w.XC[((int64_t)(0 * sh.S + s) * B + r) * KC + F + c] = clip1(out[i]);
-    w.XC[((int64_t)(2 * sh.S + s) * B + r) * KC + F + c] = clip1(out[(int64_t)B * A + i]);
-    float d = clip1(out[(int64_t)2 * B * A + i]) - b.actions[(int64_t)s * B * A + i];
-    mse += d * d;
+    if (parts & 1) {
+      w.XC[((int64_t)(0 * sh.S + s) * B + r) * KC + F + c] = clip1(out[i]);
+      w.XC[((int64_t)(2 * sh.S + s) * B + r) * KC + F + c] = clip1(out[(int64_t)B * A + i]);
+    }
+    if (parts & 2) {
+      float d = clip1(out[(int64_t)2 * B * A + i]) - b.actions[(int64_t)s * B * A + i];
+      mse += d * d;
+    }
   }
+  if (!(parts & 2)) return;
   mse = block_reduce<0>(mse, red);
   if (threadIdx.x == 0) atomicAdd(&raw[s * FQL_NUM_RAW + RAW_MSE], mse);  // raw is zeroed at the start of the step
 }
 
 // TD target + critic loss gradient (fql.py:28-44) and the actor's Q statistics / dQ seed (fql.py:70-76).
 // qout: [3][S][2][B]  (0: target critic on (s',a'), 1: critic on (s,a), 2: critic on (s, clip a_pi))
-__global__ void critic_post_kernel(StepShape sh, FqlHparams hp, FqlBatch b, WsPtrs w, float* raw) {
+// parts: bit 0 = TD / critic-loss half (problems 0, 1), bit 1 = actor-Q half (problem 2)
+__global__ void critic_post_kernel(StepShape sh, FqlHparams hp, FqlBatch b, WsPtrs w, float* raw, int parts) {
   __shared__ float red[32];
   const int s = blockIdx.x;
   const int B = sh.B, S = sh.S;
@@ -101,39 +108,49 @@ __global__ void critic_post_kernel(StepShape sh, FqlHparams hp, FqlBatch b, WsPt
   const float inv_2gb = 1.0f / (2.0f * (float)sh.GB);
   float sq = 0.f, qs = 0.f, qmx = -INFINITY, qmn = INFINITY, ps = 0.f, pa = 0.f;
   for (int r = threadIdx.x; r < B; r += blockDim.x) {
-    const float t0 = q_t[r], t1 = q_t[B + r];
-    const float nq = sh.q_agg_min ? fminf(t0, t1) : (t0 + t1) * 0.5f;
-    const float y = b.rewards[(int64_t)s * B + r] + hp.discount * b.masks[(int64_t)s * B + r] * nq;
+    if (parts & 1) {
+      const float t0 = q_t[r], t1 = q_t[B + r];
+      const float nq = sh.q_agg_min ? fminf(t0, t1) : (t0 + t1) * 0.5f;
+      const float y = b.rewards[(int64_t)s * B + r] + hp.discount * b.masks[(int64_t)s * B + r] * nq;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const float q = q_c[h * B + r];
-      const float d = q - y;
-      sq += d * d;
-      qs += q;
-      qmx = fmaxf(qmx, q);
-      qmn = fminf(qmn, q);
-      w.dq[((int64_t)s * 2 + h) * B + r] = 2.0f * d * inv_2gb;
+      for (int h = 0; h < 2; h++) {
+        const float q = q_c[h * B + r];
+        const float d = q - y;
+        sq += d * d;
+        qs += q;
+        qmx = fmaxf(qmx, q);
+        qmn = fminf(qmn, q);
+        w.dq[((int64_t)s * 2 + h) * B + r] = 2.0f * d * inv_2gb;
+      }
     }
-    const float qp = (q_p[r] + q_p[B + r]) * 0.5f;
-    ps += qp;
-    pa += fabsf(qp);
+    if (parts & 2) {
+      const float qp = (q_p[r] + q_p[B + r]) * 0.5f;
+      ps += qp;
+      pa += fabsf(qp);
+    }
   }
-  sq = block_reduce<0>(sq, red);
-  qs = block_reduce<0>(qs, red);
-  ps = block_reduce<0>(ps, red);
-  pa = block_reduce<0>(pa, red);
-  qmx = block_reduce<1>(qmx, red);
-  qmn = -block_reduce<1>(-qmn, red);
-  // lam = 1/mean|q| over the (global) batch, stop-gradient (fql.py:74-76)
-  float lam = 1.0f;
-  if (sh.normalize_q_loss) lam = 1.0f / (pa / (float)sh.GB);
-  if (threadIdx.x == 0) {
-    float* rw = raw + s * FQL_NUM_RAW;
-    rw[RAW_CRITIC_SQ] = sq; rw[RAW_Q_SUM] = qs; rw[RAW_QPI_SUM] = ps; rw[RAW_QPI_ABS] = pa;
-    rw[RAW_Q_MAX] = qmx; rw[RAW_Q_NEGMIN] = -qmn;
+  float* rw = raw + s * FQL_NUM_RAW;
+  if (parts & 1) {
+    sq = block_reduce<0>(sq, red);
+    qs = block_reduce<0>(qs, red);
+    qmx = block_reduce<1>(qmx, red);
+    qmn = -block_reduce<1>(-qmn, red);
+    if (threadIdx.x == 0) {
+      rw[RAW_CRITIC_SQ] = sq; rw[RAW_Q_SUM] = qs; rw[RAW_Q_MAX] = qmx; rw[RAW_Q_NEGMIN] = -qmn;
+    }
   }
-  const float dqs = -lam * inv_2gb;
-  for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) w.dqs[(int64_t)s * 2 * B + i] = dqs;
+  if (parts & 2) {
+    ps = block_reduce<0>(ps, red);
+    pa = block_reduce<0>(pa, red);
+    // lam = 1/mean|q| over the (global) batch, stop-gradient (fql.py:74-76)
+    float lam = 1.0f;
+    if (sh.normalize_q_loss) lam = 1.0f / (pa / (float)sh.GB);
+    if (threadIdx.x == 0) {
+      rw[RAW_QPI_SUM] = ps; rw[RAW_QPI_ABS] = pa;
+    }
+    const float dqs = -lam * inv_2gb;
+    for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) w.dqs[(int64_t)s * 2 * B + i] = dqs;
+  }
 }
 
 // BC flow-matching loss gradient (fql.py:58-59): pred rows are rows [0,B) of the bc-flow pass output.
@@ -278,13 +295,13 @@ int launch_prep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, cudaStr
   FQL_CHECK_LAUNCH();
   return 0;
 }
-int launch_post_onestep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st) {
-  post_onestep_kernel<<<dim3(sh.S, loss_ctas(sh)), 1024, 0, st>>>(sh, b, w, raw);
+int launch_post_onestep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts) {
+  post_onestep_kernel<<<dim3(sh.S, loss_ctas(sh)), 1024, 0, st>>>(sh, b, w, raw, parts);
   FQL_CHECK_LAUNCH();
   return 0;
 }
-int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st) {
-  critic_post_kernel<<<sh.S, 1024, 0, st>>>(sh, hp, b, w, raw);
+int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts) {
+  critic_post_kernel<<<sh.S, 1024, 0, st>>>(sh, hp, b, w, raw, parts);
   FQL_CHECK_LAUNCH();
   return 0;
 }

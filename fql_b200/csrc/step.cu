@@ -415,6 +415,7 @@ struct FqlContext {
   std::vector<GraphEntry> graphs;
   int use_graph = 1;
   int use_euler_cluster = 1;
+  int use_cluster_fwd = 1;   // FQL_B200_CLUSTER_FWD=0: one-step actor forward layer by layer
   unsigned long long* stamps = nullptr;  // FQL_B200_STAMPS=1: %globaltimer at schedule points (diagnostics, profiles/dbg_timeline.py)
   int split_adam = 0;        // FQL_B200_SPLIT_ADAM=1: optimizer pass over bc-flow|critic(+target) overlaps the one-step actor's backward
                              // (measured: no gain -- its HBM traffic slows the Euler tail and the dgrad chain by what it saves)
@@ -486,6 +487,8 @@ extern "C" int fql_context_create(FqlContext** out) {
   if (g && g[0] == '0') c->use_graph = 0;
   const char* ec = getenv("FQL_B200_EULER_CLUSTER");
   if (ec && ec[0] == '0') c->use_euler_cluster = 0;
+  const char* cfw = getenv("FQL_B200_CLUSTER_FWD");
+  if (cfw && cfw[0] == '0') c->use_cluster_fwd = 0;
   const char* stp = getenv("FQL_B200_STAMPS");
   if (stp && stp[0] == '1') {
     FQL_CHECK_CUDA(cudaMalloc(&c->stamps, 576 * sizeof(unsigned long long)));  // 64 schedule points + [32 CTAs][16] Euler phases
@@ -674,15 +677,42 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   // ---- S0: one-step actor on {(s',z_next), (s,z), (s,z')}, grouped critic pass
   FQL_TRY(tc_pad_bf16(w.XO, w.XOb, (int64_t)S * 3 * B, sh.F + sh.A, kO, S0));
   TcActor fo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, true);
-  if (many_tiles) FQL_TRY(chain(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, w.O_out, 1, S0));
-  else FQL_TRY(tc_actor_forward(fo, w.O_out, (long long)3 * B * sh.A, 0, nullptr, S0));
+  bool split_metric = false;
+  if (many_tiles) {
+    FQL_TRY(chain(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, w.O_out, 1, S0));
+  } else {
+    // small batch: the same cluster-of-16 chain kernel as the Euler integration (2.7 us per layer instead of a GEMM launch each)
+    int rc = 1;
+    if (ctx->use_euler_cluster && ctx->use_cluster_fwd) {
+      // rows (s',z') and (s,z) feed the critic passes that everything else waits for; the (s,z'') rows only feed the mse metric
+      // and go layer by layer on a side stream (the GPU holds 7 clusters of 16: 2 Euler + 4 here)
+      TcClusterFwdSpec cf;
+      memset(&cf, 0, sizeof(cf));
+      cf.d = d; cf.L = &L; cf.params = P; cf.shadow = shadow; cf.net = FQL_NET_ACTOR_ONESTEP_FLOW; cf.X0b = w.XOb; cf.rows_cap = 3 * B; cf.r0 = 0;
+      cf.M = 2 * B; cf.Hb = w.O_Hb; cf.Zb = w.O_Zb; cf.out = w.O_out;
+      cf.t_start = ctx->stamps ? ctx->stamps + 15 : nullptr;
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[56], S0));  // XOb padded
+      rc = tc_cluster_forward(cf, row_tiles, S0);
+      if (rc < 0) return -1;
+      if (rc == 0) {
+        FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s9, ctx->ev[56], 0));
+        TcActor fm = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, 2 * B, B, w.O_Hb, w.O_Zb, true);
+        FQL_TRY(tc_actor_forward(fm, w.O_out + (int64_t)2 * B * sh.A, (long long)3 * B * sh.A, 0, nullptr, ctx->s9));
+        FQL_TRY(launch_post_onestep(sh, b, w, raw, ctx->s9, 2));
+        FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[57], ctx->s9));
+        split_metric = true;
+      }
+    }
+    if (rc == 1) FQL_TRY(tc_actor_forward(fo, w.O_out, (long long)3 * B * sh.A, 0, nullptr, S0));
+  }
   FQL_TRY(stamp(ctx, 3, S0));   // one-step actor forward done
-  FQL_TRY(launch_post_onestep(sh, b, w, raw, S0));
+  FQL_TRY(launch_post_onestep(sh, b, w, raw, S0, split_metric ? 1 : 3));
   FQL_TRY(tc_pad_bf16(w.XC, w.XCb, (int64_t)3 * S * B, sh.F + sh.A, kO, S0));
   TcCritic cr;
   memset(&cr, 0, sizeof(cr));
   cr.d = d; cr.L = &L; cr.params = P; cr.shadow = shadow; cr.M = B; cr.K0pad = kO; cr.x_ss = (long long)B * kO; cr.buf = &w.pC; cr.Hb = w.C_Hb;
   cr.cs_scratch = w.cs_scratch[2];
+  bool split_cpost = false;
   if (ctx->use_critic_chain) {
     TcChainSpec t;
     memset(&t, 0, sizeof(t));
@@ -692,22 +722,26 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   } else {
     // three independent chains {target critic(s',a'), critic(s,a), critic(s,clip a_pi)}: S0 + two forked streams
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[40], S0));
-    cudaStream_t cs[3] = {S0, ctx->s5, ctx->s6};
+    // problem 2 = critic(s, a_pi) heads the longest chain of the step (-> dQ/da -> one-step actor backward): it stays on the
+    // high-priority main stream, the two TD problems go to the side streams
+    cudaStream_t cs[3] = {ctx->s6, ctx->s5, S0};
     const int nets[3] = {FQL_NET_TARGET_CRITIC, FQL_NET_CRITIC, FQL_NET_CRITIC};
     for (int p = 0; p < 3; p++) {
-      if (p) FQL_CHECK_CUDA(cudaStreamWaitEvent(cs[p], ctx->ev[40], 0));
+      if (cs[p] != S0) FQL_CHECK_CUDA(cudaStreamWaitEvent(cs[p], ctx->ev[40], 0));
       TcCritic f = cr;
       f.p = p; f.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)p * S * B * kO;
       FQL_TRY(tc_critic_forward(f, nets[p], w.C_out, cs[p]));
-      if (p) {
-        FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[40 + p], cs[p]));
-        FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[40 + p], 0));
-      }
+      if (cs[p] != S0) FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[41 + p], cs[p]));
     }
+    // the TD half of the loss kernel follows problems 0 and 1 on their side stream; the main stream only waits for problem 2
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s5, ctx->ev[41], 0));
+    FQL_TRY(launch_critic_post(sh, hp, b, w, raw, ctx->s5, 1));
+    FQL_CHECK_CUDA(cudaEventRecord(ev_cpost, ctx->s5));
+    split_cpost = true;
   }
-  FQL_TRY(stamp(ctx, 5, S0));   // critic forward done
-  FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0));
-  FQL_CHECK_CUDA(cudaEventRecord(ev_cpost, S0));
+  FQL_TRY(stamp(ctx, 5, S0));   // critic forward (problem 2) done
+  FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0, split_cpost ? 2 : 3));
+  if (!split_cpost) FQL_CHECK_CUDA(cudaEventRecord(ev_cpost, S0));
 
   if (c.do_backward) {
     // critic backward (fql.py:36-37) on S2, after the bc-flow backward
@@ -748,6 +782,8 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   }
   FQL_CHECK_CUDA(cudaEventRecord(ev_s2, S2));
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_euler, 0));
+  if (split_metric) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[57], 0));
+  if (split_cpost) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_cpost, 0));
   FQL_TRY(launch_actor_grad(sh, hp, w, raw, S0));
   FQL_TRY(stamp(ctx, 7, S0));   // joined Euler, dL/da done
   if (c.do_backward) {

@@ -61,8 +61,8 @@ StepShape make_shape(const FqlDims* d);
 size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w);  // returns bytes needed
 
 int launch_prep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, cudaStream_t st);
-int launch_post_onestep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st);
-int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st);
+int launch_post_onestep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts = 3);
+int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts = 3);
 int launch_bc_post(const StepShape& sh, const WsPtrs& w, float* raw, cudaStream_t st);
 int launch_euler_update(const StepShape& sh, const WsPtrs& w, int step, cudaStream_t st);
 int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w, float* raw, cudaStream_t st);
@@ -200,6 +200,20 @@ struct TcEulerSpec {
   void* t_start;       // optional: %globaltimer when CTA 0 starts / ends (2 x u64, diagnostics)
 };
 size_t tc_euler_scratch_elems(const FqlDims* d, int M);
+struct TcClusterFwdSpec {
+  const FqlDims* d;
+  const Layout* L;
+  const float* params;
+  const void* shadow;
+  int net;
+  const void* X0b;          // bf16 [S][rows_cap][K0pad]
+  int rows_cap, r0, M;      // rows [r0, r0 + M) of every seed
+  void* const* Hb;          // bf16 [S][rows_cap][H] per hidden layer (saved activations)
+  void* const* Zb;          // bf16 pre-activations
+  float* out;               // fp32 [S][rows_cap][out_dim]
+  void* t_start;            // optional: %globaltimer at start / end of CTA 0 (diagnostics)
+};
+int tc_cluster_forward(const TcClusterFwdSpec& f, int other_clusters, cudaStream_t st);
 int tc_euler_cluster(const TcEulerSpec& f, cudaStream_t st);
 
 // encoder.cu
