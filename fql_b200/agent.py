@@ -365,22 +365,49 @@ class FQLAgent:
             return self._info_out(bufs['info'])
 
     def _dp_step(self, bufs):
-        """Data-parallel step: gradients -> all-reduce (the bc-flow + critic prefix of the arena starts on a side stream as soon as
-        the library's early event fires, while the one-step actor's backward is still running) -> all-gather of the 64-byte metric
-        accumulators -> identical Adam/Polyak step on every rank."""
+        """Data-parallel step: gradients -> NCCL all-reduce of the trainable part of the gradient arena -> all-gather of the 64-byte
+        metric accumulators -> identical Adam/Polyak step on every rank.  After two eager steps the whole sequence (library
+        kernels and both collectives) is captured once into one CUDA graph per batch size and replayed: a step is then a single
+        graph launch instead of two library calls and two process-group calls (the host side was the bottleneck at batch 256)."""
+        if not self._dp_graph:
+            return self._dp_body(bufs)
+        st = bufs.setdefault('dp_graph', {'n': 0, 'graph': None})
+        if st['graph'] is not None:
+            st['graph'].replay()
+            return
+        st['n'] += 1
+        if st['n'] <= 2:
+            return self._dp_body(bufs)
+        try:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                self._dp_body(bufs)
+            st['graph'] = g
+            g.replay()                                   # capture does not execute: this runs the step that was captured
+        except Exception as e:                           # keep training on the eager sequence
+            import warnings
+            warnings.warn(f'fql_b200: data-parallel step could not be captured into a CUDA graph ({e!r}); running it eagerly')
+            type(self)._dp_graph = False
+            torch.cuda.synchronize(self.device)
+            self._dp_body(bufs)
+
+    def _dp_body(self, bufs):
+        """The data-parallel sequence itself.  With FQL_DP_OVERLAP=1 (eager mode only) the bc-flow + critic prefix of the arena starts
+        on a side stream as soon as the library's early event fires, while the one-step actor's backward is still running."""
         import torch.distributed as dist
         from . import dist as fdist
         main = torch.cuda.current_stream(self.device)
-        if self._dp_side is None:
+        overlap = self._dp_overlap and not self._dp_graph
+        if overlap and self._dp_side is None:
             self._dp_side = torch.cuda.Stream(device=self.device)
             self._dp_early = torch.cuda.Event()
             self._dp_early.record(main)                 # materialise the cudaEvent_t
             self._n_early = int(self._lib.fql_early_grads_floats(C.byref(bufs['d'])))
-            if self._dp_overlap:
-                _lib.check(self._lib.fql_set_early_grads_event(self._ctx, C.c_void_p(self._dp_early.cuda_event)), 'fql_set_early_grads_event')
+            _lib.check(self._lib.fql_set_early_grads_event(self._ctx, C.c_void_p(self._dp_early.cuda_event)), 'fql_set_early_grads_event')
         self.grads_phase(bufs)
         t0, _ = self._net_range('target_critic')
-        if self._dp_overlap:
+        if overlap:
             with torch.cuda.stream(self._dp_side):
                 self._dp_side.wait_event(self._dp_early)
                 w1 = dist.all_reduce(self._grads[:, :self._n_early], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
@@ -394,10 +421,11 @@ class FQLAgent:
         _lib.check(self._lib.fql_step_apply_gathered(self._ctx, C.byref(bufs['d']), C.byref(self._hp), C.byref(bufs['st']), _ptr(raw_all),
                                                      self.world, _ptr(bufs['info']), _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()),
                    'fql_step_apply_gathered')
-        self._raw_all = raw_all                         # keep alive until the stream has consumed it
+        bufs['raw_all'] = raw_all                       # keep alive (and at a fixed address for the captured graph)
 
     _dp_side = None
-    _dp_overlap = os.environ.get('FQL_DP_OVERLAP', '1') != '0'
+    _dp_overlap = os.environ.get('FQL_DP_OVERLAP', '0') != '0'
+    _dp_graph = os.environ.get('FQL_DP_GRAPH', '1') != '0'
 
     def grads_phase(self, bufs):
         """Data-parallel half 1 (fql_step_grads): this rank's gradient contribution (already divided by the global batch) into
