@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
   uint8_t* sA = smem;                        // [NSUB][8 KB]: sub-block i = columns [32i, 32i+32) of the layer input
   uint8_t* sB = sA + NSUB * A_SUB;           // [nkb][B_BLK]  weight slice of the current layer
   uint8_t* sX = sB + nkb * B_BLK;            // [nkb_x][16 KB] first-layer operand tile, resident for all steps
-  float* sBias = reinterpret_cast<float*>(sX + nkb_x * A_BLK);  // [FQL_MAXL][64]: this CTA's bias slice of every layer (constant over the steps)
-  float* sT = sBias + FQL_MAXL * 64;  // [n_steps + 1]: the flow time i / n_steps as the reference rounds it (double quotient -> f32)
+  float* sBias = reinterpret_cast<float*>(sX + nkb_x * A_BLK);  // [NL][64]: this CTA's bias slice of every layer (constant over the steps)
+  float* sT = sBias + a.NL * 64;  // [n_steps + 1]: the flow time i / n_steps as the reference rounds it (double quotient -> f32)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sT + 64);
   uint64_t* full_a = bars;          // [NSUB]
   uint64_t* full_b = bars + 16;
@@ -462,7 +462,7 @@ template <int NC, int AMAX, int MODE>
 int launch_euler(const EulerArgs& a, const TcEulerSpec& f, cudaStream_t st, bool query_only, int* max_clusters) {
   constexpr int NCOL = 512 / NC;
   const FqlDims* d = f.d;
-  const int smem = NSUB * A_SUB + (a.H / KB) * (KB * NCOL * 2) + (a.K0pad / KB) * A_BLK + FQL_MAXL * 64 * 4 + 64 * 4 + 256 + 1024;
+  const int smem = NSUB * A_SUB + (a.H / KB) * (KB * NCOL * 2) + (a.K0pad / KB) * A_BLK + a.NL * 64 * 4 + 64 * 4 + 256 + 1024;
   FQL_REQUIRE(smem <= 232448, "euler_cluster_kernel: shared memory %d > 227 KB", smem);
   auto kern = euler_cluster_kernel<NC, AMAX, MODE>;
   static bool attr_set = false;

@@ -18,7 +18,7 @@ from tests.helpers import cuda_agent_from_state, f32, info_close, make_case, rel
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('hidden,F,A,rows', [(128, 11, 3, 40), (512, 29, 8, 256), (512, 69, 21, 300), (512, 83, 5, 129), (256, 28, 5, 1)])
+@pytest.mark.parametrize('hidden,F,A,rows', [(128, 11, 3, 40), (512, 29, 8, 256), (512, 69, 21, 300), (512, 69, 21, 1100), (512, 83, 5, 129), (256, 28, 5, 1)])
 def test_tc_forward_chains(hidden, F, A, rows):
     cfg, state, _, _ = make_case(dict(), 8, F, A, seed=hidden + rows, hidden=hidden)
     agent = cuda_agent_from_state(cfg, state, 8, F, A, precision='bf16')
