@@ -41,31 +41,47 @@ int64_t wl_offset(const FqlDims* d, const Layout& L, int net) {
   return o;
 }
 
-// H = [LayerNorm](gelu(Z)) -> bf16 (+ row statistics); one warp per row.  Z: fp32 [rows][N] contiguous; scale/bias per (s, e).
-__global__ void __launch_bounds__(256) act_ln_bf16_kernel(const float* __restrict__ Z, const float* __restrict__ scale_base,
-                                                          const float* __restrict__ bias_base, int64_t par_s, int64_t par_e,
-                                                          bf16* __restrict__ Hb, float* __restrict__ mu_out, float* __restrict__ rstd_out,
-                                                          int M, int N, int S, int E, int ln) {
+// Row kernels of the critic chain: one warp per row, the whole row (N <= 512, N % 4 == 0) in registers as four float4 per lane
+// (lane owns columns 128 i + 4 lane .. + 3): one trip to memory, 16-byte loads, 8/16-byte stores, gelu / gelu' evaluated once.
+constexpr int ROW_V = 4;        // float4 per lane
+constexpr int ROW_WARPS = 4;    // rows per CTA
+
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+// H = [LayerNorm](gelu(Z)) -> bf16 (+ row statistics).  Z: fp32 [rows][N] contiguous; scale/bias per (s, e).
+__global__ void __launch_bounds__(32 * ROW_WARPS) act_ln_bf16_kernel(const float* __restrict__ Z, const float* __restrict__ scale_base,
+                                                                     const float* __restrict__ bias_base, int64_t par_s, int64_t par_e,
+                                                                     bf16* __restrict__ Hb, float* __restrict__ mu_out,
+                                                                     float* __restrict__ rstd_out, int M, int N, int S, int E, int ln) {
   FQL_PDL_SYNC();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp;
   if (row >= (int64_t)S * E * M) return;
   const int g = (int)(row / M), e = g % E, s = g / E;
   const float* z = Z + row * N;
   bf16* h = Hb + row * N;
+  float gv[ROW_V][4];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROW_V; i++) {
+    const int c = i * 128 + lane * 4;
+    if (c < N) {
+      const float4 zz = *reinterpret_cast<const float4*>(z + c);
+      gv[i][0] = gelu_fast(zz.x); gv[i][1] = gelu_fast(zz.y); gv[i][2] = gelu_fast(zz.z); gv[i][3] = gelu_fast(zz.w);
+#pragma unroll
+      for (int k = 0; k < 4; k++) { s1 += gv[i][k]; s2 += gv[i][k] * gv[i][k]; }
+    }
+  }
   if (!ln) {
-    for (int c = lane * 2; c < N; c += 64) {
-      const float2 zz = *reinterpret_cast<const float2*>(z + c);
-      *reinterpret_cast<__nv_bfloat162*>(h + c) = __floats2bfloat162_rn(gelu_fast(zz.x), gelu_fast(zz.y));
+#pragma unroll
+    for (int i = 0; i < ROW_V; i++) {
+      const int c = i * 128 + lane * 4;
+      if (c < N) *reinterpret_cast<uint2*>(h + c) = pack4_bf16(gv[i][0], gv[i][1], gv[i][2], gv[i][3]);
     }
     return;
-  }
-  float s1 = 0.f, s2 = 0.f;
-  for (int c = lane * 2; c < N; c += 64) {
-    const float2 zz = *reinterpret_cast<const float2*>(z + c);
-    const float g0 = gelu_fast(zz.x), g1 = gelu_fast(zz.y);
-    s1 += g0 + g1;
-    s2 += g0 * g0 + g1 * g1;
   }
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
@@ -75,11 +91,14 @@ __global__ void __launch_bounds__(256) act_ln_bf16_kernel(const float* __restric
   const float rstd = rsqrtf(var + FQL_LN_EPS);
   const float* sc = scale_base + s * par_s + e * par_e;
   const float* bi = bias_base + s * par_s + e * par_e;
-  for (int c = lane * 2; c < N; c += 64) {
-    const float2 zz = *reinterpret_cast<const float2*>(z + c);
-    const float h0 = (gelu_fast(zz.x) - mu) * rstd * sc[c] + bi[c];
-    const float h1 = (gelu_fast(zz.y) - mu) * rstd * sc[c + 1] + bi[c + 1];
-    *reinterpret_cast<__nv_bfloat162*>(h + c) = __floats2bfloat162_rn(h0, h1);
+#pragma unroll
+  for (int i = 0; i < ROW_V; i++) {
+    const int c = i * 128 + lane * 4;
+    if (c < N) {
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + c), b4 = *reinterpret_cast<const float4*>(bi + c);
+      *reinterpret_cast<uint2*>(h + c) = pack4_bf16((gv[i][0] - mu) * rstd * s4.x + b4.x, (gv[i][1] - mu) * rstd * s4.y + b4.y,
+                                                    (gv[i][2] - mu) * rstd * s4.z + b4.z, (gv[i][3] - mu) * rstd * s4.w + b4.w);
+    }
   }
   if (lane == 0 && mu_out) {
     mu_out[row] = mu;
@@ -88,15 +107,13 @@ __global__ void __launch_bounds__(256) act_ln_bf16_kernel(const float* __restric
 }
 
 // dZ rows kernel for LayerNorm nets with an extra bf16 copy: dZ = LNbwd(dH; Z) * gelu'(Z)
-__global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const float* __restrict__ dH, const float* __restrict__ Z,
-                                                          const float* __restrict__ scale_base, int64_t scale_s, int64_t scale_e,
-                                                          float* __restrict__ dZ, bf16* __restrict__ dZb, int M, int N, int S, int E,
-                                                          int64_t z_rows_e, int64_t z_rows_s) {
-  // one warp per row; every element's gelu / gelu' is evaluated once and kept in registers (N <= 512 -> 16 per lane)
-  constexpr int MAXC = 16;
+__global__ void __launch_bounds__(32 * ROW_WARPS) ln_bwd_bf16_kernel(const float* __restrict__ dH, const float* __restrict__ Z,
+                                                                     const float* __restrict__ scale_base, int64_t scale_s, int64_t scale_e,
+                                                                     float* __restrict__ dZ, bf16* __restrict__ dZb, int M, int N, int S, int E,
+                                                                     int64_t z_rows_e, int64_t z_rows_s) {
   FQL_PDL_SYNC();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp;
   if (row >= (int64_t)S * E * M) return;
   const int r = (int)(row % M), g = (int)(row / M), e = g % E, s = g / E;
   const float* z = Z + ((int64_t)s * z_rows_s + (int64_t)e * z_rows_e + r) * N;
@@ -104,18 +121,25 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const float* __restric
   float* dz = dZ + row * N;
   bf16* dzb = dZb + row * N;
   const float* sc = scale_base + s * scale_s + e * scale_e;
-  float gv[MAXC], dg[MAXC], dx[MAXC];
+  float gv[ROW_V][4], dg[ROW_V][4], dx[ROW_V][4];
   float s1 = 0.f, s2 = 0.f, m1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXC; i++) {
-    const int c = lane + 32 * i;
-    gv[i] = dg[i] = dx[i] = 0.f;
+  for (int i = 0; i < ROW_V; i++) {
+    const int c = i * 128 + lane * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) gv[i][k] = dg[i][k] = dx[i][k] = 0.f;
     if (c < N) {
-      gelu_and_grad_fast(z[c], &gv[i], &dg[i]);
-      dx[i] = dh[c] * sc[c];
-      s1 += gv[i];
-      s2 += gv[i] * gv[i];
-      m1 += dx[i];
+      const float4 zz = *reinterpret_cast<const float4*>(z + c), dd = *reinterpret_cast<const float4*>(dh + c),
+                   s4 = *reinterpret_cast<const float4*>(sc + c);
+      const float zv[4] = {zz.x, zz.y, zz.z, zz.w}, dv[4] = {dd.x, dd.y, dd.z, dd.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        gelu_and_grad_fast(zv[k], &gv[i][k], &dg[i][k]);
+        dx[i][k] = dv[k] * sv[k];
+        s1 += gv[i][k];
+        s2 += gv[i][k] * gv[i][k];
+        m1 += dx[i][k];
+      }
     }
   }
   s1 = warp_sum(s1);
@@ -127,19 +151,25 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const float* __restric
   const float rstd = rsqrtf(var + FQL_LN_EPS);
   float m2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXC; i++) {
-    gv[i] = (gv[i] - mu) * rstd;  // xhat
-    if (lane + 32 * i < N) m2 += dx[i] * gv[i];
+  for (int i = 0; i < ROW_V; i++) {
+    const int c = i * 128 + lane * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      gv[i][k] = (gv[i][k] - mu) * rstd;  // xhat
+      if (c < N) m2 += dx[i][k] * gv[i][k];
+    }
   }
   m1 *= inv_n;
   m2 = warp_sum(m2) * inv_n;
 #pragma unroll
-  for (int i = 0; i < MAXC; i++) {
-    const int c = lane + 32 * i;
+  for (int i = 0; i < ROW_V; i++) {
+    const int c = i * 128 + lane * 4;
     if (c < N) {
-      const float v = rstd * (dx[i] - m1 - gv[i] * m2) * dg[i];
-      dz[c] = v;
-      dzb[c] = __float2bfloat16(v);
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = rstd * (dx[i][k] - m1 - gv[i][k] * m2) * dg[i][k];
+      *reinterpret_cast<float4*>(dz + c) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<uint2*>(dzb + c) = pack4_bf16(v[0], v[1], v[2], v[3]);
     }
   }
 }
@@ -350,7 +380,7 @@ int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cu
     const float* Zp = t.buf->Z[l - 1] + prow * H;
     if (nv.ln) {
       const int64_t rows = (int64_t)S * E * M;
-      FQL_CHECK_CUDA(fql_launch_pdl(ln_bwd_bf16_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, t.dHf[l - 1], Zp,
+      FQL_CHECK_CUDA(fql_launch_pdl(ln_bwd_bf16_kernel, dim3((unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS)), dim3(32 * ROW_WARPS), 0, st, t.dHf[l - 1], Zp,
                                     t.params + nv.off_lns[l - 1], L.arena, H, t.dZf[l - 1], reinterpret_cast<bf16*>(t.dZb[l - 1]), M, H, S, E, Mcap,
                                     (int64_t)E * Mcap));
       FQL_CHECK_LAUNCH();
@@ -426,7 +456,7 @@ int tc_critic_forward(const TcCritic& t, int net, float* out, cudaStream_t st) {
       g.out_f = tp(t.buf->Z[l] + prow * H, z_se, z_ss, H);
       FQL_TRY(tc_gemm(g, st));
       const int64_t rows = (int64_t)S * E * M;
-      FQL_CHECK_CUDA(fql_launch_pdl(act_ln_bf16_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, t.buf->Z[l] + prow * H,
+      FQL_CHECK_CUDA(fql_launch_pdl(act_ln_bf16_kernel, dim3((unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS)), dim3(32 * ROW_WARPS), 0, st, t.buf->Z[l] + prow * H,
                                     nv.ln ? t.params + nv.off_lns[l] : nullptr, nv.ln ? t.params + nv.off_lnb[l] : nullptr, L.arena, (int64_t)H,
                                     reinterpret_cast<bf16*>(t.Hb[l]) + prow * H, nv.ln ? t.buf->mu[l] + prow : nullptr,
                                     nv.ln ? t.buf->rstd[l] + prow : nullptr, M, H, S, E, (int)nv.ln));
