@@ -2,6 +2,8 @@
 // loss reductions and the loss-side gradients.  One CTA per seed for the reductions (deterministic order).
 #include "step.cuh"
 
+#include <cuda_bf16.h>
+
 namespace {
 
 __device__ __forceinline__ float clip1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
@@ -189,13 +191,19 @@ __global__ void euler_update_kernel(StepShape sh, WsPtrs w, int step) {
 
 // Distillation loss + dL/da_pi (fql.py:65-79): da = alpha*2(a_pi-target)/(GB*A) + [dQ/da through clip].
 // dX0: [S][2][B][KC] input-gradient of the critic(s, clip a_pi) pass; the two heads are summed (input broadcast).
-__global__ void actor_grad_kernel(StepShape sh, FqlHparams hp, WsPtrs w, float* raw) {
+__global__ void actor_grad_kernel(StepShape sh, FqlHparams hp, WsPtrs w, float* raw, __nv_bfloat16* dapib) {
   __shared__ float red[32];
   const int s = blockIdx.x;
   const int A = sh.A, B = sh.B, KC = sh.F + sh.A;
   const float* api = w.O_out + ((int64_t)s * 3 * B + B) * A;
   const float scale = hp.alpha * 2.0f / ((float)sh.GB * (float)A);
   float sq = 0.f;
+  // dapib (tensor-core mode): the same gradient as the zero-padded bf16 [B][64] operand of the first dgrad GEMM
+  if (dapib) {
+    const int P = 64 - A;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < B * P; i += gridDim.y * blockDim.x)
+      dapib[((int64_t)s * B + i / P) * 64 + A + i % P] = __float2bfloat16(0.f);
+  }
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < B * A; i += gridDim.y * blockDim.x) {
     const int r = i / A, c = i % A;
     const float a = api[i];
@@ -204,7 +212,9 @@ __global__ void actor_grad_kernel(StepShape sh, FqlHparams hp, WsPtrs w, float* 
     const float g0 = w.dX0[(((int64_t)s * 2 + 0) * B + r) * KC + sh.F + c];
     const float g1 = w.dX0[(((int64_t)s * 2 + 1) * B + r) * KC + sh.F + c];
     const float inside = (a >= -1.0f && a <= 1.0f) ? 1.0f : 0.0f;
-    w.dapi[(int64_t)s * B * A + i] = scale * d + (g0 + g1) * inside;
+    const float g = scale * d + (g0 + g1) * inside;
+    w.dapi[(int64_t)s * B * A + i] = g;
+    if (dapib) dapib[((int64_t)s * B + r) * 64 + c] = __float2bfloat16(g);
   }
   sq = block_reduce<0>(sq, red);
   if (threadIdx.x == 0) atomicAdd(&raw[s * FQL_NUM_RAW + RAW_DISTILL_SQ], sq);
@@ -215,40 +225,7 @@ __global__ void finalize_info_kernel(StepShape sh, FqlHparams hp, const float* r
                                      int with_grad_stats) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= sh.S) return;
-  // data parallel: `raw` is the all-gather of every rank's accumulators [ranks][S][FQL_NUM_RAW]: sums add, max / -min take the max
-  float rw[FQL_NUM_RAW];
-  for (int i = 0; i < FQL_NUM_RAW; i++) rw[i] = raw[s * FQL_NUM_RAW + i];
-  for (int r = 1; r < ranks; r++) {
-    const float* o = raw + ((int64_t)r * sh.S + s) * FQL_NUM_RAW;
-    for (int i = 0; i < 9; i++) rw[i] += o[i];
-    rw[RAW_Q_MAX] = fmaxf(rw[RAW_Q_MAX], o[RAW_Q_MAX]);
-    rw[RAW_Q_NEGMIN] = fmaxf(rw[RAW_Q_NEGMIN], o[RAW_Q_NEGMIN]);
-  }
-  float* o = info + s * FQL_NUM_INFO;
-  const float gb = (float)sh.GB, A = (float)sh.A;
-  const float critic_loss = rw[RAW_CRITIC_SQ] / (2.0f * gb);
-  const float bc = rw[RAW_BC_SQ] / (gb * A);
-  const float distill = rw[RAW_DISTILL_SQ] / (gb * A);
-  const float q = rw[RAW_QPI_SUM] / gb;
-  float q_loss = -q;
-  if (sh.normalize_q_loss) q_loss = (1.0f / (rw[RAW_QPI_ABS] / gb)) * q_loss;
-  o[0] = critic_loss;
-  o[1] = rw[RAW_Q_SUM] / (2.0f * gb);
-  o[2] = rw[RAW_Q_MAX];
-  o[3] = -rw[RAW_Q_NEGMIN];
-  o[4] = bc + hp.alpha * distill + q_loss;
-  o[5] = bc;
-  o[6] = distill;
-  o[7] = q_loss;
-  o[8] = q;
-  o[9] = rw[RAW_MSE] / (gb * A);
-  if (with_grad_stats) {
-    o[10] = gstats[s * 4 + 0];
-    o[11] = gstats[s * 4 + 1];
-    o[12] = gstats[s * 4 + 2];
-  } else {
-    o[10] = o[11] = o[12] = 0.f;
-  }
+  fql_finalize_info_seed(sh, hp, raw, ranks, gstats, info, s, with_grad_stats);
 }
 
 // clip(x) elementwise (fql.py:152)
@@ -316,8 +293,8 @@ int launch_euler_update(const StepShape& sh, const WsPtrs& w, int step, cudaStre
   FQL_CHECK_LAUNCH();
   return 0;
 }
-int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w, float* raw, cudaStream_t st) {
-  actor_grad_kernel<<<dim3(sh.S, loss_ctas(sh)), 1024, 0, st>>>(sh, hp, w, raw);
+int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w, float* raw, cudaStream_t st, void* dapib) {
+  actor_grad_kernel<<<dim3(sh.S, loss_ctas(sh)), 1024, 0, st>>>(sh, hp, w, raw, reinterpret_cast<__nv_bfloat16*>(dapib));
   FQL_CHECK_LAUNCH();
   return 0;
 }

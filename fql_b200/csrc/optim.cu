@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) adam_polyak_stats_kernel(Layout L, FqlHpa
 // one CTA per seed, one WARP per leaf (lanes stride over the leaf's block partials): per-leaf L2 norms, then the three
 // scalars of flax_utils.py:147-149
 __global__ void __launch_bounds__(1024) grad_stats_final_kernel(Layout L, const float* __restrict__ partials,
-                                                                float* __restrict__ gstats, int32_t* count_inc) {
+                                                                float* __restrict__ gstats, int32_t* count_inc, FinArgs fin) {
   const int s = blockIdx.x;
   const int nblk = L.leaf_blk[L.n_leaves];
   const float* part = partials + (int64_t)s * nblk * 4;
@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(1024) grad_stats_final_kernel(Layout L, const 
     gstats[s * 4 + 1] = b;
     gstats[s * 4 + 2] = c;
     if (s == 0 && count_inc) count_inc[0] += 1;  // optax count / TrainState.step advance (flax_utils.py:126)
+    if (fin.info) fql_finalize_info_seed(fin.sh, fin.hp, fin.raw, fin.ranks, gstats, fin.info, s, 1);
   }
 }
 
@@ -177,8 +178,12 @@ int launch_adam_polyak_stats(const Layout& L, const FqlHparams& hp, int S, float
   return 0;
 }
 
-int launch_grad_stats_final(const Layout& L, int S, const float* partials, float* gstats, int32_t* count_inc, cudaStream_t st) {
-  grad_stats_final_kernel<<<S, 1024, 0, st>>>(L, partials, gstats, count_inc);
+int launch_grad_stats_final(const Layout& L, int S, const float* partials, float* gstats, int32_t* count_inc, cudaStream_t st,
+                            const FinArgs* fin) {
+  FinArgs f;
+  memset(&f, 0, sizeof(f));
+  if (fin) f = *fin;
+  grad_stats_final_kernel<<<S, 1024, 0, st>>>(L, partials, gstats, count_inc, f);
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -784,11 +784,11 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_euler, 0));
   if (split_metric) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[57], 0));
   if (split_cpost) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_cpost, 0));
-  FQL_TRY(launch_actor_grad(sh, hp, w, raw, S0));
+  FQL_TRY(launch_actor_grad(sh, hp, w, raw, S0, w.O_dOutb));
   FQL_TRY(stamp(ctx, 7, S0));   // joined Euler, dL/da done
   if (c.do_backward) {
     TcActor bo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, B, B, w.O_Hb, w.O_Zb, true);
-    FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, ctx->s9, &ctx->ev[18]));
+    FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, ctx->s9, &ctx->ev[18], true));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[55], ctx->s9));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s4, ctx->ev[55], 0));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[26], ctx->s4));
@@ -927,10 +927,13 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
       FQL_TRY(tc_refresh_shadow_lastlayer(c.d, L, c.st->params, c.st->shadow, ctx->s1));
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[51], ctx->s1));
     }
-    FQL_TRY(launch_grad_stats_final(L, S, w.partials, w.gstats, c.st->count, S0));
+    FinArgs fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.sh = sh; fin.hp = hp; fin.raw = raw; fin.ranks = c.raw_ranks > 1 ? c.raw_ranks : 1; fin.info = c.info;
+    FQL_TRY(launch_grad_stats_final(L, S, w.partials, w.gstats, c.st->count, S0, c.info ? &fin : nullptr));
     if (tcm) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[51], 0));
   }
-  if (c.info) FQL_TRY(launch_finalize_info(sh, hp, raw, c.raw_ranks > 1 ? c.raw_ranks : 1, w.gstats, c.info, c.do_apply, S0));
+  if (c.info && !c.do_apply) FQL_TRY(launch_finalize_info(sh, hp, raw, c.raw_ranks > 1 ? c.raw_ranks : 1, w.gstats, c.info, 0, S0));
   FQL_TRY(stamp(ctx, 12, S0));    // step end
   return 0;
 }

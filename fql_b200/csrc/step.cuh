@@ -65,7 +65,7 @@ int launch_post_onestep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w,
 int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts = 3);
 int launch_bc_post(const StepShape& sh, const WsPtrs& w, float* raw, cudaStream_t st);
 int launch_euler_update(const StepShape& sh, const WsPtrs& w, int step, cudaStream_t st);
-int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w, float* raw, cudaStream_t st);
+int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w, float* raw, cudaStream_t st, void* dapib = nullptr);
 int launch_finalize_info(const StepShape& sh, const FqlHparams& hp, const float* raw, int ranks, const float* gstats, float* info,
                          int with_grad_stats, cudaStream_t st);
 int launch_clip(const float* in, float* out, int64_t n, cudaStream_t st);
@@ -76,7 +76,57 @@ int launch_euler_inplace(float* X, const float* v, int F, int A, int64_t rows, i
 int launch_adam_polyak_stats(const Layout& L, const FqlHparams& hp, int S, float* params, float* mu, float* nu,
                              const float* grads, const float* bc, float* partials, void* shadow, int64_t shadow_seed, cudaStream_t st,
                              int blk0 = 0, int blk1 = -1);  // CTA range in FQL_LEAF_PAD blocks (default: the whole arena)
-int launch_grad_stats_final(const Layout& L, int S, const float* partials, float* gstats, int32_t* count_inc, cudaStream_t st);
+// fin != NULL: the same launch also writes the info vector (finalize_info_kernel folded in: one launch less at the end of the step)
+struct FinArgs {
+  StepShape sh;
+  FqlHparams hp;
+  const float* raw;
+  int ranks;
+  float* info;
+};
+int launch_grad_stats_final(const Layout& L, int S, const float* partials, float* gstats, int32_t* count_inc, cudaStream_t st,
+                            const FinArgs* fin = nullptr);
+
+#ifdef __CUDACC__
+// info[13] of one seed from the (all-gathered) raw accumulators + gradient statistics (agents/fql.py:38-44, 78-90, flax_utils.py:147-149).
+// data parallel: `raw` is the all-gather of every rank's accumulators [ranks][S][FQL_NUM_RAW]: sums add, max / -min take the max
+__device__ __forceinline__ void fql_finalize_info_seed(const StepShape& sh, const FqlHparams& hp, const float* raw, int ranks, const float* gstats,
+                                                       float* info, int s, int with_grad_stats) {
+  float rw[FQL_NUM_RAW];
+  for (int i = 0; i < FQL_NUM_RAW; i++) rw[i] = raw[s * FQL_NUM_RAW + i];
+  for (int r = 1; r < ranks; r++) {
+    const float* o = raw + ((int64_t)r * sh.S + s) * FQL_NUM_RAW;
+    for (int i = 0; i < 9; i++) rw[i] += o[i];
+    rw[RAW_Q_MAX] = fmaxf(rw[RAW_Q_MAX], o[RAW_Q_MAX]);
+    rw[RAW_Q_NEGMIN] = fmaxf(rw[RAW_Q_NEGMIN], o[RAW_Q_NEGMIN]);
+  }
+  float* o = info + s * FQL_NUM_INFO;
+  const float gb = (float)sh.GB, A = (float)sh.A;
+  const float critic_loss = rw[RAW_CRITIC_SQ] / (2.0f * gb);
+  const float bc = rw[RAW_BC_SQ] / (gb * A);
+  const float distill = rw[RAW_DISTILL_SQ] / (gb * A);
+  const float q = rw[RAW_QPI_SUM] / gb;
+  float q_loss = -q;
+  if (sh.normalize_q_loss) q_loss = (1.0f / (rw[RAW_QPI_ABS] / gb)) * q_loss;
+  o[0] = critic_loss;
+  o[1] = rw[RAW_Q_SUM] / (2.0f * gb);
+  o[2] = rw[RAW_Q_MAX];
+  o[3] = -rw[RAW_Q_NEGMIN];
+  o[4] = bc + hp.alpha * distill + q_loss;
+  o[5] = bc;
+  o[6] = distill;
+  o[7] = q_loss;
+  o[8] = q;
+  o[9] = rw[RAW_MSE] / (gb * A);
+  if (with_grad_stats) {
+    o[10] = gstats[s * 4 + 0];
+    o[11] = gstats[s * 4 + 1];
+    o[12] = gstats[s * 4 + 2];
+  } else {
+    o[10] = o[11] = o[12] = 0.f;
+  }
+}
+#endif
 int launch_zero(float* p, int64_t n, cudaStream_t st);
 // zero p[0..n) and (count != NULL) write optax's float32 bias corrections {1 - b1^(count+1), 1 - b2^(count+1)} to bc[0..1]
 int launch_zero_bc(float* p, int64_t n, const int32_t* count, const FqlHparams& hp, float* bc, cudaStream_t st);
@@ -181,7 +231,7 @@ struct TcCritic {
 };
 int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, const TcEuler* eu, cudaStream_t st);
 int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
-                      cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev);
+                      cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev, bool dOutb_ready = false);
 int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev);
 int tc_critic_forward(const TcCritic& t, int net, float* out, cudaStream_t st);
 

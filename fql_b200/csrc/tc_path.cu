@@ -241,7 +241,7 @@ int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, c
 // actor backward: dOut fp32 [S][M][A] -> parameter gradients (fp32, into the arena)
 // ---------------------------------------------------------------------------------------------------------------
 int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
-                      cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev) {
+                      cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev, bool dOutb_ready) {
   // side: weight-gradient GEMMs, side2: bias-gradient column sums (one stream for both was measured to be the longest chain of
   // the backward: 8 us of side work per 5 us dgrad step)
   if (!side2) side2 = side;
@@ -262,7 +262,7 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
     c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena;
     return launch_colsum(c, side2, t.cs_scratch, t.cs_scratch ? 65536 : 0);
   };
-  FQL_TRY(tc_pad_bf16(dOut, dOutb, (int64_t)S * t.M, A, 64, st));
+  if (!dOutb_ready) FQL_TRY(tc_pad_bf16(dOut, dOutb, (int64_t)S * t.M, A, 64, st));  // else: written by the loss kernel
   FQL_CHECK_CUDA(cudaEventRecord(ev[0], st));
   {  // dZ_{NL-2} = (dOut W^T) * gelu'(Z)
     TcGemmSpec g;
