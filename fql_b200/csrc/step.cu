@@ -417,8 +417,8 @@ struct FqlContext {
   int use_euler_cluster = 1;
   int use_cluster_fwd = 1;   // FQL_B200_CLUSTER_FWD=0: one-step actor forward layer by layer
   unsigned long long* stamps = nullptr;  // FQL_B200_STAMPS=1: %globaltimer at schedule points (diagnostics, profiles/dbg_timeline.py)
-  int split_adam = 0;        // FQL_B200_SPLIT_ADAM=1: optimizer pass over bc-flow|critic(+target) overlaps the one-step actor's backward
-                             // (measured: no gain -- its HBM traffic slows the Euler tail and the dgrad chain by what it saves)
+  int split_adam = 1;        // optimizer pass over bc-flow|critic(+target) overlaps the one-step actor's backward (FQL_B200_SPLIT_ADAM=0:
+                             // one pass at the end).  Measured -4 us: its HBM traffic slows the dgrad chain by most of what it saves.
   int adam_done_blk = 0;     // blocks [0, adam_done_blk) were already applied by enqueue_grads_tc in this enqueue
   int use_critic_chain = 0;
   int chain_min_tiles = 48;  // row tiles (x seeds) from which the fused per-tile chain kernels replace the per-layer GEMMs
