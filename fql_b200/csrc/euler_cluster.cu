@@ -66,6 +66,8 @@ struct EulerArgs {
   __nv_bfloat16* Zsave[FQL_MAXL];
   float* out;
   int rows_cap, r0;
+  float* Fsave[FQL_MAXL];       // MODE_DGRAD: fp32 copy of iteration it's output, same indexing as Hsave
+  int z_rows_cap, z_r0;         // MODE_DGRAD: row geometry of Zsave (the forward pass's buffers)
   unsigned long long* dbg;  // optional [CTA][16] globaltimer stamps of iteration DBG_IT (diagnostics)
   unsigned long long* t_start;  // optional: kernel start / end time of CTA 0 (diagnostics)
   int dbg_it;                   // layer iteration the dbg stamps are taken at
@@ -74,7 +76,10 @@ struct EulerArgs {
 struct HMaps {
   CUtensorMap m[4];  // MODE_EULER: m[0] = exchange scratch; MODE_FWD: m[l] = H buffer of layer l
 };
-constexpr int MODE_EULER = 0, MODE_FWD = 1;
+// MODE_DGRAD: the input-gradient chain of a backward pass, dZ_{l-1} = (dZ_l W_l^T) * gelu'(Z_{l-1}): iteration `it` consumes
+// W_{NL-it}^T (K-major slices straight from the [in,out] shadow: rows = this CTA's 32 inputs, k contiguous), multiplies by
+// gelu' of the saved pre-activation and writes dZ as bf16 (exchange buffer = the wgrad operand) and fp32 (bias gradients).
+constexpr int MODE_EULER = 0, MODE_FWD = 1, MODE_DGRAD = 2;
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -85,6 +90,13 @@ __device__ __forceinline__ unsigned long long gtime() {
 __device__ __forceinline__ float gelu_fast(float x) {
   const float u = FQL_GELU_C * (x + FQL_GELU_A * x * x * x);
   return 0.5f * x * (1.0f + tanh_approx(u));
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float x2 = x * x;
+  const float u = FQL_GELU_C * (x + FQL_GELU_A * x2 * x);
+  const float th = tanh_approx(u);
+  const float du = FQL_GELU_C * (1.0f + 3.0f * FQL_GELU_A * x2);
+  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * du;
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     tma_prefetch_desc(&mapX);
     tma_prefetch_desc(&mapW);
     tma_prefetch_desc(&mapWL);
-    for (int i = 0; i < (MODE == MODE_FWD ? NL - 1 : 1); i++) tma_prefetch_desc(&mapsH.m[i]);
+    for (int i = 0; i < (MODE == MODE_EULER ? 1 : NL - 1); i++) tma_prefetch_desc(&mapsH.m[i]);
     for (int i = 0; i < NSUB; i++) mbar_init(&full_a[i], 1);
     mbar_init(&half_ready[0], NEPI);
     mbar_init(&half_ready[1], NEPI);
@@ -178,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC_SET);  // two accumulator sets
-  for (int i = threadIdx.x; i < NL * 64; i += NTHREADS) {
+  for (int i = threadIdx.x; i < (MODE == MODE_DGRAD ? 0 : NL * 64); i += NTHREADS) {
     const int l = i >> 6, c = i & 63;
     const bool lastl = (l == NL - 1);
     const int N = lastl ? a.A : a.H;
@@ -209,8 +221,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
         if (it > 0) mbar_wait(acc_full, (it - 1) & 1);
         mbar_expect_tx(full_b, kblocks * B_BLK);
         for (int kb = 0; kb < kblocks; kb++) {
-          if (!last) tma_load_2d(sB + kb * B_BLK, &mapW, full_b, (int)j * NCOL, a.w_row[l] + s * a.w_rows_s + kb * KB);
-          else tma_load_2d(sB + kb * B_BLK, &mapWL, full_b, 0, a.wl_row + s * a.wl_rows_s + kb * KB);
+          if constexpr (MODE == MODE_DGRAD) {  // K-major: box = [NCOL input rows][64 k]
+            if (l == 0) tma_load_2d(sB, &mapWL, full_b, 0, a.wl_row + s * a.wl_rows_s + (int)j * NCOL);
+            else tma_load_2d(sB + kb * B_BLK, &mapW, full_b, kb * KB, a.w_row[l] + s * a.w_rows_s + (int)j * NCOL);
+          } else {
+            if (!last) tma_load_2d(sB + kb * B_BLK, &mapW, full_b, (int)j * NCOL, a.w_row[l] + s * a.w_rows_s + kb * KB);
+            else tma_load_2d(sB + kb * B_BLK, &mapWL, full_b, 0, a.wl_row + s * a.wl_rows_s + kb * KB);
+          }
         }
         if (l >= 1) {
           // arm the per-sub-block barriers, then publish this CTA's slice of the layer input (= the previous layer's output, which
@@ -226,9 +243,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
             const int sbk = (int)j * HALVES + h;
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-                ::"r"(smem_u32(sA + sbk * A_SUB)), "l"(reinterpret_cast<uint64_t>(MODE == MODE_FWD ? &mapsH.m[l - 1] : &mapsH.m[0])),
+                ::"r"(smem_u32(sA + sbk * A_SUB)), "l"(reinterpret_cast<uint64_t>(MODE != MODE_EULER ? &mapsH.m[l - 1] : &mapsH.m[0])),
                 "r"(smem_u32(&full_a[sbk])), "r"(sbk * SUB),
-                "r"(MODE == MODE_FWD ? s * a.rows_cap + a.r0 + tile * TILE_M : buf * (a.S * a.tiles * TILE_M) + hx_row), "h"(MASK)
+                "r"(MODE != MODE_EULER ? s * a.rows_cap + a.r0 + tile * TILE_M : buf * (a.S * a.tiles * TILE_M) + hx_row), "h"(MASK)
                 : "memory");
           }
           n_pub++;
@@ -241,11 +258,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     // warps issue a quarter of the K range each into their own TMEM columns (summed by the epilogue).
     if (lane == 0) {
       const int mw = warp - 1;
-      const uint32_t idesc = make_idesc_bf16(TILE_M, NCOL, false, true);
+      const uint32_t idesc = make_idesc_bf16(TILE_M, NCOL, false, MODE != MODE_DGRAD);
       const uint64_t ax_t = make_smem_desc(0, 16, 1024);            // first-layer operand: [128][64] bf16 blocks, SWIZZLE_128B
       const uint64_t a64_t0 = make_smem_desc_sw64(0, 16, 512);      // [128][32] bf16 sub-blocks, SWIZZLE_64B: 8-row groups 512 B apart
-      const uint64_t b_t0 = (NC == 8) ? make_smem_desc(0, B_BLK, 1024) : make_smem_desc_sw64(0, B_BLK, 512);  // MN-major [k][NCOL]
-      constexpr uint64_t B_KSTEP = (16 * B_ROWB) >> 4;              // 16 K rows
+      // B: MN-major [k][NCOL] tiles (forward) or K-major [NCOL][64 k] SWIZZLE_128B tiles (MODE_DGRAD: W^T)
+      const uint64_t b_t0 = (MODE == MODE_DGRAD) ? make_smem_desc(0, 16, 1024)
+                                                 : ((NC == 8) ? make_smem_desc(0, B_BLK, 1024) : make_smem_desc_sw64(0, B_BLK, 512));
+      constexpr uint64_t B_KSTEP = (MODE == MODE_DGRAD) ? 2 : ((16 * B_ROWB) >> 4);   // 16 k: 32 B inside a row / 16 K rows
+      constexpr uint64_t B_SUBH = (MODE == MODE_DGRAD) ? 4 : ((32 * B_ROWB) >> 4);    // second 32-k half of a 64-k block
       const uint32_t sa0 = smem_u32(sA) >> 4, sx0 = smem_u32(sX) >> 4, sb0 = smem_u32(sB) >> 4;
       int n_a = 0;  // uses of the full_a barriers
       int n_step = 0;
@@ -272,7 +292,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
             if (dbg && mw == 0 && it == DBG_IT && i == 0) dbg[5] = gtime();
             if (dbg && mw == NMMA - 1 && it == DBG_IT && i == 3) dbg[6] = gtime();
             umma_bf16_x2(tacc, a64_t0 + (uint64_t)(sa0 + sbk * (A_SUB >> 4)),
-                         b_t0 + (uint64_t)(sb0 + (sbk >> 1) * (B_BLK >> 4) + (sbk & 1) * ((32 * B_ROWB) >> 4)), 2, B_KSTEP, idesc, i != 0);
+                         b_t0 + (uint64_t)(sb0 + (sbk >> 1) * (B_BLK >> 4) + (sbk & 1) * B_SUBH), 2, B_KSTEP, idesc, i != 0);
           }
         } else {
           // first layer (K0 <= 128): k-step w of every block -> warp w
@@ -303,6 +323,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     for (int it = 0; it < total; it++, l = (l + 1 == NL) ? 0 : l + 1, step += (l == 0)) {
       const bool last = (l == NL - 1);
       const float* sb = sBias + l * 64;
+      uint4 zq[4];  // MODE_DGRAD: this row's 32 saved pre-activations, fetched while the MMAs run
+      if constexpr (MODE == MODE_DGRAD) {
+        static_assert(MODE != MODE_DGRAD || HALVES == 1, "the dgrad chain is built for clusters of 16");
+        if (valid) {
+          const uint4* zp = reinterpret_cast<const uint4*>(a.Zsave[l] + ((int64_t)s * a.z_rows_cap + a.z_r0 + grow) * a.H + j * NCOL);
+#pragma unroll
+          for (int c = 0; c < 4; c++) zq[c] = __ldg(zp + c);
+        }
+      }
       float ac[AMAX];  // Euler state of this row: fetched while the last layer's MMAs run (registers are free in this phase)
       if (MODE == MODE_EULER && last) {
 #pragma unroll
@@ -343,7 +372,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
             }
           }
         }
-        if (!last) {
+        if constexpr (MODE == MODE_DGRAD) {
+          if (valid) {
+            const int64_t e0 = ((int64_t)s * a.rows_cap + a.r0 + grow) * a.H + j * NCOL;
+            uint4* dh = reinterpret_cast<uint4*>(a.Hsave[l] + e0);
+            float4* df = reinterpret_cast<float4*>(a.Fsave[l] + e0);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              const uint32_t zw[4] = {zq[c].x, zq[c].y, zq[c].z, zq[c].w};
+              float dv[8];
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const __nv_bfloat162 zb = *reinterpret_cast<const __nv_bfloat162*>(&zw[i]);
+                dv[2 * i] = __uint_as_float(r0[c * 8 + 2 * i]) * gelu_grad_fast(__low2float(zb));
+                dv[2 * i + 1] = __uint_as_float(r0[c * 8 + 2 * i + 1]) * gelu_grad_fast(__high2float(zb));
+              }
+              dh[c] = make_uint4(pack2(dv[0], dv[1]), pack2(dv[2], dv[3]), pack2(dv[4], dv[5]), pack2(dv[6], dv[7]));
+              df[2 * c] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+              df[2 * c + 1] = make_float4(dv[4], dv[5], dv[6], dv[7]);
+            }
+          }
+          if (!last) {  // the next layer's input: the producer thread multicasts it once all NEPI warps arrived
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&half_ready[half]);
+          }
+        } else if (!last) {
           if constexpr (MODE == MODE_EULER) {
             uint4* dst = reinterpret_cast<uint4*>(a.hx + (int64_t)buf * a.hx_buf_elems + (int64_t)(hx_row + row) * a.H + j * NCOL + half * 32);
 #pragma unroll
@@ -492,13 +545,18 @@ int launch_euler(const EulerArgs& a, const TcEulerSpec& f, cudaStream_t st, bool
     }
     return 0;
   }
-  const CUtensorMapSwizzle wsw = (NC == 8) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle wsw = (NC == 8 || MODE == MODE_DGRAD) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap mapX, mapW, mapWL;
   HMaps mapsH;
   memset(&mapsH, 0, sizeof(mapsH));
   FQL_TRY(make_map_2d(&mapX, f.X0b, a.K0pad, (uint64_t)a.S * f.Mcap0, 64, TILE_M));
-  FQL_TRY(make_map_2d(&mapW, f.shadow, d->hidden, (uint64_t)a.S * a.w_rows_s, NCOL, KB, wsw));
-  FQL_TRY(make_map_2d(&mapWL, f.shadow, 64, (uint64_t)a.S * a.wl_rows_s, NCOL, KB, wsw));  // NC = 16: the first 32 (>= action_dim) columns
+  if (MODE == MODE_DGRAD) {  // K-major W^T slices: [NCOL input rows][64 k]
+    FQL_TRY(make_map_2d(&mapW, f.shadow, d->hidden, (uint64_t)a.S * a.w_rows_s, 64, NCOL, wsw));
+    FQL_TRY(make_map_2d(&mapWL, f.shadow, 64, (uint64_t)a.S * a.wl_rows_s, 64, NCOL, wsw));
+  } else {
+    FQL_TRY(make_map_2d(&mapW, f.shadow, d->hidden, (uint64_t)a.S * a.w_rows_s, NCOL, KB, wsw));
+    FQL_TRY(make_map_2d(&mapWL, f.shadow, 64, (uint64_t)a.S * a.wl_rows_s, NCOL, KB, wsw));  // NC = 16: the first 32 (>= action_dim) columns
+  }
   if (MODE == MODE_EULER) {
     FQL_TRY(make_map_2d(&mapsH.m[0], f.scratch, d->hidden, (uint64_t)2 * a.S * a.tiles * TILE_M, SUB, TILE_M, CU_TENSOR_MAP_SWIZZLE_64B));
   } else {
@@ -593,4 +651,33 @@ int tc_cluster_forward(const TcClusterFwdSpec& f, int other_clusters, cudaStream
   if (a.A <= 8) return launch_euler<16, 8, MODE_FWD>(a, e, st, false, nullptr) ? -1 : 0;
   if (a.A <= 16) return launch_euler<16, 16, MODE_FWD>(a, e, st, false, nullptr) ? -1 : 0;
   return launch_euler<16, 32, MODE_FWD>(a, e, st, false, nullptr) ? -1 : 0;
+}
+
+// The input-gradient chain of an actor network's backward (no LayerNorm) on M rows as one cluster-of-16 launch:
+// dZ_{NL-2} = (dOut W_last^T) * gelu'(Z_{NL-2}), then dZ_{l-1} = (dZ_l W_l^T) * gelu'(Z_{l-1}) down to dZ_0 (bf16 + fp32 copies).
+// Returns 1 when the kernel cannot take the problem (the caller then uses the layer-by-layer path), 0 on success, -1 on error.
+int tc_cluster_dgrad(const TcClusterBwdSpec& f, int other_clusters, cudaStream_t st) {
+  const FqlDims* d = f.d;
+  const NetView& nv = f.L->net[f.net];
+  if (d->hidden != 512 || nv.ln || nv.n_layers > 5 || nv.n_layers < 3 || nv.out_dim > 64) return 1;
+  EulerArgs a;
+  if (fill_args(a, d, *f.L, f.net, nullptr, f.M, f.M, 0)) return -1;
+  const int NLn = nv.n_layers;
+  a.NL = NLn - 1;          // chain GEMMs
+  a.K0 = 64; a.K0pad = 64; // dOut zero-padded to 64 columns
+  for (int it = 1; it < a.NL; it++) a.w_row[it] = (int)(nv.off_w[NLn - 1 - it] / d->hidden);  // iteration it multiplies by W_{NL-it}^T
+  TcEulerSpec e;
+  memset(&e, 0, sizeof(e));
+  e.d = d; e.L = f.L; e.shadow = f.shadow; e.X0b = f.dOutb; e.Mcap0 = f.M; e.r0_in = 0; e.M = f.M;
+  if (a.tiles * a.S + other_clusters > max_clusters16(a, e)) return 1;
+  for (int it = 0; it < a.NL; it++) {
+    const int lo = NLn - 2 - it;  // iteration it produces dZ_lo
+    a.Hsave[it] = reinterpret_cast<__nv_bfloat16*>(f.dZb[lo]);
+    a.Fsave[it] = f.dZf[lo];
+    a.Zsave[it] = reinterpret_cast<__nv_bfloat16*>(f.Zb[lo]);
+    if (!a.Hsave[it] || !a.Fsave[it] || !a.Zsave[it]) return 1;
+  }
+  a.rows_cap = f.M; a.r0 = 0; a.z_rows_cap = f.z_rows_cap; a.z_r0 = f.z_r0;
+  a.t_start = reinterpret_cast<unsigned long long*>(f.t_start);
+  return launch_euler<16, 8, MODE_DGRAD>(a, e, st, false, nullptr) ? -1 : 0;
 }

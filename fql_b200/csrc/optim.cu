@@ -121,10 +121,18 @@ __global__ void __launch_bounds__(1024) grad_stats_final_kernel(Layout L, const 
   for (int leaf = w; leaf < L.n_leaves; leaf += 32) {
     if (L.leaf_net[leaf] == FQL_NET_TARGET_CRITIC) continue;
     float mx = -INFINITY, mn = INFINITY, sq = 0.f;
-    for (int b = L.leaf_blk[leaf] + lane; b < L.leaf_blk[leaf + 1]; b += 32) {
-      mx = fmaxf(mx, part[b * 4 + 0]);
-      mn = fminf(mn, part[b * 4 + 1]);
-      sq += part[b * 4 + 2];
+    const int bend = L.leaf_blk[leaf + 1];
+    const float4* p4 = reinterpret_cast<const float4*>(part);
+    for (int b0 = L.leaf_blk[leaf] + lane; b0 < bend; b0 += 128) {  // four independent 16-byte loads in flight per lane
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = (b0 + 32 * u < bend) ? p4[b0 + 32 * u] : make_float4(-INFINITY, INFINITY, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        mx = fmaxf(mx, v[u].x);
+        mn = fminf(mn, v[u].y);
+        sq += v[u].z;
+      }
     }
     mx = warp_max(mx);
     mn = warp_min(mn);

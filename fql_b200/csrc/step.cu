@@ -416,9 +416,10 @@ struct FqlContext {
   int use_graph = 1;
   int use_euler_cluster = 1;
   int use_cluster_fwd = 1;   // FQL_B200_CLUSTER_FWD=0: one-step actor forward layer by layer
+  int use_cluster_bwd = 1;   // FQL_B200_CLUSTER_BWD=0: one-step actor dgrad chain layer by layer
   unsigned long long* stamps = nullptr;  // FQL_B200_STAMPS=1: %globaltimer at schedule points (diagnostics, profiles/dbg_timeline.py)
-  int split_adam = 1;        // optimizer pass over bc-flow|critic(+target) overlaps the one-step actor's backward (FQL_B200_SPLIT_ADAM=0:
-                             // one pass at the end).  Measured -4 us: its HBM traffic slows the dgrad chain by most of what it saves.
+  int split_adam = 0;        // FQL_B200_SPLIT_ADAM: 0 = one optimizer pass at the end (default: the others measured within noise), 1 = bc-flow's part right behind the Euler chain,
+                             // 2 = bc-flow and critic parts before the one-step actor's gradients are complete
   int adam_done_blk = 0;     // blocks [0, adam_done_blk) were already applied by enqueue_grads_tc in this enqueue
   int use_critic_chain = 0;
   int chain_min_tiles = 48;  // row tiles (x seeds) from which the fused per-tile chain kernels replace the per-layer GEMMs
@@ -487,6 +488,8 @@ extern "C" int fql_context_create(FqlContext** out) {
   if (g && g[0] == '0') c->use_graph = 0;
   const char* ec = getenv("FQL_B200_EULER_CLUSTER");
   if (ec && ec[0] == '0') c->use_euler_cluster = 0;
+  const char* cbw = getenv("FQL_B200_CLUSTER_BWD");
+  if (cbw && cbw[0] == '0') c->use_cluster_bwd = 0;
   const char* cfw = getenv("FQL_B200_CLUSTER_FWD");
   if (cfw && cfw[0] == '0') c->use_cluster_fwd = 0;
   const char* stp = getenv("FQL_B200_STAMPS");
@@ -495,7 +498,7 @@ extern "C" int fql_context_create(FqlContext** out) {
     FQL_CHECK_CUDA(cudaMemset(c->stamps, 0, 576 * sizeof(unsigned long long)));
   }
   const char* sa = getenv("FQL_B200_SPLIT_ADAM");
-  if (sa) c->split_adam = sa[0] == '1';
+  if (sa) c->split_adam = atoi(sa);
   const char* cm = getenv("FQL_B200_CHAIN_MIN_TILES");
   if (cm) c->chain_min_tiles = atoi(cm);
   const char* cc = getenv("FQL_B200_CRITIC_CHAIN");
@@ -677,7 +680,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   // ---- S0: one-step actor on {(s',z_next), (s,z), (s,z')}, grouped critic pass
   FQL_TRY(tc_pad_bf16(w.XO, w.XOb, (int64_t)S * 3 * B, sh.F + sh.A, kO, S0));
   TcActor fo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, true);
-  bool split_metric = false;
+  bool split_metric = false, early_adam_s1 = false;
   if (many_tiles) {
     FQL_TRY(chain(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, w.O_out, 1, S0));
   } else {
@@ -765,9 +768,20 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     for (int l = 0; l < NH; l++) { q.dZb[l] = w.C2_dZb[l]; q.dZf[l] = w.C2_dZf[l]; q.dHf[l] = w.C2_dHf[l]; }
     FQL_TRY(tc_critic_backward(q, S0, nullptr, nullptr, &ctx->ev[44]));
     FQL_TRY(stamp(ctx, 6, S0));   // critic input-gradient chain done
-    if (c.do_apply && ctx->split_adam && d->reserved[0] == 0) {
-      // bc-flow and critic are finished with (gradients complete, last readers of their weights: the Euler chain and the critic
-      // input-gradient chain above): their optimizer pass overlaps the one-step actor's backward instead of following it
+    if (c.do_apply && ctx->split_adam == 1 && d->reserved[0] == 0) {
+      // bc-flow is finished with once the Euler chain (the last reader of its weights) has ended and its gradients are complete:
+      // its quarter of the optimizer pass runs behind the Euler kernel, beside the one-step actor's dgrad chain
+      const int blk0 = (int)(L.net[FQL_NET_CRITIC].begin / FQL_LEAF_PAD);
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(S1, ctx->ev[16], 0));
+      FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, w.gstats + S * 4, w.partials, c.st->shadow,
+                                       tc_shadow_seed_elems(d, L), S1, 0, blk0));
+      FQL_TRY(stamp(ctx, 9, S1)); // early optimizer pass done
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[58], S1));
+      early_adam_s1 = true;
+      ctx->adam_done_blk = blk0;
+    }
+    if (c.do_apply && ctx->split_adam == 2 && d->reserved[0] == 0) {
+      // (measured slower than mode 1: the critic's half of the pass then competes with the one-step actor's parameter gradients)
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[52], S0));
       FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[52], 0));
       const int blk0 = (int)(L.net[FQL_NET_CRITIC].begin / FQL_LEAF_PAD), blk1 = (int)(L.net[FQL_NET_ACTOR_ONESTEP_FLOW].begin / FQL_LEAF_PAD);
@@ -788,15 +802,40 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   FQL_TRY(stamp(ctx, 7, S0));   // joined Euler, dL/da done
   if (c.do_backward) {
     TcActor bo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, B, B, w.O_Hb, w.O_Zb, true);
-    FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, ctx->s9, &ctx->ev[18], true));
-    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[55], ctx->s9));
-    FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s4, ctx->ev[55], 0));
-    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[26], ctx->s4));
-    FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[26], 0));
+    int rc = 1;
+    if (!many_tiles && ctx->use_euler_cluster && ctx->use_cluster_bwd) {
+      // small batch: the dgrad chain as ONE cluster-of-16 launch (the Euler chain has finished: its clusters are free), then the
+      // ten independent parameter-gradient launches dealt onto five idle side streams
+      TcClusterBwdSpec cb;
+      memset(&cb, 0, sizeof(cb));
+      cb.d = d; cb.L = &L; cb.shadow = shadow; cb.net = FQL_NET_ACTOR_ONESTEP_FLOW; cb.dOutb = w.O_dOutb; cb.M = B;
+      cb.Zb = w.O_Zb; cb.z_rows_cap = 3 * B; cb.z_r0 = B; cb.dZb = w.O_dZb; cb.dZf = w.O_dZf;
+      cb.t_start = ctx->stamps ? ctx->stamps + 17 : nullptr;
+      rc = tc_cluster_dgrad(cb, 0, S0);
+      if (rc < 0) return -1;
+      if (rc == 0) {
+        cudaStream_t ss[5] = {ctx->s4, ctx->s9, ctx->s3, ctx->s7, ctx->s1};  // one weight gradient + one column sum each
+        FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[18], S0));
+        for (int i = 0; i < 5; i++) FQL_CHECK_CUDA(cudaStreamWaitEvent(ss[i], ctx->ev[18], 0));
+        FQL_TRY(tc_actor_param_grads(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, ss, 5));
+        for (int i = 0; i < 5; i++) {
+          FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[19 + i], ss[i]));
+          FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[19 + i], 0));
+        }
+      }
+    }
+    if (rc == 1) {
+      FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, ctx->s9, &ctx->ev[18], true));
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[55], ctx->s9));
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s4, ctx->ev[55], 0));
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[26], ctx->s4));
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[26], 0));
+    }
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[16], 0));
     FQL_TRY(stamp(ctx, 10, S0));  // one-step actor gradients complete
   }
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
+  if (early_adam_s1) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[58], 0));
   return 0;
 }
 

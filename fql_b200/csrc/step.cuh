@@ -264,6 +264,23 @@ struct TcClusterFwdSpec {
   void* t_start;            // optional: %globaltimer at start / end of CTA 0 (diagnostics)
 };
 int tc_cluster_forward(const TcClusterFwdSpec& f, int other_clusters, cudaStream_t st);
+struct TcClusterBwdSpec {
+  const FqlDims* d;
+  const Layout* L;
+  const void* shadow;
+  int net;
+  const void* dOutb;        // bf16 [S][M][64]: dL/d(output), zero padded
+  int M;
+  void* const* Zb;          // bf16 pre-activations saved by the forward: [S][z_rows_cap][H], rows [z_r0, z_r0 + M)
+  int z_rows_cap, z_r0;
+  void* const* dZb;         // out: bf16 [S][M][H] per hidden layer
+  float* const* dZf;        // out: fp32 copies (bias gradients)
+  void* t_start;            // optional diagnostics
+};
+int tc_cluster_dgrad(const TcClusterBwdSpec& f, int other_clusters, cudaStream_t st);
+// parameter gradients of an actor network from finished dZ buffers: 2 * n_layers independent launches spread over `streams`
+int tc_actor_param_grads(const TcActor& t, const float* dOut, const void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
+                         cudaStream_t* streams, int n_streams);
 int tc_euler_cluster(const TcEulerSpec& f, cudaStream_t st);
 
 // encoder.cu

@@ -321,6 +321,47 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
   return 0;
 }
 
+// Parameter gradients only (the dgrad chain already ran, e.g. as one cluster launch): the weight-gradient GEMMs and the bias column
+// sums are independent of each other, so they are dealt round-robin onto the caller's streams (which the caller forked / joins).
+int tc_actor_param_grads(const TcActor& t, const float* dOut, const void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
+                         cudaStream_t* streams, int n_streams) {
+  const FqlDims* d = t.d;
+  const Layout& L = *t.L;
+  const NetView& nv = L.net[t.net];
+  const int H = d->hidden, NL = nv.n_layers, S = d->num_seeds, A = nv.out_dim;
+  const long long dz_ss = (long long)t.M * H;
+  int k = 0;
+  auto next = [&]() { return streams[(k++) % n_streams]; };
+  auto colsum = [&](const float* X, int N, int ld, long long ss, int64_t goff) {
+    ColSumArgs c;
+    memset(&c, 0, sizeof(c));
+    c.P = 1; c.S = S; c.E = 1; c.M = t.M; c.N = N; c.ld = ld;
+    c.X.base[0] = X; c.X.stride_s = ss;
+    c.out.base[0] = t.grads + goff; c.out.stride_s = L.arena;
+    return launch_colsum(c, next(), nullptr, 0);
+  };
+  for (int l = 0; l <= NL - 1; l++) {  // weight gradients first (the longer launches), layer 0 .. last
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.K = t.M; g.G0 = 1; g.G1 = S; g.a_mn = 1; g.b_mn = 1; g.mode = TC_MODE_STORE_F32;
+    if (l == 0) g.A = op(t.X0b, t.K0pad, t.M, t.K0pad, 1, 0, S, t.x_ss);
+    else g.A = op(t.Hb[l - 1], H, t.M, H, 1, 0, S, t.h_ss);
+    if (l == NL - 1) {
+      g.M = H; g.N = A;
+      g.B = op(dOutb, 64, t.M, 64, 1, 0, S, (long long)t.M * 64);
+      g.out_f = tp(t.grads + nv.off_w[l], 0, L.arena, A);
+    } else {
+      g.M = nv.k_of(l); g.N = H;
+      g.B = op(dZb[l], H, t.M, H, 1, 0, S, dz_ss);
+      g.out_f = tp(t.grads + nv.off_w[l], 0, L.arena, H);
+    }
+    FQL_TRY(tc_gemm(g, next()));
+  }
+  FQL_TRY(colsum(dOut, A, A, (long long)t.M * A, nv.off_b[NL - 1]));
+  for (int l = NL - 2; l >= 0; l--) FQL_TRY(colsum(dZf[l], H, H, dz_ss, nv.off_b[l]));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // critic backward (2 heads, optional LayerNorm) on saved fp32 Z / mu / rstd and bf16 H of one problem of the grouped pass
 //   grads != NULL : full backward (critic loss, fql.py:36-37)

@@ -11,7 +11,7 @@ from fql_b200 import FQLAgent, get_config, _lib
 
 NAMES = {0: 'step start', 1: 'prep done', 2: 'Euler done (S1)', 3: 'one-step fwd done', 4: 'bc-flow dgrad chain done (S2)',
          5: 'critic fwd done', 6: 'critic input-grad chain done', 7: 'join Euler + dL/da done', 8: 'bc+critic grads complete (S2)',
-         9: 'early optimizer pass done (S2)', 13: 'Euler kernel CTA 0 started', 14: 'Euler kernel CTA 0 finished', 15: 'one-step cluster fwd CTA 0 started', 16: 'one-step cluster fwd CTA 0 finished', 10: 'one-step grads complete', 11: 'optimizer pass done', 12: 'step end'}
+         9: 'early optimizer pass done (S2)', 13: 'Euler kernel CTA 0 started', 14: 'Euler kernel CTA 0 finished', 15: 'one-step cluster fwd CTA 0 started', 16: 'one-step cluster fwd CTA 0 finished', 17: 'one-step cluster dgrad CTA 0 started', 18: 'one-step cluster dgrad CTA 0 finished', 10: 'one-step grads complete', 11: 'optimizer pass done', 12: 'step end'}
 B, F, A = int(os.environ.get('B', 256)), 29, 8
 cfg = get_config()
 cfg['q_agg'] = 'min'
@@ -35,7 +35,7 @@ for it in range(30):
     out = np.zeros(576, np.uint64)
     assert lib.fql_debug_stamps(agent._ctx, out.ctypes.data, 576) == 0
     if it >= 10:
-        acc.append((out[:17].astype(np.int64) - int(out[0])) / 1e3)
+        acc.append((out[:19].astype(np.int64) - int(out[0])) / 1e3)
         eul.append(out[64:].astype(np.int64).reshape(32, 16))
 m = np.median(np.stack(acc), axis=0)
 for i in np.argsort(m):
