@@ -1,12 +1,15 @@
 // step.cu -- arena layout, workspace map and the stream-level schedule of FQLAgent.update (agents/fql.py:122-133).
 //
-// Schedule of one step (three streams, forked/joined with events; capturable into a CUDA graph):
-//   S0: prep -> onestep actor on {(s',z_next),(s,z),(s,z')} (fql.py:25,65,82) -> {target critic, critic(s,a),
-//       critic(s,clip a_pi)} x 2 heads as ONE grouped pass (fql.py:28,36,70) -> TD/Q post -> critic input-gradient
-//       -> [join Euler] distill + dL/da_pi -> onestep backward
-//   S1: bc-flow on {(s,x_t,t), Euler step 0} -> Euler steps 1..n-1 (fql.py:155-171)      <- longest dependent chain
-//   S2: BC loss + bc-flow backward (fql.py:58-59); critic backward (fql.py:36-37)
-//   S0: join -> grad stats + Adam + Polyak (optim.cu) -> info
+// Two schedules of one step, both forked/joined with events on the context's internal streams and capturable into a CUDA graph:
+//   fp32 parity mode (enqueue_step): three streams
+//     S0: prep -> onestep actor on {(s',z_next),(s,z),(s,z')} (fql.py:25,65,82) -> {target critic, critic(s,a),
+//         critic(s,clip a_pi)} x 2 heads as ONE grouped pass (fql.py:28,36,70) -> TD/Q post -> critic input-gradient
+//         -> [join Euler] distill + dL/da_pi -> onestep backward
+//     S1: bc-flow on {(s,x_t,t), Euler step 0} -> Euler steps 1..n-1 (fql.py:155-171)      <- longest dependent chain
+//     S2: BC loss + bc-flow backward (fql.py:58-59); critic backward (fql.py:36-37)
+//     S0: join -> grad stats + Adam + Polyak (optim.cu) -> info
+//   bf16 tensor-core mode (enqueue_grads_tc): the same dependency graph with the dependent chains on the high-priority streams
+//     S0/S1 and everything that only consumes on low-priority side streams; timeline in DESIGN.md section 5.
 #include "step.cuh"
 
 #include <cuda_bf16.h>

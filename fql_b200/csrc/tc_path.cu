@@ -1,6 +1,7 @@
 // tc_path.cu -- layer-by-layer tensor-core schedules built from tc_gemm (+ the SIMT row/column kernels):
-//   actor networks (no LayerNorm by default): forward incl. the Euler integration, backward (dgrad chain + wgrads)
-//   critic (LayerNorm): backward; its forward is the fused chain kernel of mlp_tc.cu
+//   actor networks (no LayerNorm by default): forward incl. the Euler integration, backward (dgrad chain + wgrads); at small
+//     batch the Euler integration, the one-step actor's forward and its dgrad chain are cluster launches instead (euler_cluster.cu)
+//   critic (LayerNorm): forward (GEMM + GELU/LayerNorm row kernel per layer, one chain per problem) and backward
 // Reference: utils/networks.py:34-61 (layer arithmetic), agents/fql.py:155-171 (Euler), utils/flax_utils.py:137 (jax.grad).
 #include "step.cuh"
 
