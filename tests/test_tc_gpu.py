@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from oracle import fql_oracle as O
-from tests.helpers import cuda_agent_from_state, f32, info_close, make_case, rel_err
+from tests.helpers import cuda_agent_from_state, f32, info_close, make_case, rel_err, stack_trees
 
 pytestmark = pytest.mark.gpu
 
@@ -42,6 +42,7 @@ TC_CASES = [
     ('tc-antmaze-large', dict(q_agg='min', alpha=10.0), 256, 29, 8, 512),
     ('tc-humanoidmaze', dict(discount=0.995, alpha=30.0), 256, 69, 21, 512),
     ('tc-puzzle-normq', dict(normalize_q_loss=True, alpha=1000.0), 256, 83, 5, 512),
+    ('tc-ragged-512', dict(q_agg='min'), 200, 29, 8, 512),   # partial 128-row tiles in the cluster kernels
 ]
 
 
@@ -90,3 +91,28 @@ def test_tc_unsupported_configs_fail_loudly():
     cfg, state, batch, noise = make_case(dict(), 32, 9, 4, seed=1, hidden=96)
     with pytest.raises(FqlError, match='hidden'):
         cuda_agent_from_state(cfg, state, 32, 9, 4, precision='bf16')
+
+
+def test_tc_update_two_seeds_cluster_kernels():
+    """Vectorised seeds through the cluster kernels (seed strides of the activation saves, per-seed weight slices): every seed
+    must match its own single-seed fp64 oracle run within the bf16 tolerance."""
+    B, F, A, S = 160, 28, 5, 2
+    cases = [make_case(dict(alpha=300.0), B, F, A, seed=50 + i, hidden=512) for i in range(S)]
+    cfg = cases[0][0]
+    agent = cuda_agent_from_state(cfg, cases[0][1], B, F, A, precision='bf16', num_seeds=S)
+    cat = stack_trees
+    agent.load_tree(f32(cat([c[1]['params'] for c in cases])), f32(cat([c[1]['mu'] for c in cases])), f32(cat([c[1]['nu'] for c in cases])),
+                    cases[0][1]['count'])
+    batch = {k: np.stack([c[2][k] for c in cases]) for k in cases[0][2]}
+    noise = {k: np.stack([c[3][k] for c in cases]) for k in cases[0][3]}
+    _, info = agent.update(f32(batch), noise=f32(noise))
+    grads = agent.export_tree('grads')
+    params = agent.export_tree('params')
+    for si, (cfg_i, state, ba, nz) in enumerate(cases):
+        new_state, ref_info, ref_grads = O.update(copy.deepcopy(state), cfg, ba, nz)
+        for k in ('critic/critic_loss', 'actor/bc_flow_loss', 'actor/distill_loss', 'actor/q_loss'):
+            info_close(k, info[k][si], ref_info, 5e-2)
+        for (path, r), (_, g) in zip(O.tree_leaves(ref_grads), O.tree_leaves(grads)):
+            assert rel_err(np.asarray(g)[si], r) <= 8e-2, ('grads', si, path)
+        for (path, r), (_, g) in zip(O.tree_leaves(new_state['params']), O.tree_leaves(params)):
+            assert rel_err(np.asarray(g)[si], r) <= 3e-3, ('params', si, path)
