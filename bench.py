@@ -55,6 +55,23 @@ def hbm_bytes_per_step(p_train, p_target, B, F, A):
     return 28 * p_train + 8 * p_target + 4 * (p_train + p_target) + B * (2 * F + A + 2) * 4
 
 
+def _shutdown(agent):
+    """Orderly multi-rank teardown: captured graphs that hold NCCL kernels are released before the process group goes away, and a
+    watchdog turns a stuck communicator teardown into a clean exit (the result line is already printed and flushed)."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    threading.Thread(target=lambda: (time.sleep(30.0), os._exit(0)), daemon=True).start()
+    try:
+        agent.release_graphs()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def load_peaks():
     try:
         p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -279,7 +296,7 @@ def main():
         e2e_s = e2e_ms / 1e3
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _shutdown(agent)
         return 0
 
     n = max(world, 1)
@@ -366,9 +383,9 @@ def main():
         out['cpu_baseline'] = dict(value=cv, unit='samples/s', steps_per_sec=1e3 / r['ms_per_step'], cores=r['cores'], kind='port',
                                    sample=f"{r['steps_measured']} full updates at batch {args.batch}, 1 seed (median), fp32 torch-CPU "
                                           f"restatement of the reference (JAX not installable)")
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _shutdown(agent)
     return 0
 
 

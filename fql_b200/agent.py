@@ -392,6 +392,14 @@ class FQLAgent:
             torch.cuda.synchronize(self.device)
             self._dp_body(bufs)
 
+    def release_graphs(self):
+        """Drop the captured data-parallel step graphs (call before torch.distributed.destroy_process_group())."""
+        torch.cuda.synchronize(self.device)
+        for bufs in list(getattr(self, '_bufs', {}).values()):
+            if isinstance(bufs, dict) and 'dp_graph' in bufs:
+                bufs['dp_graph']['graph'] = None
+                bufs.pop('raw_all', None)
+
     def _dp_body(self, bufs):
         """The data-parallel sequence itself.  With FQL_DP_OVERLAP=1 (eager mode only) the bc-flow + critic prefix of the arena starts
         on a side stream as soon as the library's early event fires, while the one-step actor's backward is still running."""
@@ -425,7 +433,9 @@ class FQLAgent:
 
     _dp_side = None
     _dp_overlap = os.environ.get('FQL_DP_OVERLAP', '0') != '0'
-    _dp_graph = os.environ.get('FQL_DP_GRAPH', '1') != '0'
+    # opt-in: a captured graph that contains NCCL kernels must be released (FQLAgent.release_graphs) before the process group is
+    # destroyed, otherwise teardown deadlocks; the eager sequence has the same device time (the step is not host-bound)
+    _dp_graph = os.environ.get('FQL_DP_GRAPH', '0') != '0'
 
     def grads_phase(self, bufs):
         """Data-parallel half 1 (fql_step_grads): this rank's gradient contribution (already divided by the global batch) into
