@@ -139,6 +139,11 @@ def cpu_reference_arm(wl, B, steps, warmup, budget_s=20.0):
     import torch
     from oracle import fql_oracle as O
     from oracle.fql_torch_cpu import TorchCpuAgent
+    # every host core this process may use, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     cfg = dict(O.DEFAULT_CONFIG)
     cfg.update(wl['cfg'])
     F, A = wl['F'], wl['A']
