@@ -25,6 +25,7 @@ INFO_KEYS = ('critic/critic_loss', 'critic/q_mean', 'critic/q_max', 'critic/q_mi
              'actor/distill_loss', 'actor/q_loss', 'actor/q', 'actor/mse', 'grad/max', 'grad/min', 'grad/norm')
 NOISE_KEYS = ('z_next', 'x0', 't', 'z', 'z_metric')
 _BATCH_KEYS = ('observations', 'actions', 'next_observations', 'rewards', 'masks')
+_PIN_RING = 4   # pinned staging blocks per batch size
 
 
 def _ptr(t):
@@ -291,8 +292,21 @@ class FQLAgent:
         shapes = dict(observations=(S, B) + ob, actions=(S, B, A), next_observations=(S, B) + ob, rewards=(S, B), masks=(S, B),
                       z_next=(S, B, A), x0=(S, B, A), t=(S, B, 1), z=(S, B, A), z_metric=(S, B, A))
         dt = lambda k: torch.uint8 if (self._image and k in ('observations', 'next_observations')) else torch.float32
-        dev = {k: torch.empty(s, dtype=dt(k), device=self.device) for k, s in shapes.items()}
-        pin = {k: torch.empty(s, dtype=dt(k)).pin_memory() for k, s in shapes.items()}
+        # One contiguous device block (batch keys first, then the noise keys) and a ring of pinned staging blocks with the same
+        # layout: a host batch goes up as ONE copy, and a staging block is only rewritten once the copy that read it has run
+        # (the host runs ahead of the GPU by many steps).
+        offs, off = {}, 0
+        for k, shp in shapes.items():
+            nb = int(np.prod(shp)) * (1 if dt(k) == torch.uint8 else 4)
+            offs[k] = (off, nb)
+            off = (off + nb + 255) // 256 * 256
+        view = lambda blk, k: blk[offs[k][0]:offs[k][0] + offs[k][1]].view(dt(k)).view(shapes[k])
+        dev_block = torch.empty(off, dtype=torch.uint8, device=self.device)
+        dev = {k: view(dev_block, k) for k in shapes}
+        pins = []
+        for _ in range(_PIN_RING):
+            blk = torch.empty(off, dtype=torch.uint8).pin_memory()
+            pins.append(dict(block=blk, views={k: view(blk, k) for k in shapes}, event=torch.cuda.Event(), pending=False))
         ws_bytes = int(self._lib.fql_workspace_bytes(C.byref(d)))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         fb = _lib.FqlBatch(*[dev[k].data_ptr() for k in _BATCH_KEYS + NOISE_KEYS])
@@ -300,20 +314,43 @@ class FQLAgent:
                            self._count.data_ptr(), self._shadow.data_ptr() if self._shadow is not None else None)
         info = torch.zeros(S, _lib.NUM_INFO, dtype=torch.float32, device=self.device)
         raw = torch.zeros(S, _lib.NUM_RAW, dtype=torch.float32, device=self.device)
-        self._bufs[B] = dict(d=d, dev=dev, pin=pin, ws=ws, ws_bytes=ws_bytes, fb=fb, st=st, info=info, raw=raw)
+        self._bufs[B] = dict(d=d, dev=dev, dev_block=dev_block, pins=pins, pin_i=0, offs=offs, ws=ws, ws_bytes=ws_bytes, fb=fb, st=st,
+                             info=info, raw=raw)
         return self._bufs[B]
 
-    def _stage_one(self, bufs, k, src):
-        dst = bufs['dev'][k]
-        if isinstance(src, torch.Tensor) and src.is_cuda:
-            dst.copy_(src.reshape(dst.shape), non_blocking=True)
+    def _stage(self, bufs, items):
+        """items: [(key, source)], keys in buffer order.  Host sources are packed into the next pinned staging block and sent with
+        one copy when they are adjacent in the block (the usual case: all five batch keys, or batch + noise); device tensors are
+        copied device to device.  Returns the host-to-device bytes."""
+        host = [(k, v) for k, v in items if not (isinstance(v, torch.Tensor) and v.is_cuda)]
+        for k, v in items:
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                bufs['dev'][k].copy_(v.reshape(bufs['dev'][k].shape), non_blocking=True)
+        if not host:
             return 0
-        npdt = np.uint8 if dst.dtype == torch.uint8 else np.float32
-        t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src, dtype=npdt))
-        pin = bufs['pin'][k]
-        pin.copy_(t.reshape(pin.shape))
-        dst.copy_(pin, non_blocking=True)
-        return pin.numel() * pin.element_size()
+        slot = bufs['pins'][bufs['pin_i'] % _PIN_RING]
+        bufs['pin_i'] += 1
+        if slot['pending']:
+            slot['event'].synchronize()
+        h2d = 0
+        for k, v in host:
+            pv = slot['views'][k]
+            npdt = np.uint8 if pv.dtype == torch.uint8 else np.float32
+            t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v, dtype=npdt))
+            pv.copy_(t.reshape(pv.shape))
+            h2d += bufs['offs'][k][1]
+        order = list(bufs['offs'])
+        idx = [order.index(k) for k, _ in host]
+        if idx == list(range(idx[0], idx[0] + len(idx))):         # adjacent keys: one transfer over the whole span
+            lo = bufs['offs'][host[0][0]][0]
+            hi = bufs['offs'][host[-1][0]][0] + bufs['offs'][host[-1][0]][1]
+            bufs['dev_block'][lo:hi].copy_(slot['block'][lo:hi], non_blocking=True)
+        else:
+            for k, _ in host:
+                bufs['dev'][k].copy_(slot['views'][k], non_blocking=True)
+        slot['event'].record(torch.cuda.current_stream(self.device))
+        slot['pending'] = True
+        return h2d
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -340,13 +377,10 @@ class FQLAgent:
         B = int(np.shape(batch['actions'])[-2])
         bufs = self._step_bufs(B)
         with torch.cuda.device(self.device):
-            h2d = 0
-            for k in _BATCH_KEYS:
-                h2d += self._stage_one(bufs, k, batch[k])
+            items = [(k, batch[k]) for k in _BATCH_KEYS]
             if noise is not None:
-                for k in NOISE_KEYS:
-                    h2d += self._stage_one(bufs, k, noise[k])
-            self.last_h2d_bytes = h2d
+                items += [(k, noise[k]) for k in NOISE_KEYS]
+            self.last_h2d_bytes = self._stage(bufs, items)
         return bufs
 
     def step(self, bufs, fill_noise=True):
