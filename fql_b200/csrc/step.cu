@@ -419,6 +419,8 @@ struct FqlContext {
   int use_graph = 1;
   int use_euler_cluster = 1;
   int use_cluster_fwd = 1;   // FQL_B200_CLUSTER_FWD=0: one-step actor forward layer by layer
+  int fused_prep = 0;        // FQL_B200_FUSED_PREP=1: the prep kernel also writes the bf16 first-layer operands (measured: no gain over
+                             // the two PDL-launched conversion kernels, which run in parallel on their own streams)
   int use_cluster_bwd = 1;   // FQL_B200_CLUSTER_BWD=0: one-step actor dgrad chain layer by layer
   unsigned long long* stamps = nullptr;  // FQL_B200_STAMPS=1: %globaltimer at schedule points (diagnostics, profiles/dbg_timeline.py)
   int split_adam = 0;        // FQL_B200_SPLIT_ADAM: 0 = one optimizer pass at the end (default: the others measured within noise), 1 = bc-flow's part right behind the Euler chain,
@@ -491,6 +493,8 @@ extern "C" int fql_context_create(FqlContext** out) {
   if (g && g[0] == '0') c->use_graph = 0;
   const char* ec = getenv("FQL_B200_EULER_CLUSTER");
   if (ec && ec[0] == '0') c->use_euler_cluster = 0;
+  const char* fp = getenv("FQL_B200_FUSED_PREP");
+  if (fp) c->fused_prep = fp[0] == '1';
   const char* cbw = getenv("FQL_B200_CLUSTER_BWD");
   if (cbw && cbw[0] == '0') c->use_cluster_bwd = 0;
   const char* cfw = getenv("FQL_B200_CLUSTER_FWD");
@@ -607,7 +611,8 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   FQL_TRY(stamp(ctx, 0, S0));   // step start
   FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0));
   FQL_TRY(encode_observations(c, L, w, S0));
-  FQL_TRY(launch_prep(sh, b, w, S0));
+  const bool fused_prep = ctx->fused_prep;
+  FQL_TRY(launch_prep(sh, b, w, S0, fused_prep ? kF : 0, fused_prep ? kO : 0));  // also writes the bf16 first-layer operands XFb / XOb
   FQL_TRY(stamp(ctx, 1, S0));   // prep done
   FQL_CHECK_CUDA(cudaEventRecord(ev_prep, S0));
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S1, ev_prep, 0));
@@ -627,7 +632,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   };
 
   // ---- S1: Euler (agents/fql.py:155-171) on rows [B, 2B) of the bc-flow buffers
-  FQL_TRY(tc_pad_bf16(w.XF, w.XFb, (int64_t)S * 2 * B, sh.F + sh.A + 1, kF, S1));
+  if (!fused_prep) FQL_TRY(tc_pad_bf16(w.XF, w.XFb, (int64_t)S * 2 * B, sh.F + sh.A + 1, kF, S1));
   FQL_CHECK_CUDA(cudaEventRecord(ev_pad, S1));
   const int row_tiles = S * ((B + 127) / 128);
   const bool many_tiles = row_tiles >= ctx->chain_min_tiles;  // enough 128-row tiles to fill the GPU: fused per-tile chain kernels
@@ -681,7 +686,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   (void)ev_f0;
 
   // ---- S0: one-step actor on {(s',z_next), (s,z), (s,z')}, grouped critic pass
-  FQL_TRY(tc_pad_bf16(w.XO, w.XOb, (int64_t)S * 3 * B, sh.F + sh.A, kO, S0));
+  if (!fused_prep) FQL_TRY(tc_pad_bf16(w.XO, w.XOb, (int64_t)S * 3 * B, sh.F + sh.A, kO, S0));
   TcActor fo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, 0, 3 * B, w.O_Hb, w.O_Zb, true);
   bool split_metric = false, early_adam_s1 = false;
   if (many_tiles) {
