@@ -203,7 +203,8 @@ def main():
         val = sps * args.batch
         sample = f"{r['steps_measured']} full updates of the same workload at batch {args.batch} (median), fp32 torch-CPU (MKL, autograd)"
         print(json.dumps(dict(
-            impl='reference', metric='fql_update_samples_per_sec', value=val, unit='samples/s', steps_per_sec=sps, n_gpus=0,
+            impl='reference', metric='fql_update_samples_per_sec', value=val, unit='samples/s', steps_per_sec=sps, n_gpus=args.gpus,
+            device='cpu (host cores of the box; no GPU is used by this arm)',
             steps=r['steps_measured'], warmup=max(1, min(args.warmup, 3)), ms_per_step=r['ms_per_step'], higher_is_better=True,
             scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', config=config,
             cpu_baseline=dict(value=val, unit='samples/s', cores=r['cores'], kind='port', sample=sample),
