@@ -528,6 +528,7 @@ extern "C" int fql_context_destroy(FqlContext* c) {
   if (c->s7) cudaStreamDestroy(c->s7);
   if (c->s8) cudaStreamDestroy(c->s8);
   if (c->s9) cudaStreamDestroy(c->s9);
+  if (c->stamps) cudaFree(c->stamps);
   delete c;
   return 0;
 }
