@@ -116,3 +116,38 @@ def test_tc_update_two_seeds_cluster_kernels():
             assert rel_err(np.asarray(g)[si], r) <= 8e-2, ('grads', si, path)
         for (path, r), (_, g) in zip(O.tree_leaves(new_state['params']), O.tree_leaves(params)):
             assert rel_err(np.asarray(g)[si], r) <= 3e-3, ('params', si, path)
+
+
+SWITCHES = [
+    dict(FQL_B200_CRITIC_CHAIN='1'),                                  # critic forward: fused chain kernel, LayerNorm in the TMEM epilogue
+    dict(FQL_B200_CLUSTER_FWD='0', FQL_B200_CLUSTER_BWD='0'),         # one-step actor layer by layer
+    dict(FQL_B200_EULER_CLUSTER='0'),                                 # Euler integration layer by layer (tc_gemm Euler epilogue)
+    dict(FQL_B200_CHAIN_MIN_TILES='1'),                               # large-batch routing: fused per-tile chain kernels everywhere
+    dict(FQL_B200_SPLIT_ADAM='1'),
+    dict(FQL_B200_SPLIT_ADAM='2'),
+    dict(FQL_B200_FUSED_PREP='1'),
+    dict(FQL_B200_GRAPH='0'),                                         # every step enqueued eagerly
+]
+
+
+@pytest.mark.parametrize('env', SWITCHES, ids=['+'.join(f'{k[9:]}={v}' for k, v in e.items()) for e in SWITCHES])
+def test_tc_alternative_schedules_match_oracle(env, monkeypatch):
+    """Every alternative code path behind a schedule switch computes the same update (stated bf16 tolerance vs the fp64 oracle)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)                                      # read by fql_context_create
+    B, F, A = 256, 29, 8
+    cfg, state, batch, noise = make_case(dict(q_agg='min', alpha=10.0), B, F, A, seed=31, hidden=512)
+    agent = cuda_agent_from_state(cfg, state, B, F, A, precision='bf16')
+    agent.load_tree(f32(state['params']), f32(state['mu']), f32(state['nu']), state['count'])
+    st = copy.deepcopy(state)
+    for i in range(3):                                                # eager call, graph capture, graph replay
+        ba, nz = (batch, noise) if i == 0 else (O.make_batch(500 + i, B, F, A, np.float64), O.make_noise(600 + i, B, A, np.float64))
+        st, ref_info, ref_grads = O.update(st, cfg, ba, nz)
+        _, info = agent.update(f32(ba), noise=f32(nz))
+        for k in ('critic/critic_loss', 'actor/bc_flow_loss', 'actor/distill_loss', 'actor/q_loss', 'actor/mse'):
+            info_close(k, info[k], ref_info, 8e-2 if k == 'actor/distill_loss' else 5e-2)
+        if i == 0:
+            for (path, r), (_, g) in zip(O.tree_leaves(ref_grads), O.tree_leaves(agent.export_tree('grads'))):
+                assert rel_err(g, r) <= 8e-2, ('grads', path, rel_err(g, r))
+    for (path, r), (_, g) in zip(O.tree_leaves(st['params']), O.tree_leaves(agent.export_tree('params'))):
+        assert rel_err(g, r) <= 5e-3, ('params', path, rel_err(g, r))
