@@ -3,12 +3,15 @@
 //
 //   warp 0   TMA producer : streams the bf16 shadow weights of every layer as MN-major SWIZZLE_128B B-tiles
 //                           (kernel leaves are Flax [in,out] row-major, so a [16 k][64 n] box IS the canonical MN-major atom)
-//   warp 1   MMA issuer   : tcgen05.mma kind::f16, M=128, N<=256 per instruction, fp32 accumulators in all 512 TMEM columns
-//   warps 2-5 epilogue    : one thread per row (tcgen05.ld 32x32b): + bias, GELU(tanh), optional LayerNorm with per-thread row
+//   warps 1-2 MMA issuers : tcgen05.mma kind::f16, M=128, N<=256 per instruction, one 256-column half of the accumulator each
+//                           (a tcgen05.mma costs its issuing warp ~80 ns); fp32 accumulators in all 512 TMEM columns
+//   warps 3-6 epilogue    : one thread per row (tcgen05.ld 32x32b): + bias, GELU(tanh), optional LayerNorm with per-thread row
 //                           statistics (the 128x512 fp32 accumulator is exactly one SM's TMEM, so LN needs no cross-thread
 //                           reduction), bf16 re-pack straight into the next layer's K-major SWIZZLE_128B A operand in smem.
 //
-// Activations never leave the SM between layers (or Euler steps); optional fp32 copies of Z / H go to HBM for the backward.
+// Activations never leave the SM between layers (or Euler steps); optional fp32 / bf16 copies of Z / H go to HBM for the backward.
+// Used where there are enough 128-row tiles to fill the GPU (large batch, many seeds) and for sample_actions; at batch 256 the
+// cluster kernels of euler_cluster.cu split one tile over 16 SMs instead.
 // Reference arithmetic: utils/networks.py:34-61 (MLP), :153-195 (Value), :198-235 (ActorVectorField).
 #include "step.cuh"
 #include "tc_prims.cuh"
