@@ -79,12 +79,16 @@ _SIGS = {
                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     'fql_mlp_forward': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    'fql_target_update': (C.c_int, [C.POINTER(FqlDims), C.POINTER(FqlHparams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    'fql_debug_stamps': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     'fql_refresh_shadow': (C.c_int, [C.POINTER(FqlDims), C.c_void_p, C.c_void_p, C.c_void_p]),
     'fql_gather_rows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     'fql_gather_frames': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'fql_fill_noise': (C.c_int, [C.POINTER(FqlDims), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    'fql_fill_noise_rows': (C.c_int, [C.POINTER(FqlDims), C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -78,6 +79,24 @@ class LazyInfo(dict):
         self._fill()
         return dict.__repr__(self)
 
+    def get(self, k, default=None):
+        self._fill()
+        return dict.get(self, k, default)
+
+    def copy(self):
+        self._fill()
+        return dict(dict.items(self))
+
+    def pop(self, k, *default):
+        self._fill()
+        return dict.pop(self, k, *default)
+
+    def __eq__(self, other):
+        self._fill()
+        return dict.__eq__(self, other)
+
+    __hash__ = None
+
 
 class TrainStateView:
     """`agent.network`: params / opt_state / step with the reference's nesting (utils/flax_utils.py:53-70)."""
@@ -109,7 +128,7 @@ class FQLAgent:
     # ------------------------------------------------------------------ construction (agents/fql.py:173-246)
     @classmethod
     def create(cls, seed, ex_observations, ex_actions, config, *, num_seeds=1, device=None, precision='fp32',
-               process_group=None, world_size=None):
+               process_group=None, world_size=None, rank=None):
         self = cls.__new__(cls)
         cfg = dict(config)
         ex_observations = np.asarray(ex_observations)
@@ -163,6 +182,15 @@ class FQLAgent:
             self._shadow = torch.zeros(nb, dtype=torch.uint8, device=self.device)
         self._bufs = {}
         self._ring, self._ring_i = [], 0
+        self._host_step = 0          # updates enqueued so far == optax count: the Philox step of the next noise draw
+        self.last_h2d_bytes = 0
+        self.rank = 0
+        if process_group is not None:
+            import torch.distributed as dist
+            self.rank = dist.get_rank(process_group)
+        if rank is not None:
+            self.rank = int(rank)
+        self._dp_side = None
         self._init_params(seed)
         # agent.rng: a (2,) uint32 key; noise for update k comes from Philox(key, k)
         ss = np.random.SeedSequence(int(seed) if np.ndim(seed) == 0 else [int(x) for x in np.ravel(seed)])
@@ -259,6 +287,9 @@ class FQLAgent:
             rec(src, views)
         if count is not None:
             self._count.fill_(int(count))
+            # the noise of update k is Philox(rng, k): a restored run continues the stream instead of replaying it from 0
+            # (the reference replaces agent.rng every update, fql.py:125,133; here the key is fixed and the step advances)
+            self._host_step = int(count)
         self.refresh_shadow()
         return self
 
@@ -356,14 +387,23 @@ class FQLAgent:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _info_out(self, info_dev):
+        """Async copy of the metrics into the next slot of a ring of 64 pinned buffers.  A slot is reused only after the LazyInfo that
+        still points at it (if the caller kept it, e.g. for periodic logging) has been materialised, so a late read never returns a
+        later step's metrics."""
         i = self._ring_i % 64
         if i >= len(self._ring):
-            self._ring.append((torch.empty(info_dev.shape, dtype=torch.float32).pin_memory(), torch.cuda.Event()))
-        host, ev = self._ring[i]
+            self._ring.append([torch.empty(info_dev.shape, dtype=torch.float32).pin_memory(), torch.cuda.Event(), None])
+        slot = self._ring[i]
+        host, ev, owner = slot
+        prev = owner() if owner is not None else None
+        if prev is not None:
+            prev._fill()
         self._ring_i += 1
         host.copy_(info_dev, non_blocking=True)
         ev.record(torch.cuda.current_stream(self.device))
-        return LazyInfo(INFO_KEYS, host, ev)
+        out = LazyInfo(INFO_KEYS, host, ev)
+        slot[2] = weakref.ref(out)
+        return out
 
     # ------------------------------------------------------------------ the hot path (agents/fql.py:122-133)
     def update(self, batch, noise=None):
@@ -465,7 +505,6 @@ class FQLAgent:
                    'fql_step_apply_gathered')
         bufs['raw_all'] = raw_all                       # keep alive (and at a fixed address for the captured graph)
 
-    _dp_side = None
     _dp_overlap = os.environ.get('FQL_DP_OVERLAP', '0') != '0'
     # opt-in: a captured graph that contains NCCL kernels must be released (FQLAgent.release_graphs) before the process group is
     # destroyed, otherwise teardown deadlocks; the eager sequence has the same device time (the step is not host-bound)
@@ -483,21 +522,24 @@ class FQLAgent:
                                             _ptr(bufs['info']), _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_step_apply')
 
     def _fill_noise(self, bufs, step_for_noise):
+        """Philox(agent.rng, step) noise for this rank's rows of the GLOBAL batch (rows [rank*B, (rank+1)*B) of every seed): all
+        ranks share the key -- they must, to hold identical parameters -- and differ in the counter range."""
         dev = bufs['dev']
         seed = int(self.rng[0]) | (int(self.rng[1]) << 32)
-        _lib.check(self._lib.fql_fill_noise(C.byref(bufs['d']), C.c_uint64(seed), C.c_uint64(step_for_noise),
-                                            _ptr(dev['z_next']), _ptr(dev['x0']), _ptr(dev['t']), _ptr(dev['z']),
-                                            _ptr(dev['z_metric']), self._stream()), 'fql_fill_noise')
+        row0 = self.rank * int(bufs['d'].batch) if self.world > 1 else 0
+        _lib.check(self._lib.fql_fill_noise_rows(C.byref(bufs['d']), C.c_uint64(seed), C.c_uint64(step_for_noise), C.c_int64(row0),
+                                                 _ptr(dev['z_next']), _ptr(dev['x0']), _ptr(dev['t']), _ptr(dev['z']),
+                                                 _ptr(dev['z_metric']), self._stream()), 'fql_fill_noise_rows')
 
     def launch_count(self):
         """Kernels this agent's context has enqueued so far (graph replays count their kernel nodes)."""
         return int(self._lib.fql_launch_count(self._ctx))
 
-    _host_step = 0
-    last_h2d_bytes = 0
-
     def total_loss(self, batch, grad_params=None, rng=None, noise=None):
         """Forward-only losses (agents/fql.py:94-111 as called by main.py:284): returns (loss, info[10 keys])."""
+        if grad_params is not None and grad_params is not self.network.params:
+            raise NotImplementedError('total_loss evaluates the stored parameters (grad_params=None, main.py:284); gradients are '
+                                      'taken inside update()')
         with torch.cuda.device(self.device):
             bufs = self.stage(batch, noise)
             if noise is None:
@@ -508,6 +550,29 @@ class FQLAgent:
             info = self._info_out(bufs['info'])
         vals = {k: info[k] for k in INFO_KEYS[:10]}
         return vals['critic/critic_loss'] + vals['actor/actor_loss'], vals
+
+    def critic_loss(self, batch, grad_params=None, rng=None, noise=None):
+        """agents/fql.py:22-44: (critic_loss, {critic_loss, q_mean, q_max, q_min}), forward only -- the gradient of this loss is
+        part of `update` (one fused step); `grad_params` is accepted for signature parity and must be None or the stored params."""
+        _, info = self.total_loss(batch, grad_params, rng, noise)
+        out = {k.split('/', 1)[1]: v for k, v in info.items() if k.startswith('critic/')}
+        return out['critic_loss'], out
+
+    def actor_loss(self, batch, grad_params=None, rng=None, noise=None):
+        """agents/fql.py:46-92: (actor_loss, {actor_loss, bc_flow_loss, distill_loss, q_loss, q, mse}), forward only."""
+        _, info = self.total_loss(batch, grad_params, rng, noise)
+        out = {k.split('/', 1)[1]: v for k, v in info.items() if k.startswith('actor/')}
+        return out['actor_loss'], out
+
+    def target_update(self, network=None, module_name='critic'):
+        """agents/fql.py:113-120: target_critic <- tau * critic + (1 - tau) * target_critic, in place (`update` already does this,
+        fused into the optimizer pass; this is the standalone method of the reference's surface)."""
+        if module_name != 'critic':
+            raise ValueError(f"target_update: FQL only has a target network for 'critic' (got {module_name!r})")
+        d = self._dims(int(self.config.get('batch_size', 256)))
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.fql_target_update(C.byref(d), C.byref(self._hp), _ptr(self._params), _ptr(self._shadow), self._stream()),
+                       'fql_target_update')
 
     # ------------------------------------------------------------------ agents/fql.py:135-171
     def _fwd_call(self, fn, observations, noises):

@@ -54,6 +54,14 @@ inline cudaError_t fql_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block,
   cfg.numAttrs = fql_pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+// cudaFuncSetAttribute / occupancy results are per DEVICE: caches of them are indexed by the current device (FQLAgent.create(device=...)
+// may put a second GPU under the same process)
+#define FQL_MAX_DEVICES 64
+inline int fql_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < FQL_MAX_DEVICES ? dev : 0;
+}
 #define FQL_REQUIRE(cond, ...)       \
   do {                               \
     if (!(cond)) {                   \

@@ -518,11 +518,12 @@ int launch_euler(const EulerArgs& a, const TcEulerSpec& f, cudaStream_t st, bool
   const int smem = NSUB * A_SUB + (a.H / KB) * (KB * NCOL * 2) + (a.K0pad / KB) * A_BLK + a.NL * 64 * 4 + 64 * 4 + 256 + 1024;
   FQL_REQUIRE(smem <= 232448, "euler_cluster_kernel: shared memory %d > 227 KB", smem);
   auto kern = euler_cluster_kernel<NC, AMAX, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[FQL_MAX_DEVICES] = {};
+  const int dev = fql_current_device();
+  if (!attr_set[dev]) {
     FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     if (NC > 8) FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -591,17 +592,21 @@ int fill_args(EulerArgs& a, const FqlDims* d, const Layout& L, int net, const fl
   a.wl_row = (int)(wl / 64);
   a.params = params; a.arena = L.arena;
   FQL_REQUIRE(a.A <= MAX_A, "euler_cluster_kernel: output width %d > %d", a.A, MAX_A);
-  a.dbg_it = getenv("FQL_B200_EULER_DBG_IT") ? atoi(getenv("FQL_B200_EULER_DBG_IT")) : 7;
+  a.dbg_it = 7;  // layer iteration the optional phase stamps (FQL_B200_STAMPS) are taken at
   return 0;
 }
 // clusters of 16 CTAs the GPU can hold at once (one per GPC); 0 when FQL_B200_EULER_NC=8 forces clusters of 8
 int max_clusters16(const EulerArgs& a, const TcEulerSpec& f) {
-  static int max16 = -1;
-  if (max16 < 0) {
+  static int max16_dev[FQL_MAX_DEVICES];
+  static bool known[FQL_MAX_DEVICES] = {};
+  const int dev = fql_current_device();
+  int& max16 = max16_dev[dev];
+  if (!known[dev]) {
     const char* e = getenv("FQL_B200_EULER_NC");
     if (e && atoi(e) == 8) max16 = 0;
     else if (launch_euler<16, 8, MODE_EULER>(a, f, nullptr, true, &max16)) max16 = 0;
-    if (getenv("FQL_B200_VERBOSE")) fprintf(stderr, "fql_b200: clusters of 16 CTAs resident at once: %d\n", max16);
+    if (getenv("FQL_B200_VERBOSE")) fprintf(stderr, "fql_b200: clusters of 16 CTAs resident at once (device %d): %d\n", dev, max16);
+    known[dev] = true;
   }
   return max16;
 }

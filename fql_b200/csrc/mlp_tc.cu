@@ -547,10 +547,11 @@ int tc_mlp_chain(const TcChainSpec& f, cudaStream_t st) {
   FQL_TRY(make_map_2d(&mapX, f.X0b, a.K0pad, x_rows, 64, TILE_M));
   FQL_TRY(make_map_2d(&mapW, f.shadow, d->hidden, (uint64_t)a.S * a.w_rows_s, 64, STAGE_K));
   FQL_TRY(make_map_2d(&mapWL, f.shadow, 64, (uint64_t)a.S * a.wl_rows_s, 64, STAGE_K));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[FQL_MAX_DEVICES] = {};
+  const int dev = fql_current_device();
+  if (!attr_set[dev]) {
     FQL_CHECK_CUDA(cudaFuncSetAttribute(mlp_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int grid = a.tiles * a.P * a.S * a.E;
   mlp_chain_tc_kernel<<<grid, CH_THREADS, smem, st>>>(mapX, mapW, mapWL, a);

@@ -166,6 +166,25 @@ __global__ void zero_bc_kernel(float4* p, int64_t n4, const int32_t* __restrict_
   }
 }
 
+// FQLAgent.target_update (agents/fql.py:113-120) on its own: target <- tau * critic + (1 - tau) * target, plus the bf16 shadow.
+__global__ void target_update_kernel(float* __restrict__ params, __nv_bfloat16* __restrict__ shadow, int64_t arena, int64_t shadow_seed,
+                                     int64_t cri0, int64_t tgt0, int64_t n, float tau, float omt) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int s = blockIdx.y;
+  if (i >= n) return;
+  const float4 p = *reinterpret_cast<const float4*>(params + s * arena + cri0 + i);
+  float4 t = *reinterpret_cast<const float4*>(params + s * arena + tgt0 + i);
+  t.x = p.x * tau + t.x * omt;
+  t.y = p.y * tau + t.y * omt;
+  t.z = p.z * tau + t.z * omt;
+  t.w = p.w * tau + t.w * omt;
+  *reinterpret_cast<float4*>(params + s * arena + tgt0 + i) = t;
+  if (shadow) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+    *reinterpret_cast<uint2*>(shadow + s * shadow_seed + tgt0 + i) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
 __global__ void zero_kernel(float4* p, int64_t n4) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -201,6 +220,25 @@ int launch_zero_bc(float* p, int64_t n, const int32_t* count, const FqlHparams& 
   const unsigned blocks = (unsigned)((n4 + 255) / 256);
   zero_bc_kernel<<<blocks ? blocks : 1, 256, 0, st>>>(reinterpret_cast<float4*>(p), n4, count, hp.beta1, hp.beta2, bc);
   FQL_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fql_target_update(const FqlDims* d, const FqlHparams* hp, float* params, void* shadow, void* stream) {
+  Layout L;
+  FQL_TRY(fql_build_layout(d, &L));
+  FQL_REQUIRE(hp && params, "fql_target_update: NULL argument");
+  const NetView& cri = L.net[FQL_NET_CRITIC];
+  const NetView& tgt = L.net[FQL_NET_TARGET_CRITIC];
+  const int64_t n = cri.end - cri.begin;
+  FQL_REQUIRE(n == tgt.end - tgt.begin && n % 4 == 0, "critic / target critic ranges differ");
+  const bool tcm = d->precision == FQL_PRECISION_BF16_TC;
+  FQL_REQUIRE(!tcm || shadow, "FQL_PRECISION_BF16_TC needs the bf16 shadow");
+  dim3 grid((unsigned)((n / 4 + 255) / 256), d->num_seeds);
+  target_update_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      params, tcm ? reinterpret_cast<__nv_bfloat16*>(shadow) : nullptr, L.arena, tcm ? tc_shadow_seed_elems(d, L) : 0, cri.begin, tgt.begin, n,
+      hp->tau, hp->one_minus_tau);
+  FQL_CHECK_LAUNCH();
+  if (tcm) FQL_TRY(tc_refresh_shadow_lastlayer(d, L, params, shadow, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 

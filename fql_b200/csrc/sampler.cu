@@ -69,34 +69,37 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 }
 
 // tensor ids 0..4 = z_next, x0, t, z, z_metric.  normal via Box-Muller, uniform = 24 random bits in [0,1).
+// The Philox counter is the element's index in the GLOBAL [S][global_batch][A] tensor (quad = index / 4, lane = index % 4): a
+// data-parallel rank that holds rows [row0, row0 + B) of every seed draws exactly the slice a single device would have drawn for
+// those rows (R ranks == 1 device), and no two ranks share a noise row.
 __global__ void fill_noise_kernel(uint64_t seed, uint64_t step, float* z_next, float* x0, float* t, float* z, float* z_metric,
-                                  int64_t n_act, int64_t n_t) {
+                                  int S, int B, int A, int64_t GB, int64_t row0) {
   const int tensor = blockIdx.y;
   float* out = tensor == 0 ? z_next : tensor == 1 ? x0 : tensor == 2 ? t : tensor == 3 ? z : z_metric;
-  const int64_t n = tensor == 2 ? n_t : n_act;
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // quad index
-  if (out == nullptr || q * 4 >= n) return;
+  const int w = tensor == 2 ? 1 : A;
+  const int64_t n = (int64_t)S * B * w;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // local element
+  if (out == nullptr || i >= n) return;
+  const int64_t per_seed = (int64_t)B * w;
+  const int64_t s = i / per_seed, r = i - s * per_seed;
+  const int64_t ge = (s * GB + row0) * w + r;                        // global element
+  const int64_t q = ge >> 2;
+  const int lane = (int)(ge & 3);
   uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32) ^ ((uint32_t)tensor << 28), (uint32_t)step, (uint32_t)(step >> 32)};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-  float v[4];
+  float v;
   if (tensor == 2) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = (float)(c[i] >> 8) * (1.0f / 16777216.0f);
+    v = (float)(c[lane] >> 8) * (1.0f / 16777216.0f);
   } else {
-#pragma unroll
-    for (int i = 0; i < 4; i += 2) {
-      const float u1 = ((float)(c[i] >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
-      const float u2 = (float)(c[i + 1] >> 8) * (1.0f / 16777216.0f);
-      const float r = sqrtf(-2.0f * logf(u1));
-      float sn, cs;
-      sincospif(2.0f * u2, &sn, &cs);
-      v[i] = r * cs;
-      v[i + 1] = r * sn;
-    }
+    const int p = lane & 2;
+    const float u1 = ((float)(c[p] >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
+    const float u2 = (float)(c[p + 1] >> 8) * (1.0f / 16777216.0f);
+    const float rr = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    v = (lane & 1) ? rr * sn : rr * cs;
   }
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-    if (q * 4 + i < n) out[q * 4 + i] = v[i];
+  out[i] = v;
 }
 
 }  // namespace
@@ -137,14 +140,22 @@ extern "C" int fql_gather_frames(const uint8_t* obs_src, const uint8_t* next_src
   return 0;
 }
 
-extern "C" int fql_fill_noise(const FqlDims* d, uint64_t seed, uint64_t step, float* z_next, float* x0, float* t, float* z,
-                              float* z_metric, void* stream) {
+extern "C" int fql_fill_noise_rows(const FqlDims* d, uint64_t seed, uint64_t step, int64_t row_offset, float* z_next, float* x0, float* t,
+                                   float* z, float* z_metric, void* stream) {
   FQL_TRY(fql_validate_dims(d));
-  const int64_t n_t = (int64_t)d->num_seeds * d->batch;
-  const int64_t n_act = n_t * d->action_dim;
-  const int64_t quads = (n_act + 3) / 4;
-  dim3 grid((unsigned)((quads + 127) / 128), 5);
-  fill_noise_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(seed, step, z_next, x0, t, z, z_metric, n_act, n_t);
+  FQL_REQUIRE(row_offset >= 0 && row_offset + d->batch <= d->global_batch, "fql_fill_noise_rows: rows [%lld, %lld) outside the global batch %d",
+              (long long)row_offset, (long long)row_offset + d->batch, d->global_batch);
+  const int64_t n_act = (int64_t)d->num_seeds * d->batch * d->action_dim;
+  dim3 grid((unsigned)((n_act + 255) / 256), 5);
+  fill_noise_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(seed, step, z_next, x0, t, z, z_metric, d->num_seeds, d->batch,
+                                                                               d->action_dim, d->global_batch, row_offset);
   FQL_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int fql_fill_noise(const FqlDims* d, uint64_t seed, uint64_t step, float* z_next, float* x0, float* t, float* z,
+                              float* z_metric, void* stream) {
+  FQL_REQUIRE(d && d->global_batch == d->batch, "fql_fill_noise: data-parallel ranks (global_batch != batch) must call fql_fill_noise_rows "
+                                                "with their row offset, or every rank draws the same noise");
+  return fql_fill_noise_rows(d, seed, step, 0, z_next, x0, t, z, z_metric, stream);
 }

@@ -1242,10 +1242,6 @@ extern "C" int fql_compute_flow_actions(FqlContext*, const FqlDims* d, const flo
       memset(&e, 0, sizeof(e));
       e.d = d; e.L = &L; e.params = params; e.shadow = shadow; e.X0b = Xb; e.Mcap0 = rows; e.r0_in = 0; e.M = rows;
       e.a0 = noise; e.target = actions_out; e.scratch = Hx;
-      {
-        const char* dp = getenv("FQL_B200_EULER_DBG");
-        if (dp) e.dbg = reinterpret_cast<void*>(strtoull(dp, nullptr, 0));
-      }
       return tc_euler_cluster(e, st);
     }
     TcChainSpec t;

@@ -341,10 +341,11 @@ int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
     case TC_MODE_EULER: kern = tc_gemm_kernel<TC_MODE_EULER>; break;
     default: FQL_REQUIRE(false, "tc_gemm: unknown epilogue mode %d", s.mode);
   }
-  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
-  if (!attr_set[s.mode & 7]) {
+  static bool attr_set[FQL_MAX_DEVICES][8] = {};
+  const int dev = fql_current_device();
+  if (!attr_set[dev][s.mode & 7]) {
     FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set[s.mode & 7] = true;
+    attr_set[dev][s.mode & 7] = true;
   }
   dim3 grid((s.N + BN - 1) / BN, (s.M + BM - 1) / BM, a.G0 * a.G1);
   cudaLaunchConfig_t cfg;

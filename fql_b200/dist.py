@@ -7,7 +7,6 @@ The reference itself is single-device (no pmap/shard_map anywhere): 
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -57,32 +56,3 @@ def shard_seeds(num_seeds: int, rank: int, world: int) -> range:
         raise ValueError(f'{num_seeds} seeds do not divide over {world} ranks')
     per = num_seeds // world
     return range(rank * per, (rank + 1) * per)
-
-
-def raw_from_losses(info: dict, q: np.ndarray, q_pi: np.ndarray, local_rows: int, action_dim: int) -> np.ndarray:
-    """Raw accumulators a rank would produce, reconstructed from per-rank MEAN metrics (used by the CPU tests to exercise the
-    reduction semantics against the oracle)."""
-    raw = np.zeros(16, np.float64)
-    B, A = local_rows, action_dim
-    raw[0] = info['critic/critic_loss'] * 2 * B
-    raw[1] = info['critic/q_mean'] * 2 * B
-    raw[2] = info['actor/bc_flow_loss'] * B * A
-    raw[3] = info['actor/distill_loss'] * B * A
-    raw[4] = info['actor/q'] * B
-    raw[5] = np.abs(q_pi).sum()
-    raw[6] = info['actor/mse'] * B * A
-    raw[9] = info['critic/q_max']
-    raw[10] = -info['critic/q_min']
-    return raw
-
-
-def info_from_raw(raw: np.ndarray, global_rows: int, action_dim: int, alpha: float, normalize_q_loss: bool) -> dict:
-    """finalize_info_kernel in NumPy (losses.cu): the 10 loss metrics from the reduced accumulators."""
-    gb, A = float(global_rows), float(action_dim)
-    bc, distill, q = raw[2] / (gb * A), raw[3] / (gb * A), raw[4] / gb
-    q_loss = -q
-    if normalize_q_loss:
-        q_loss = q_loss / (raw[5] / gb)
-    return {'critic/critic_loss': raw[0] / (2 * gb), 'critic/q_mean': raw[1] / (2 * gb), 'critic/q_max': raw[9], 'critic/q_min': -raw[10],
-            'actor/actor_loss': bc + alpha * distill + q_loss, 'actor/bc_flow_loss': bc, 'actor/distill_loss': distill, 'actor/q_loss': q_loss,
-            'actor/q': q, 'actor/mse': raw[6] / (gb * A)}

@@ -160,6 +160,9 @@ int fql_compute_flow_actions(FqlContext* ctx, const FqlDims* d, const float* par
 /* One network forward (utils/networks.py MLP/Value/ActorVectorField __call__): x [S,rows,in] -> y [S,ens,rows,out]. */
 int fql_mlp_forward(FqlContext* ctx, const FqlDims* d, int32_t net, const float* params, const float* x, float* y,
                     int32_t rows, void* workspace, size_t ws_bytes, void* stream);
+/* FQLAgent.target_update(network, 'critic') (agents/fql.py:113-120) on its own: target_critic <- tau * critic + (1 - tau) * target_critic
+ * in place in the parameter arena (fql_update_step already contains it, fused into the optimizer pass). */
+int fql_target_update(const FqlDims* d, const FqlHparams* hp, float* params, void* shadow, void* stream);
 /* Rebuild the bf16 operand shadow from fp32 params (after create()/restore; the step keeps it current itself). */
 int fql_refresh_shadow(const FqlDims* d, const float* params, void* shadow, void* stream);
 
@@ -176,6 +179,17 @@ int fql_gather_frames(const uint8_t* obs_src, const uint8_t* next_src, uint8_t* 
  * SURVEY 8c): fills the five noise tensors of one update from (seed, step). */
 int fql_fill_noise(const FqlDims* d, uint64_t seed, uint64_t step, float* z_next, float* x0, float* t, float* z,
                    float* z_metric, void* stream);
+/* The same for a data-parallel rank holding rows [row_offset, row_offset + batch) of the global batch: the Philox counters are
+ * indices into the GLOBAL [S][global_batch][A] tensors, so R ranks draw exactly the noise one device would draw for the global
+ * batch and no two ranks share a row.  fql_fill_noise == row_offset 0 with global_batch == batch. */
+int fql_fill_noise_rows(const FqlDims* d, uint64_t seed, uint64_t step, int64_t row_offset, float* z_next, float* x0, float* t,
+                        float* z, float* z_metric, void* stream);
+
+
+/* ---- diagnostics -------------------------------------------------------------------------------------- */
+/* %globaltimer stamps taken at the schedule points of the last step when the context was created with FQL_B200_STAMPS=1
+ * (profiles/dbg_timeline.py); fails otherwise.  Synchronises the device: not for the hot path. */
+int fql_debug_stamps(FqlContext* ctx, unsigned long long* host_out, int n);
 
 #ifdef __cplusplus
 }

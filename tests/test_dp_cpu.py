@@ -11,6 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import fql_oracle as O
+from tests.helpers import info_from_raw, raw_from_losses
 
 
 def _free_port():
@@ -41,12 +42,12 @@ def _worker(rank, world, port, q_agg, out):
     g = torch.from_numpy(_flat(grads) * (B // world) / B).reshape(1, -1)
     qs = O.critic_forward(params['modules_critic'], cfg, lb['observations'], np.clip(O.actor_forward(
         params['modules_actor_onestep_flow'], cfg, lb['observations'], ln['z']), -1, 1)).mean(0)
-    raw = torch.from_numpy(fdist.raw_from_losses({k: float(v) for k, v in info.items()}, None, qs, B // world, A)).reshape(1, -1)
+    raw = torch.from_numpy(raw_from_losses({k: float(v) for k, v in info.items()}, None, qs, B // world, A)).reshape(1, -1)
     fdist.allreduce_step(g, raw, group=None)
     if rank == 0:
         _, info_full, grads_full = O.total_loss(params, cfg, batch, noise)
         np.testing.assert_allclose(g.numpy()[0], _flat(grads_full), rtol=1e-9, atol=1e-12)
-        got = fdist.info_from_raw(raw.numpy()[0], B, A, cfg['alpha'], cfg['normalize_q_loss'])
+        got = info_from_raw(raw.numpy()[0], B, A, cfg['alpha'], cfg['normalize_q_loss'])
         for k, v in got.items():
             np.testing.assert_allclose(v, float(info_full[k]), rtol=1e-9, atol=1e-12, err_msg=k)
         out.put('ok')
