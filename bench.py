@@ -8,8 +8,11 @@
 A "step" is one FQLAgent.update (agents/fql.py:122-133) on one synthetic batch of the named OGBench shape.
   value   device-timed samples/s with the batch already resident in HBM (CUDA events around every step, max over ranks)
   e2e     the same through the public API `agent.update(host_batch)`: pinned H2D of the batch + D2H of the 13 metrics
-N > 1 is data parallel, weak scaling: every rank holds `--batch` rows of a global batch of N*batch, gradients are
-all-reduced over NCCL, value = global samples/s.
+N > 1 is data parallel, weak scaling: every rank holds `--batch` rows of a global batch of N*batch; the gradient buckets are
+reduced by the library's own kernels over NVLink peer memory / NVLS multicast inside the step graph (FQL_DP_BACKEND=nccl: NCCL
+all-reduce instead); value = global samples/s.  `--seeds S` with N > 1 shards SEEDS: every rank trains its own S independent
+agents, no collective on the step.  Every line also carries `scaling_configs`: the two sharded north_star configurations
+(humanoidmaze-medium batch 8192/GPU data parallel; puzzle-4x4 8 seeds/GPU seed-sharded) timed in the same run at this N.
 """
 import argparse
 import json
@@ -156,7 +159,7 @@ def cpu_reference_arm(wl, B, steps, warmup, budget_s=20.0):
     agent = TorchCpuAgent(params, cfg)
     batches = make_host_batches(4, B, F, A, 1, image=wl.get('image'))
     noises = [O.make_noise(i, B, A, np.float32) for i in range(4)]
-    for i in range(max(1, min(warmup, 3))):
+    for i in range(max(1, warmup)):
         agent.update(batches[i % 4], noises[i % 4])
     times = []
     t_begin = time.perf_counter()
@@ -169,6 +172,62 @@ def cpu_reference_arm(wl, B, steps, warmup, budget_s=20.0):
     times.sort()
     med = times[len(times) // 2]
     return dict(ms_per_step=med * 1e3, steps_measured=len(times), cores=torch.get_num_threads(), loss=info['critic/critic_loss'])
+
+
+def time_config(name, batch, seeds, mode, world, rank, pg, stream, flush, steps=20, warmup=5):
+    """One more configuration timed at this N in the same run (device-timed, L2 flushed, max over ranks): mode 'dp' = rows sharded,
+    gradient buckets reduced across ranks inside the step; 'seeds' = independent agents per rank, no collective; 'single' = rank-local."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fql_b200 import FQLAgent, get_config
+    wl = WORKLOADS[name]
+    F, A = wl['F'], wl['A']
+    cfg = get_config()
+    cfg.update(wl['cfg'])
+    cfg['batch_size'] = batch
+    precision = 'fp32' if wl.get('image') and not PIXEL_BF16 else 'bf16'
+    ex_obs = np.zeros((1,) + tuple(wl['image']), np.uint8) if wl.get('image') else np.zeros((1, F), np.float32)
+    out = dict(workload=name, batch_per_gpu=batch, seeds_per_gpu=seeds, n_gpus=world, mode=mode, precision=precision)
+    try:
+        with torch.cuda.stream(stream):
+            agent = FQLAgent.create(rank if mode == 'seeds' else 0, ex_obs, np.zeros((1, A), np.float32), cfg, num_seeds=seeds, precision=precision,
+                                    process_group=pg if (mode == 'dp' and world > 1) else None)
+            bufs = agent.stage(make_host_batches(1, batch, F, A, seeds, seed0=77 + rank, image=wl.get('image'))[0])
+            for _ in range(warmup):
+                agent.step(bufs)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for i in range(steps):
+                flush.zero_()
+                ev[i][0].record()
+                info = agent.step(bufs)
+                ev[i][1].record()
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+            loss = float(np.ravel(info['critic/critic_loss'])[0])
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        n_units = world if mode in ('dp', 'seeds') else 1
+        samples = batch * seeds * n_units
+        peaks = load_peaks()
+        flops_gpu = flops_per_sample(F, A, pixels=bool(wl.get('image'))) * batch * seeds
+        out.update(ms_per_step=ms, steps_per_sec=1e3 / ms, value=samples / (ms / 1e3), unit='samples/s', steps=steps, warmup=warmup,
+                   global_batch=batch * (world if mode == 'dp' else 1), total_seeds=seeds * (world if mode == 'seeds' else 1),
+                   tensor_tflops_per_gpu=flops_gpu / (ms / 1e3) / 1e12, tensor_frac=flops_gpu / (ms / 1e3) / 1e12 / peaks['tc'],
+                   finite=bool(np.isfinite(loss)), transport=getattr(agent, 'dp_transport', None))
+        del agent, bufs
+        torch.cuda.empty_cache()
+    except Exception as e:  # a scaling entry must never cost the headline line
+        out['error'] = repr(e)[:300]
+    return out
+
+
+PIXEL_BF16 = False   # the pixel configuration runs its MLPs/encoders in fp32 until the tensor-core encoder lands
 
 
 def main():
@@ -184,6 +243,7 @@ def main():
                     help='bf16: tcgen05 operands, fp32 accumulate/master weights (default); fp32: FFMA parity mode')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fp32-leg', action='store_true')
+    ap.add_argument('--no-scaling-configs', action='store_true')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if wl.get('image'):
@@ -194,7 +254,8 @@ def main():
     config = dict(workload=f'{args.workload}-shaped synthetic (obs {F}, act {A}), FQL update, batch {args.batch}/GPU, '
                            f'{args.seeds} seed(s)/GPU, 4x512 MLPs, flow_steps 10, ' + ', '.join(f'{k}={v}' for k, v in wl['cfg'].items()),
                   batch_per_gpu=args.batch, global_batch=args.batch * max(world, 1), seeds_per_gpu=args.seeds,
-                  parallelism=f'dp{world}' if world > 1 else 'single', l2='flushed between timed steps (256 MiB write)')
+                  parallelism=(f'seeds sharded over {world} GPUs (no collective)' if world > 1 and args.seeds > 1 else f'dp{world}') if world > 1 else 'single',
+                  l2='flushed between timed steps (256 MiB write)')
 
     if args.impl == 'reference':
         if rank != 0:
@@ -206,7 +267,7 @@ def main():
         print(json.dumps(dict(
             impl='reference', metric='fql_update_samples_per_sec', value=val, unit='samples/s', steps_per_sec=sps, n_gpus=args.gpus,
             device='cpu (host cores of the box; no GPU is used by this arm)',
-            steps=r['steps_measured'], warmup=max(1, min(args.warmup, 3)), ms_per_step=r['ms_per_step'], higher_is_better=True,
+            steps=r['steps_measured'], warmup=max(1, args.warmup), ms_per_step=r['ms_per_step'], higher_is_better=True,
             scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', config=config,
             cpu_baseline=dict(value=val, unit='samples/s', cores=r['cores'], kind='port', sample=sample),
             e2e=dict(value=val, unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -220,18 +281,18 @@ def main():
     from fql_b200 import FQLAgent, get_config
 
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    os.environ['NCCL_DEBUG'] = os.environ.get('FQL_BENCH_NCCL_DEBUG', 'WARN')  # keep stdout to the one JSON line
     torch.cuda.set_device(local_rank)
     pg = None
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
         pg = dist.group.WORLD
+    seed_sharded = world > 1 and args.seeds > 1       # independent agents per rank: no process group on the agent, no collective
     cfg = get_config()
     cfg.update(wl['cfg'])
     cfg['batch_size'] = args.batch
     ex_obs = np.zeros((1,) + tuple(wl['image']), np.uint8) if wl.get('image') else np.zeros((1, F), np.float32)
-    agent = FQLAgent.create(0, ex_obs, np.zeros((1, A), np.float32), cfg, num_seeds=args.seeds,
-                            precision=args.precision, process_group=pg)
+    agent = FQLAgent.create(rank if seed_sharded else 0, ex_obs, np.zeros((1, A), np.float32), cfg, num_seeds=args.seeds,
+                            precision=args.precision, process_group=None if seed_sharded else pg)
     batches = make_host_batches(8, args.batch, F, A, args.seeds, seed0=1000 * rank, image=wl.get('image'))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     stream = torch.cuda.Stream()  # a real (non-legacy) stream: the library captures its step graph on it
@@ -301,6 +362,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, warm_ms, e2e_ms = [float(x) for x in t.tolist()]
         e2e_s = e2e_ms / 1e3
+    # the sharded north_star configurations at this N (every rank takes part), and BASELINE config 1 beside the headline config 2
+    scaling_configs = []
+    if not args.no_scaling_configs:
+        scaling_configs.append(time_config('humanoidmaze-medium', 8192, 1, 'dp', world, rank, pg, stream, flush))
+        scaling_configs.append(time_config('puzzle-4x4', 256, 8, 'seeds', world, rank, pg, stream, flush))
+        if world == 1:
+            scaling_configs.append(time_config('cube-single', 256, 1, 'single', world, rank, pg, stream, flush, steps=50))
     if rank != 0:
         if world > 1:
             _shutdown(agent)
@@ -376,7 +444,8 @@ def main():
                ms_per_step_l2_warm=(warm_ms / K) if n == 1 else None,
                e2e=dict(value=samples_per_step * K / e2e_s, unit='samples/s', steps_per_sec=K / e2e_s, h2d_bytes_per_step=h2d,
                         d2h_bytes_per_step=13 * 4 * args.seeds, api='FQLAgent.update(host numpy batch)'),
-               gpu_launches=launches, gpu_launches_per_step=launches / K, roofline=roof, clocks=clk, last_critic_loss=last_loss)
+               gpu_launches=launches, gpu_launches_per_step=launches / K, roofline=roof, clocks=clk, last_critic_loss=last_loss,
+               scaling_configs=scaling_configs, dp_transport=getattr(agent, 'dp_transport', None))
     if n == 1 and args.precision == 'bf16' and not args.no_fp32_leg:
         with torch.cuda.stream(stream):
             a32 = FQLAgent.create(0, np.zeros((1, F), np.float32), np.zeros((1, A), np.float32), cfg, num_seeds=args.seeds, precision='fp32')

@@ -43,6 +43,13 @@ class FqlState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('params', 'mu', 'nu', 'grads', 'count', 'shadow')]
 
 
+DP_MAX_RANKS = 8
+
+
+class FqlDpComm(C.Structure):
+    _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('base', C.c_void_p * DP_MAX_RANKS), ('base_mc', C.c_void_p)]
+
+
 class FqlError(RuntimeError):
     pass
 
@@ -69,6 +76,8 @@ _SIGS = {
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'fql_step_apply_gathered': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlHparams), C.POINTER(FqlState), C.c_void_p, C.c_int32,
                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'fql_dp_symmetric_bytes': (C.c_size_t, [C.POINTER(FqlDims), C.c_int32]),
+    'fql_dp_attach': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlDpComm)]),
     'fql_set_early_grads_event': (C.c_int, [C.c_void_p, C.c_void_p]),
     'fql_early_grads_floats': (C.c_int64, [C.POINTER(FqlDims)]),
     'fql_total_loss': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlHparams), C.POINTER(FqlBatch), C.POINTER(FqlState),

@@ -172,7 +172,11 @@ class FQLAgent:
         self._params = torch.zeros(S, self._arena, dtype=torch.float32, device=self.device)
         self._mu = torch.zeros_like(self._params)
         self._nu = torch.zeros_like(self._params)
-        self._grads = torch.zeros_like(self._params)
+        self._dp_peer = False
+        if process_group is not None and self.world > 1 and os.environ.get('FQL_DP_BACKEND', 'peer') != 'nccl':
+            self._attach_peer_memory(d, process_group)      # the gradient arena lives in NVLink peer-mapped memory
+        else:
+            self._grads = torch.zeros_like(self._params)
         self._count = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._shadow = None
         if self._precision == _lib.PRECISION_BF16_TC:
@@ -197,6 +201,37 @@ class FQLAgent:
         self.rng = ss.generate_state(2, dtype=np.uint32)
         self.network = TrainStateView(self)
         return self
+
+    def _attach_peer_memory(self, d, group):
+        """Data parallel over NVLink peer memory (include/fql_b200.h, fql_dp_attach): the gradient arena, the metric gather buffer and
+        the synchronisation flags of every rank are mapped into every rank (torch's symmetric-memory rendezvous does the CUDA VMM /
+        NVLS multicast plumbing), and the library's own kernels reduce the gradient buckets inside the step graph.  No NCCL call
+        remains on the step.  FQL_DP_BACKEND=nccl keeps the NCCL all-reduce sequence instead (A/B measurements)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        nbytes = int(self._lib.fql_dp_symmetric_bytes(C.byref(d), self.world))
+        if nbytes == 0:
+            raise _lib.FqlError('fql_dp_symmetric_bytes: ' + self._lib.fql_last_error().decode())
+        with torch.cuda.device(self.device):
+            buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(buf, group)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)                             # every rank's flags are zero before anyone can signal
+        comm = _lib.FqlDpComm()
+        comm.rank, comm.world = dist.get_rank(group), self.world
+        ptrs = list(hdl.buffer_ptrs)
+        if ptrs[comm.rank] != buf.data_ptr():
+            raise _lib.FqlError('symmetric memory rendezvous: local buffer pointer mismatch')
+        for r in range(self.world):
+            comm.base[r] = ptrs[r]
+        mc = int(hdl.multicast_ptr) if os.environ.get('FQL_DP_MULTICAST', '1') != '0' else 0
+        comm.base_mc = mc or None
+        _lib.check(self._lib.fql_dp_attach(self._ctx, C.byref(d), C.byref(comm)), 'fql_dp_attach')
+        self._symm, self._symm_hdl, self._comm = buf, hdl, comm
+        self._grads = buf[:self.num_seeds * self._arena].view(self.num_seeds, self._arena)
+        self._dp_peer = True
+        self.dp_transport = 'nvls-multicast' if mc else 'nvlink-peer'
 
     def _dims(self, batch):
         if batch not in self._dims_cache:
@@ -430,7 +465,7 @@ class FQLAgent:
             if fill_noise:
                 self._fill_noise(bufs, self._host_step)
             self._host_step += 1
-            if self.world == 1:
+            if self.world == 1 or self._dp_peer:
                 a = (self._ctx, C.byref(bufs['d']), C.byref(self._hp))
                 _lib.check(self._lib.fql_update_step(*a, C.byref(bufs['fb']), C.byref(bufs['st']), _ptr(bufs['info']),
                                                      _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_update_step')

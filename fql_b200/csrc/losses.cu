@@ -1,6 +1,7 @@
 // losses.cu -- the non-GEMM arithmetic of FQLAgent.total_loss (agents/fql.py:22-111): input assembly, TD target,
 // loss reductions and the loss-side gradients.  One CTA per seed for the reductions (deterministic order).
 #include "step.cuh"
+#include "dp_comm.cuh"
 
 #include <cuda_bf16.h>
 
@@ -119,7 +120,37 @@ __global__ void post_onestep_kernel(StepShape sh, FqlBatch b, WsPtrs w, float* r
 // TD target + critic loss gradient (fql.py:28-44) and the actor's Q statistics / dQ seed (fql.py:70-76).
 // qout: [3][S][2][B]  (0: target critic on (s',a'), 1: critic on (s,a), 2: critic on (s, clip a_pi))
 // parts: bit 0 = TD / critic-loss half (problems 0, 1), bit 1 = actor-Q half (problem 2)
-__global__ void critic_post_kernel(StepShape sh, FqlHparams hp, FqlBatch b, WsPtrs w, float* raw, int parts) {
+// Sum of one float per rank over the data-parallel ranks, identical bits on every rank (rank order): thread 0 of the CTA stores a
+// {epoch, value} word into slot [rank][s] of every peer (one aligned 8-byte store: the flag travels with the datum, no fence)
+// and collects the world words of its own pad.
+__device__ float dp_sum_over_ranks(const DpLamArgs& l, int s, int S, float mine) {
+  const uint32_t ep = l.epoch[s] + 1;
+  const unsigned long long word = ((unsigned long long)ep << 32) | (unsigned long long)__float_as_uint(mine);
+  for (int r = 0; r < l.world; r++)
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(l.slots[r] + (int64_t)l.rank * S + s), "l"(word) : "memory");
+  float tot = 0.f;
+  for (int r = 0; r < l.world; r++) {
+    const unsigned long long* src = l.slots[l.rank] + (int64_t)r * S + s;
+    unsigned long long v;
+    unsigned long long t0 = 0;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+      if ((uint32_t)(v >> 32) == ep) break;
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      if (t - t0 > 60ull * 1000000000ull) {
+        printf("fql_b200: data-parallel |q| exchange timed out waiting for rank %d (seed %d)\n", r, s);
+        __trap();
+      }
+    }
+    tot += __uint_as_float((uint32_t)v);
+  }
+  l.epoch[s] = ep;
+  return tot;
+}
+
+__global__ void critic_post_kernel(StepShape sh, FqlHparams hp, FqlBatch b, WsPtrs w, float* raw, int parts, DpLamArgs dpl) {
   __shared__ float red[32];
   const int s = blockIdx.x;
   const int B = sh.B, S = sh.S;
@@ -163,11 +194,19 @@ __global__ void critic_post_kernel(StepShape sh, FqlHparams hp, FqlBatch b, WsPt
   if (parts & 2) {
     ps = block_reduce<0>(ps, red);
     pa = block_reduce<0>(pa, red);
-    // lam = 1/mean|q| over the (global) batch, stop-gradient (fql.py:74-76)
-    float lam = 1.0f;
-    if (sh.normalize_q_loss) lam = 1.0f / (pa / (float)sh.GB);
     if (threadIdx.x == 0) {
       rw[RAW_QPI_SUM] = ps; rw[RAW_QPI_ABS] = pa;
+    }
+    // lam = 1/mean|q| over the GLOBAL batch, stop-gradient (fql.py:74-76): data-parallel ranks exchange their sums here
+    float lam = 1.0f;
+    if (sh.normalize_q_loss) {
+      if (dpl.world > 1) {
+        __shared__ float s_pa;
+        if (threadIdx.x == 0) s_pa = dp_sum_over_ranks(dpl, s, sh.S, pa);
+        __syncthreads();
+        pa = s_pa;
+      }
+      lam = 1.0f / (pa / (float)sh.GB);
     }
     const float dqs = -lam * inv_2gb;
     for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) w.dqs[(int64_t)s * 2 * B + i] = dqs;
@@ -296,8 +335,12 @@ int launch_post_onestep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w,
   FQL_CHECK_LAUNCH();
   return 0;
 }
-int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts) {
-  critic_post_kernel<<<sh.S, 1024, 0, st>>>(sh, hp, b, w, raw, parts);
+int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts,
+                       const DpLamArgs* dpl) {
+  DpLamArgs l;
+  memset(&l, 0, sizeof(l));
+  if (dpl) l = *dpl;
+  critic_post_kernel<<<sh.S, 1024, 0, st>>>(sh, hp, b, w, raw, parts, l);
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -11,6 +11,7 @@
 //   bf16 tensor-core mode (enqueue_grads_tc): the same dependency graph with the dependent chains on the high-priority streams
 //     S0/S1 and everything that only consumes on low-priority side streams; timeline in DESIGN.md section 5.
 #include "step.cuh"
+#include "dp_comm.cuh"
 
 #include <cuda_bf16.h>
 #include <stdarg.h>
@@ -46,9 +47,6 @@ int fql_validate_dims(const FqlDims* d) {
     FQL_REQUIRE(d->num_seeds == 1, "pixel configs are built for num_seeds == 1");
     FQL_REQUIRE(d->precision == FQL_PRECISION_FP32, "pixel configs run in FQL_PRECISION_FP32 in this version (encoders are fp32 CUDA-core kernels)");
   }
-  FQL_REQUIRE(!(d->normalize_q_loss && d->global_batch != d->batch),
-              "normalize_q_loss with a data-parallel split needs a global |q| exchange inside the step: not supported; "
-              "shard seeds instead (SURVEY 8e)");
   return 0;
 }
 
@@ -413,6 +411,8 @@ struct GraphEntry {
   long long kernels;  // kernel nodes in the captured graph
 };
 struct FqlContext {
+  cudaStream_t sc = nullptr;  // data-parallel exchange (dp_comm.cu): bucket reductions overlap the rest of the backward
+  DpState dp;                 // attached peer-memory communicator (fql_dp_attach)
   cudaStream_t s0 = nullptr, s1 = nullptr, s2 = nullptr, s3 = nullptr, s4 = nullptr, s5 = nullptr, s6 = nullptr, s7 = nullptr, s8 = nullptr, s9 = nullptr;  // s0 stands in for the caller's stream when that is the legacy default
   cudaEvent_t ev[64] = {};
   std::vector<GraphEntry> graphs;
@@ -445,6 +445,25 @@ extern "C" int64_t fql_early_grads_floats(const FqlDims* d) {
   if (fql_build_layout(d, &L)) return -1;
   return L.net[FQL_NET_ACTOR_ONESTEP_FLOW].begin;
 }
+extern "C" int fql_dp_attach(FqlContext* c, const FqlDims* d, const FqlDpComm* comm) {
+  FQL_REQUIRE(c != nullptr, "context is NULL");
+  for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  c->graphs.clear();  // the communicator's pointers are baked into captured graphs
+  c->dp = DpState();
+  if (!comm) return 0;
+  Layout L;
+  FQL_TRY(fql_build_layout(d, &L));
+  FQL_REQUIRE(comm->world >= 2 && comm->world <= FQL_DP_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world, "fql_dp_attach: rank %d of %d",
+              comm->rank, comm->world);
+  for (int r = 0; r < comm->world; r++) FQL_REQUIRE(comm->base[r] != nullptr && ((uintptr_t)comm->base[r] & 15) == 0, "fql_dp_attach: base[%d] is NULL / unaligned", r);
+  c->dp.comm = *comm;
+  c->dp.S = d->num_seeds;
+  c->dp.arena = L.arena;
+  c->dp.lay = dp_layout(d->num_seeds, L.arena);
+  c->dp.active = 1;
+  return 0;
+}
+
 __global__ void stamp_kernel(unsigned long long* slot) {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -488,6 +507,7 @@ extern "C" int fql_context_create(FqlContext** out) {
   FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s7, cudaStreamNonBlocking, prio_lo));
   FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s8, cudaStreamNonBlocking, prio_lo));
   FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->s9, cudaStreamNonBlocking, prio_lo));
+  FQL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->sc, cudaStreamNonBlocking, prio_hi));
   for (auto& e : c->ev) FQL_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const char* g = getenv("FQL_B200_GRAPH");
   if (g && g[0] == '0') c->use_graph = 0;
@@ -528,6 +548,7 @@ extern "C" int fql_context_destroy(FqlContext* c) {
   if (c->s7) cudaStreamDestroy(c->s7);
   if (c->s8) cudaStreamDestroy(c->s8);
   if (c->s9) cudaStreamDestroy(c->s9);
+  if (c->sc) cudaStreamDestroy(c->sc);
   if (c->stamps) cudaFree(c->stamps);
   delete c;
   return 0;
@@ -609,6 +630,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   cudaStream_t S1 = ctx->s1, S2 = ctx->s2;
   cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4], ev_pad = ctx->ev[5];
   const int kO = (int)round_up64(sh.F + sh.A, 64), kF = (int)round_up64(sh.F + sh.A + 1, 64);
+  const bool dp_grads = ctx->dp.active && c.do_backward;   // data parallel: per-network bucket reductions on ctx->sc
   FQL_TRY(stamp(ctx, 0, S0));   // step start
   FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0));
   FQL_TRY(encode_observations(c, L, w, S0));
@@ -682,6 +704,11 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[53], ctx->s7));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s3, ctx->ev[53], 0));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], ctx->s3));
+    if (dp_grads) {  // bc-flow's gradients are final long before the rest: its bucket crosses NVLink under the remaining backward
+      const NetView& nb = L.net[FQL_NET_ACTOR_BC_FLOW];
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[16], 0));
+      FQL_TRY(dp_reduce_bucket(ctx->dp, 0, nb.begin, nb.end - nb.begin, nullptr, ctx->sc));
+    }
     FQL_TRY(stamp(ctx, 4, S2));   // bc-flow dgrad chain done (weight gradients on s3 may still run)
   }
   (void)ev_f0;
@@ -752,7 +779,8 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     split_cpost = true;
   }
   FQL_TRY(stamp(ctx, 5, S0));   // critic forward (problem 2) done
-  FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0, split_cpost ? 2 : 3));
+  const DpLamArgs dpl = dp_lam_args(ctx->dp);
+  FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0, split_cpost ? 2 : 3, &dpl));
   if (!split_cpost) FQL_CHECK_CUDA(cudaEventRecord(ev_cpost, S0));
 
   if (c.do_backward) {
@@ -766,6 +794,12 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[54], ctx->s8));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s5, ctx->ev[54], 0));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], ctx->s5));
+    if (dp_grads) {
+      const NetView& nc = L.net[FQL_NET_CRITIC];
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[36], 0));
+      FQL_TRY(dp_reduce_bucket(ctx->dp, 1, nc.begin, nc.end - nc.begin, nullptr, ctx->sc));
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[59], ctx->sc));
+    }
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[36], 0));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[16], 0));  // bc-flow weight gradients (side stream s3)
     FQL_TRY(stamp(ctx, 8, S2));   // bc-flow + critic gradients complete
@@ -845,6 +879,11 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   }
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
   if (early_adam_s1) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[58], 0));
+  if (dp_grads) {  // the one-step actor's bucket + the metric accumulators close the exchange; the optimizer pass follows on S0
+    const NetView& no = L.net[FQL_NET_ACTOR_ONESTEP_FLOW];
+    FQL_TRY(dp_reduce_bucket(ctx->dp, 2, no.begin, no.end - no.begin, raw, S0));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[59], 0));
+  }
   return 0;
 }
 
@@ -860,6 +899,14 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
   const StepShape sh = make_shape(c.d);
   const FqlHparams hp = *c.hp;
   const int S = sh.S, B = sh.B, H = sh.H;
+  FQL_REQUIRE(!(c.d->normalize_q_loss && c.d->global_batch != c.d->batch) || ctx->dp.active,
+              "normalize_q_loss with a data-parallel split needs the global mean|q| inside the step (agents/fql.py:74-76): attach a peer-memory "
+              "communicator (fql_dp_attach); the fql_step_grads / fql_step_apply split cannot provide it");
+  if (ctx->dp.active && c.do_grads) {
+    FQL_REQUIRE(c.st->grads == ctx->dp.comm.base[ctx->dp.comm.rank], "data parallel: FqlState.grads must be this rank's symmetric buffer (base[rank])");
+    FQL_REQUIRE(c.d->global_batch == (int64_t)c.d->batch * ctx->dp.comm.world && ctx->dp.S == S && !c.raw,
+                "data parallel: global_batch must be world x batch (%d x %d), seeds as attached, and the raw accumulators internal", ctx->dp.comm.world, c.d->batch);
+  }
   float* raw = c.raw ? c.raw : w.raw_local;
   const float* P = c.st->params;
 
@@ -906,7 +953,10 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     fC.params = P; fC.arena = L.arena; fC.S = S; fC.E = 2; fC.M = B; fC.H = H; fC.X0 = w.XC; fC.Mcap0 = B; fC.r0_in = 0;
     fC.buf = &w.pC; fC.r0 = 0; fC.save_z = 1;
     FQL_TRY(mlp_forward(fC, S0));
-    FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0));
+    {
+      const DpLamArgs dpl = dp_lam_args(ctx->dp);
+      FQL_TRY(launch_critic_post(sh, hp, b, w, raw, S0, 3, &dpl));
+    }
     FQL_CHECK_CUDA(cudaEventRecord(ev_cpost, S0));
 
     // ---- S2: BC loss + bc-flow backward, critic backward
@@ -956,10 +1006,22 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
       if (pix) FQL_TRY(encoder_grads(c, L, w, FQL_NET_ACTOR_ONESTEP_FLOW, w.dX0O, 1, sh.F + sh.A, w.dfeat[2], 1, S0));
     }
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
+    if (ctx->dp.active && c.do_backward) {  // parity mode: one reduction over the trainable prefix of the arena (+ metric gather)
+      const int64_t t0 = L.net[FQL_NET_TARGET_CRITIC].begin;
+      FQL_TRY(dp_reduce_bucket(ctx->dp, 3, 0, t0, raw, S0));
+    }
   }
 
   ctx->adam_done_blk = 0;
   if (c.do_grads && tcm) FQL_TRY(enqueue_grads_tc(ctx, c, L, w, sh, hp, raw, S0));
+  int raw_ranks = c.raw_ranks > 1 ? c.raw_ranks : 1;
+  const float* raw_fin = raw;
+  if (ctx->dp.active && c.do_grads) {
+    // forward-only calls (fql_total_loss) still gather the accumulators so that info describes the GLOBAL batch
+    if (!c.do_backward) FQL_TRY(dp_reduce_bucket(ctx->dp, 2, 0, 0, raw, S0));
+    raw_fin = dp_raw_all(ctx->dp);
+    raw_ranks = ctx->dp.comm.world;
+  }
   if (c.do_apply) {
     if (!c.do_grads) FQL_TRY(launch_zero_bc(nullptr, 0, c.st->count, hp, w.gstats + S * 4, S0));
     // Adam + Polyak + gradient statistics (+ the bf16 operand shadow of the new parameters) in one pass over the arenas
@@ -977,11 +1039,11 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     }
     FinArgs fin;
     memset(&fin, 0, sizeof(fin));
-    fin.sh = sh; fin.hp = hp; fin.raw = raw; fin.ranks = c.raw_ranks > 1 ? c.raw_ranks : 1; fin.info = c.info;
+    fin.sh = sh; fin.hp = hp; fin.raw = raw_fin; fin.ranks = raw_ranks; fin.info = c.info;
     FQL_TRY(launch_grad_stats_final(L, S, w.partials, w.gstats, c.st->count, S0, c.info ? &fin : nullptr));
     if (tcm) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[51], 0));
   }
-  if (c.info && !c.do_apply) FQL_TRY(launch_finalize_info(sh, hp, raw, c.raw_ranks > 1 ? c.raw_ranks : 1, w.gstats, c.info, 0, S0));
+  if (c.info && !c.do_apply) FQL_TRY(launch_finalize_info(sh, hp, raw_fin, raw_ranks, w.gstats, c.info, 0, S0));
   FQL_TRY(stamp(ctx, 12, S0));    // step end
   return 0;
 }

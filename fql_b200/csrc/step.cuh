@@ -62,7 +62,9 @@ size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w)
 
 int launch_prep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, cudaStream_t st, int kF = 0, int kO = 0);
 int launch_post_onestep(const StepShape& sh, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts = 3);
-int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts = 3);
+struct DpLamArgs;
+int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch& b, const WsPtrs& w, float* raw, cudaStream_t st, int parts = 3,
+                       const DpLamArgs* dpl = nullptr);
 int launch_bc_post(const StepShape& sh, const WsPtrs& w, float* raw, cudaStream_t st);
 int launch_euler_update(const StepShape& sh, const WsPtrs& w, int step, cudaStream_t st);
 int launch_actor_grad(const StepShape& sh, const FqlHparams& hp, const WsPtrs& w, float* raw, cudaStream_t st, void* dapib = nullptr);

@@ -145,6 +145,28 @@ int fql_step_apply_gathered(FqlContext* ctx, const FqlDims* d, const FqlHparams*
  * actor's backward is still running; the caller may start all-reducing that prefix on another stream behind the event. */
 int fql_set_early_grads_event(FqlContext* ctx, void* event);
 int64_t fql_early_grads_floats(const FqlDims* d);
+/* ---- data parallel over NVLink peer memory (no NCCL on the step) --------------------------------------------
+ * Every rank maps every rank's "symmetric" buffer (fql_dp_symmetric_bytes() bytes: [gradient arena S x arena floats | metric
+ * gather | lam exchange | flags]) into its address space -- CUDA IPC / VMM peer mappings, plus the NVLS multicast mapping of the
+ * same allocations when the fabric offers one (torch.distributed._symmetric_memory.rendezvous provides both; any allocator
+ * that yields the pointers below works).  The caller zero-fills its buffer once, synchronises all ranks, and attaches.  From
+ * then on fql_update_step / fql_total_loss on this context ARE the data-parallel step (FqlDims.global_batch = world x batch,
+ * FqlState.grads must be base[rank]): as soon as a network's gradients are final, one kernel of this library reduces that
+ * bucket across ranks -- rank r owns 1/world of it: multimem.ld_reduce through the switch (or loads from the world peer
+ * mappings, summed in rank order) and multimem.st (or peer stores) of the sum back into every rank's arena -- overlapped with
+ * the rest of the backward; the metric accumulators are gathered by the last bucket's kernel; config['normalize_q_loss'] gets its
+ * global mean|q| (agents/fql.py:74-76) from a one-word-per-rank exchange inside the loss kernel.  Ranks synchronise through
+ * release/acquire flags in the peer-mapped buffers; every rank applies the identical Adam / Polyak step (replicas stay
+ * bit-identical, no parameter broadcast).  The whole step stays one CUDA graph. */
+#define FQL_DP_MAX_RANKS 8
+typedef struct FqlDpComm {
+  int32_t rank, world;
+  void* base[FQL_DP_MAX_RANKS]; /* this process's mapping of rank i's symmetric buffer; base[rank] is the local one */
+  void* base_mc;                /* NVLS multicast mapping of the same buffers, or NULL (peer loads / stores are used instead) */
+} FqlDpComm;
+size_t fql_dp_symmetric_bytes(const FqlDims* d, int32_t world);
+int fql_dp_attach(FqlContext* ctx, const FqlDims* d, const FqlDpComm* comm); /* comm == NULL detaches */
+
 /* Forward-only total_loss(grad_params=None) (agents/fql.py:94-111 as called from main.py:284): 10 info floats
  * [0..9] and the scalar loss in info[FQL_NUM_INFO-3] slot order documented in fql_info_name. */
 int fql_total_loss(FqlContext* ctx, const FqlDims* d, const FqlHparams* hp, const FqlBatch* batch,

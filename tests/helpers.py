@@ -63,6 +63,27 @@ def info_close(key, got, ref_info, tol):
     assert abs(got - r) <= tol * scale, (key, got, r, scale)
 
 
+def check_update_delta(old_params, ref_new_params, got_new_params, tol, pick=None, what=''):
+    """The parameter UPDATE itself (new - old) against the oracle's, per leaf: tensor-norm-relative error <= tol and the sign of
+    every significant element agrees.  This is the check with power for one Adam step: the step moves a weight by ~lr = 3e-4
+    against |p| ~ 0.1, so comparing the new VALUES at 3e-3 would pass even if the optimizer never ran (delta error = 1)."""
+    pick = pick or (lambda x: x)
+    worst = 0.0
+    for (path, new), (_, old), (_, g) in zip(O.tree_leaves(ref_new_params), O.tree_leaves(old_params), O.tree_leaves(got_new_params)):
+        new, old = np.asarray(new, np.float64), np.asarray(old, np.float64)
+        d_ref = new - old
+        if np.abs(d_ref).max() == 0:
+            assert np.array_equal(np.asarray(pick(g), np.float64), old.astype(np.float32).astype(np.float64)), (what, 'frozen leaf moved', path)
+            continue
+        d_got = np.asarray(pick(g), np.float64) - old.astype(np.float32).astype(np.float64)
+        e = rel_err(d_got, d_ref)
+        worst = max(worst, e)
+        assert e <= tol, (what, 'delta', path, e)
+        big = np.abs(d_ref) > 0.25 * np.abs(d_ref).max()
+        assert np.array_equal(np.sign(d_got[big]), np.sign(d_ref[big])), (what, 'delta sign', path)
+    return worst
+
+
 # ---- reduction semantics of the data-parallel metric accumulators, in NumPy (used by the CPU tests; include/fql_b200.h raw[]) ----
 def raw_from_losses(info: dict, q: np.ndarray, q_pi: np.ndarray, local_rows: int, action_dim: int) -> np.ndarray:
     """Raw accumulators a rank would produce, reconstructed from per-rank MEAN metrics (used by the CPU tests to exercise the

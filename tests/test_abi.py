@@ -63,8 +63,13 @@ def test_validation_errors_are_reported_not_thrown(L):
     bad = L.make_dims(0, 4, 2)
     assert lib.fql_arena_floats(C.byref(bad)) == -1
     assert b'batch' in lib.fql_last_error()
-    dp_norm = L.make_dims(128, 4, 2, global_batch=256, normalize_q_loss=True)
-    assert lib.fql_workspace_bytes(C.byref(dp_norm)) == 0 and b'normalize_q_loss' in lib.fql_last_error()
+    # the peer-memory data-parallel interface: sizes and argument validation (no GPU needed)
+    d = L.make_dims(128, 29, 8, global_batch=256, normalize_q_loss=True)
+    arena = lib.fql_arena_floats(C.byref(d))
+    nb = lib.fql_dp_symmetric_bytes(C.byref(d), 2)
+    assert arena * 4 < nb < arena * 4 + (1 << 16) and nb % 256 == 0     # the gradient arena + gather / flag pads
+    assert lib.fql_dp_symmetric_bytes(C.byref(d), 9) == 0 and b'world' in lib.fql_last_error()
+    assert lib.fql_dp_attach(None, C.byref(d), None) != 0 and b'context' in lib.fql_last_error()
     with pytest.raises(L.FqlError):
         L.check(lib.fql_layout(C.byref(bad), None, 0, None), 'fql_layout')
     assert [lib.fql_info_name(i).decode() for i in range(13)] == list(__import__('fql_b200').INFO_KEYS)

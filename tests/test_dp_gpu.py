@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import fql_oracle as O
-from tests.helpers import cuda_agent_from_state, f32, info_close, make_case, rel_err
+from tests.helpers import check_update_delta, cuda_agent_from_state, f32, info_close, make_case, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -56,6 +56,83 @@ def test_two_emulated_ranks_match_single_rank_oracle(precision, tol):
     p0, p1 = agents[0].export_tree('params'), agents[1].export_tree('params')
     for (_, x), (_, y) in zip(O.tree_leaves(p0), O.tree_leaves(p1)):
         assert np.array_equal(x, y)                      # replicas stay bit-identical without a parameter broadcast
+
+
+def _dp_worker(rank, world, port, ret, backend, precision, over):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ['FQL_DP_BACKEND'] = 'nccl' if backend == 'nccl' else 'peer'
+    os.environ['FQL_DP_MULTICAST'] = '0' if backend == 'peer-loads' else '1'
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(f'cuda:{rank}'))
+    from fql_b200 import FQLAgent, dist as fdist
+    B, F, A, H = 256, 29, 8, 512
+    cfg, state, batch, noise = make_case(over, B, F, A, seed=6, hidden=H)
+    c = dict(cfg)
+    c['batch_size'] = B // world
+    agent = FQLAgent.create(0, np.zeros((1, F), np.float32), np.zeros((1, A), np.float32), c, process_group=dist.group.WORLD, precision=precision)
+    assert agent._dp_peer == (backend != 'nccl')
+    agent.load_tree(f32(state['params']), f32(state['mu']), f32(state['nu']), state['count'])
+    tol_info, tol_grad = (3e-5, 1e-5) if precision == 'fp32' else (5e-2, 4e-2)
+    st = copy.deepcopy(state)
+    for i in range(3):                                   # eager, graph capture, graph replay
+        ba, nz = (batch, noise) if i == 0 else (O.make_batch(40 + i, B, F, A, np.float64), O.make_noise(50 + i, B, A, np.float64))
+        prev = copy.deepcopy(st['params'])
+        st, ref_info, ref_grads = O.update(st, cfg, ba, nz)
+        _, info = agent.update(f32(fdist.shard_rows(ba, rank, world)), noise=f32(fdist.shard_rows(nz, rank, world)))
+        for k in O.INFO_KEYS[:10]:
+            info_close(k, info[k], ref_info, tol_info)
+        if i == 0:
+            for (path, r), (_, g) in zip(O.tree_leaves(ref_grads), O.tree_leaves(agent.export_tree('grads'))):
+                assert rel_err(g, r) <= tol_grad, ('grads', path, rel_err(g, r))   # the arena holds the REDUCED gradient
+            check_update_delta(prev, st['params'], agent.export_tree('params'), 2e-3 if precision == 'fp32' else 0.1, what=f'rank {rank}')
+    if precision == 'fp32':
+        worst = max(rel_err(g, r) for (_, r), (_, g) in zip(O.tree_leaves(st['params']), O.tree_leaves(agent.export_tree('params'))))
+        assert worst <= 3e-5, worst
+    # forward-only losses describe the GLOBAL batch on every rank
+    loss, vinfo = agent.total_loss(f32(fdist.shard_rows(batch, rank, world)), noise=f32(fdist.shard_rows(noise, rank, world)))
+    _, ref_v, _ = O.total_loss(st['params'], cfg, batch, noise, with_grads=False)
+    info_close('critic/critic_loss', vinfo['critic/critic_loss'], ref_v, 10 * tol_info)
+    # replicas stay bit-identical without a parameter broadcast
+    mine = agent._params.view(torch.int32).sum(dtype=torch.int64).reshape(1)
+    both = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    assert all(int(x) == int(both[0]) for x in both), [int(x) for x in both]
+    # production noise (noise=None): ranks share the key but draw disjoint rows of the global tensors
+    agent.update(f32(fdist.shard_rows(batch, rank, world)))
+    z = agent._bufs[B // world]['dev']['z'].clone()
+    zs = [torch.zeros_like(z) for _ in range(world)]
+    dist.all_gather(zs, z)
+    assert not torch.equal(zs[0], zs[1])
+    if rank == 0:
+        ret.put('ok')
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+@pytest.mark.parametrize('backend,precision,over', [
+    ('peer', 'fp32', dict(q_agg='min', alpha=10.0)),
+    ('peer', 'bf16', dict(q_agg='min', alpha=10.0)),
+    ('peer', 'fp32', dict(normalize_q_loss=True, alpha=1000.0)),     # global mean|q| exchange inside the loss kernel
+    ('peer-loads', 'bf16', dict(alpha=300.0)),                       # no NVLS multicast: peer loads / stores
+    ('nccl', 'bf16', dict(q_agg='min', alpha=10.0)),
+], ids=['peer-fp32', 'peer-bf16', 'peer-fp32-normq', 'peerloads-bf16', 'nccl-bf16'])
+def test_two_ranks_data_parallel_step(backend, precision, over):
+    """Two processes, one per GPU: the data-parallel step (library kernels over NVLink peer memory / NVLS multicast by default,
+    NCCL as the A/B alternative) reproduces the single-device oracle step on the concatenated batch."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, ret, backend, precision, over)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(420)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 'ok'
 
 
 def _nccl_worker(rank, world, port, ret):

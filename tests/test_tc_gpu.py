@@ -4,8 +4,11 @@ fp32, master weights fp32.  Tensor-norm-relative error bounds used below:
     single 5-layer MLP output            <= 2e-2
     10-step Euler integration            <= 5e-2
     losses / metrics of one update       <= 5e-2 (relative to the scale of the quantity)
-    gradients, per leaf                  <= 8e-2
-    updated parameters                   <= 3e-3  (an Adam step moves a weight by ~lr = 3e-4 against |p|max ~ 0.1-0.3)
+    gradients, per leaf                  <= TOL_GRAD = 4e-2  (measured worst over every case below: ~1.2e-2)
+    Adam moments mu / nu, per leaf       <= 1e-2 / 2e-2
+    the parameter UPDATE new - old       <= TOL_DELTA (tests/helpers.py::check_update_delta; an optimizer that never ran scores 1.0)
+The new parameter VALUES are not compared on their own: one Adam step moves a weight by ~lr = 3e-4 against |p| ~ 0.1, so any
+value-level bound a bf16 path can meet would also be met by a step that skipped the optimizer.
 """
 import copy
 
@@ -13,9 +16,11 @@ import numpy as np
 import pytest
 
 from oracle import fql_oracle as O
-from tests.helpers import cuda_agent_from_state, f32, info_close, make_case, rel_err, stack_trees
+from tests.helpers import check_update_delta, cuda_agent_from_state, f32, info_close, make_case, rel_err, stack_trees
 
 pytestmark = pytest.mark.gpu
+TOL_GRAD = 4e-2
+TOL_DELTA = 0.1
 
 
 @pytest.mark.parametrize('hidden,F,A,rows', [(128, 11, 3, 40), (512, 29, 8, 256), (512, 69, 21, 300), (512, 69, 21, 1100), (512, 83, 5, 129), (256, 28, 5, 1)])
@@ -60,15 +65,13 @@ def test_tc_update_step(name, over, B, F, A, hidden):
             assert abs(info[k] - r) <= 0.1 * abs(r) + 1e-6, (k, info[k], r)
         else:
             info_close(k, info[k], ref_info, 5e-2)
-    got = {w: agent.export_tree(w) for w in ('grads', 'params')}
-    for (path, r), (_, g) in zip(O.tree_leaves(ref_grads), O.tree_leaves(got['grads'])):
-        e = rel_err(g, r)
-        worst['grads'] = max(worst.get('grads', 0), e)
-        assert e <= 8e-2, ('grads', path, e)
-    for (path, r), (_, g) in zip(O.tree_leaves(new_state['params']), O.tree_leaves(got['params'])):
-        e = rel_err(g, r)
-        worst['params'] = max(worst.get('params', 0), e)
-        assert e <= 3e-3, ('params', path, e)
+    got = {w: agent.export_tree(w) for w in ('grads', 'params', 'mu', 'nu')}
+    for which, ref, tol in (('grads', ref_grads, TOL_GRAD), ('mu', new_state['mu'], 1e-2), ('nu', new_state['nu'], 2e-2)):
+        for (path, r), (_, g) in zip(O.tree_leaves(ref), O.tree_leaves(got[which])):
+            e = rel_err(g, r)
+            worst[which] = max(worst.get(which, 0), e)
+            assert e <= tol, (which, path, e)
+    worst['delta'] = check_update_delta(state['params'], new_state['params'], got['params'], TOL_DELTA, what=name)
     print(name, {k: f'{v:.2e}' for k, v in worst.items()})
     # second and third step exercise graph capture / replay and the in-graph shadow refresh
     st = new_state
@@ -113,9 +116,8 @@ def test_tc_update_two_seeds_cluster_kernels():
         for k in ('critic/critic_loss', 'actor/bc_flow_loss', 'actor/distill_loss', 'actor/q_loss'):
             info_close(k, info[k][si], ref_info, 5e-2)
         for (path, r), (_, g) in zip(O.tree_leaves(ref_grads), O.tree_leaves(grads)):
-            assert rel_err(np.asarray(g)[si], r) <= 8e-2, ('grads', si, path)
-        for (path, r), (_, g) in zip(O.tree_leaves(new_state['params']), O.tree_leaves(params)):
-            assert rel_err(np.asarray(g)[si], r) <= 3e-3, ('params', si, path)
+            assert rel_err(np.asarray(g)[si], r) <= TOL_GRAD, ('grads', si, path)
+        check_update_delta(state['params'], new_state['params'], params, TOL_DELTA, pick=lambda x: np.asarray(x)[si], what=f'seed {si}')
 
 
 SWITCHES = [
@@ -142,12 +144,15 @@ def test_tc_alternative_schedules_match_oracle(env, monkeypatch):
     st = copy.deepcopy(state)
     for i in range(3):                                                # eager call, graph capture, graph replay
         ba, nz = (batch, noise) if i == 0 else (O.make_batch(500 + i, B, F, A, np.float64), O.make_noise(600 + i, B, A, np.float64))
+        prev = copy.deepcopy(st['params'])
         st, ref_info, ref_grads = O.update(st, cfg, ba, nz)
         _, info = agent.update(f32(ba), noise=f32(nz))
+        if i == 0:
+            check_update_delta(prev, st['params'], agent.export_tree('params'), TOL_DELTA, what=str(env))
         for k in ('critic/critic_loss', 'actor/bc_flow_loss', 'actor/distill_loss', 'actor/q_loss', 'actor/mse'):
             info_close(k, info[k], ref_info, 8e-2 if k == 'actor/distill_loss' else 5e-2)
         if i == 0:
             for (path, r), (_, g) in zip(O.tree_leaves(ref_grads), O.tree_leaves(agent.export_tree('grads'))):
-                assert rel_err(g, r) <= 8e-2, ('grads', path, rel_err(g, r))
-    for (path, r), (_, g) in zip(O.tree_leaves(st['params']), O.tree_leaves(agent.export_tree('params'))):
-        assert rel_err(g, r) <= 5e-3, ('params', path, rel_err(g, r))
+                assert rel_err(g, r) <= TOL_GRAD, ('grads', path, rel_err(g, r))
+    # after three steps the accumulated movement (3 x ~lr) against the oracle's: still a delta check, from the initial parameters
+    check_update_delta(state['params'], st['params'], agent.export_tree('params'), 2 * TOL_DELTA, what=f'{env} 3 steps')
