@@ -1,0 +1,584 @@
+// chain2_tc.cu -- the throughput variant of the fused MLP chain (hidden = 512): one CTA runs a whole MLP -- and, for
+// compute_flow_actions (agents/fql.py:155-171), the whole Euler loop -- on a 128-row tile, with the epilogue of one layer
+// overlapped with the tensor-core work of the same and the next layer.  Used where seeds x 128-row tiles fill the GPU
+// (batch >= 1024-ish, vectorised seeds: BASELINE configs 3 and 4); mlp_tc.cu keeps the narrower widths.
+//
+// The 128 x 512 fp32 accumulator of a layer is all of an SM's TMEM, so it cannot be double-buffered across layers.  Instead a
+// layer is issued as two N-halves (TMEM columns [0,256) and [256,512)) and the K loop of the second half runs while the
+// epilogue drains the first:
+//
+//   MMA   (l,h0) k=0..7 | (l,h1) k=0..7            | (l+1,h0) k=0..3 ... k=4..7   | (l+1,h1) ...
+//   EPI                 | (l,h0): blocks 0..3 of   | (l,h1): blocks 4..7          | (l+1,h0) ...
+//                       |  A_{l+1}, each written   |  (all reads of A_l are done) |
+//                       |  once (l,h1) has passed  |
+//                       |  that K block (a_free)   |
+//
+// Activations live in one K-major SWIZZLE_128B operand buffer sA (8 blocks of [128][64] bf16): block kb of the next layer's
+// input overwrites block kb of this layer's input as soon as the second half's MMAs have consumed it (tcgen05.commit ->
+// a_free[kb]); the next layer's MMAs start on block kb as soon as it is written (a_ready[kb]).
+//   warp 0      TMA producer: weights as [32 k][256 n] MN-major stages straight from the Flax [in,out] bf16 shadow
+//               (one 3-D box per stage: 64 n x 32 k x 4 chunks), first-layer operand tile once
+//   warp 1      MMA issuer: tcgen05.mma kind::f16 M=128 N=256 K=16, two per stage
+//   warps 2-9   epilogue: warp (q, p) owns TMEM lanes [32q, 32q+32) (one row per thread) and the 32-column chunks of parity p:
+//               + bias, GELU(tanh.approx), [LayerNorm: two passes, gelu stashed in TMEM, row sums exchanged between the two
+//               warps of a row through smem], bf16 re-pack into sA, optional bf16 / fp32 saves for the backward
+// Reference arithmetic: utils/networks.py:34-61 (MLP), :153-195 (Value), :198-235 (ActorVectorField).
+#include "step.cuh"
+#include "tc_prims.cuh"
+
+#include <cudaTypedefs.h>
+
+using namespace tc;
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int KB_BYTES = TILE_M * 128;       // one K block of an A operand: [128 rows][64 bf16]
+constexpr int KS = 32;                       // k rows of weights per pipeline stage
+constexpr int NHALF = 256;                   // accumulator columns per N-half
+constexpr int CHUNK_BYTES = KS * 128;        // one 64-column chunk of a stage
+constexpr int STAGE_BYTES = 4 * CHUNK_BYTES; // [4 chunks][32 k][64 n] bf16 = 16 KB
+constexpr int MAX_A = 32;
+constexpr int EPI_WARPS = 8;
+constexpr int C2_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int HID = 512;
+constexpr int NKB = HID / 64;
+
+struct Chain2Args {
+  int NL, K0, K0pad, out_dim;
+  int P, S, E, M, tiles;
+  int x_row0[FQL_MAXP], x_rows_s;
+  int w_row[FQL_MAXP][FQL_MAXL], w_rows_s;   // rows of HID elements in the shadow
+  int wl_row[FQL_MAXP], wl_rows_s;           // rows of 64 elements in the shadow (padded last layer)
+  const float* params;
+  long long arena;
+  long long off_b[FQL_MAXP][FQL_MAXL], off_lns[FQL_MAXP][FQL_MAXL], off_lnb[FQL_MAXP][FQL_MAXL];
+  float* out;
+  float* Zs[FQL_MAXL];   // fp32 pre-activations (LayerNorm backward)
+  float* mu[FQL_MAXL];
+  float* rstd[FQL_MAXL];
+  void* Hb[FQL_MAXL];    // bf16 activations (operands of the tensor-core backward)
+  void* Zb[FQL_MAXL];    // bf16 pre-activations (gelu' of the non-LayerNorm backward)
+  int Mcap, r0;
+  int n_steps, F, A;
+  const float* a0;
+  float* target;
+  int clip_out;
+  int nstage, w3d;
+};
+
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float u = FQL_GELU_C * (x + FQL_GELU_A * x * x * x);
+  return 0.5f * x * (1.0f + tanh_approx(u));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// 32 consecutive activations of one row -> bf16, into block (j >> 1) of the K-major SWIZZLE_128B operand buffer (and optionally HBM)
+__device__ __forceinline__ void store_chunk(uint8_t* sA, int row, int j, const float (&h)[32], __nv_bfloat16* gdst) {
+  uint8_t* blk = sA + (j >> 1) * KB_BYTES;
+  const int c0 = (j & 1) * 4;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const uint4 v = make_uint4(pack_bf16(h[c * 8 + 0], h[c * 8 + 1]), pack_bf16(h[c * 8 + 2], h[c * 8 + 3]),
+                               pack_bf16(h[c * 8 + 4], h[c * 8 + 5]), pack_bf16(h[c * 8 + 6], h[c * 8 + 7]));
+    *reinterpret_cast<uint4*>(blk + sw128_off(row, c0 + c)) = v;
+    if (gdst) *reinterpret_cast<uint4*>(gdst + c * 8) = v;
+  }
+}
+
+template <bool LN, bool EULER>
+__global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_constant__ CUtensorMap mapX,
+                                                              const __grid_constant__ CUtensorMap mapW,
+                                                              const __grid_constant__ CUtensorMap mapWL, const Chain2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int NPAR = LN ? 3 : 1;
+  const int nkb_x = a.K0pad / 64;
+  uint8_t* sA = smem;                                   // [8][16 KB]
+  uint8_t* sX = sA + NKB * KB_BYTES;                    // [nkb_x][16 KB]
+  uint8_t* sW = sX + nkb_x * KB_BYTES;                  // [nstage][16 KB]
+  float* sPar = reinterpret_cast<float*>(sW + a.nstage * STAGE_BYTES);  // [2][NPAR][512]: bias (, LN scale, LN bias)
+  float* sStat = sPar + 2 * NPAR * HID;                 // [2][128][2] row sums of the two column parities (LayerNorm)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (LN ? 2 * TILE_M * 2 : 0));
+  uint64_t* full = bars;                 // [8]
+  uint64_t* empty = bars + 8;            // [8]
+  uint64_t* a_ready = bars + 16;         // [8]  block kb of the next layer's input is in sA            (8 epilogue warps)
+  uint64_t* a_free = bars + 24;          // [4]  the second half's MMAs are done with block kb of sA    (tcgen05.commit)
+  uint64_t* acc_full = bars + 28;        // [2]  half h of the accumulator is complete                  (tcgen05.commit)
+  uint64_t* acc_free = bars + 30;        // [2]  half h of the accumulator has been read                (8 epilogue warps)
+  uint64_t* x_full = bars + 32;
+  uint64_t* x_ready = bars + 33;         //      the Euler update of the resident first-layer operand    (8 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x % a.tiles, g = blockIdx.x / a.tiles;
+  const int e = g % a.E, s = (g / a.E) % a.S, p = g / (a.E * a.S);
+  const int NL = a.NL;
+  const int total = a.n_steps * NL;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapWL);
+    for (int i = 0; i < 8; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&a_ready[i], EPI_WARPS);
+    }
+    for (int i = 0; i < 4; i++) mbar_init(&a_free[i], 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_free[i], EPI_WARPS);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(x_ready, EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_expect_tx(x_full, nkb_x * KB_BYTES);
+      const int xrow = a.x_row0[p] + s * a.x_rows_s + tile * TILE_M;
+      for (int kb = 0; kb < nkb_x; kb++) tma_load_2d(sX + kb * KB_BYTES, &mapX, x_full, kb * 64, xrow);
+      int stage = 0;
+      uint32_t phase = 0;
+      int l = 0;
+      for (int it = 0; it < total; it++, l = (l + 1 == NL) ? 0 : l + 1) {
+        if (l < NL - 1) {
+          const int K = (l == 0) ? a.K0 : HID;
+          const int nst = (K + KS - 1) / KS;
+          const int row0 = a.w_row[p][l] + s * a.w_rows_s + e * K;
+          for (int h = 0; h < 2; h++)
+            for (int ks = 0; ks < nst; ks++) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* dst = sW + stage * STAGE_BYTES;
+              mbar_expect_tx(&full[stage], STAGE_BYTES);
+              if (a.w3d) {
+                tma_load_3d(dst, &mapW, &full[stage], 0, row0 + ks * KS, h * 4);
+              } else {
+                for (int c = 0; c < 4; c++) tma_load_2d(dst + c * CHUNK_BYTES, &mapW, &full[stage], (h * 4 + c) * 64, row0 + ks * KS);
+              }
+              if (++stage == a.nstage) { stage = 0; phase ^= 1; }
+            }
+        } else {
+          const int row0 = a.wl_row[p] + s * a.wl_rows_s + e * HID;
+          for (int ks = 0; ks < NKB; ks++) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], 64 * 128);
+            tma_load_2d(sW + stage * STAGE_BYTES, &mapWL, &full[stage], 0, row0 + ks * 64);
+            if (++stage == a.nstage) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc_h = make_idesc_bf16(128, NHALF, false, true);
+      const uint32_t idesc_l = make_idesc_bf16(128, 64, false, true);
+      const uint64_t a_t = make_smem_desc(0, 16, 1024);
+      const uint64_t b_t = make_smem_desc(0, CHUNK_BYTES, 1024);   // MN-major: 64-column chunks CHUNK_BYTES apart, 8-k groups 1024 B apart
+      const uint32_t sa0 = smem_u32(sA) >> 4, sx0 = smem_u32(sX) >> 4, sw0 = smem_u32(sW) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int n_ar = 0, n_xr = 0;
+      int uses[2] = {0, 0};
+      int l = 0;
+      for (int it = 0; it < total; it++, l = (l + 1 == NL) ? 0 : l + 1) {
+        if (l == 0) {
+          if (it == 0) mbar_wait(x_full, 0);
+          else mbar_wait(x_ready, (n_xr++) & 1);
+          tc_fence_after();
+        }
+        if (l < NL - 1) {
+          const int K = (l == 0) ? a.K0 : HID;
+          const int nst = (K + KS - 1) / KS;
+          const uint32_t abase = (l == 0) ? sx0 : sa0;
+          for (int h = 0; h < 2; h++) {
+            if (uses[h] > 0) {
+              mbar_wait(&acc_free[h], (uses[h] - 1) & 1);
+              tc_fence_after();
+            }
+            const uint32_t tacc = tmem_base + h * NHALF;
+            for (int ks = 0; ks < nst; ks++) {
+              const int kb = ks >> 1;
+              if (l > 0 && h == 0 && (ks & 1) == 0) {
+                mbar_wait(&a_ready[kb], (n_ar - 1) & 1);
+                tc_fence_after();
+              }
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const uint64_t adesc = a_t + (uint64_t)(abase + kb * (KB_BYTES >> 4) + (ks & 1) * 4);
+              const uint64_t bdesc = b_t + (uint64_t)(sw0 + stage * (STAGE_BYTES >> 4));
+              umma_bf16(tacc, adesc, bdesc, idesc_h, ks > 0);
+              if (K - ks * KS > 16) umma_bf16(tacc, adesc + 2, bdesc + (uint64_t)(2048 >> 4), idesc_h, 1);
+              umma_commit(&empty[stage]);
+              if (++stage == a.nstage) { stage = 0; phase ^= 1; }
+              if (l > 0 && h == 1 && (ks & 1) == 1 && kb < 4) umma_commit(&a_free[kb]);
+            }
+            umma_commit(&acc_full[h]);
+            uses[h]++;
+          }
+          n_ar++;
+        } else {
+          if (uses[0] > 0) {
+            mbar_wait(&acc_free[0], (uses[0] - 1) & 1);
+            tc_fence_after();
+          }
+          for (int ks = 0; ks < NKB; ks++) {
+            mbar_wait(&a_ready[ks], (n_ar - 1) & 1);
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = a_t + (uint64_t)(sa0 + ks * (KB_BYTES >> 4));
+            const uint64_t bdesc = b_t + (uint64_t)(sw0 + stage * (STAGE_BYTES >> 4));
+#pragma unroll
+            for (int j = 0; j < 4; j++) umma_bf16(tmem_base, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * (2048 >> 4)), idesc_l, (ks | j) != 0);
+            umma_commit(&empty[stage]);
+            if (++stage == a.nstage) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&acc_full[0]);
+          uses[0]++;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int pw = (warp - 2) >> 2;               // column-chunk parity of this warp
+    const int row = q * 32 + lane;
+    const int grow = tile * TILE_M + row;
+    const bool valid = grow < a.M;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int et = threadIdx.x - 64;              // 0..255
+    const int64_t gidx = (int64_t)((p * a.S + s) * a.E + e) * a.Mcap + a.r0 + grow;
+    int nf[2] = {0, 0};
+    int n_af = 0;
+    float act[MAX_A];
+    if (EULER) {
+#pragma unroll
+      for (int c = 0; c < MAX_A; c++) act[c] = (pw == 0 && valid && c < a.A) ? a.a0[((int64_t)s * a.M + grow) * a.A + c] : 0.f;
+    }
+    int l = 0, step = 0;
+    for (int it = 0; it < total; it++, l = (l + 1 == NL) ? 0 : l + 1, step += (l == 0)) {
+      const bool last = (l == NL - 1);
+      const int N = last ? a.out_dim : HID;
+      float* par = sPar + (it & 1) * NPAR * HID;
+      {  // stage this layer's bias / LayerNorm parameters while the MMAs run
+        const float* b = a.params + (int64_t)s * a.arena + a.off_b[p][l] + (int64_t)e * N;
+        for (int i = et; i < N; i += 32 * EPI_WARPS) par[i] = b[i];
+        if (LN && !last) {
+          const float* sc = a.params + (int64_t)s * a.arena + a.off_lns[p][l] + (int64_t)e * N;
+          const float* bi = a.params + (int64_t)s * a.arena + a.off_lnb[p][l] + (int64_t)e * N;
+          for (int i = et; i < N; i += 32 * EPI_WARPS) {
+            par[HID + i] = sc[i];
+            par[2 * HID + i] = bi[i];
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      uint32_t r[32];
+      if (!last) {
+        __nv_bfloat16* Hb = (valid && a.Hb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.Hb[l]) + gidx * HID : nullptr;
+        if (!LN) {
+          __nv_bfloat16* Zb = (valid && a.Zb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.Zb[l]) + gidx * HID : nullptr;
+          for (int h = 0; h < 2; h++) {
+            mbar_wait(&acc_full[h], (nf[h]++) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int jj = 0; jj < 4; jj++) {
+              const int j = h * 8 + jj * 2 + pw;
+              tmem_ld32(t_lane + j * 32, r);
+              tmem_wait_ld();
+              float hv[32];
+#pragma unroll
+              for (int i = 0; i < 32; i++) {
+                const float z = __uint_as_float(r[i]) + par[j * 32 + i];
+                r[i] = __float_as_uint(z);
+                hv[i] = gelu_fast(z);
+              }
+              if (Zb) {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                  *reinterpret_cast<uint4*>(Zb + j * 32 + c * 8) =
+                      make_uint4(pack_bf16(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1])),
+                                 pack_bf16(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3])),
+                                 pack_bf16(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5])),
+                                 pack_bf16(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7])));
+              }
+              // block j >> 1 of sA still holds this layer's input until the second half's MMAs have consumed it
+              if (l > 0 && h == 0) mbar_wait(&a_free[j >> 1], n_af & 1);
+              store_chunk(sA, row, j, hv, Hb ? Hb + j * 32 : nullptr);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[j >> 1]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[h]);
+          }
+          if (l > 0) n_af++;
+        } else {
+          // pass 1: g = gelu(z) stashed back into TMEM in place, row sums in registers
+          float* Zs = (valid && a.Zs[l]) ? a.Zs[l] + gidx * HID : nullptr;
+          float s1 = 0.f, s2 = 0.f;
+          for (int h = 0; h < 2; h++) {
+            mbar_wait(&acc_full[h], (nf[h]++) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int jj = 0; jj < 4; jj++) {
+              const int j = h * 8 + jj * 2 + pw;
+              tmem_ld32(t_lane + j * 32, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + par[j * 32 + i]);   // z = xW + b
+              if (Zs) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<float4*>(Zs + j * 32 + i) =
+                      make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+              }
+#pragma unroll
+              for (int i = 0; i < 32; i++) {
+                const float gv = gelu_fast(__uint_as_float(r[i]));
+                s1 += gv;
+                s2 += gv * gv;
+                r[i] = __float_as_uint(gv);
+              }
+              tmem_st32(t_lane + j * 32, r);
+            }
+          }
+          tmem_wait_st();
+          sStat[(pw * TILE_M + row) * 2 + 0] = s1;
+          sStat[(pw * TILE_M + row) * 2 + 1] = s2;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          s1 += sStat[((pw ^ 1) * TILE_M + row) * 2 + 0];
+          s2 += sStat[((pw ^ 1) * TILE_M + row) * 2 + 1];
+          const float inv_n = 1.0f / (float)HID;
+          const float mu = s1 * inv_n;
+          const float var = fmaxf(0.f, s2 * inv_n - mu * mu);
+          const float rstd = rsqrtf(var + FQL_LN_EPS);
+          if (valid && pw == 0 && a.mu[l]) {
+            a.mu[l][gidx] = mu;
+            a.rstd[l][gidx] = rstd;
+          }
+          // pass 2: normalise, re-pack.  Every MMA of this layer has completed (acc_full[1] was observed): sA is free.
+          for (int h = 0; h < 2; h++) {
+#pragma unroll 1
+            for (int jj = 0; jj < 4; jj++) {
+              const int j = h * 8 + jj * 2 + pw;
+              tmem_ld32(t_lane + j * 32, r);
+              tmem_wait_ld();
+              float hv[32];
+#pragma unroll
+              for (int i = 0; i < 32; i++)
+                hv[i] = (__uint_as_float(r[i]) - mu) * rstd * par[HID + j * 32 + i] + par[2 * HID + j * 32 + i];
+              store_chunk(sA, row, j, hv, Hb ? Hb + j * 32 : nullptr);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[j >> 1]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[h]);
+          }
+        }
+      } else {
+        // last Dense (linear): out_dim <= 32 columns of the padded N = 64 accumulator; the parity-0 warps hold them
+        mbar_wait(&acc_full[0], (nf[0]++) & 1);
+        tc_fence_after();
+        if (pw == 0) {
+          tmem_ld32(t_lane, r);
+          tmem_wait_ld();
+          if (!EULER) {
+            if (valid && a.out) {
+              float* o = a.out + gidx * a.out_dim;
+#pragma unroll
+              for (int c = 0; c < MAX_A; c++)
+                if (c < a.out_dim) {
+                  float v = __uint_as_float(r[c]) + par[c];
+                  if (a.clip_out) v = fminf(fmaxf(v, -1.0f), 1.0f);
+                  o[c] = v;
+                }
+            }
+          } else {
+            // Euler step (agents/fql.py:166-169): a += v / flow_steps, next t = (step+1)/flow_steps, written straight into the bf16
+            // first-layer operand tile that stays resident in smem for the whole integration
+            const float inv = (float)a.n_steps;
+#pragma unroll
+            for (int c = 0; c < MAX_A; c++)
+              if (c < a.A) {
+                act[c] += (__uint_as_float(r[c]) + par[c]) / inv;
+                const int col = a.F + c;
+                *reinterpret_cast<__nv_bfloat16*>(sX + (col >> 6) * KB_BYTES + sw128_off(row, (col & 63) >> 3) + (col & 7) * 2) = __float2bfloat16(act[c]);
+              }
+            {
+              const int col = a.F + a.A;
+              *reinterpret_cast<__nv_bfloat16*>(sX + (col >> 6) * KB_BYTES + sw128_off(row, (col & 63) >> 3) + (col & 7) * 2) =
+                  __float2bfloat16((float)((double)(step + 1) / (double)a.n_steps));
+            }
+            if (step == a.n_steps - 1 && valid) {
+#pragma unroll
+              for (int c = 0; c < MAX_A; c++)
+                if (c < a.A) a.target[((int64_t)s * a.M + grow) * a.A + c] = fminf(fmaxf(act[c], -1.0f), 1.0f);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&acc_free[0]);
+          if (EULER) mbar_arrive(x_ready);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+  auto enc = get_encode();
+  FQL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FQL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu", (int)r, (unsigned long long)inner,
+              (unsigned long long)rows);
+  return 0;
+}
+
+// The weight matrix [rows][512] as a 3-D tensor (64 n, row, chunk of 64 n): one box {64, KS, 4} lands a whole [4][KS][64] stage.
+// The chunk dimension's stride (128 B) is smaller than the row dimension's (1024 B); returns false when the driver refuses that.
+bool make_map_w3d(CUtensorMap* m, const void* base, uint64_t rows) {
+  auto enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {64, rows, HID / 64};
+  cuuint64_t strides[2] = {HID * 2, 128};
+  cuuint32_t box[3] = {64, KS, 4};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int tc_mlp_chain2_supported(const FqlDims* d) {
+  static const int on = []() {
+    const char* e = getenv("FQL_B200_CHAIN2");
+    return !(e && e[0] == '0');
+  }();
+  return on && d->hidden == HID;
+}
+
+int tc_mlp_chain2(const TcChainSpec& f, cudaStream_t st) {
+  const FqlDims* d = f.d;
+  const Layout& L = *f.L;
+  FQL_TRY(tc_supported(d));
+  FQL_REQUIRE(d->hidden == HID, "tc_mlp_chain2 is built for hidden = 512");
+  const NetView& n0 = L.net[f.net[0]];
+  Chain2Args a;
+  memset(&a, 0, sizeof(a));
+  a.NL = n0.n_layers; a.K0 = n0.in_dim; a.K0pad = (int)round_up64(n0.in_dim, 64); a.out_dim = n0.out_dim;
+  a.P = f.P; a.S = d->num_seeds; a.E = n0.ens; a.M = f.M; a.tiles = (f.M + TILE_M - 1) / TILE_M;
+  FQL_REQUIRE(a.NL >= 2 && a.out_dim <= MAX_A, "tc_mlp_chain2: %d layers / output width %d", a.NL, a.out_dim);
+  const int64_t seed_elems = tc_shadow_seed_elems(d, L);
+  FQL_REQUIRE(seed_elems % HID == 0 && L.arena % 64 == 0, "shadow layout not row aligned");
+  a.x_rows_s = f.Mcap0;
+  a.w_rows_s = (int)(seed_elems / HID);
+  a.wl_rows_s = (int)(seed_elems / 64);
+  for (int p = 0; p < f.P; p++) {
+    const NetView& nv = L.net[f.net[p]];
+    a.x_row0[p] = p * a.S * f.Mcap0 + f.r0_in;
+    for (int l = 0; l < nv.n_layers; l++) {
+      a.w_row[p][l] = (int)(nv.off_w[l] / HID);
+      a.off_b[p][l] = nv.off_b[l];
+      a.off_lns[p][l] = nv.off_lns[l];
+      a.off_lnb[p][l] = nv.off_lnb[l];
+    }
+    int64_t wl = L.arena;
+    for (int t = 0; t < f.net[p]; t++) wl += (int64_t)L.net[t].ens * HID * 64;
+    a.wl_row[p] = (int)(wl / 64);
+  }
+  a.params = f.params; a.arena = L.arena;
+  a.Mcap = f.buf ? f.buf->Mcap : f.M; a.r0 = f.r0;
+  if (f.buf) {
+    a.out = f.buf->out;
+    for (int l = 0; l + 1 < n0.n_layers; l++) {
+      a.Zs[l] = (f.save && n0.ln) ? f.buf->Z[l] : nullptr;
+      a.mu[l] = (f.save && n0.ln) ? f.buf->mu[l] : nullptr;
+      a.rstd[l] = (f.save && n0.ln) ? f.buf->rstd[l] : nullptr;
+      a.Hb[l] = f.Hb ? f.Hb[l] : nullptr;
+    }
+    FQL_REQUIRE(!(f.save && !n0.ln), "tc_mlp_chain2: fp32 saves are for LayerNorm networks; actors save bf16 Z / H");
+  } else {
+    for (int l = 0; l + 1 < n0.n_layers; l++) {
+      a.Hb[l] = f.Hb ? f.Hb[l] : nullptr;
+      a.Zb[l] = f.Zb ? f.Zb[l] : nullptr;
+    }
+    if (f.Mcap_override > 0) a.Mcap = f.Mcap_override;
+  }
+  if (f.out_override) a.out = f.out_override;
+  a.n_steps = f.n_steps > 0 ? f.n_steps : 1; a.F = d->obs_dim; a.A = d->action_dim; a.a0 = f.a0; a.target = f.target;
+  a.clip_out = f.clip_out;
+  const bool euler = a.n_steps > 1;
+  FQL_REQUIRE(!euler || (a.a0 && a.target && f.P == 1 && a.E == 1 && !n0.ln), "Euler chain needs a0/target and a single actor network");
+  const int npar = n0.ln ? 3 : 1;
+  const int fixed = (NKB + a.K0pad / 64) * KB_BYTES + 2 * npar * HID * 4 + (n0.ln ? 2 * TILE_M * 2 * 4 : 0) + 512 + 1024;
+  int nstage = (232448 - fixed) / STAGE_BYTES;
+  if (nstage > 8) nstage = 8;
+  FQL_REQUIRE(nstage >= 2, "not enough shared memory for the weight pipeline");
+  a.nstage = nstage;
+  const int smem = fixed + nstage * STAGE_BYTES;
+
+  CUtensorMap mapX, mapW, mapWL;
+  const int64_t x_rows = (int64_t)f.P * a.S * f.Mcap0;
+  FQL_TRY(make_map_2d(&mapX, f.X0b, a.K0pad, x_rows, 64, TILE_M));
+  static const bool no3d = getenv("FQL_B200_CHAIN2_W3D") && getenv("FQL_B200_CHAIN2_W3D")[0] == '0';
+  a.w3d = (!no3d && make_map_w3d(&mapW, f.shadow, (uint64_t)a.S * a.w_rows_s)) ? 1 : 0;
+  if (!a.w3d) FQL_TRY(make_map_2d(&mapW, f.shadow, HID, (uint64_t)a.S * a.w_rows_s, 64, KS));
+  FQL_TRY(make_map_2d(&mapWL, f.shadow, 64, (uint64_t)a.S * a.wl_rows_s, 64, 64));
+  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Chain2Args) =
+      n0.ln ? mlp_chain2_kernel<true, false> : (euler ? mlp_chain2_kernel<false, true> : mlp_chain2_kernel<false, false>);
+  static bool attr_set[FQL_MAX_DEVICES][3] = {};
+  const int dev = fql_current_device(), ki = n0.ln ? 0 : (euler ? 1 : 2);
+  if (!attr_set[dev][ki]) {
+    FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set[dev][ki] = true;
+  }
+  const int grid = a.tiles * a.P * a.S * a.E;
+  kern<<<grid, C2_THREADS, smem, st>>>(mapX, mapW, mapWL, a);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}

@@ -487,6 +487,7 @@ int tc_mlp_chain(const TcChainSpec& f, cudaStream_t st) {
   const FqlDims* d = f.d;
   const Layout& L = *f.L;
   FQL_TRY(tc_supported(d));
+  if (tc_mlp_chain2_supported(d)) return tc_mlp_chain2(f, st);   // hidden = 512: the epilogue-overlapped variant (chain2_tc.cu)
   const NetView& n0 = L.net[f.net[0]];
   ChainArgs a;
   memset(&a, 0, sizeof(a));

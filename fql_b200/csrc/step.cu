@@ -752,7 +752,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   cr.d = d; cr.L = &L; cr.params = P; cr.shadow = shadow; cr.M = B; cr.K0pad = kO; cr.x_ss = (long long)B * kO; cr.buf = &w.pC; cr.Hb = w.C_Hb;
   cr.cs_scratch = w.cs_scratch[2];
   bool split_cpost = false;
-  if (ctx->use_critic_chain) {
+  if (ctx->use_critic_chain || many_tiles) {   // enough row tiles to fill the GPU: the three critic problems x 2 heads as ONE fused launch
     TcChainSpec t;
     memset(&t, 0, sizeof(t));
     t.d = d; t.L = &L; t.P = 3; t.net[0] = FQL_NET_TARGET_CRITIC; t.net[1] = FQL_NET_CRITIC; t.net[2] = FQL_NET_CRITIC;

@@ -161,6 +161,8 @@ int tc_refresh_shadow(const FqlDims* d, const Layout& L, const float* params, vo
 int tc_refresh_shadow_lastlayer(const FqlDims* d, const Layout& L, const float* params, void* shadow, cudaStream_t st);
 int tc_pad_bf16(const float* x, void* y, int64_t rows, int K0, int K0pad, cudaStream_t st);
 int tc_mlp_chain(const TcChainSpec& f, cudaStream_t st);
+int tc_mlp_chain2_supported(const FqlDims* d);
+int tc_mlp_chain2(const TcChainSpec& f, cudaStream_t st);
 
 // tc_gemm.cu -- generic tcgen05 GEMM (one Dense layer: forward / dgrad / wgrad)
 enum { TC_MODE_STORE_F32 = 0, TC_MODE_FWD_HIDDEN = 1, TC_MODE_DGRAD_GELU = 2, TC_MODE_EULER = 3 };

@@ -63,12 +63,35 @@ def info_close(key, got, ref_info, tol):
     assert abs(got - r) <= tol * scale, (key, got, r, scale)
 
 
-def check_update_delta(old_params, ref_new_params, got_new_params, tol, pick=None, what=''):
-    """The parameter UPDATE itself (new - old) against the oracle's, per leaf: tensor-norm-relative error <= tol and the sign of
-    every significant element agrees.  This is the check with power for one Adam step: the step moves a weight by ~lr = 3e-4
-    against |p| ~ 0.1, so comparing the new VALUES at 3e-3 would pass even if the optimizer never ran (delta error = 1)."""
+def check_update_delta(old_params, ref_new_params, got_new_params, tol, pick=None, what='', opt=None):
+    """The parameter UPDATE itself (new - old), per leaf.  Comparing the new VALUES has no power for one Adam step (the step moves
+    a weight by ~lr = 3e-4 against |p| ~ 0.1: a value-level bound a bf16 path can meet is also met by an optimizer that never
+    ran, whose update error is 1.0).  Two checks:
+      (a) opt = dict(state=..., cfg=..., grads=<the gradients the device step produced>): the device's update equals the oracle's
+          Adam / Polyak arithmetic applied to THOSE gradients, to 2e-3 (fp32 rounding of p + dp) -- the optimizer itself is exact
+          whatever the precision of the gradients;
+      (b) against the reference update: tensor-norm-relative error <= tol (and, without (a), the sign of every significant
+          element agrees).  Adam divides by sqrt(v): with the warm moments of these cases d(update)/d(gradient) reaches ~16 lr per
+          unit gradient, so a gradient error of 1e-2 of the leaf's max legitimately moves some elements by a large fraction of a
+          whole step (measured up to 0.67 of the leaf's largest step).  In bf16 mode the PRECISION of the update is therefore
+          established by (a) together with the per-leaf gradient bound; (b) only has to tell a real update (error < 1) from a missing
+          (1.0) or mirrored (2.0) one."""
     pick = pick or (lambda x: x)
     worst = 0.0
+    exp_new = None
+    if opt is not None:
+        st, cfg = opt['state'], opt['cfg']
+        old32 = O.cast_tree(O.cast_tree(st['params'], np.float32), np.float64)
+        g64 = O.tree_map(lambda g: np.asarray(pick(g), np.float64), opt['grads'])
+        exp_new, _, _, _ = O.adam_update(old32, g64, O.cast_tree(O.cast_tree(st['mu'], np.float32), np.float64),
+                                         O.cast_tree(O.cast_tree(st['nu'], np.float32), np.float64), st['count'], cfg['lr'])
+        tau = cfg['tau']
+        exp_new['modules_target_critic'] = O.tree_map(lambda p, tp: p * tau + tp * (1 - tau), old32['modules_critic'], old32['modules_target_critic'])
+        for (path, e_new), (_, old), (_, g) in zip(O.tree_leaves(exp_new), O.tree_leaves(old32), O.tree_leaves(got_new_params)):
+            d_exp = e_new - old
+            d_got = np.asarray(pick(g), np.float64) - old
+            if np.abs(d_exp).max() > 0:
+                assert rel_err(d_got, d_exp) <= 2e-3, (what, 'optimizer arithmetic on the device gradients', path, rel_err(d_got, d_exp))
     for (path, new), (_, old), (_, g) in zip(O.tree_leaves(ref_new_params), O.tree_leaves(old_params), O.tree_leaves(got_new_params)):
         new, old = np.asarray(new, np.float64), np.asarray(old, np.float64)
         d_ref = new - old
@@ -79,8 +102,9 @@ def check_update_delta(old_params, ref_new_params, got_new_params, tol, pick=Non
         e = rel_err(d_got, d_ref)
         worst = max(worst, e)
         assert e <= tol, (what, 'delta', path, e)
-        big = np.abs(d_ref) > 0.25 * np.abs(d_ref).max()
-        assert np.array_equal(np.sign(d_got[big]), np.sign(d_ref[big])), (what, 'delta sign', path)
+        if opt is None:
+            big = np.abs(d_ref) > 0.5 * np.abs(d_ref).max()
+            assert np.array_equal(np.sign(d_got[big]), np.sign(d_ref[big])), (what, 'delta sign', path)
     return worst
 
 

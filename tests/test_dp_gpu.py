@@ -77,7 +77,7 @@ def _dp_worker(rank, world, port, ret, backend, precision, over):
     st = copy.deepcopy(state)
     for i in range(3):                                   # eager, graph capture, graph replay
         ba, nz = (batch, noise) if i == 0 else (O.make_batch(40 + i, B, F, A, np.float64), O.make_noise(50 + i, B, A, np.float64))
-        prev = copy.deepcopy(st['params'])
+        prev, prev_mu, prev_nu = copy.deepcopy(st['params']), copy.deepcopy(st['mu']), copy.deepcopy(st['nu'])
         st, ref_info, ref_grads = O.update(st, cfg, ba, nz)
         _, info = agent.update(f32(fdist.shard_rows(ba, rank, world)), noise=f32(fdist.shard_rows(nz, rank, world)))
         for k in O.INFO_KEYS[:10]:
@@ -85,7 +85,8 @@ def _dp_worker(rank, world, port, ret, backend, precision, over):
         if i == 0:
             for (path, r), (_, g) in zip(O.tree_leaves(ref_grads), O.tree_leaves(agent.export_tree('grads'))):
                 assert rel_err(g, r) <= tol_grad, ('grads', path, rel_err(g, r))   # the arena holds the REDUCED gradient
-            check_update_delta(prev, st['params'], agent.export_tree('params'), 2e-3 if precision == 'fp32' else 0.1, what=f'rank {rank}')
+            check_update_delta(prev, st['params'], agent.export_tree('params'), 2e-3 if precision == 'fp32' else 0.9, what=f'rank {rank}',
+                               opt=dict(state=dict(st, params=prev, mu=prev_mu, nu=prev_nu, count=st['count'] - 1), cfg=cfg, grads=agent.export_tree('grads')))
     if precision == 'fp32':
         worst = max(rel_err(g, r) for (_, r), (_, g) in zip(O.tree_leaves(st['params']), O.tree_leaves(agent.export_tree('params'))))
         assert worst <= 3e-5, worst
