@@ -406,13 +406,13 @@ def main():
                 obs_d = torch.randn(args.batch, F, device='cuda')
                 nz_d = torch.randn(args.batch, A, device='cuda')
                 for _ in range(3):
-                    agent._fwd_call(agent._lib.fql_compute_flow_actions, obs_d, nz_d)
+                    agent._fwd_call(agent._lib.fql_compute_flow_actions, obs_d, nz_d, to_host=False)
                 kk = 20
                 ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(kk)]
                 for i in range(kk):
                     flush.zero_()
                     ev[i][0].record()
-                    agent._fwd_call(agent._lib.fql_compute_flow_actions, obs_d, nz_d)
+                    agent._fwd_call(agent._lib.fql_compute_flow_actions, obs_d, nz_d, to_host=False)
                     ev[i][1].record()
                 torch.cuda.synchronize()
             k_us = 1e3 * float(np.median([x.elapsed_time(y) for x, y in ev]))
@@ -446,6 +446,25 @@ def main():
                         d2h_bytes_per_step=13 * 4 * args.seeds, api='FQLAgent.update(host numpy batch)'),
                gpu_launches=launches, gpu_launches_per_step=launches / K, roofline=roof, clocks=clk, last_critic_loss=last_loss,
                scaling_configs=scaling_configs, dp_transport=getattr(agent, 'dp_transport', None))
+    if n == 1 and not wl.get('image'):
+        # online / evaluation path (main.py:225, evaluation.py:98-150): host observation in, host action out, one row and ten rows
+        try:
+            lat = {}
+            with torch.cuda.stream(stream):
+                for rows in (1, 10):
+                    ob = np.random.default_rng(5).standard_normal((rows, F)).astype(np.float32)
+                    for _ in range(20):
+                        agent.sample_actions(ob, seed=np.array([1, 2], np.uint32))
+                    ts = []
+                    for _ in range(200):
+                        t0 = time.perf_counter()
+                        agent.sample_actions(ob, seed=np.array([1, 2], np.uint32))
+                        ts.append(time.perf_counter() - t0)
+                    lat[f'rows_{rows}_us_median'] = 1e6 * float(np.median(ts))
+            out['sample_actions_latency'] = dict(lat, api='FQLAgent.sample_actions(host obs) -> host actions, noise drawn on the host',
+                                                 note='preallocated buffers, pinned staging, one H2D + 3 kernels + one D2H + stream sync')
+        except Exception as e:
+            out['sample_actions_latency'] = dict(error=repr(e)[:200])
     if n == 1 and args.precision == 'bf16' and not args.no_fp32_leg:
         with torch.cuda.stream(stream):
             a32 = FQLAgent.create(0, np.zeros((1, F), np.float32), np.zeros((1, A), np.float32), cfg, num_seeds=args.seeds, precision='fp32')

@@ -185,6 +185,7 @@ class FQLAgent:
                 raise _lib.FqlError('fql_shadow_bytes: ' + self._lib.fql_last_error().decode())
             self._shadow = torch.zeros(nb, dtype=torch.uint8, device=self.device)
         self._bufs = {}
+        self._fwd_cache = {}
         self._ring, self._ring_i = [], 0
         self._host_step = 0          # updates enqueued so far == optax count: the Philox step of the next noise draw
         self.last_h2d_bytes = 0
@@ -610,23 +611,47 @@ class FQLAgent:
                        'fql_target_update')
 
     # ------------------------------------------------------------------ agents/fql.py:135-171
-    def _fwd_call(self, fn, observations, noises):
+    def _fwd_bufs(self, rows):
+        """Static buffers of the standalone forward entry points for one row count: device inputs / output / workspace and a
+        pinned staging pair, allocated once (the online loop and the evaluator call sample_actions every environment step,
+        main.py:225, evaluation.py:98-150)."""
+        fb = self._fwd_cache.get(rows)
+        if fb is None:
+            S, A = self.num_seeds, self.config['action_dim']
+            ob = tuple(self.config['ob_dims'])
+            odt = torch.uint8 if self._image else torch.float32
+            d = self._dims(int(self.config.get('batch_size', 256)))
+            wsb = int(self._lib.fql_forward_workspace_bytes(C.byref(d), rows))
+            fb = dict(d=d, wsb=wsb, ws=torch.empty(wsb, dtype=torch.uint8, device=self.device),
+                      obs=torch.empty((S, rows) + ob, dtype=odt, device=self.device), nz=torch.empty(S, rows, A, device=self.device),
+                      out=torch.empty(S, rows, A, device=self.device),
+                      obs_pin=torch.empty((S, rows) + ob, dtype=odt).pin_memory(), nz_pin=torch.empty(S, rows, A).pin_memory(),
+                      out_pin=torch.empty(S, rows, A).pin_memory())
+            if len(self._fwd_cache) >= 8:
+                self._fwd_cache.pop(next(iter(self._fwd_cache)))
+            self._fwd_cache[rows] = fb
+        return fb
+
+    def _fwd_call(self, fn, observations, noises, to_host=True):
         nob = len(self.config['ob_dims'])
-        odt, onp = (torch.uint8, np.uint8) if self._image else (torch.float32, np.float32)
-        obs = torch.as_tensor(np.asarray(observations, dtype=onp) if not isinstance(observations, torch.Tensor) else observations)
         A, S = self.config['action_dim'], self.num_seeds
-        lead = tuple(obs.shape[:-nob])
-        obs = obs.to(self.device, odt).reshape((S, -1) + tuple(self.config['ob_dims'])).contiguous()
-        rows = obs.shape[1]
-        nz = torch.as_tensor(noises).to(self.device, torch.float32).reshape(S, rows, A).contiguous()
-        d = self._dims(int(self.config.get('batch_size', 256)))
-        wsb = int(self._lib.fql_forward_workspace_bytes(C.byref(d), rows))
-        ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
-        out = torch.empty(S, rows, A, dtype=torch.float32, device=self.device)
+        lead = tuple(np.shape(observations)[:-nob])
+        rows = (int(np.prod(lead)) if lead else 1) // S
+        fb = self._fwd_bufs(rows)
         with torch.cuda.device(self.device):
-            _lib.check(fn(self._ctx, C.byref(d), _ptr(self._params), _ptr(self._shadow), _ptr(obs), _ptr(nz), _ptr(out), rows,
-                          _ptr(ws), wsb, self._stream()), fn.__name__)
-        return out.reshape(lead + (A,))
+            for src, dev, pin in ((observations, fb['obs'], fb['obs_pin']), (noises, fb['nz'], fb['nz_pin'])):
+                if isinstance(src, torch.Tensor) and src.is_cuda:
+                    dev.copy_(src.reshape(dev.shape), non_blocking=True)
+                else:
+                    pin.copy_(torch.as_tensor(np.asarray(src)).reshape(pin.shape))
+                    dev.copy_(pin, non_blocking=True)
+            _lib.check(fn(self._ctx, C.byref(fb['d']), _ptr(self._params), _ptr(self._shadow), _ptr(fb['obs']), _ptr(fb['nz']), _ptr(fb['out']), rows,
+                          _ptr(fb['ws']), fb['wsb'], self._stream()), fn.__name__)
+            if not to_host:
+                return fb['out'].reshape(lead + (A,))       # a view of the static output buffer (overwritten by the next call)
+            fb['out_pin'].copy_(fb['out'], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        return fb['out_pin'].numpy().reshape(lead + (A,)).copy()
 
     def sample_actions(self, observations, seed=None, temperature=1.0, noise=None):
         """clip(actor_onestep_flow(obs, z)), z ~ N(0, I) of shape obs.shape[:-1] + (A,).  `temperature` is accepted and
@@ -637,10 +662,10 @@ class FQLAgent:
             key = np.ravel(np.asarray(seed if seed is not None else self.rng)).astype(np.uint64)
             g = torch.Generator(device='cpu').manual_seed(int(key[0]) ^ (int(key[-1]) << 32) if key.size else 0)
             noise = torch.randn(lead + (A,), generator=g, dtype=torch.float32)
-        return self._fwd_call(self._lib.fql_sample_actions, observations, noise).cpu().numpy()
+        return self._fwd_call(self._lib.fql_sample_actions, observations, noise)
 
     def compute_flow_actions(self, observations, noises):
-        return self._fwd_call(self._lib.fql_compute_flow_actions, observations, noises).cpu().numpy()
+        return self._fwd_call(self._lib.fql_compute_flow_actions, observations, noises)
 
     def __del__(self):
         try:

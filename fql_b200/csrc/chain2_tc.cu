@@ -1,7 +1,8 @@
-// chain2_tc.cu -- the throughput variant of the fused MLP chain (hidden = 512): one CTA runs a whole MLP -- and, for
-// compute_flow_actions (agents/fql.py:155-171), the whole Euler loop -- on a 128-row tile, with the epilogue of one layer
-// overlapped with the tensor-core work of the same and the next layer.  Used where seeds x 128-row tiles fill the GPU
-// (batch >= 1024-ish, vectorised seeds: BASELINE configs 3 and 4); mlp_tc.cu keeps the narrower widths.
+// chain2_tc.cu -- the throughput variant of the fused MLP chain (hidden = 512): one CTA runs a whole MLP forward -- for
+// compute_flow_actions (agents/fql.py:155-171) the whole Euler loop -- or the whole input-gradient chain of its backward on a
+// 128-row tile, with the epilogue of one layer overlapped with the tensor-core work of the same and the next layer.  Used
+// where seeds x 128-row tiles fill the GPU (batch >= 1024-ish, vectorised seeds: BASELINE configs 3 and 4); mlp_tc.cu keeps
+// the narrower widths and euler_cluster.cu the batch-256 latency path.
 //
 // The 128 x 512 fp32 accumulator of a layer is all of an SM's TMEM, so it cannot be double-buffered across layers.  Instead a
 // layer is issued as two N-halves (TMEM columns [0,256) and [256,512)) and the K loop of the second half runs while the
@@ -16,13 +17,17 @@
 // Activations live in one K-major SWIZZLE_128B operand buffer sA (8 blocks of [128][64] bf16): block kb of the next layer's
 // input overwrites block kb of this layer's input as soon as the second half's MMAs have consumed it (tcgen05.commit ->
 // a_free[kb]); the next layer's MMAs start on block kb as soon as it is written (a_ready[kb]).
-//   warp 0      TMA producer: weights as [32 k][256 n] MN-major stages straight from the Flax [in,out] bf16 shadow
-//               (one 3-D box per stage: 64 n x 32 k x 4 chunks), first-layer operand tile once
+//   warp 0      TMA producer: one box per 16 KB weight stage, straight from the Flax [in,out] bf16 shadow --
+//               forward: [32 k][256 n] MN-major (3-D box 64 n x 32 k x 4 chunks, SWIZZLE_128B);
+//               backward (W^T): [256 n = in][32 k = out] K-major (2-D box, SWIZZLE_64B).  No transposed weight copy exists.
 //   warp 1      MMA issuer: tcgen05.mma kind::f16 M=128 N=256 K=16, two per stage
-//   warps 2-9   epilogue: warp (q, p) owns TMEM lanes [32q, 32q+32) (one row per thread) and the 32-column chunks of parity p:
-//               + bias, GELU(tanh.approx), [LayerNorm: two passes, gelu stashed in TMEM, row sums exchanged between the two
-//               warps of a row through smem], bf16 re-pack into sA, optional bf16 / fp32 saves for the backward
-// Reference arithmetic: utils/networks.py:34-61 (MLP), :153-195 (Value), :198-235 (ActorVectorField).
+//   warps 2-9   epilogue: warp (q, p) owns TMEM lanes [32q, 32q+32) (one row per thread) and the 32-column chunks of parity p
+//     forward            + bias, GELU(tanh.approx) [, LayerNorm: two passes, gelu stashed in TMEM, row sums exchanged between
+//                        the two warps of a row through smem], bf16 re-pack into sA; saves for the backward: H (or xhat), gelu'
+//     backward           dZ_{l-1} = (dZ_l W_l^T) * gelu'(Z_{l-1})                          (utils/networks.py:54-56 reversed)
+//     backward, LN       dZ_{l-1} = gelu' * rstd * (dx - mean(dx) - xhat * mean(dx * xhat)),  dx = gamma * (dZ_l W_l^T)
+//                        from the forward's bf16 xhat / gelu' saves: no transcendental, no fp32 round trip through HBM
+// Reference arithmetic: utils/networks.py:34-61 (MLP), :153-195 (Value), :198-235 (ActorVectorField); jax.grad of the same.
 #include "step.cuh"
 #include "tc_prims.cuh"
 
@@ -36,37 +41,51 @@ constexpr int TILE_M = 128;
 constexpr int KB_BYTES = TILE_M * 128;       // one K block of an A operand: [128 rows][64 bf16]
 constexpr int KS = 32;                       // k rows of weights per pipeline stage
 constexpr int NHALF = 256;                   // accumulator columns per N-half
-constexpr int CHUNK_BYTES = KS * 128;        // one 64-column chunk of a stage
-constexpr int STAGE_BYTES = 4 * CHUNK_BYTES; // [4 chunks][32 k][64 n] bf16 = 16 KB
+constexpr int CHUNK_BYTES = KS * 128;        // one 64-column chunk of a forward stage
+constexpr int STAGE_BYTES = 4 * CHUNK_BYTES; // 16 KB: [4 chunks][32 k][64 n] (forward) / [256 n][32 k] (backward)
 constexpr int MAX_A = 32;
 constexpr int EPI_WARPS = 8;
 constexpr int C2_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int HID = 512;
 constexpr int NKB = HID / 64;
 
+enum { C2_FWD = 0, C2_EULER = 1, C2_FWD_LN = 2, C2_BWD = 3, C2_BWD_LN = 4 };
+
 struct Chain2Args {
   int NL, K0, K0pad, out_dim;
   int P, S, E, M, tiles;
-  int x_row0[FQL_MAXP], x_rows_s;
+  int x_row0[FQL_MAXP], x_rows_s, x_rows_e;
   int w_row[FQL_MAXP][FQL_MAXL], w_rows_s;   // rows of HID elements in the shadow
   int wl_row[FQL_MAXP], wl_rows_s;           // rows of 64 elements in the shadow (padded last layer)
   const float* params;
   long long arena;
   long long off_b[FQL_MAXP][FQL_MAXL], off_lns[FQL_MAXP][FQL_MAXL], off_lnb[FQL_MAXP][FQL_MAXL];
-  float* out;
-  float* Zs[FQL_MAXL];   // fp32 pre-activations (LayerNorm backward)
+  float* out;            // forward: [G][Mcap][out_dim]; backward: dX0 [G][Mcap][K0] (optional)
+  float* Zs[FQL_MAXL];   // forward: fp32 pre-activations (the per-layer LayerNorm backward of the small-batch schedule)
   float* mu[FQL_MAXL];
-  float* rstd[FQL_MAXL];
-  void* Hb[FQL_MAXL];    // bf16 activations (operands of the tensor-core backward)
-  void* Zb[FQL_MAXL];    // bf16 pre-activations (gelu' of the non-LayerNorm backward)
+  float* rstd[FQL_MAXL]; // forward: out; backward (LN): in
+  void* Hb[FQL_MAXL];    // forward: bf16 activations (wgrad operands); LN + XHb given: not written
+  void* Zb[FQL_MAXL];    // forward: bf16 pre-activations (small-batch backward)
+  void* DGb[FQL_MAXL];   // bf16 gelu'(z): forward out, backward in
+  void* XHb[FQL_MAXL];   // bf16 xhat = (gelu(z) - mu) * rstd (LayerNorm): forward out, backward in (also the wgrad operand)
+  void* dZb[FQL_MAXL];   // backward: bf16 dZ_l out (wgrad operands), optional
   int Mcap, r0;
+  int Mcap_dz;           // backward: row capacity per group of the dZb buffers
+  int save_mask;         // forward: bit p set = problem p writes its Hb / Zb / DGb / XHb / Zs / mu / rstd saves
   int n_steps, F, A;
   const float* a0;
   float* target;
   int clip_out;
-  int nstage, w3d;
+  int nstage, w3d, has_dx0;
 };
 
+// gelu(x) and gelu'(x) with one MUFU tanh
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
+  const float x2 = x * x;
+  const float th = tanh_approx(FQL_GELU_C * (x + FQL_GELU_A * x2 * x));
+  g = 0.5f * x * (1.0f + th);
+  dg = 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * (FQL_GELU_C * (1.0f + 3.0f * FQL_GELU_A * x2));
+}
 __device__ __forceinline__ float gelu_fast(float x) {
   const float u = FQL_GELU_C * (x + FQL_GELU_A * x * x * x);
   return 0.5f * x * (1.0f + tanh_approx(u));
@@ -82,7 +101,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
-// 32 consecutive activations of one row -> bf16, into block (j >> 1) of the K-major SWIZZLE_128B operand buffer (and optionally HBM)
+// 32 consecutive values of one row -> bf16, into block (j >> 1) of the K-major SWIZZLE_128B operand buffer (and optionally HBM)
 __device__ __forceinline__ void store_chunk(uint8_t* sA, int row, int j, const float (&h)[32], __nv_bfloat16* gdst) {
   uint8_t* blk = sA + (j >> 1) * KB_BYTES;
   const int c0 = (j & 1) * 4;
@@ -94,19 +113,38 @@ __device__ __forceinline__ void store_chunk(uint8_t* sA, int row, int j, const f
     if (gdst) *reinterpret_cast<uint4*>(gdst + c * 8) = v;
   }
 }
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* gdst, const float (&h)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+    *reinterpret_cast<uint4*>(gdst + c * 8) = make_uint4(pack_bf16(h[c * 8 + 0], h[c * 8 + 1]), pack_bf16(h[c * 8 + 2], h[c * 8 + 3]),
+                                                         pack_bf16(h[c * 8 + 4], h[c * 8 + 5]), pack_bf16(h[c * 8 + 6], h[c * 8 + 7]));
+}
+// 32 consecutive bf16 of one row from HBM (zeros for rows outside the problem)
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, bool valid, uint4 (&q)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; c++) q[c] = valid ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ float bf16_at(const uint4 (&q)[4], int i) {
+  const uint32_t w = (&q[i >> 3].x)[(i >> 1) & 3];
+  return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+}
 
-template <bool LN, bool EULER>
+template <int MODE>
 __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_constant__ CUtensorMap mapX,
                                                               const __grid_constant__ CUtensorMap mapW,
-                                                              const __grid_constant__ CUtensorMap mapWL, const Chain2Args a) {
+                                                              const __grid_constant__ CUtensorMap mapWL,
+                                                              const __grid_constant__ CUtensorMap mapW0, const Chain2Args a) {
+  constexpr bool LN = (MODE == C2_FWD_LN || MODE == C2_BWD_LN);
+  constexpr bool BWD = (MODE == C2_BWD || MODE == C2_BWD_LN);
+  constexpr bool EULER = (MODE == C2_EULER);
+  constexpr int NPAR = BWD ? (LN ? 1 : 0) : (LN ? 3 : 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int NPAR = LN ? 3 : 1;
-  const int nkb_x = a.K0pad / 64;
+  const int nkb_x = BWD ? 1 : a.K0pad / 64;
   uint8_t* sA = smem;                                   // [8][16 KB]
   uint8_t* sX = sA + NKB * KB_BYTES;                    // [nkb_x][16 KB]
   uint8_t* sW = sX + nkb_x * KB_BYTES;                  // [nstage][16 KB]
-  float* sPar = reinterpret_cast<float*>(sW + a.nstage * STAGE_BYTES);  // [2][NPAR][512]: bias (, LN scale, LN bias)
+  float* sPar = reinterpret_cast<float*>(sW + a.nstage * STAGE_BYTES);  // [2][NPAR][512]: bias (, LN scale, LN bias) / LN scale
   float* sStat = sPar + 2 * NPAR * HID;                 // [2][128][2] row sums of the two column parities (LayerNorm)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (LN ? 2 * TILE_M * 2 : 0));
   uint64_t* full = bars;                 // [8]
@@ -122,13 +160,17 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x % a.tiles, g = blockIdx.x / a.tiles;
   const int e = g % a.E, s = (g / a.E) % a.S, p = g / (a.E * a.S);
-  const int NL = a.NL;
-  const int total = a.n_steps * NL;
+  // iterations of one pass: forward = NL layers (the last one narrow); backward = NL-1 hidden dZ's (+ the narrow dX0 GEMM)
+  const int NIT = BWD ? (a.NL - 1 + (a.has_dx0 ? 1 : 0)) : a.NL;
+  const int NWIDE = a.NL - 1;            // iterations with a 512-wide output
+  const int total = a.n_steps * NIT;
+  const int ntail = BWD ? a.K0pad : 64;  // output width of the narrow tail iteration
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
     tma_prefetch_desc(&mapW);
     tma_prefetch_desc(&mapWL);
+    if (BWD) tma_prefetch_desc(&mapW0);
     for (int i = 0; i < 8; i++) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -153,22 +195,27 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
     // ================= TMA producer =================
     if (lane == 0) {
       mbar_expect_tx(x_full, nkb_x * KB_BYTES);
-      const int xrow = a.x_row0[p] + s * a.x_rows_s + tile * TILE_M;
+      const int xrow = a.x_row0[p] + s * a.x_rows_s + e * a.x_rows_e + tile * TILE_M;
       for (int kb = 0; kb < nkb_x; kb++) tma_load_2d(sX + kb * KB_BYTES, &mapX, x_full, kb * 64, xrow);
       int stage = 0;
       uint32_t phase = 0;
-      int l = 0;
-      for (int it = 0; it < total; it++, l = (l + 1 == NL) ? 0 : l + 1) {
-        if (l < NL - 1) {
-          const int K = (l == 0) ? a.K0 : HID;
+      int it = 0;
+      for (int n = 0; n < total; n++, it = (it + 1 == NIT) ? 0 : it + 1) {
+        if (it < NWIDE) {
+          // forward: layer it, K rows of W_it; backward: W^T of layer NL-1-it (it = 0: the padded last layer, K = 64 outputs)
+          const int l = BWD ? a.NL - 1 - it : it;
+          const int K = BWD ? (it == 0 ? 64 : HID) : (it == 0 ? a.K0 : HID);
           const int nst = (K + KS - 1) / KS;
-          const int row0 = a.w_row[p][l] + s * a.w_rows_s + e * K;
+          const int row0 = BWD ? (it == 0 ? a.wl_row[p] + s * a.wl_rows_s + e * HID : a.w_row[p][l] + s * a.w_rows_s + e * HID)
+                               : a.w_row[p][l] + s * a.w_rows_s + e * K;
           for (int h = 0; h < 2; h++)
             for (int ks = 0; ks < nst; ks++) {
               mbar_wait(&empty[stage], phase ^ 1);
               uint8_t* dst = sW + stage * STAGE_BYTES;
               mbar_expect_tx(&full[stage], STAGE_BYTES);
-              if (a.w3d) {
+              if (BWD) {
+                tma_load_2d(dst, it == 0 ? &mapWL : &mapW, &full[stage], ks * KS, row0 + h * NHALF);
+              } else if (a.w3d) {
                 tma_load_3d(dst, &mapW, &full[stage], 0, row0 + ks * KS, h * 4);
               } else {
                 for (int c = 0; c < 4; c++) tma_load_2d(dst + c * CHUNK_BYTES, &mapW, &full[stage], (h * 4 + c) * 64, row0 + ks * KS);
@@ -176,11 +223,13 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
               if (++stage == a.nstage) { stage = 0; phase ^= 1; }
             }
         } else {
-          const int row0 = a.wl_row[p] + s * a.wl_rows_s + e * HID;
-          for (int ks = 0; ks < NKB; ks++) {
+          // narrow tail: forward = the last Dense (padded to 64 outputs); backward = dX0 = dZ_0 W_0^T (K0pad inputs)
+          const int row0 = BWD ? a.w_row[p][0] + s * a.w_rows_s + e * a.K0 : a.wl_row[p] + s * a.wl_rows_s + e * HID;
+          for (int ks = 0; ks < HID / KS; ks++) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], 64 * 128);
-            tma_load_2d(sW + stage * STAGE_BYTES, &mapWL, &full[stage], 0, row0 + ks * 64);
+            mbar_expect_tx(&full[stage], BWD ? a.K0pad * 64 : KS * 128);
+            if (BWD) tma_load_2d(sW + stage * STAGE_BYTES, &mapW0, &full[stage], ks * KS, row0);
+            else tma_load_2d(sW + stage * STAGE_BYTES, &mapWL, &full[stage], 0, row0 + ks * KS);
             if (++stage == a.nstage) { stage = 0; phase ^= 1; }
           }
         }
@@ -189,26 +238,28 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc_h = make_idesc_bf16(128, NHALF, false, true);
-      const uint32_t idesc_l = make_idesc_bf16(128, 64, false, true);
+      const uint32_t idesc_h = make_idesc_bf16(128, NHALF, false, !BWD);
+      const uint32_t idesc_t = make_idesc_bf16(128, ntail, false, !BWD);
       const uint64_t a_t = make_smem_desc(0, 16, 1024);
-      const uint64_t b_t = make_smem_desc(0, CHUNK_BYTES, 1024);   // MN-major: 64-column chunks CHUNK_BYTES apart, 8-k groups 1024 B apart
+      // B: forward MN-major (64-column chunks CHUNK_BYTES apart, 8-k groups 1024 B apart); backward K-major rows of 64 B (SWIZZLE_64B)
+      const uint64_t b_t = BWD ? make_smem_desc_sw64(0, 16, 512) : make_smem_desc(0, CHUNK_BYTES, 1024);
+      const uint64_t b_k16 = BWD ? 2 : (2048 >> 4);      // second 16-k step inside a stage
       const uint32_t sa0 = smem_u32(sA) >> 4, sx0 = smem_u32(sX) >> 4, sw0 = smem_u32(sW) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int n_ar = 0, n_xr = 0;
       int uses[2] = {0, 0};
-      int l = 0;
-      for (int it = 0; it < total; it++, l = (l + 1 == NL) ? 0 : l + 1) {
-        if (l == 0) {
-          if (it == 0) mbar_wait(x_full, 0);
+      int it = 0;
+      for (int n = 0; n < total; n++, it = (it + 1 == NIT) ? 0 : it + 1) {
+        if (it == 0) {
+          if (n == 0) mbar_wait(x_full, 0);
           else mbar_wait(x_ready, (n_xr++) & 1);
           tc_fence_after();
         }
-        if (l < NL - 1) {
-          const int K = (l == 0) ? a.K0 : HID;
+        if (it < NWIDE) {
+          const int K = BWD ? (it == 0 ? 64 : HID) : (it == 0 ? a.K0 : HID);
           const int nst = (K + KS - 1) / KS;
-          const uint32_t abase = (l == 0) ? sx0 : sa0;
+          const uint32_t abase = (it == 0) ? sx0 : sa0;
           for (int h = 0; h < 2; h++) {
             if (uses[h] > 0) {
               mbar_wait(&acc_free[h], (uses[h] - 1) & 1);
@@ -217,7 +268,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
             const uint32_t tacc = tmem_base + h * NHALF;
             for (int ks = 0; ks < nst; ks++) {
               const int kb = ks >> 1;
-              if (l > 0 && h == 0 && (ks & 1) == 0) {
+              if (it > 0 && h == 0 && (ks & 1) == 0) {
                 mbar_wait(&a_ready[kb], (n_ar - 1) & 1);
                 tc_fence_after();
               }
@@ -226,10 +277,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
               const uint64_t adesc = a_t + (uint64_t)(abase + kb * (KB_BYTES >> 4) + (ks & 1) * 4);
               const uint64_t bdesc = b_t + (uint64_t)(sw0 + stage * (STAGE_BYTES >> 4));
               umma_bf16(tacc, adesc, bdesc, idesc_h, ks > 0);
-              if (K - ks * KS > 16) umma_bf16(tacc, adesc + 2, bdesc + (uint64_t)(2048 >> 4), idesc_h, 1);
+              if (K - ks * KS > 16) umma_bf16(tacc, adesc + 2, bdesc + b_k16, idesc_h, 1);
               umma_commit(&empty[stage]);
               if (++stage == a.nstage) { stage = 0; phase ^= 1; }
-              if (l > 0 && h == 1 && (ks & 1) == 1 && kb < 4) umma_commit(&a_free[kb]);
+              if (it > 0 && h == 1 && (ks & 1) == 1 && kb < 4) umma_commit(&a_free[kb]);
             }
             umma_commit(&acc_full[h]);
             uses[h]++;
@@ -240,14 +291,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
             mbar_wait(&acc_free[0], (uses[0] - 1) & 1);
             tc_fence_after();
           }
-          for (int ks = 0; ks < NKB; ks++) {
-            mbar_wait(&a_ready[ks], (n_ar - 1) & 1);
+          for (int ks = 0; ks < HID / KS; ks++) {
+            const int kb = ks >> 1;
+            if ((ks & 1) == 0) mbar_wait(&a_ready[kb], (n_ar - 1) & 1);
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint64_t adesc = a_t + (uint64_t)(sa0 + ks * (KB_BYTES >> 4));
+            const uint64_t adesc = a_t + (uint64_t)(sa0 + kb * (KB_BYTES >> 4) + (ks & 1) * 4);
             const uint64_t bdesc = b_t + (uint64_t)(sw0 + stage * (STAGE_BYTES >> 4));
-#pragma unroll
-            for (int j = 0; j < 4; j++) umma_bf16(tmem_base, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * (2048 >> 4)), idesc_l, (ks | j) != 0);
+            umma_bf16(tmem_base, adesc, bdesc, idesc_t, ks > 0);
+            umma_bf16(tmem_base, adesc + 2, bdesc + b_k16, idesc_t, 1);
             umma_commit(&empty[stage]);
             if (++stage == a.nstage) { stage = 0; phase ^= 1; }
           }
@@ -266,6 +318,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int et = threadIdx.x - 64;              // 0..255
     const int64_t gidx = (int64_t)((p * a.S + s) * a.E + e) * a.Mcap + a.r0 + grow;
+    const int64_t gidx_dz = (int64_t)(s * a.E + e) * a.Mcap_dz + grow;
+    const bool vsave = valid && ((a.save_mask >> p) & 1);
     int nf[2] = {0, 0};
     int n_af = 0;
     float act[MAX_A];
@@ -273,29 +327,37 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
 #pragma unroll
       for (int c = 0; c < MAX_A; c++) act[c] = (pw == 0 && valid && c < a.A) ? a.a0[((int64_t)s * a.M + grow) * a.A + c] : 0.f;
     }
-    int l = 0, step = 0;
-    for (int it = 0; it < total; it++, l = (l + 1 == NL) ? 0 : l + 1, step += (l == 0)) {
-      const bool last = (l == NL - 1);
-      const int N = last ? a.out_dim : HID;
-      float* par = sPar + (it & 1) * NPAR * HID;
-      {  // stage this layer's bias / LayerNorm parameters while the MMAs run
-        const float* b = a.params + (int64_t)s * a.arena + a.off_b[p][l] + (int64_t)e * N;
-        for (int i = et; i < N; i += 32 * EPI_WARPS) par[i] = b[i];
-        if (LN && !last) {
-          const float* sc = a.params + (int64_t)s * a.arena + a.off_lns[p][l] + (int64_t)e * N;
-          const float* bi = a.params + (int64_t)s * a.arena + a.off_lnb[p][l] + (int64_t)e * N;
-          for (int i = et; i < N; i += 32 * EPI_WARPS) {
-            par[HID + i] = sc[i];
-            par[2 * HID + i] = bi[i];
+    int it = 0, step = 0;
+    for (int n = 0; n < total; n++, it = (it + 1 == NIT) ? 0 : it + 1, step += (it == 0)) {
+      const bool wide = it < NWIDE;
+      const int l = BWD ? a.NL - 2 - it : it;     // forward: the layer computed; backward: the hidden layer whose dZ is produced
+      float* par = sPar + (n & 1) * NPAR * HID;
+      if (NPAR > 0) {  // stage this iteration's per-column parameters while the MMAs run
+        if (!BWD) {
+          const int N = wide ? HID : a.out_dim;
+          const float* b = a.params + (int64_t)s * a.arena + a.off_b[p][l] + (int64_t)e * N;
+          for (int i = et; i < N; i += 32 * EPI_WARPS) par[i] = b[i];
+          if (LN && wide) {
+            const float* sc = a.params + (int64_t)s * a.arena + a.off_lns[p][l] + (int64_t)e * HID;
+            const float* bi = a.params + (int64_t)s * a.arena + a.off_lnb[p][l] + (int64_t)e * HID;
+            for (int i = et; i < HID; i += 32 * EPI_WARPS) {
+              par[HID + i] = sc[i];
+              par[2 * HID + i] = bi[i];
+            }
           }
+        } else if (wide) {
+          const float* sc = a.params + (int64_t)s * a.arena + a.off_lns[p][l] + (int64_t)e * HID;
+          for (int i = et; i < HID; i += 32 * EPI_WARPS) par[i] = sc[i];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       uint32_t r[32];
-      if (!last) {
-        __nv_bfloat16* Hb = (valid && a.Hb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.Hb[l]) + gidx * HID : nullptr;
-        if (!LN) {
-          __nv_bfloat16* Zb = (valid && a.Zb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.Zb[l]) + gidx * HID : nullptr;
+      if (wide) {
+        const int64_t rowoff = gidx * HID;
+        if (MODE == C2_FWD || MODE == C2_EULER) {
+          __nv_bfloat16* Hb = (vsave && a.Hb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.Hb[l]) + rowoff : nullptr;
+          __nv_bfloat16* Zb = (vsave && a.Zb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.Zb[l]) + rowoff : nullptr;
+          __nv_bfloat16* DGb = (vsave && a.DGb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.DGb[l]) + rowoff : nullptr;
           for (int h = 0; h < 2; h++) {
             mbar_wait(&acc_full[h], (nf[h]++) & 1);
             tc_fence_after();
@@ -305,23 +367,22 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
               tmem_ld32(t_lane + j * 32, r);
               tmem_wait_ld();
               float hv[32];
+              if (DGb) {        // z -> gelu(z) for the next layer, gelu'(z) saved for the backward (the large-batch backward reads no z)
+                float dv[32];
 #pragma unroll
-              for (int i = 0; i < 32; i++) {
-                const float z = __uint_as_float(r[i]) + par[j * 32 + i];
-                r[i] = __float_as_uint(z);
-                hv[i] = gelu_fast(z);
-              }
-              if (Zb) {
+                for (int i = 0; i < 32; i++) gelu_and_grad(__uint_as_float(r[i]) + par[j * 32 + i], hv[i], dv[i]);
+                store_bf16x32(DGb + j * 32, dv);
+              } else {
+                float zv[32];
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                  *reinterpret_cast<uint4*>(Zb + j * 32 + c * 8) =
-                      make_uint4(pack_bf16(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1])),
-                                 pack_bf16(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3])),
-                                 pack_bf16(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5])),
-                                 pack_bf16(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7])));
+                for (int i = 0; i < 32; i++) {
+                  zv[i] = __uint_as_float(r[i]) + par[j * 32 + i];
+                  hv[i] = gelu_fast(zv[i]);
+                }
+                if (Zb) store_bf16x32(Zb + j * 32, zv);
               }
               // block j >> 1 of sA still holds this layer's input until the second half's MMAs have consumed it
-              if (l > 0 && h == 0) mbar_wait(&a_free[j >> 1], n_af & 1);
+              if (it > 0 && h == 0) mbar_wait(&a_free[j >> 1], n_af & 1);
               store_chunk(sA, row, j, hv, Hb ? Hb + j * 32 : nullptr);
               fence_proxy_async_smem();
               __syncwarp();
@@ -331,10 +392,39 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_free[h]);
           }
-          if (l > 0) n_af++;
-        } else {
+          if (it > 0) n_af++;
+        } else if (MODE == C2_BWD) {
+          const __nv_bfloat16* DGb = reinterpret_cast<const __nv_bfloat16*>(a.DGb[l]) + rowoff;
+          __nv_bfloat16* dZb = (valid && a.dZb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.dZb[l]) + gidx_dz * HID : nullptr;
+          for (int h = 0; h < 2; h++) {
+            uint4 dq[4];
+            load_bf16x32(DGb + (h * 8 + pw) * 32, valid, dq);   // the first chunk's gelu' is fetched while the MMAs run
+            mbar_wait(&acc_full[h], (nf[h]++) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int jj = 0; jj < 4; jj++) {
+              const int j = h * 8 + jj * 2 + pw;
+              tmem_ld32(t_lane + j * 32, r);
+              tmem_wait_ld();
+              float hv[32];
+#pragma unroll
+              for (int i = 0; i < 32; i++) hv[i] = __uint_as_float(r[i]) * bf16_at(dq, i);
+              if (jj < 3) load_bf16x32(DGb + (j + 2) * 32, valid, dq);
+              if (it > 0 && h == 0) mbar_wait(&a_free[j >> 1], n_af & 1);
+              store_chunk(sA, row, j, hv, dZb ? dZb + j * 32 : nullptr);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[j >> 1]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[h]);
+          }
+          if (it > 0) n_af++;
+        } else if (MODE == C2_FWD_LN) {
           // pass 1: g = gelu(z) stashed back into TMEM in place, row sums in registers
-          float* Zs = (valid && a.Zs[l]) ? a.Zs[l] + gidx * HID : nullptr;
+          float* Zs = (vsave && a.Zs[l]) ? a.Zs[l] + rowoff : nullptr;
+          __nv_bfloat16* DGb = (vsave && a.DGb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.DGb[l]) + rowoff : nullptr;
           float s1 = 0.f, s2 = 0.f;
           for (int h = 0; h < 2; h++) {
             mbar_wait(&acc_full[h], (nf[h]++) & 1);
@@ -352,12 +442,25 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
                   *reinterpret_cast<float4*>(Zs + j * 32 + i) =
                       make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
               }
+              if (DGb) {
+                float dv[32];
 #pragma unroll
-              for (int i = 0; i < 32; i++) {
-                const float gv = gelu_fast(__uint_as_float(r[i]));
-                s1 += gv;
-                s2 += gv * gv;
-                r[i] = __float_as_uint(gv);
+                for (int i = 0; i < 32; i++) {
+                  float gv;
+                  gelu_and_grad(__uint_as_float(r[i]), gv, dv[i]);
+                  s1 += gv;
+                  s2 += gv * gv;
+                  r[i] = __float_as_uint(gv);
+                }
+                store_bf16x32(DGb + j * 32, dv);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                  const float gv = gelu_fast(__uint_as_float(r[i]));
+                  s1 += gv;
+                  s2 += gv * gv;
+                  r[i] = __float_as_uint(gv);
+                }
               }
               tmem_st32(t_lane + j * 32, r);
             }
@@ -372,11 +475,13 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
           const float mu = s1 * inv_n;
           const float var = fmaxf(0.f, s2 * inv_n - mu * mu);
           const float rstd = rsqrtf(var + FQL_LN_EPS);
-          if (valid && pw == 0 && a.mu[l]) {
-            a.mu[l][gidx] = mu;
-            a.rstd[l][gidx] = rstd;
+          if (vsave && pw == 0) {
+            if (a.mu[l]) a.mu[l][gidx] = mu;
+            if (a.rstd[l]) a.rstd[l][gidx] = rstd;
           }
           // pass 2: normalise, re-pack.  Every MMA of this layer has completed (acc_full[1] was observed): sA is free.
+          __nv_bfloat16* Hb = (vsave && a.Hb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.Hb[l]) + rowoff : nullptr;
+          __nv_bfloat16* XHb = (vsave && a.XHb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.XHb[l]) + rowoff : nullptr;
           for (int h = 0; h < 2; h++) {
 #pragma unroll 1
             for (int jj = 0; jj < 4; jj++) {
@@ -385,9 +490,67 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
               tmem_wait_ld();
               float hv[32];
 #pragma unroll
-              for (int i = 0; i < 32; i++)
-                hv[i] = (__uint_as_float(r[i]) - mu) * rstd * par[HID + j * 32 + i] + par[2 * HID + j * 32 + i];
+              for (int i = 0; i < 32; i++) hv[i] = (__uint_as_float(r[i]) - mu) * rstd;       // xhat
+              if (XHb) store_bf16x32(XHb + j * 32, hv);
+#pragma unroll
+              for (int i = 0; i < 32; i++) hv[i] = hv[i] * par[HID + j * 32 + i] + par[2 * HID + j * 32 + i];
               store_chunk(sA, row, j, hv, Hb ? Hb + j * 32 : nullptr);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_ready[j >> 1]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[h]);
+          }
+        } else {  // C2_BWD_LN
+          const __nv_bfloat16* XHb = reinterpret_cast<const __nv_bfloat16*>(a.XHb[l]) + rowoff;
+          const __nv_bfloat16* DGb = reinterpret_cast<const __nv_bfloat16*>(a.DGb[l]) + rowoff;
+          __nv_bfloat16* dZb = (valid && a.dZb[l]) ? reinterpret_cast<__nv_bfloat16*>(a.dZb[l]) + gidx_dz * HID : nullptr;
+          const float rstd = valid ? a.rstd[l][gidx] : 0.f;
+          // pass 1: dx = gamma * dH stashed in TMEM, row sums of dx and dx * xhat
+          float m1 = 0.f, m2 = 0.f;
+          for (int h = 0; h < 2; h++) {
+            uint4 xq[4];
+            load_bf16x32(XHb + (h * 8 + pw) * 32, valid, xq);
+            mbar_wait(&acc_full[h], (nf[h]++) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int jj = 0; jj < 4; jj++) {
+              const int j = h * 8 + jj * 2 + pw;
+              tmem_ld32(t_lane + j * 32, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; i++) {
+                const float dx = __uint_as_float(r[i]) * par[j * 32 + i];
+                m1 += dx;
+                m2 = fmaf(dx, bf16_at(xq, i), m2);
+                r[i] = __float_as_uint(dx);
+              }
+              if (jj < 3) load_bf16x32(XHb + (j + 2) * 32, valid, xq);
+              tmem_st32(t_lane + j * 32, r);
+            }
+          }
+          tmem_wait_st();
+          sStat[(pw * TILE_M + row) * 2 + 0] = m1;
+          sStat[(pw * TILE_M + row) * 2 + 1] = m2;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          m1 = (m1 + sStat[((pw ^ 1) * TILE_M + row) * 2 + 0]) * (1.0f / (float)HID);
+          m2 = (m2 + sStat[((pw ^ 1) * TILE_M + row) * 2 + 1]) * (1.0f / (float)HID);
+          // pass 2: dz = gelu' * rstd * (dx - m1 - xhat * m2)       (flax LayerNorm backward, fast-variance form)
+          for (int h = 0; h < 2; h++) {
+#pragma unroll 1
+            for (int jj = 0; jj < 4; jj++) {
+              const int j = h * 8 + jj * 2 + pw;
+              uint4 xq[4], dq[4];
+              load_bf16x32(XHb + j * 32, valid, xq);
+              load_bf16x32(DGb + j * 32, valid, dq);
+              tmem_ld32(t_lane + j * 32, r);
+              tmem_wait_ld();
+              float hv[32];
+#pragma unroll
+              for (int i = 0; i < 32; i++) hv[i] = bf16_at(dq, i) * rstd * (__uint_as_float(r[i]) - m1 - bf16_at(xq, i) * m2);
+              store_chunk(sA, row, j, hv, dZb ? dZb + j * 32 : nullptr);
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) mbar_arrive(&a_ready[j >> 1]);
@@ -398,10 +561,23 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
           }
         }
       } else {
-        // last Dense (linear): out_dim <= 32 columns of the padded N = 64 accumulator; the parity-0 warps hold them
+        // narrow tail
         mbar_wait(&acc_full[0], (nf[0]++) & 1);
         tc_fence_after();
-        if (pw == 0) {
+        if (BWD) {
+          // dX0 = dZ_0 W_0^T: columns [0, K0) in fp32 (the actor loss only reads the action columns)
+          for (int j = pw; j * 32 < a.K0; j += 2) {
+            tmem_ld32(t_lane + j * 32, r);
+            tmem_wait_ld();
+            if (valid && a.out) {
+              float* o = a.out + gidx_dz * a.K0 + j * 32;
+#pragma unroll
+              for (int c = 0; c < 32; c++)
+                if (j * 32 + c < a.K0) o[c] = __uint_as_float(r[c]);
+            }
+          }
+        } else if (pw == 0) {
+          // last Dense (linear): out_dim <= 32 columns of the padded N = 64 accumulator
           tmem_ld32(t_lane, r);
           tmem_wait_ld();
           if (!EULER) {
@@ -464,7 +640,8 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows,
+                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto enc = get_encode();
   FQL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {inner, rows};
@@ -472,7 +649,7 @@ int make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows,
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FQL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu", (int)r, (unsigned long long)inner,
               (unsigned long long)rows);
   return 0;
@@ -492,6 +669,60 @@ bool make_map_w3d(CUtensorMap* m, const void* base, uint64_t rows) {
   return r == CUDA_SUCCESS;
 }
 
+int fill_common(Chain2Args& a, const FqlDims* d, const Layout& L, int P, const int* net, int M, int Mcap0, int r0_in) {
+  const NetView& n0 = L.net[net[0]];
+  memset(&a, 0, sizeof(a));
+  a.NL = n0.n_layers; a.K0 = n0.in_dim; a.K0pad = (int)round_up64(n0.in_dim, 64); a.out_dim = n0.out_dim;
+  a.P = P; a.S = d->num_seeds; a.E = n0.ens; a.M = M; a.tiles = (M + TILE_M - 1) / TILE_M;
+  FQL_REQUIRE(a.NL >= 3 && a.NL <= FQL_MAXL && a.out_dim <= MAX_A && a.K0pad <= 128, "tc_mlp_chain2: %d layers / output width %d / input width %d",
+              a.NL, a.out_dim, a.K0);
+  const int64_t seed_elems = tc_shadow_seed_elems(d, L);
+  FQL_REQUIRE(seed_elems % HID == 0 && L.arena % 64 == 0, "shadow layout not row aligned");
+  a.x_rows_s = Mcap0;
+  a.w_rows_s = (int)(seed_elems / HID);
+  a.wl_rows_s = (int)(seed_elems / 64);
+  for (int p = 0; p < P; p++) {
+    const NetView& nv = L.net[net[p]];
+    a.x_row0[p] = p * a.S * Mcap0 + r0_in;
+    for (int l = 0; l < nv.n_layers; l++) {
+      a.w_row[p][l] = (int)(nv.off_w[l] / HID);
+      a.off_b[p][l] = nv.off_b[l];
+      a.off_lns[p][l] = nv.off_lns[l];
+      a.off_lnb[p][l] = nv.off_lnb[l];
+    }
+    int64_t wl = L.arena;
+    for (int t = 0; t < net[p]; t++) wl += (int64_t)L.net[t].ens * HID * 64;
+    a.wl_row[p] = (int)(wl / 64);
+  }
+  a.arena = L.arena;
+  a.n_steps = 1; a.F = d->obs_dim; a.A = d->action_dim;
+  a.save_mask = 0xff;
+  return 0;
+}
+
+template <int MODE>
+int launch_chain2(const Chain2Args& a0, int nkb_x, int npar, bool ln, const CUtensorMap& mapX, const CUtensorMap& mapW, const CUtensorMap& mapWL,
+                  const CUtensorMap& mapW0, cudaStream_t st) {
+  Chain2Args a = a0;
+  const int fixed = (NKB + nkb_x) * KB_BYTES + 2 * npar * HID * 4 + (ln ? 2 * TILE_M * 2 * 4 : 0) + 512 + 1024;
+  int nstage = (232448 - fixed) / STAGE_BYTES;
+  if (nstage > 8) nstage = 8;
+  FQL_REQUIRE(nstage >= 2, "not enough shared memory for the weight pipeline");
+  a.nstage = nstage;
+  const int smem = fixed + nstage * STAGE_BYTES;
+  auto kern = mlp_chain2_kernel<MODE>;
+  static bool attr_set[FQL_MAX_DEVICES] = {};
+  const int dev = fql_current_device();
+  if (!attr_set[dev]) {
+    FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set[dev] = true;
+  }
+  const int grid = a.tiles * a.P * a.S * a.E;
+  kern<<<grid, C2_THREADS, smem, st>>>(mapX, mapW, mapWL, mapW0, a);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace
 
 int tc_mlp_chain2_supported(const FqlDims* d) {
@@ -509,29 +740,8 @@ int tc_mlp_chain2(const TcChainSpec& f, cudaStream_t st) {
   FQL_REQUIRE(d->hidden == HID, "tc_mlp_chain2 is built for hidden = 512");
   const NetView& n0 = L.net[f.net[0]];
   Chain2Args a;
-  memset(&a, 0, sizeof(a));
-  a.NL = n0.n_layers; a.K0 = n0.in_dim; a.K0pad = (int)round_up64(n0.in_dim, 64); a.out_dim = n0.out_dim;
-  a.P = f.P; a.S = d->num_seeds; a.E = n0.ens; a.M = f.M; a.tiles = (f.M + TILE_M - 1) / TILE_M;
-  FQL_REQUIRE(a.NL >= 2 && a.out_dim <= MAX_A, "tc_mlp_chain2: %d layers / output width %d", a.NL, a.out_dim);
-  const int64_t seed_elems = tc_shadow_seed_elems(d, L);
-  FQL_REQUIRE(seed_elems % HID == 0 && L.arena % 64 == 0, "shadow layout not row aligned");
-  a.x_rows_s = f.Mcap0;
-  a.w_rows_s = (int)(seed_elems / HID);
-  a.wl_rows_s = (int)(seed_elems / 64);
-  for (int p = 0; p < f.P; p++) {
-    const NetView& nv = L.net[f.net[p]];
-    a.x_row0[p] = p * a.S * f.Mcap0 + f.r0_in;
-    for (int l = 0; l < nv.n_layers; l++) {
-      a.w_row[p][l] = (int)(nv.off_w[l] / HID);
-      a.off_b[p][l] = nv.off_b[l];
-      a.off_lns[p][l] = nv.off_lns[l];
-      a.off_lnb[p][l] = nv.off_lnb[l];
-    }
-    int64_t wl = L.arena;
-    for (int t = 0; t < f.net[p]; t++) wl += (int64_t)L.net[t].ens * HID * 64;
-    a.wl_row[p] = (int)(wl / 64);
-  }
-  a.params = f.params; a.arena = L.arena;
+  FQL_TRY(fill_common(a, d, L, f.P, f.net, f.M, f.Mcap0, f.r0_in));
+  a.params = f.params;
   a.Mcap = f.buf ? f.buf->Mcap : f.M; a.r0 = f.r0;
   if (f.buf) {
     a.out = f.buf->out;
@@ -549,18 +759,20 @@ int tc_mlp_chain2(const TcChainSpec& f, cudaStream_t st) {
     }
     if (f.Mcap_override > 0) a.Mcap = f.Mcap_override;
   }
+  for (int l = 0; l + 1 < n0.n_layers; l++) {
+    if (f.DGb) {            // large-batch backward: gelu' (and xhat for LayerNorm networks) instead of the pre-activations
+      a.DGb[l] = f.DGb[l];
+      a.Zb[l] = nullptr;
+      a.Zs[l] = nullptr;
+    }
+    if (f.XHb) { a.XHb[l] = f.XHb[l]; a.Hb[l] = nullptr; }
+  }
+  if (f.save_mask) a.save_mask = f.save_mask;
   if (f.out_override) a.out = f.out_override;
-  a.n_steps = f.n_steps > 0 ? f.n_steps : 1; a.F = d->obs_dim; a.A = d->action_dim; a.a0 = f.a0; a.target = f.target;
+  a.n_steps = f.n_steps > 0 ? f.n_steps : 1; a.a0 = f.a0; a.target = f.target;
   a.clip_out = f.clip_out;
   const bool euler = a.n_steps > 1;
   FQL_REQUIRE(!euler || (a.a0 && a.target && f.P == 1 && a.E == 1 && !n0.ln), "Euler chain needs a0/target and a single actor network");
-  const int npar = n0.ln ? 3 : 1;
-  const int fixed = (NKB + a.K0pad / 64) * KB_BYTES + 2 * npar * HID * 4 + (n0.ln ? 2 * TILE_M * 2 * 4 : 0) + 512 + 1024;
-  int nstage = (232448 - fixed) / STAGE_BYTES;
-  if (nstage > 8) nstage = 8;
-  FQL_REQUIRE(nstage >= 2, "not enough shared memory for the weight pipeline");
-  a.nstage = nstage;
-  const int smem = fixed + nstage * STAGE_BYTES;
 
   CUtensorMap mapX, mapW, mapWL;
   const int64_t x_rows = (int64_t)f.P * a.S * f.Mcap0;
@@ -568,17 +780,42 @@ int tc_mlp_chain2(const TcChainSpec& f, cudaStream_t st) {
   static const bool no3d = getenv("FQL_B200_CHAIN2_W3D") && getenv("FQL_B200_CHAIN2_W3D")[0] == '0';
   a.w3d = (!no3d && make_map_w3d(&mapW, f.shadow, (uint64_t)a.S * a.w_rows_s)) ? 1 : 0;
   if (!a.w3d) FQL_TRY(make_map_2d(&mapW, f.shadow, HID, (uint64_t)a.S * a.w_rows_s, 64, KS));
-  FQL_TRY(make_map_2d(&mapWL, f.shadow, 64, (uint64_t)a.S * a.wl_rows_s, 64, 64));
-  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Chain2Args) =
-      n0.ln ? mlp_chain2_kernel<true, false> : (euler ? mlp_chain2_kernel<false, true> : mlp_chain2_kernel<false, false>);
-  static bool attr_set[FQL_MAX_DEVICES][3] = {};
-  const int dev = fql_current_device(), ki = n0.ln ? 0 : (euler ? 1 : 2);
-  if (!attr_set[dev][ki]) {
-    FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set[dev][ki] = true;
+  FQL_TRY(make_map_2d(&mapWL, f.shadow, 64, (uint64_t)a.S * a.wl_rows_s, 64, KS));
+  const int nkb_x = a.K0pad / 64;
+  if (n0.ln) return launch_chain2<C2_FWD_LN>(a, nkb_x, 3, true, mapX, mapW, mapWL, mapWL, st);
+  if (euler) return launch_chain2<C2_EULER>(a, nkb_x, 1, false, mapX, mapW, mapWL, mapWL, st);
+  return launch_chain2<C2_FWD>(a, nkb_x, 1, false, mapX, mapW, mapWL, mapWL, st);
+}
+
+// The input-gradient chain of one network's backward on M rows per group: dZ_{NL-2} ... dZ_0 as bf16 (operands of the weight
+// gradients) and optionally dX0 = dZ_0 W_0^T in fp32 -- from the forward's bf16 gelu' (and xhat / rstd) saves.
+int tc_mlp_chain2_backward(const TcChain2BwdSpec& f, cudaStream_t st) {
+  const FqlDims* d = f.d;
+  const Layout& L = *f.L;
+  FQL_TRY(tc_supported(d));
+  FQL_REQUIRE(d->hidden == HID, "tc_mlp_chain2_backward is built for hidden = 512");
+  const NetView& nv = L.net[f.net];
+  Chain2Args a;
+  const int nets[1] = {f.net};
+  FQL_TRY(fill_common(a, d, L, 1, nets, f.M, f.M * nv.ens, 0));
+  a.params = f.params;
+  a.Mcap = f.Mcap; a.r0 = f.r0; a.Mcap_dz = f.Mcap_dz > 0 ? f.Mcap_dz : f.M;
+  // dOut: bf16 [S][E][M][64] zero padded; one 128-row tile of group (s, e) starts at row ((s * E + e) * M + tile * 128)
+  a.x_row0[0] = 0; a.x_rows_s = f.M * nv.ens; a.x_rows_e = f.M;
+  for (int l = 0; l + 1 < nv.n_layers; l++) {
+    a.DGb[l] = f.DGb[l];
+    a.XHb[l] = nv.ln ? f.XHb[l] : nullptr;
+    a.rstd[l] = nv.ln ? f.rstd[l] : nullptr;
+    a.dZb[l] = f.dZb ? f.dZb[l] : nullptr;
+    FQL_REQUIRE(a.DGb[l] && (!nv.ln || (a.XHb[l] && a.rstd[l])), "tc_mlp_chain2_backward: missing forward saves of layer %d", l);
   }
-  const int grid = a.tiles * a.P * a.S * a.E;
-  kern<<<grid, C2_THREADS, smem, st>>>(mapX, mapW, mapWL, a);
-  FQL_CHECK_LAUNCH();
-  return 0;
+  a.has_dx0 = f.dX0 ? 1 : 0;
+  a.out = f.dX0;
+  CUtensorMap mapX, mapW, mapWL, mapW0;
+  FQL_TRY(make_map_2d(&mapX, f.dOutb, 64, (uint64_t)a.S * nv.ens * f.M, 64, TILE_M));
+  FQL_TRY(make_map_2d(&mapW, f.shadow, HID, (uint64_t)a.S * a.w_rows_s, KS, NHALF, CU_TENSOR_MAP_SWIZZLE_64B));
+  FQL_TRY(make_map_2d(&mapWL, f.shadow, 64, (uint64_t)a.S * a.wl_rows_s, KS, NHALF, CU_TENSOR_MAP_SWIZZLE_64B));
+  FQL_TRY(make_map_2d(&mapW0, f.shadow, HID, (uint64_t)a.S * a.w_rows_s, KS, a.K0pad, CU_TENSOR_MAP_SWIZZLE_64B));
+  if (nv.ln) return launch_chain2<C2_BWD_LN>(a, 1, 1, true, mapX, mapW, mapWL, mapW0, st);
+  return launch_chain2<C2_BWD>(a, 1, 0, false, mapX, mapW, mapWL, mapW0, st);
 }

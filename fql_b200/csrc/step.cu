@@ -197,6 +197,8 @@ size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w)
       w->F_Hb[l] = c.take(S * 2 * B * H / 2);
       w->F_Zb[l] = c.take(S * 2 * B * H / 2);
       w->C_Hb[l] = c.take(3 * S * 2 * B * H / 2);
+      w->C_XHb[l] = c.take(3 * S * 2 * B * H / 2);
+      w->C_DGb[l] = c.take(3 * S * 2 * B * H / 2);
     }
     for (int i = 0; i < NH; i++) {
       w->O_dZb[i] = c.take(S * B * H / 2);
@@ -427,6 +429,7 @@ struct FqlContext {
                              // 2 = bc-flow and critic parts before the one-step actor's gradients are complete
   int adam_done_blk = 0;     // blocks [0, adam_done_blk) were already applied by enqueue_grads_tc in this enqueue
   int use_critic_chain = 0;
+  int use_big_bwd = 1;       // FQL_B200_BIG_BWD=0: per-layer backward (tc_gemm + row kernels) also at large batch
   int chain_min_tiles = 48;  // row tiles (x seeds) from which the fused per-tile chain kernels replace the per-layer GEMMs
   cudaEvent_t early_event = nullptr;  // optional: recorded when the bc-flow and critic gradients of fql_step_grads are complete
   long long launches = 0;  // kernels enqueued through this context
@@ -528,6 +531,8 @@ extern "C" int fql_context_create(FqlContext** out) {
   if (sa) c->split_adam = atoi(sa);
   const char* cm = getenv("FQL_B200_CHAIN_MIN_TILES");
   if (cm) c->chain_min_tiles = atoi(cm);
+  const char* bb = getenv("FQL_B200_BIG_BWD");
+  if (bb && bb[0] == '0') c->use_big_bwd = 0;
   const char* cc = getenv("FQL_B200_CRITIC_CHAIN");
   if (cc && cc[0] == '1') c->use_critic_chain = 1;
   *out = c;
@@ -659,12 +664,15 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   FQL_CHECK_CUDA(cudaEventRecord(ev_pad, S1));
   const int row_tiles = S * ((B + 127) / 128);
   const bool many_tiles = row_tiles >= ctx->chain_min_tiles;  // enough 128-row tiles to fill the GPU: fused per-tile chain kernels
+  // ... and the whole backward as chain launches on bf16 gelu' / xhat saves (chain2_tc.cu, tc_path.cu "large-batch backward")
+  const bool big_bwd = many_tiles && ctx->use_big_bwd && tc_mlp_chain2_supported(d) && d->critic_layer_norm && d->reserved[0] == 0;
   auto chain = [&](int net, const void* X0b, int rows_cap, int r0_in, int M, void* const* Hb, void* const* Zb, float* out, int n_steps,
                    cudaStream_t st) {
     TcChainSpec t;
     memset(&t, 0, sizeof(t));
     t.d = d; t.L = &L; t.P = 1; t.net[0] = net; t.params = P; t.shadow = shadow; t.M = M; t.X0b = X0b; t.Mcap0 = rows_cap; t.r0_in = r0_in;
     t.r0 = r0_in; t.Hb = Hb; t.Zb = Zb; t.Mcap_override = rows_cap; t.out_override = out; t.n_steps = n_steps;
+    if (big_bwd && Zb) { t.DGb = Zb; t.Zb = nullptr; }   // the pre-activation buffers hold gelu'(z) on this path
     if (n_steps > 1) { t.a0 = b.z; t.target = w.target; }
     return tc_mlp_chain(t, st);
   };
@@ -699,7 +707,16 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   if (many_tiles) FQL_TRY(chain(FQL_NET_ACTOR_BC_FLOW, w.XFb, 2 * B, 0, B, w.F_Hb, w.F_Zb, w.F_out, 1, S2));
   else FQL_TRY(tc_actor_forward(fbc, w.F_out, (long long)2 * B * sh.A, 0, nullptr, S2));
   FQL_TRY(launch_bc_post(sh, w, raw, S2));
-  if (c.do_backward) {
+  if (c.do_backward && big_bwd) {
+    FQL_TRY(tc_actor_backward_big(fbc, w.dpred, w.F_dOutb, w.F_dZb, false, S2));
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], S2));
+    if (dp_grads) {
+      const NetView& nb = L.net[FQL_NET_ACTOR_BC_FLOW];
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[16], 0));
+      FQL_TRY(dp_reduce_bucket(ctx->dp, 0, nb.begin, nb.end - nb.begin, nullptr, ctx->sc));
+    }
+    FQL_TRY(stamp(ctx, 4, S2));
+  } else if (c.do_backward) {
     FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.F_dZf, S2, ctx->s3, ctx->s7, &ctx->ev[8]));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[53], ctx->s7));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s3, ctx->ev[53], 0));
@@ -757,6 +774,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     memset(&t, 0, sizeof(t));
     t.d = d; t.L = &L; t.P = 3; t.net[0] = FQL_NET_TARGET_CRITIC; t.net[1] = FQL_NET_CRITIC; t.net[2] = FQL_NET_CRITIC;
     t.params = P; t.shadow = shadow; t.M = B; t.X0b = w.XCb; t.Mcap0 = B; t.buf = &w.pC; t.save = 1; t.n_steps = 1; t.Hb = w.C_Hb;
+    if (big_bwd) { t.DGb = w.C_DGb; t.XHb = w.C_XHb; t.save_mask = 6; }   // problems 1 (critic loss) and 2 (actor Q loss) have a backward
     FQL_TRY(tc_mlp_chain(t, S0));
   } else {
     // three independent chains {target critic(s',a'), critic(s,a), critic(s,clip a_pi)}: S0 + two forked streams
@@ -790,10 +808,15 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     t.grads = c.st->grads; t.p = 1; t.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)1 * S * B * kO;
     t.dOut = w.dq; t.dOutb = w.C1_dOutb;
     for (int l = 0; l < NH; l++) { t.dZb[l] = w.C1_dZb[l]; t.dZf[l] = w.C1_dZf[l]; t.dHf[l] = w.C1_dHf[l]; }
-    FQL_TRY(tc_critic_backward(t, S2, ctx->s5, ctx->s8, &ctx->ev[28]));
-    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[54], ctx->s8));
-    FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s5, ctx->ev[54], 0));
-    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], ctx->s5));
+    if (big_bwd) {
+      FQL_TRY(tc_critic_backward_big(t, w.C_XHb, w.C_DGb, S2));
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], S2));
+    } else {
+      FQL_TRY(tc_critic_backward(t, S2, ctx->s5, ctx->s8, &ctx->ev[28]));
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[54], ctx->s8));
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s5, ctx->ev[54], 0));
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], ctx->s5));
+    }
     if (dp_grads) {
       const NetView& nc = L.net[FQL_NET_CRITIC];
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[36], 0));
@@ -809,7 +832,8 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     q.grads = nullptr; q.p = 2; q.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)2 * S * B * kO;
     q.dOut = w.dqs; q.dOutb = w.C2_dOutb; q.dX0 = w.dX0;
     for (int l = 0; l < NH; l++) { q.dZb[l] = w.C2_dZb[l]; q.dZf[l] = w.C2_dZf[l]; q.dHf[l] = w.C2_dHf[l]; }
-    FQL_TRY(tc_critic_backward(q, S0, nullptr, nullptr, &ctx->ev[44]));
+    if (big_bwd) FQL_TRY(tc_critic_backward_big(q, w.C_XHb, w.C_DGb, S0));
+    else FQL_TRY(tc_critic_backward(q, S0, nullptr, nullptr, &ctx->ev[44]));
     FQL_TRY(stamp(ctx, 6, S0));   // critic input-gradient chain done
     if (c.do_apply && ctx->split_adam == 1 && d->reserved[0] == 0) {
       // bc-flow is finished with once the Euler chain (the last reader of its weights) has ended and its gradients are complete:
@@ -867,7 +891,9 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
         }
       }
     }
-    if (rc == 1) {
+    if (rc == 1 && big_bwd) {
+      FQL_TRY(tc_actor_backward_big(bo, w.dapi, w.O_dOutb, w.O_dZb, true, S0));
+    } else if (rc == 1) {
       FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, ctx->s9, &ctx->ev[18], true));
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[55], ctx->s9));
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s4, ctx->ev[55], 0));

@@ -42,6 +42,7 @@ struct WsPtrs {
   // per-layer tensor-core path (actor networks): bf16 activations / pre-activations, backward ping-pong, Euler state
   void *O_Hb[FQL_MAXL], *O_Zb[FQL_MAXL], *F_Hb[FQL_MAXL], *F_Zb[FQL_MAXL], *E_Hb[FQL_MAXL];
   void *C_Hb[FQL_MAXL];        // bf16 post-LN activations of the grouped critic pass [3][S][2][B][H]
+  void *C_XHb[FQL_MAXL], *C_DGb[FQL_MAXL];  // large-batch backward: bf16 xhat and gelu' of the same pass
   void *O_dZb[FQL_MAXL], *F_dZb[FQL_MAXL], *O_dOutb, *F_dOutb;
   float *O_dZf[FQL_MAXL], *F_dZf[FQL_MAXL];
   void *C1_dZb[FQL_MAXL], *C1_dOutb, *C2_dZb[FQL_MAXL], *C2_dOutb;
@@ -154,7 +155,28 @@ struct TcChainSpec {
   const float* a0;
   float* target;
   int clip_out;
+  void* const* DGb;  // chain2 only: save bf16 gelu'(z) per hidden layer instead of the pre-activations (large-batch backward)
+  void* const* XHb;  // chain2 + LayerNorm only: save bf16 xhat per hidden layer instead of the normalised activations
+  int save_mask;     // chain2 only: bit p set = problem p writes its saves (0 = all)
 };
+// chain2_tc.cu: the whole input-gradient chain of one network's backward, one launch.  Every pointer is already offset to the
+// first row of the problem; rows of group (s, e) start at ((s * ens + e) * Mcap + r0).
+struct TcChain2BwdSpec {
+  const FqlDims* d;
+  const Layout* L;
+  int net;
+  const float* params;   // LayerNorm scales
+  const void* shadow;
+  const void* dOutb;     // bf16 [S][ens][M][64]: dL/d(output), zero padded
+  int M, Mcap, r0;       // rows per group, row capacity per group and first row of the forward's saves
+  int Mcap_dz;           // row capacity per group of dZb / dX0 (0: M)
+  void* const* DGb;      // bf16 gelu'(z_l)           [S][ens][Mcap][H] per hidden layer
+  void* const* XHb;      // bf16 xhat_l (LayerNorm)
+  float* const* rstd;    // fp32 [S][ens][Mcap]   (LayerNorm)
+  void* const* dZb;      // out (optional): bf16 dZ_l [S][ens][Mcap_dz][H] -- operands of the weight gradients
+  float* dX0;            // out (optional): fp32 [S][ens][Mcap_dz][K0] input gradient
+};
+int tc_mlp_chain2_backward(const TcChain2BwdSpec& f, cudaStream_t st);
 int tc_supported(const FqlDims* d);
 int64_t tc_shadow_seed_elems(const FqlDims* d, const Layout& L);
 int tc_refresh_shadow(const FqlDims* d, const Layout& L, const float* params, void* shadow, cudaStream_t st);
@@ -165,7 +187,7 @@ int tc_mlp_chain2_supported(const FqlDims* d);
 int tc_mlp_chain2(const TcChainSpec& f, cudaStream_t st);
 
 // tc_gemm.cu -- generic tcgen05 GEMM (one Dense layer: forward / dgrad / wgrad)
-enum { TC_MODE_STORE_F32 = 0, TC_MODE_FWD_HIDDEN = 1, TC_MODE_DGRAD_GELU = 2, TC_MODE_EULER = 3 };
+enum { TC_MODE_STORE_F32 = 0, TC_MODE_FWD_HIDDEN = 1, TC_MODE_DGRAD_GELU = 2, TC_MODE_EULER = 3, TC_MODE_WGRAD_LN = 4 };
 struct TcOperand {   // bf16 tensor [g1][g0][rows][inner] with pitches ld / s0 / s1 (elements)
   const void* ptr;
   int inner, rows;
@@ -187,8 +209,12 @@ struct TcGemmSpec {
   int mode;
   TcPtr bias, out_f, out_h, out_z, zin, act, xb, target;
   int F, Adim, step, n_steps, clip;
+  int ksplit;        // > 1: split K over CTAs, partial tiles ADDED into a zeroed fp32 output (STORE_F32 / WGRAD_LN)
+  TcPtr ln_s, ln_b, dbias, wmaster, dln_s, dln_b;   // TC_MODE_WGRAD_LN: LayerNorm scale / bias [M], db [N], fp32 weights [M][N], out dgamma / dbeta [M]
   void* dbg;  // optional device buffer for per-CTA timestamps
 };
+// column sums over rows of a bf16 tensor [G][M][N] ADDED into fp32 out[g * out_stride + n] (bias gradients from the bf16 dZ saves)
+int launch_colsum_bf16(const void* X, int64_t G, int64_t M, int N, float* out, int64_t out_stride_g0, int G0, int64_t out_stride_g1, cudaStream_t st);
 int tc_gemm(const TcGemmSpec& s, cudaStream_t st);
 
 // tc_path.cu -- layer-by-layer tensor-core schedules
@@ -238,6 +264,9 @@ int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* co
                       cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev, bool dOutb_ready = false);
 int tc_critic_backward(const TcCritic& t, cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev);
 int tc_critic_forward(const TcCritic& t, int net, float* out, cudaStream_t st);
+// large-batch backward: one chain2 launch per network + split-K weight gradients (tc_path.cu)
+int tc_actor_backward_big(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], bool dOutb_ready, cudaStream_t st);
+int tc_critic_backward_big(const TcCritic& t, void* const* XHb, void* const* DGb, cudaStream_t st);
 
 // euler_cluster.cu -- compute_flow_actions as one persistent thread-block-cluster kernel (hidden = 512)
 struct TcEulerSpec {

@@ -54,6 +54,8 @@ struct TcGemmArgs {
   GPtrB xb;      // bf16 [M][ld]   first-layer operand whose action/time columns the Euler step rewrites
   GPtrB target;  // fp32 [M][A]
   int F, A, step, n_steps, clip;
+  int ksplit;    // > 1: the K range is split over blockIdx.z, partial tiles are added into a zeroed fp32 output (red.global.add)
+  GPtrB ln_s, ln_b, dbias, wmaster, dln_s, dln_b;   // TC_MODE_WGRAD_LN (see the epilogue)
   unsigned long long* dbg;  // optional [CTA][8] globaltimer stamps (diagnostics)
 };
 
@@ -100,8 +102,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int g0 = blockIdx.z % a.G0, g1 = blockIdx.z / a.G0;
-  const int nkb = (a.K + BK - 1) / BK;
+  const int zg = blockIdx.z / a.ksplit, kz = blockIdx.z % a.ksplit;
+  const int g0 = zg % a.G0, g1 = zg / a.G0;
+  const int nkb_all = (a.K + BK - 1) / BK;
+  const int kb0 = (int)((long long)nkb_all * kz / a.ksplit), kb1 = (int)((long long)nkb_all * (kz + 1) / a.ksplit);
+  const int nkb = kb1 - kb0;   // this CTA's K blocks [kb0, kb1)
   unsigned long long* dbg = a.dbg ? a.dbg + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = gtime();
 
@@ -135,14 +140,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         uint8_t* sa = smem + st * STAGE;
         uint8_t* sb = sa + A_STAGE;
         mbar_expect_tx(&full[st], STAGE);
+        const int kc = (kb0 + kb) * BK;
         if (!a.a_mn) {
-          tma_load_4d(sa, &mapA, &full[st], kb * BK, m0, ga0, g1);
+          tma_load_4d(sa, &mapA, &full[st], kc, m0, ga0, g1);
         } else {
-          tma_load_4d(sa, &mapA, &full[st], m0, kb * BK, ga0, g1);
-          tma_load_4d(sa + A_STAGE / 2, &mapA, &full[st], m0 + 64, kb * BK, ga0, g1);
+          tma_load_4d(sa, &mapA, &full[st], m0, kc, ga0, g1);
+          tma_load_4d(sa + A_STAGE / 2, &mapA, &full[st], m0 + 64, kc, ga0, g1);
         }
-        if (!a.b_mn) tma_load_4d(sb, &mapB, &full[st], kb * BK, n0, gb0, g1);
-        else tma_load_4d(sb, &mapB, &full[st], n0, kb * BK, gb0, g1);
+        if (!a.b_mn) tma_load_4d(sb, &mapB, &full[st], kc, n0, gb0, g1);
+        else tma_load_4d(sb, &mapB, &full[st], n0, kc, gb0, g1);
       }
     }
   } else if (warp <= NACC) {
@@ -200,9 +206,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]) + ((bias && nb + i < a.N) ? bias[nb + i] : 0.f);
-      if constexpr (MODE == TC_MODE_STORE_F32) {
+      if constexpr (MODE == TC_MODE_WGRAD_LN) {
+        // Weight gradient of a Dense layer that follows a LayerNorm, from G = xhat^T dZ (this tile, this K split):
+        //   h = gamma * xhat + beta   =>   dW[m][n] = gamma_m G[m][n] + beta_m db[n]        (db = column sums of dZ, already reduced)
+        //   dgamma_m = sum_n W[m][n] G[m][n],   dbeta_m = sum_n W[m][n] db[n]              (the LayerNorm parameter gradients:
+        //   sum_rows dH * xhat and sum_rows dH with dH = dZ W^T, re-associated so that no dH ever exists in HBM)
+        const float gam = a.ln_s.at<const float>(g0, g1)[m], bet = a.ln_b.at<const float>(g0, g1)[m];
+        const float* db = a.dbias.at<const float>(g0, g1);
+        const float* wrow = a.wmaster.at<const float>(g0, g1) + (int64_t)m * a.out_f.ld + nb;
         float* o = a.out_f.at<float>(g0, g1) + (int64_t)m * a.out_f.ld + nb;
-        if (nb + 32 <= a.N && (a.out_f.ld & 3) == 0) {
+        float dg = 0.f, dbt = 0.f;
+        const bool vec = (nb + 32 <= a.N) && ((a.out_f.ld & 3) == 0);
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          if (nb + i < a.N) {
+            const float gacc = __uint_as_float(r[i]);    // no bias in this mode: v[] == the accumulator
+            const float w = vec ? __ldg(wrow + i) : wrow[i];
+            const float dbn = db[nb + i];
+            dg = fmaf(w, gacc, dg);
+            if (kz == 0) dbt = fmaf(w, dbn, dbt);
+            atomicAdd(o + i, gam * gacc + (kz == 0 ? bet * dbn : 0.f));
+          }
+        }
+        atomicAdd(a.dln_s.at<float>(g0, g1) + m, dg);
+        if (kz == 0) atomicAdd(a.dln_b.at<float>(g0, g1) + m, dbt);
+      } else if constexpr (MODE == TC_MODE_STORE_F32) {
+        float* o = a.out_f.at<float>(g0, g1) + (int64_t)m * a.out_f.ld + nb;
+        if (a.ksplit > 1) {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (nb + i < a.N) atomicAdd(o + i, v[i]);
+        } else if (nb + 32 <= a.N && (a.out_f.ld & 3) == 0) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float4 w4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -327,6 +361,17 @@ int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
   a.bias = gp(s.bias); a.out_f = gp(s.out_f); a.out_h = gp(s.out_h); a.out_z = gp(s.out_z); a.zin = gp(s.zin);
   a.act = gp(s.act); a.xb = gp(s.xb); a.target = gp(s.target);
   a.F = s.F; a.A = s.Adim; a.step = s.step; a.n_steps = s.n_steps; a.clip = s.clip;
+  a.ksplit = s.ksplit > 1 ? s.ksplit : 1;
+  {
+    const int nkb_all = (s.K + BK - 1) / BK;
+    if (a.ksplit > nkb_all) a.ksplit = nkb_all;
+  }
+  FQL_REQUIRE(a.ksplit == 1 || s.mode == TC_MODE_STORE_F32 || s.mode == TC_MODE_WGRAD_LN, "tc_gemm: split-K needs an accumulating fp32 epilogue");
+  FQL_REQUIRE(!(a.ksplit > 1 && s.bias.base), "tc_gemm: split-K with a bias");
+  a.ln_s = gp(s.ln_s); a.ln_b = gp(s.ln_b); a.dbias = gp(s.dbias); a.wmaster = gp(s.wmaster); a.dln_s = gp(s.dln_s); a.dln_b = gp(s.dln_b);
+  if (s.mode == TC_MODE_WGRAD_LN)
+    FQL_REQUIRE(s.ln_s.base && s.ln_b.base && s.dbias.base && s.wmaster.base && s.dln_s.base && s.dln_b.base && s.out_f.base && !s.bias.base,
+                "tc_gemm: TC_MODE_WGRAD_LN needs the LayerNorm parameters, db, the master weights and zeroed outputs");
   a.dbg = reinterpret_cast<unsigned long long*>(s.dbg);
   if (s.mode == TC_MODE_FWD_HIDDEN || s.mode == TC_MODE_DGRAD_GELU)
     FQL_REQUIRE(s.N % 64 == 0 && s.out_h.base, "tc_gemm: hidden/dgrad epilogues need N %% 64 == 0 and a bf16 output");
@@ -339,6 +384,7 @@ int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
     case TC_MODE_FWD_HIDDEN: kern = tc_gemm_kernel<TC_MODE_FWD_HIDDEN>; break;
     case TC_MODE_DGRAD_GELU: kern = tc_gemm_kernel<TC_MODE_DGRAD_GELU>; break;
     case TC_MODE_EULER: kern = tc_gemm_kernel<TC_MODE_EULER>; break;
+    case TC_MODE_WGRAD_LN: kern = tc_gemm_kernel<TC_MODE_WGRAD_LN>; break;
     default: FQL_REQUIRE(false, "tc_gemm: unknown epilogue mode %d", s.mode);
   }
   static bool attr_set[FQL_MAX_DEVICES][8] = {};
@@ -347,7 +393,7 @@ int tc_gemm(const TcGemmSpec& s, cudaStream_t st) {
     FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set[dev][s.mode & 7] = true;
   }
-  dim3 grid((s.N + BN - 1) / BN, (s.M + BM - 1) / BM, a.G0 * a.G1);
+  dim3 grid((s.N + BN - 1) / BN, (s.M + BM - 1) / BM, a.G0 * a.G1 * a.ksplit);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;

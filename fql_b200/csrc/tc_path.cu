@@ -191,7 +191,43 @@ __global__ void gelu_bwd_bf16_kernel(const float* __restrict__ dH, const float* 
   dZb[i] = __float2bfloat16(v);
 }
 
+// Column sums over rows of a bf16 tensor [G][M][N] (N % 64 == 0), ADDED into fp32 out (zeroed by the caller): bias gradients from
+// the bf16 dZ saves of the large-batch backward.  grid (N / 64, row chunks, G); a warp reads 128 contiguous bytes of one row.
+constexpr int CS_ROWS = 512;
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ X, int64_t M, int N, float* __restrict__ out, int64_t os0, int G0,
+                                                          int64_t os1) {
+  const int g = blockIdx.z, g0 = g % G0, g1 = g / G0;
+  const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+  const int rl = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS, r1 = (r0 + CS_ROWS < M) ? r0 + CS_ROWS : M;
+  const bf16* x = X + (int64_t)g * M * N + c;
+  float a0 = 0.f, a1 = 0.f;
+  for (int64_t r = r0 + rl; r < r1; r += 8) {
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + r * N);
+    a0 += __low2float(v);
+    a1 += __high2float(v);
+  }
+  __shared__ float sh[8][64];
+  sh[rl][(threadIdx.x & 31) * 2] = a0;
+  sh[rl][(threadIdx.x & 31) * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += sh[i][threadIdx.x];
+    atomicAdd(out + g0 * os0 + g1 * os1 + blockIdx.x * 64 + threadIdx.x, t);
+  }
+}
+
 }  // namespace
+
+int launch_colsum_bf16(const void* X, int64_t G, int64_t M, int N, float* out, int64_t out_stride_g0, int G0, int64_t out_stride_g1, cudaStream_t st) {
+  FQL_REQUIRE(N % 64 == 0 && G >= 1 && M >= 1, "launch_colsum_bf16: N=%d", N);
+  dim3 grid(N / 64, (unsigned)((M + CS_ROWS - 1) / CS_ROWS), (unsigned)G);
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(X), M, N, out, out_stride_g0, G0, out_stride_g1);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // actor forward (optionally one Euler step: the last layer's epilogue applies a += v/n and rewrites the operand tile)
@@ -509,6 +545,160 @@ int tc_critic_forward(const TcCritic& t, int net, float* out, cudaStream_t st) {
       g.out_f = tp(out + prow, Mcap, (long long)E * Mcap, 1);
       FQL_TRY(tc_gemm(g, st));
     }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Large-batch backward (seeds x 128-row tiles fill the GPU): the whole input-gradient chain is ONE chain2 launch per network
+// reading the forward's bf16 gelu' (/ xhat / rstd) saves; bias gradients are column sums of the bf16 dZ saves; weight gradients are
+// split-K tc_gemm launches (LayerNorm networks: TC_MODE_WGRAD_LN on the xhat saves, which also yields the LayerNorm parameter
+// gradients).  No fp32 dH / dZ tensor, no LayerNorm row kernel and no per-layer dgrad launch remains.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void zero2d_kernel(float* __restrict__ p, int64_t n, int64_t stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[(int64_t)blockIdx.y * stride + i] = 0.f;
+}
+int zero_leaf(float* p, int64_t n, int64_t stride, int count, cudaStream_t st) {
+  zero2d_kernel<<<dim3((unsigned)((n + 255) / 256), count), 256, 0, st>>>(p, n, stride);
+  FQL_CHECK_LAUNCH();
+  return 0;
+}
+// K splits that bring a weight-gradient GEMM to about two CTAs per SM
+int wgrad_ksplit(int Mw, int N, int groups, int K) {
+  const int base = ((Mw + 127) / 128) * ((N + 63) / 64) * groups;
+  int ks = 296 / (base > 0 ? base : 1);
+  const int nkb = (K + 63) / 64;
+  if (ks > nkb / 4) ks = nkb / 4;     // at least four K blocks per CTA
+  return ks < 1 ? 1 : ks;
+}
+}  // namespace
+
+int tc_actor_backward_big(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], bool dOutb_ready, cudaStream_t st) {
+  const FqlDims* d = t.d;
+  const Layout& L = *t.L;
+  const NetView& nv = L.net[t.net];
+  const int H = d->hidden, NL = nv.n_layers, S = d->num_seeds, A = nv.out_dim;
+  const long long dz_ss = (long long)t.M * H;
+  FQL_REQUIRE(!nv.ln && nv.ens == 1, "tc_actor_backward_big: actor networks only");
+  if (!dOutb_ready) FQL_TRY(tc_pad_bf16(dOut, dOutb, (int64_t)S * t.M, A, 64, st));
+  TcChain2BwdSpec b;
+  memset(&b, 0, sizeof(b));
+  b.d = d; b.L = &L; b.net = t.net; b.params = t.params; b.shadow = t.shadow; b.dOutb = dOutb;
+  b.M = t.M; b.Mcap = (int)(t.h_ss / H); b.r0 = 0; b.Mcap_dz = t.M;
+  b.DGb = t.Zb;                 // the forward saved gelu'(z) in the pre-activation buffers
+  b.dZb = dZb;
+  FQL_TRY(tc_mlp_chain2_backward(b, st));
+  // bias gradients
+  {
+    ColSumArgs c;
+    memset(&c, 0, sizeof(c));
+    c.P = 1; c.S = S; c.E = 1; c.M = t.M; c.N = A; c.ld = A;
+    c.X.base[0] = dOut; c.X.stride_s = (long long)t.M * A;
+    c.out.base[0] = t.grads + nv.off_b[NL - 1]; c.out.stride_s = L.arena;
+    FQL_TRY(launch_colsum(c, st, t.cs_scratch, t.cs_scratch ? 65536 : 0));
+  }
+  for (int l = 0; l + 1 < NL; l++) {
+    FQL_TRY(zero_leaf(t.grads + nv.off_b[l], H, L.arena, S, st));
+    FQL_TRY(launch_colsum_bf16(dZb[l], S, t.M, H, t.grads + nv.off_b[l], 0, 1, L.arena, st));
+  }
+  // weight gradients dW_l = A_l^T dZ_l
+  for (int l = 0; l < NL; l++) {
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.K = t.M; g.G0 = 1; g.G1 = S; g.a_mn = 1; g.b_mn = 1; g.mode = TC_MODE_STORE_F32;
+    if (l == 0) g.A = op(t.X0b, t.K0pad, t.M, t.K0pad, 1, 0, S, t.x_ss);
+    else g.A = op(t.Hb[l - 1], H, t.M, H, 1, 0, S, t.h_ss);
+    if (l == NL - 1) {
+      g.M = H; g.N = A;
+      g.B = op(dOutb, 64, t.M, 64, 1, 0, S, (long long)t.M * 64);
+    } else {
+      g.M = nv.k_of(l); g.N = H;
+      g.B = op(dZb[l], H, t.M, H, 1, 0, S, dz_ss);
+    }
+    g.out_f = tp(t.grads + nv.off_w[l], 0, L.arena, g.N);
+    g.ksplit = wgrad_ksplit(g.M, g.N, S, g.K);
+    if (g.ksplit > 1) FQL_TRY(zero_leaf(t.grads + nv.off_w[l], (int64_t)g.M * g.N, L.arena, S, st));
+    FQL_TRY(tc_gemm(g, st));
+  }
+  return 0;
+}
+
+// Critic (2 heads, LayerNorm) on the saves of problem t.p of the grouped forward.
+//   grads != NULL: critic-loss backward (agents/fql.py:36-37): every parameter gradient of the critic
+//   grads == NULL: input gradient only with the stored parameters (actor Q loss, agents/fql.py:70) -> dX0 [S][2][M][K0]
+int tc_critic_backward_big(const TcCritic& t, void* const* XHb, void* const* DGb, cudaStream_t st) {
+  const FqlDims* d = t.d;
+  const Layout& L = *t.L;
+  const NetView& nv = L.net[FQL_NET_CRITIC];
+  const int H = d->hidden, NL = nv.n_layers, S = d->num_seeds, E = 2, M = t.M, K0 = nv.in_dim;
+  FQL_REQUIRE(nv.ln, "tc_critic_backward_big: built for the LayerNorm critic (config['layer_norm'] = True)");
+  const int64_t Mcap = t.buf->Mcap;
+  const int64_t prow = (int64_t)t.p * S * E * Mcap;   // first row of the problem inside the grouped pass buffers
+  const long long z_se = Mcap * H, z_ss = (long long)E * Mcap * H;
+  const long long dz_se = (long long)M * H, dz_ss = (long long)E * M * H;
+  FQL_TRY(tc_pad_bf16(t.dOut, t.dOutb, (int64_t)S * E * M, 1, 64, st));
+  void* xh[FQL_MAXL] = {};
+  void* dg[FQL_MAXL] = {};
+  float* rs[FQL_MAXL] = {};
+  for (int l = 0; l + 1 < NL; l++) {
+    xh[l] = reinterpret_cast<bf16*>(XHb[l]) + prow * H;
+    dg[l] = reinterpret_cast<bf16*>(DGb[l]) + prow * H;
+    rs[l] = t.buf->rstd[l] + prow;
+  }
+  TcChain2BwdSpec b;
+  memset(&b, 0, sizeof(b));
+  b.d = d; b.L = &L; b.net = FQL_NET_CRITIC; b.params = t.params; b.shadow = t.shadow; b.dOutb = t.dOutb;
+  b.M = M; b.Mcap = (int)Mcap; b.r0 = 0; b.Mcap_dz = M;
+  b.DGb = dg; b.XHb = xh; b.rstd = rs;
+  b.dZb = t.grads ? t.dZb : nullptr;
+  b.dX0 = t.dX0;
+  FQL_TRY(tc_mlp_chain2_backward(b, st));
+  if (!t.grads) return 0;
+  // bias gradients: last layer from the fp32 dQ, hidden layers from the bf16 dZ saves
+  {
+    ColSumArgs c;
+    memset(&c, 0, sizeof(c));
+    c.P = 1; c.S = S; c.E = E; c.M = M; c.N = 1; c.ld = 1;
+    c.X.base[0] = t.dOut; c.X.stride_s = (long long)E * M; c.X.stride_e = M;
+    c.out.base[0] = t.grads + nv.off_b[NL - 1]; c.out.stride_s = L.arena; c.out.stride_e = 1;
+    FQL_TRY(launch_colsum(c, st, t.cs_scratch, t.cs_scratch ? 65536 : 0));
+  }
+  for (int l = 0; l + 1 < NL; l++) {
+    FQL_TRY(zero_leaf(t.grads + nv.off_b[l], (int64_t)E * H, L.arena, S, st));
+    FQL_TRY(launch_colsum_bf16(t.dZb[l], (int64_t)S * E, M, H, t.grads + nv.off_b[l], H, E, L.arena, st));
+    FQL_TRY(zero_leaf(t.grads + nv.off_lns[l], (int64_t)E * H, L.arena, S, st));
+    FQL_TRY(zero_leaf(t.grads + nv.off_lnb[l], (int64_t)E * H, L.arena, S, st));
+  }
+  for (int l = 0; l < NL; l++) {
+    const bool last = (l == NL - 1);
+    const void* dzb = last ? t.dOutb : t.dZb[l];
+    const int dz_inner = last ? 64 : H;
+    const long long dzb_se = (long long)M * dz_inner, dzb_ss = (long long)E * M * dz_inner;
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.M = nv.k_of(l); g.N = nv.n_of(l); g.K = M; g.G0 = E; g.G1 = S; g.a_mn = 1; g.b_mn = 1;
+    g.B = op(dzb, dz_inner, M, dz_inner, E, dzb_se, S, dzb_ss);
+    g.out_f = tp(t.grads + nv.off_w[l], (long long)nv.k_of(l) * nv.n_of(l), L.arena, nv.n_of(l));
+    g.ksplit = wgrad_ksplit(g.M, g.N, S * E, g.K);
+    if (l == 0) {
+      g.A = op(t.X0b, t.K0pad, M, t.K0pad, 1, 0, S, t.x_ss);  // input shared by both heads
+      g.mode = TC_MODE_STORE_F32;
+      if (g.ksplit > 1) FQL_TRY(zero_leaf(t.grads + nv.off_w[l], (int64_t)E * K0 * H, L.arena, S, st));
+    } else {
+      // h_{l-1} = gamma * xhat + beta feeds this layer: G = xhat^T dZ_l, transformed in the epilogue (tc_gemm.cu)
+      g.A = op(xh[l - 1], H, M, H, E, z_se, S, z_ss);
+      g.mode = TC_MODE_WGRAD_LN;
+      g.ln_s = tp(t.params + nv.off_lns[l - 1], H, L.arena, 0);
+      g.ln_b = tp(t.params + nv.off_lnb[l - 1], H, L.arena, 0);
+      g.dbias = tp(t.grads + nv.off_b[l], nv.n_of(l), L.arena, 0);
+      g.wmaster = tp(t.params + nv.off_w[l], (long long)H * nv.n_of(l), L.arena, 0);
+      g.dln_s = tp(t.grads + nv.off_lns[l - 1], H, L.arena, 0);
+      g.dln_b = tp(t.grads + nv.off_lnb[l - 1], H, L.arena, 0);
+      FQL_TRY(zero_leaf(t.grads + nv.off_w[l], (int64_t)E * H * nv.n_of(l), L.arena, S, st));
+    }
+    FQL_TRY(tc_gemm(g, st));
   }
   return 0;
 }

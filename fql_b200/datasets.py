@@ -4,6 +4,11 @@ numpy MT19937 (randint(size, B) -> [rand() -> randint(0, 7, (B,2))]), so sampled
 to the reference given the same np.random.seed.  The arrays live in HBM; the fancy-index gather, frame stacking and
 edge-padded crop run as CUDA kernels (fql_gather_rows / fql_gather_frames) and the batch never visits the host.
 No CPU path: the gather is always the CUDA kernel.
+
+`sample` leaves the step: the index upload (a ring of pinned staging buffers, never waited on until it wraps) and the gather
+kernels are enqueued on the dataset's own stream, so the batch of update k+1 is assembled while update k is still running; the
+caller's stream only waits (on the device) for the event behind the gathers.  The host never blocks and the RNG draw order is
+untouched (nothing is drawn ahead of the reference's call order).
 """
 from __future__ import annotations
 
@@ -34,7 +39,8 @@ class Dataset:
         self.terminal_locs = np.nonzero(term > 0)[0]                               # datasets.py:61
         self.initial_locs = np.concatenate([[0], self.terminal_locs[:-1] + 1])     # datasets.py:62
         self._lib = _lib.lib()
-        self._idx_pin = None
+        self._pins, self._pin_i = [], 0
+        self._side = None            # the sampler's own stream (created on first use)
 
     @classmethod
     def create(cls, freeze=True, device=None, **fields):
@@ -50,18 +56,27 @@ class Dataset:
         return np.random.randint(self.size, size=num_idxs)                          # datasets.py:66
 
     # -- device helpers ------------------------------------------------------------------------------------
+    _PIN_RING = 16
+
     def _to_dev(self, arr):
+        """int64 indices -> device through the next slot of a ring of pinned staging buffers: a slot is only waited on when the
+        ring wraps around to a copy that has not run yet (the host may be many steps ahead of the GPU)."""
         t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64))
         n = t.numel()
-        if self._idx_pin is None or self._idx_pin.numel() < n:
-            self._idx_pin = torch.empty(max(n, 4096), dtype=torch.int64).pin_memory()
-            self._pin_ev = torch.cuda.Event()
-        else:
-            self._pin_ev.synchronize()  # the previous async copy out of this staging buffer must be done
-        self._idx_pin[:n].copy_(t.reshape(-1))
+        i = self._pin_i % self._PIN_RING
+        self._pin_i += 1
+        if i >= len(self._pins):
+            self._pins.append([torch.empty(max(n, 4096), dtype=torch.int64).pin_memory(), torch.cuda.Event(), False])
+        slot = self._pins[i]
+        if slot[2]:
+            slot[1].synchronize()
+        if slot[0].numel() < n:
+            slot[0] = torch.empty(n, dtype=torch.int64).pin_memory()
+        slot[0][:n].copy_(t.reshape(-1))
         d = torch.empty(t.shape, dtype=torch.int64, device=self.device)
-        d.reshape(-1).copy_(self._idx_pin[:n], non_blocking=True)
-        self._pin_ev.record(torch.cuda.current_stream(self.device))
+        d.reshape(-1).copy_(slot[0][:n], non_blocking=True)
+        slot[1].record(torch.cuda.current_stream(self.device))
+        slot[2] = True
         return d
 
     def _stream(self):
@@ -89,7 +104,11 @@ class Dataset:
         if idxs is None:
             idxs = self.get_random_idxs(batch_size)
         idxs = np.asarray(idxs)
-        with torch.cuda.device(self.device):
+        caller = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._done = torch.cuda.Event()
+        with torch.cuda.device(self.device), torch.cuda.stream(self._side):
             idx_dev = self._to_dev(idxs)
             obs = self._dev['observations']
             is_img = obs.dim() == 4
@@ -107,7 +126,11 @@ class Dataset:
                 batch['observations'], batch['next_observations'] = self._frames(idx_dev, init_dev, crop, len(idxs))
             elif self.frame_stack is not None:
                 batch['observations'], batch['next_observations'] = self._stack_state(idxs, initial_state_idxs, idx_dev)
-            return batch
+            self._done.record(self._side)
+        caller.wait_event(self._done)          # device-side: the consumer's stream runs behind the gathers, the host does not wait
+        for v in batch.values():
+            v.record_stream(caller)            # the caching allocator must not recycle a batch the caller's stream still reads
+        return batch
 
     def augment(self, batch, keys):
         raise NotImplementedError('augmentation is fused into sample(): set p_aug (datasets.py:88-91)')

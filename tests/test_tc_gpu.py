@@ -128,6 +128,7 @@ SWITCHES = [
     dict(FQL_B200_CLUSTER_FWD='0', FQL_B200_CLUSTER_BWD='0'),         # one-step actor layer by layer
     dict(FQL_B200_EULER_CLUSTER='0'),                                 # Euler integration layer by layer (tc_gemm Euler epilogue)
     dict(FQL_B200_CHAIN_MIN_TILES='1'),                               # large-batch routing: fused per-tile chain kernels everywhere
+    dict(FQL_B200_CHAIN_MIN_TILES='1', FQL_B200_BIG_BWD='0'),         # ... with the per-layer backward (tc_gemm + LayerNorm row kernels)
     dict(FQL_B200_CHAIN_MIN_TILES='1', FQL_B200_CHAIN2='0'),          # ... with the non-overlapped chain kernel (mlp_tc.cu)
     dict(FQL_B200_CHAIN_MIN_TILES='1', FQL_B200_CHAIN2_W3D='0'),      # ... with four 2-D weight boxes per stage instead of one 3-D box
     dict(FQL_B200_SPLIT_ADAM='1'),
