@@ -151,15 +151,18 @@ __device__ float dp_sum_over_ranks(const DpLamArgs& l, int s, int S, float mine)
 }
 
 __global__ void critic_post_kernel(StepShape sh, FqlHparams hp, FqlBatch b, WsPtrs w, float* raw, int parts, DpLamArgs dpl) {
+  // grid (S, nc): CTA c of seed s reduces rows c, c + nc, ... ; the partial sums of the nc CTAs are combined in CTA order by the
+  // last one to finish (ticket counter), so the result does not depend on scheduling
   __shared__ float red[32];
-  const int s = blockIdx.x;
+  __shared__ int s_last;
+  const int s = blockIdx.x, cta = blockIdx.y, nc = gridDim.y;
   const int B = sh.B, S = sh.S;
   const float* q_t = w.C_out + ((int64_t)(0 * S + s) * 2) * B;
   const float* q_c = w.C_out + ((int64_t)(1 * S + s) * 2) * B;
   const float* q_p = w.C_out + ((int64_t)(2 * S + s) * 2) * B;
   const float inv_2gb = 1.0f / (2.0f * (float)sh.GB);
   float sq = 0.f, qs = 0.f, qmx = -INFINITY, qmn = INFINITY, ps = 0.f, pa = 0.f;
-  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+  for (int r = cta * blockDim.x + threadIdx.x; r < B; r += nc * blockDim.x) {
     if (parts & 1) {
       const float t0 = q_t[r], t1 = q_t[B + r];
       const float nq = sh.q_agg_min ? fminf(t0, t1) : (t0 + t1) * 0.5f;
@@ -181,33 +184,56 @@ __global__ void critic_post_kernel(StepShape sh, FqlHparams hp, FqlBatch b, WsPt
       pa += fabsf(qp);
     }
   }
-  float* rw = raw + s * FQL_NUM_RAW;
+  // per-CTA partials: [half][S][64][4]
+  float* part1 = w.cpost_part + ((int64_t)(0 * S + s) * 64 + cta) * 4;
+  float* part2 = w.cpost_part + ((int64_t)(1 * S + s) * 64 + cta) * 4;
   if (parts & 1) {
     sq = block_reduce<0>(sq, red);
     qs = block_reduce<0>(qs, red);
     qmx = block_reduce<1>(qmx, red);
     qmn = -block_reduce<1>(-qmn, red);
-    if (threadIdx.x == 0) {
-      rw[RAW_CRITIC_SQ] = sq; rw[RAW_Q_SUM] = qs; rw[RAW_Q_MAX] = qmx; rw[RAW_Q_NEGMIN] = -qmn;
-    }
+    if (threadIdx.x == 0) { part1[0] = sq; part1[1] = qs; part1[2] = qmx; part1[3] = -qmn; }
   }
   if (parts & 2) {
     ps = block_reduce<0>(ps, red);
     pa = block_reduce<0>(pa, red);
+    if (threadIdx.x == 0) { part2[0] = ps; part2[1] = pa; }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int* ticket = w.cpost_ticket + ((parts & 3) - 1) * S + s;      // one counter per (call variant, seed)
+    const int t = atomicAdd(ticket, 1);
+    s_last = (t == nc - 1);
+    if (s_last) *ticket = 0;                                        // ready for the next step
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float* rw = raw + s * FQL_NUM_RAW;
+  if ((parts & 1) && threadIdx.x == 0) {
+    float a0 = 0.f, a1 = 0.f, a2 = -INFINITY, a3 = -INFINITY;
+    for (int c = 0; c < nc; c++) {
+      const float* p = w.cpost_part + ((int64_t)(0 * S + s) * 64 + c) * 4;
+      a0 += __ldcg(p); a1 += __ldcg(p + 1); a2 = fmaxf(a2, __ldcg(p + 2)); a3 = fmaxf(a3, __ldcg(p + 3));
+    }
+    rw[RAW_CRITIC_SQ] = a0; rw[RAW_Q_SUM] = a1; rw[RAW_Q_MAX] = a2; rw[RAW_Q_NEGMIN] = a3;
+  }
+  if (parts & 2) {
+    __shared__ float s_pa;
     if (threadIdx.x == 0) {
-      rw[RAW_QPI_SUM] = ps; rw[RAW_QPI_ABS] = pa;
-    }
-    // lam = 1/mean|q| over the GLOBAL batch, stop-gradient (fql.py:74-76): data-parallel ranks exchange their sums here
-    float lam = 1.0f;
-    if (sh.normalize_q_loss) {
-      if (dpl.world > 1) {
-        __shared__ float s_pa;
-        if (threadIdx.x == 0) s_pa = dp_sum_over_ranks(dpl, s, sh.S, pa);
-        __syncthreads();
-        pa = s_pa;
+      float a0 = 0.f, a1 = 0.f;
+      for (int c = 0; c < nc; c++) {
+        const float* p = w.cpost_part + ((int64_t)(1 * S + s) * 64 + c) * 4;
+        a0 += __ldcg(p); a1 += __ldcg(p + 1);
       }
-      lam = 1.0f / (pa / (float)sh.GB);
+      rw[RAW_QPI_SUM] = a0; rw[RAW_QPI_ABS] = a1;
+      // lam = 1/mean|q| over the GLOBAL batch, stop-gradient (fql.py:74-76): data-parallel ranks exchange their sums here
+      if (sh.normalize_q_loss && dpl.world > 1) a1 = dp_sum_over_ranks(dpl, s, sh.S, a1);
+      s_pa = a1;
     }
+    __syncthreads();
+    float lam = 1.0f;
+    if (sh.normalize_q_loss) lam = 1.0f / (s_pa / (float)sh.GB);
     const float dqs = -lam * inv_2gb;
     for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) w.dqs[(int64_t)s * 2 * B + i] = dqs;
   }
@@ -340,7 +366,9 @@ int launch_critic_post(const StepShape& sh, const FqlHparams& hp, const FqlBatch
   DpLamArgs l;
   memset(&l, 0, sizeof(l));
   if (dpl) l = *dpl;
-  critic_post_kernel<<<sh.S, 1024, 0, st>>>(sh, hp, b, w, raw, parts, l);
+  int nc = (sh.B + 2047) / 2048;
+  nc = nc < 1 ? 1 : (nc > 64 ? 64 : nc);
+  critic_post_kernel<<<dim3(sh.S, nc), 1024, 0, st>>>(sh, hp, b, w, raw, parts, l);
   FQL_CHECK_LAUNCH();
   return 0;
 }

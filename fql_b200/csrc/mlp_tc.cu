@@ -394,14 +394,19 @@ __global__ void shadow_lastlayer_kernel(const float* __restrict__ params, __nv_b
   shadow[(int64_t)s * shadow_seed + base + i] = __float2bfloat16(val);
 }
 
-// bf16 first-layer operands [rows][K0pad] from fp32 [rows][K0] (zero padded)
+// bf16 first-layer operands [rows][K0pad] from fp32 [rows][K0] (zero padded): one thread per 8 output columns (one 16-byte store)
 __global__ void pad_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t rows, int K0, int K0pad) {
   FQL_PDL_SYNC();
+  const int per_row = K0pad >> 3;             // K0pad is a multiple of 64
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * K0pad) return;
-  const int64_t r = i / K0pad;
-  const int c = (int)(i % K0pad);
-  y[i] = __float2bfloat16(c < K0 ? x[r * K0 + c] : 0.f);
+  if (i >= rows * per_row) return;
+  const int64_t r = i / per_row;
+  const int c0 = (int)(i - r * per_row) * 8;
+  const float* xr = x + r * K0;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) v[k] = (c0 + k < K0) ? xr[c0 + k] : 0.f;
+  *reinterpret_cast<uint4*>(y + r * K0pad + c0) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -475,8 +480,9 @@ int tc_refresh_shadow_lastlayer(const FqlDims* d, const Layout& L, const float* 
 }
 
 int tc_pad_bf16(const float* x, void* y, int64_t rows, int K0, int K0pad, cudaStream_t st) {
-  const int64_t n = rows * K0pad;
+  const int64_t n = rows * (K0pad / 8);
   if (n == 0) return 0;
+  FQL_REQUIRE(K0pad % 8 == 0, "tc_pad_bf16: K0pad=%d", K0pad);
   FQL_CHECK_CUDA(fql_launch_pdl(pad_bf16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, reinterpret_cast<__nv_bfloat16*>(y), rows, K0,
                                 K0pad));
   FQL_CHECK_LAUNCH();

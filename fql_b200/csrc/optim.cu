@@ -156,9 +156,11 @@ __global__ void __launch_bounds__(1024) grad_stats_final_kernel(Layout L, const 
 
 // A correctly rounded float pow (via double): one ulp of pow(0.999f, t) is 7.5e-6 of (1 - 0.999^8), so a sloppy powf would show
 // up in the parameters at the fp32 mode's 1e-5 tolerance.
-__global__ void zero_bc_kernel(float4* p, int64_t n4, const int32_t* __restrict__ count, float beta1, float beta2, float* bc) {
+__global__ void zero_bc_kernel(float4* p, int64_t n4, const int32_t* __restrict__ count, float beta1, float beta2, float* bc, int* tickets,
+                               int n_tickets) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tickets && i < n_tickets) tickets[i] = 0;   // arrival counters of the multi-CTA loss kernel (the workspace is not zero-initialised)
   if (i == 0 && count) {
     const double t = (double)(count[0] + 1);
     bc[0] = 1.0f - (float)pow((double)beta1, t);
@@ -215,10 +217,11 @@ int launch_grad_stats_final(const Layout& L, int S, const float* partials, float
   return 0;
 }
 
-int launch_zero_bc(float* p, int64_t n, const int32_t* count, const FqlHparams& hp, float* bc, cudaStream_t st) {
+int launch_zero_bc(float* p, int64_t n, const int32_t* count, const FqlHparams& hp, float* bc, cudaStream_t st, int* tickets, int n_tickets) {
   const int64_t n4 = n / 4;
-  const unsigned blocks = (unsigned)((n4 + 255) / 256);
-  zero_bc_kernel<<<blocks ? blocks : 1, 256, 0, st>>>(reinterpret_cast<float4*>(p), n4, count, hp.beta1, hp.beta2, bc);
+  const int64_t work = n4 > n_tickets ? n4 : n_tickets;
+  const unsigned blocks = (unsigned)((work + 255) / 256);
+  zero_bc_kernel<<<blocks ? blocks : 1, 256, 0, st>>>(reinterpret_cast<float4*>(p), n4, count, hp.beta1, hp.beta2, bc, tickets, n_tickets);
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -174,6 +174,8 @@ size_t carve_workspace(const FqlDims* d, const Layout& L, void* base, WsPtrs* w)
   w->raw_local = c.take(S * FQL_NUM_RAW);
   w->gstats = c.take(S * 4 + 4);  // + Adam bias corrections {1 - b1^t, 1 - b2^t} of the step in flight
   w->partials = c.take(S * (int64_t)L.leaf_blk[L.n_leaves] * 4);
+  w->cpost_part = c.take(2 * S * 64 * 4);
+  w->cpost_ticket = reinterpret_cast<int*>(c.take(3 * S + 4));
   if (d->reserved[0] > 0) {
     for (int i = 0; i < 5; i++) w->feat[i] = c.take(S * B * F);
     for (int i = 0; i < 3; i++) w->dfeat[i] = c.take(S * B * F);
@@ -637,7 +639,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   const int kO = (int)round_up64(sh.F + sh.A, 64), kF = (int)round_up64(sh.F + sh.A + 1, 64);
   const bool dp_grads = ctx->dp.active && c.do_backward;   // data parallel: per-network bucket reductions on ctx->sc
   FQL_TRY(stamp(ctx, 0, S0));   // step start
-  FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0));
+  FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0, w.cpost_ticket, 3 * S));
   FQL_TRY(encode_observations(c, L, w, S0));
   const bool fused_prep = ctx->fused_prep;
   FQL_TRY(launch_prep(sh, b, w, S0, fused_prep ? kF : 0, fused_prep ? kO : 0));  // also writes the bf16 first-layer operands XFb / XOb
@@ -940,7 +942,7 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     const FqlBatch& b = *c.b;
     cudaStream_t S1 = ctx->s1, S2 = ctx->s2;
     cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4];
-    FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0));
+    FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0, w.cpost_ticket, 3 * S));
     FQL_TRY(encode_observations(c, L, w, S0));
     FQL_TRY(launch_prep(sh, b, w, S0));
     const bool pix = c.d->reserved[0] > 0;

@@ -36,6 +36,8 @@ struct WsPtrs {
   float *raw_local;            // [S][FQL_NUM_RAW] when the caller passes none
   float *gstats;               // [S][4]: grad max, min, L1-of-L2 norm
   float *partials;             // [S][blocks][4] per 1024-float arena block: max, min, sumsq
+  float *cpost_part;           // [2][S][64][4] per-CTA partial sums of the TD / actor-Q loss kernel
+  int *cpost_ticket;           // [3][S] arrival counters of the same (zero between steps)
   PassBuf pO, pF, pC;
   float *dC[2], *dCp[2], *dF[2], *dO[2];  // backward ping-pong [S][E][B][H]
   void *XOb, *XFb, *XCb;       // bf16 zero-padded copies of the first-layer inputs (FQL_PRECISION_BF16_TC)
@@ -132,7 +134,8 @@ __device__ __forceinline__ void fql_finalize_info_seed(const StepShape& sh, cons
 #endif
 int launch_zero(float* p, int64_t n, cudaStream_t st);
 // zero p[0..n) and (count != NULL) write optax's float32 bias corrections {1 - b1^(count+1), 1 - b2^(count+1)} to bc[0..1]
-int launch_zero_bc(float* p, int64_t n, const int32_t* count, const FqlHparams& hp, float* bc, cudaStream_t st);
+int launch_zero_bc(float* p, int64_t n, const int32_t* count, const FqlHparams& hp, float* bc, cudaStream_t st, int* tickets = nullptr,
+                   int n_tickets = 0);
 
 // mlp_tc.cu -- tensor-core forward path
 struct TcChainSpec {

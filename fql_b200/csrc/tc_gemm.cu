@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             const float dbn = db[nb + i];
             dg = fmaf(w, gacc, dg);
             if (kz == 0) dbt = fmaf(w, dbn, dbt);
-            atomicAdd(o + i, gam * gacc + (kz == 0 ? bet * dbn : 0.f));
+            const float dw = gam * gacc + (kz == 0 ? bet * dbn : 0.f);
+            if (a.ksplit > 1) atomicAdd(o + i, dw);      // K split over CTAs: partial tiles add into the zeroed leaf
+            else o[i] = dw;
           }
         }
         atomicAdd(a.dln_s.at<float>(g0, g1) + m, dg);

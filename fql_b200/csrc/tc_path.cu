@@ -193,7 +193,7 @@ __global__ void gelu_bwd_bf16_kernel(const float* __restrict__ dH, const float* 
 
 // Column sums over rows of a bf16 tensor [G][M][N] (N % 64 == 0), ADDED into fp32 out (zeroed by the caller): bias gradients from
 // the bf16 dZ saves of the large-batch backward.  grid (N / 64, row chunks, G); a warp reads 128 contiguous bytes of one row.
-constexpr int CS_ROWS = 512;
+constexpr int CS_ROWS = 256;
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ X, int64_t M, int N, float* __restrict__ out, int64_t os0, int G0,
                                                           int64_t os1) {
   const int g = blockIdx.z, g0 = g % G0, g1 = g / G0;
@@ -202,7 +202,18 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
   const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS, r1 = (r0 + CS_ROWS < M) ? r0 + CS_ROWS : M;
   const bf16* x = X + (int64_t)g * M * N + c;
   float a0 = 0.f, a1 = 0.f;
-  for (int64_t r = r0 + rl; r < r1; r += 8) {
+  int64_t r = r0 + rl;
+  for (; r + 24 < r1; r += 32) {   // four independent loads in flight per thread
+    __nv_bfloat162 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = *reinterpret_cast<const __nv_bfloat162*>(x + (r + 8 * u) * N);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      a0 += __low2float(v[u]);
+      a1 += __high2float(v[u]);
+    }
+  }
+  for (; r < r1; r += 8) {
     const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + r * N);
     a0 += __low2float(v);
     a1 += __high2float(v);
@@ -556,15 +567,37 @@ int tc_critic_forward(const TcCritic& t, int net, float* out, cudaStream_t st) {
 // gradients).  No fp32 dH / dZ tensor, no LayerNorm row kernel and no per-layer dgrad launch remains.
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
-__global__ void zero2d_kernel(float* __restrict__ p, int64_t n, int64_t stride) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[(int64_t)blockIdx.y * stride + i] = 0.f;
+// One launch zeroes a list of gradient leaves of every seed (the leaves that are accumulated with atomics: bias / LayerNorm
+// gradients and split-K weight gradients).  Leaf lengths are multiples of 4 floats except the narrow last-layer ones.
+struct ZeroList {
+  int n;
+  long long off[24];
+  long long len[24];
+};
+__global__ void zero_list_kernel(float* __restrict__ base, ZeroList z, int64_t stride) {
+  const int seg = blockIdx.y;
+  float* p = base + (int64_t)blockIdx.z * stride + z.off[seg];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < z.len[seg]; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
-int zero_leaf(float* p, int64_t n, int64_t stride, int count, cudaStream_t st) {
-  zero2d_kernel<<<dim3((unsigned)((n + 255) / 256), count), 256, 0, st>>>(p, n, stride);
-  FQL_CHECK_LAUNCH();
-  return 0;
-}
+struct Zeroer {
+  ZeroList z;
+  int64_t longest = 0;
+  Zeroer() { z.n = 0; }
+  void add(int64_t off, int64_t len) {
+    if (z.n < 24 && len > 0) {
+      z.off[z.n] = off; z.len[z.n] = len; z.n++;
+      if (len > longest) longest = len;
+    }
+  }
+  int run(float* grads, int64_t stride, int S, cudaStream_t st) {
+    if (z.n == 0) return 0;
+    int bx = (int)((longest + 1023) / 1024);
+    if (bx > 256) bx = 256;
+    zero_list_kernel<<<dim3(bx, z.n, S), 256, 0, st>>>(grads, z, stride);
+    FQL_CHECK_LAUNCH();
+    return 0;
+  }
+};
 // K splits that bring a weight-gradient GEMM to about two CTAs per SM
 int wgrad_ksplit(int Mw, int N, int groups, int K) {
   const int base = ((Mw + 127) / 128) * ((N + 63) / 64) * groups;
@@ -599,10 +632,16 @@ int tc_actor_backward_big(const TcActor& t, const float* dOut, void* dOutb, void
     c.out.base[0] = t.grads + nv.off_b[NL - 1]; c.out.stride_s = L.arena;
     FQL_TRY(launch_colsum(c, st, t.cs_scratch, t.cs_scratch ? 65536 : 0));
   }
-  for (int l = 0; l + 1 < NL; l++) {
-    FQL_TRY(zero_leaf(t.grads + nv.off_b[l], H, L.arena, S, st));
-    FQL_TRY(launch_colsum_bf16(dZb[l], S, t.M, H, t.grads + nv.off_b[l], 0, 1, L.arena, st));
+  Zeroer zr;
+  int ksp[FQL_MAXL];
+  for (int l = 0; l < NL; l++) {
+    const int Mw = (l == NL - 1) ? H : nv.k_of(l), Nw = (l == NL - 1) ? A : H;
+    ksp[l] = wgrad_ksplit(Mw, Nw, S, t.M);
+    if (l + 1 < NL) zr.add(nv.off_b[l], H);
+    if (ksp[l] > 1) zr.add(nv.off_w[l], (int64_t)Mw * Nw);
   }
+  FQL_TRY(zr.run(t.grads, L.arena, S, st));
+  for (int l = 0; l + 1 < NL; l++) FQL_TRY(launch_colsum_bf16(dZb[l], S, t.M, H, t.grads + nv.off_b[l], 0, 1, L.arena, st));
   // weight gradients dW_l = A_l^T dZ_l
   for (int l = 0; l < NL; l++) {
     TcGemmSpec g;
@@ -618,8 +657,7 @@ int tc_actor_backward_big(const TcActor& t, const float* dOut, void* dOutb, void
       g.B = op(dZb[l], H, t.M, H, 1, 0, S, dz_ss);
     }
     g.out_f = tp(t.grads + nv.off_w[l], 0, L.arena, g.N);
-    g.ksplit = wgrad_ksplit(g.M, g.N, S, g.K);
-    if (g.ksplit > 1) FQL_TRY(zero_leaf(t.grads + nv.off_w[l], (int64_t)g.M * g.N, L.arena, S, st));
+    g.ksplit = ksp[l];
     FQL_TRY(tc_gemm(g, st));
   }
   return 0;
@@ -665,12 +703,19 @@ int tc_critic_backward_big(const TcCritic& t, void* const* XHb, void* const* DGb
     c.out.base[0] = t.grads + nv.off_b[NL - 1]; c.out.stride_s = L.arena; c.out.stride_e = 1;
     FQL_TRY(launch_colsum(c, st, t.cs_scratch, t.cs_scratch ? 65536 : 0));
   }
-  for (int l = 0; l + 1 < NL; l++) {
-    FQL_TRY(zero_leaf(t.grads + nv.off_b[l], (int64_t)E * H, L.arena, S, st));
-    FQL_TRY(launch_colsum_bf16(t.dZb[l], (int64_t)S * E, M, H, t.grads + nv.off_b[l], H, E, L.arena, st));
-    FQL_TRY(zero_leaf(t.grads + nv.off_lns[l], (int64_t)E * H, L.arena, S, st));
-    FQL_TRY(zero_leaf(t.grads + nv.off_lnb[l], (int64_t)E * H, L.arena, S, st));
+  Zeroer zr;
+  int ksp[FQL_MAXL];
+  for (int l = 0; l < NL; l++) {
+    ksp[l] = wgrad_ksplit(nv.k_of(l), nv.n_of(l), S * E, M);
+    if (l + 1 < NL) {
+      zr.add(nv.off_b[l], (int64_t)E * H);
+      zr.add(nv.off_lns[l], (int64_t)E * H);
+      zr.add(nv.off_lnb[l], (int64_t)E * H);
+    }
+    if (ksp[l] > 1) zr.add(nv.off_w[l], (int64_t)E * nv.k_of(l) * nv.n_of(l));
   }
+  FQL_TRY(zr.run(t.grads, L.arena, S, st));
+  for (int l = 0; l + 1 < NL; l++) FQL_TRY(launch_colsum_bf16(t.dZb[l], (int64_t)S * E, M, H, t.grads + nv.off_b[l], H, E, L.arena, st));
   for (int l = 0; l < NL; l++) {
     const bool last = (l == NL - 1);
     const void* dzb = last ? t.dOutb : t.dZb[l];
@@ -681,11 +726,10 @@ int tc_critic_backward_big(const TcCritic& t, void* const* XHb, void* const* DGb
     g.M = nv.k_of(l); g.N = nv.n_of(l); g.K = M; g.G0 = E; g.G1 = S; g.a_mn = 1; g.b_mn = 1;
     g.B = op(dzb, dz_inner, M, dz_inner, E, dzb_se, S, dzb_ss);
     g.out_f = tp(t.grads + nv.off_w[l], (long long)nv.k_of(l) * nv.n_of(l), L.arena, nv.n_of(l));
-    g.ksplit = wgrad_ksplit(g.M, g.N, S * E, g.K);
+    g.ksplit = ksp[l];
     if (l == 0) {
       g.A = op(t.X0b, t.K0pad, M, t.K0pad, 1, 0, S, t.x_ss);  // input shared by both heads
       g.mode = TC_MODE_STORE_F32;
-      if (g.ksplit > 1) FQL_TRY(zero_leaf(t.grads + nv.off_w[l], (int64_t)E * K0 * H, L.arena, S, st));
     } else {
       // h_{l-1} = gamma * xhat + beta feeds this layer: G = xhat^T dZ_l, transformed in the epilogue (tc_gemm.cu)
       g.A = op(xh[l - 1], H, M, H, E, z_se, S, z_ss);
@@ -696,7 +740,6 @@ int tc_critic_backward_big(const TcCritic& t, void* const* XHb, void* const* DGb
       g.wmaster = tp(t.params + nv.off_w[l], (long long)H * nv.n_of(l), L.arena, 0);
       g.dln_s = tp(t.grads + nv.off_lns[l - 1], H, L.arena, 0);
       g.dln_b = tp(t.grads + nv.off_lnb[l - 1], H, L.arena, 0);
-      FQL_TRY(zero_leaf(t.grads + nv.off_w[l], (int64_t)E * H * nv.n_of(l), L.arena, S, st));
     }
     FQL_TRY(tc_gemm(g, st));
   }
