@@ -78,6 +78,7 @@ _SIGS = {
                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'fql_dp_symmetric_bytes': (C.c_size_t, [C.POINTER(FqlDims), C.c_int32]),
     'fql_dp_attach': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlDpComm)]),
+    'fql_dp_allreduce': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]),
     'fql_set_early_grads_event': (C.c_int, [C.c_void_p, C.c_void_p]),
     'fql_early_grads_floats': (C.c_int64, [C.POINTER(FqlDims)]),
     'fql_total_loss': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlHparams), C.POINTER(FqlBatch), C.POINTER(FqlState),

@@ -226,7 +226,12 @@ class FQLAgent:
             raise _lib.FqlError('symmetric memory rendezvous: local buffer pointer mismatch')
         for r in range(self.world):
             comm.base[r] = ptrs[r]
-        mc = int(hdl.multicast_ptr) if os.environ.get('FQL_DP_MULTICAST', '1') != '0' else 0
+        # NVLS multicast (one multimem.ld_reduce / multimem.st per element whatever the world size) from 4 ranks up; between two
+        # ranks plain peer loads / stores move the same bytes faster (measured on 2 x B200: 6.5 MB bucket 30.6 vs 38.4 us alone,
+        # 0.281 vs 0.292 ms/step).  FQL_DP_MULTICAST=0/1 forces either.
+        want_mc = os.environ.get('FQL_DP_MULTICAST', 'auto')
+        use_mc = (self.world > 2) if want_mc == 'auto' else (want_mc != '0')
+        mc = int(hdl.multicast_ptr) if use_mc else 0
         comm.base_mc = mc or None
         _lib.check(self._lib.fql_dp_attach(self._ctx, C.byref(d), C.byref(comm)), 'fql_dp_attach')
         self._symm, self._symm_hdl, self._comm = buf, hdl, comm

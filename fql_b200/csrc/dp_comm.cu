@@ -3,13 +3,16 @@
 // "larger-batch runs partitioned across the 8 B200s" (north_star) one CUDA graph per step.
 //
 //   dp_reduce_kernel<MC>: one launch per gradient bucket, as soon as that network's gradients are final on this rank.
-//     CTA b of rank r   1. tells CTA b of every peer "my gradients are final" (st.release.sys into the peer's flag pad) and waits
-//                          for the same word from every peer (ld.acquire.sys on its own pad);
-//                       2. reduces ITS 1/world share of the bucket:  MC: multimem.ld_reduce.add.v4.f32 through the NVSwitch
-//                          (one load returns the sum over all ranks' arenas), multimem.st.v4.f32 of the sum into every arena;
-//                          !MC: loads from the `world` peer mappings summed in rank order, stores to every peer mapping;
-//                       3. fence.sys, second flag round: when the kernel ends on a rank, every rank's share has landed in its
-//                          arena (the optimizer pass that follows in the stream reads plain local memory).
+//     rank r            1. CTA 0 tells every peer "my gradients are final" (st.release.sys into the peer's flag pad); every CTA
+//                          waits for the same word from every peer (ld.acquire.sys on its own pad);
+//                       2. reduces ITS 1/world share of the bucket, the CTAs striding over it with several independent 16-byte
+//                          reductions in flight per thread (a round trip through the switch is ~3 us: one at a time ran at
+//                          57 GB/s):  MC: multimem.ld_reduce.add.v4.f32 through the NVSwitch (one load returns the sum over all
+//                          ranks' arenas), multimem.st.v4.f32 of the sum into every arena;  !MC: loads from the `world` peer
+//                          mappings summed in rank order, stores to every peer mapping;
+//                       3. fence.sys, arrival counter: the last CTA runs the second flag round -- when the kernel ends on a
+//                          rank, every rank's share has landed in its arena (the optimizer pass that follows in the stream reads
+//                          plain local memory).
 //     Each element is summed exactly once (by its owner) and the same bits go to all ranks: replicas stay bit-identical.
 //   Flags are monotonically increasing epochs kept in device memory, so a captured CUDA graph replays correctly.
 #include "dp_comm.cuh"
@@ -40,6 +43,7 @@ __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t want, int 
   if ((int32_t)(v - want) >= 0) return;
   const unsigned long long t0 = gtimer();
   while ((int32_t)((v = ld_acquire_sys(p)) - want) < 0) {
+    __nanosleep(32);
     if (gtimer() - t0 > 60ull * 1000000000ull) dp_timeout(bucket, cta, peer, want, v);
   }
 }
@@ -53,48 +57,88 @@ struct DpArgs {
   const float* raw_local;       // optional [S][FQL_NUM_RAW]
 };
 
-template <bool MC>
+// multimem: one load returns the sum over all ranks' arenas (reduced in the NVSwitch), one store lands in every arena
+__device__ __forceinline__ float4 mc_ld_reduce(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st(float* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// DP_UNROLL independent reductions in flight per thread (a round trip through the switch is ~3 us)
+template <bool MC, int DP_UNROLL>
 __global__ void __launch_bounds__(512) dp_reduce_kernel(const DpArgs a) {
   const int b = blockIdx.x, tid = threadIdx.x;
-  uint32_t* my_flags = reinterpret_cast<uint32_t*>(a.base[a.rank] + a.o_flags) + ((int64_t)a.bucket * DP_MAX_CTAS + b) * FQL_DP_MAX_RANKS;
-  uint32_t* my_epoch = reinterpret_cast<uint32_t*>(a.base[a.rank] + a.o_epochs) + a.bucket * DP_MAX_CTAS + b;
+  // flag words of this bucket: [rank] written by the peers (monotonic epochs); local: the epoch of the last completed exchange and
+  // the arrival counter of this launch's CTAs
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(a.base[a.rank] + a.o_flags) + (int64_t)a.bucket * DP_MAX_CTAS * FQL_DP_MAX_RANKS;
+  uint32_t* my_epoch = reinterpret_cast<uint32_t*>(a.base[a.rank] + a.o_epochs) + a.bucket * DP_MAX_CTAS;
+  uint32_t* my_count = my_epoch + 1;
   __shared__ uint32_t s_epoch;
-  if (tid == 0) s_epoch = *my_epoch;
+  __shared__ int s_last;
+  if (tid == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(my_epoch);
   __syncthreads();
   const uint32_t e1 = s_epoch + 1, e2 = s_epoch + 2;
-  // ---- 1. every rank's gradients of this bucket are final (its kernel runs behind them in its stream)
+  // ---- 1. every rank's gradients of this bucket are final (its kernel runs behind them in its stream): CTA 0 tells the peers,
+  //         every CTA waits for all of them
   if (tid < a.world) {
-    uint32_t* peer = reinterpret_cast<uint32_t*>(a.base[tid] + a.o_flags) + ((int64_t)a.bucket * DP_MAX_CTAS + b) * FQL_DP_MAX_RANKS + a.rank;
-    st_release_sys(peer, e1);
+    if (b == 0) {
+      uint32_t* peer = reinterpret_cast<uint32_t*>(a.base[tid] + a.o_flags) + (int64_t)a.bucket * DP_MAX_CTAS * FQL_DP_MAX_RANKS + a.rank;
+      st_release_sys(peer, e1);
+    }
     wait_flag(my_flags + tid, e1, a.bucket, b, tid);
   }
   __syncthreads();
-  // ---- 2. my share of every seed's bucket
+  // ---- 2. my share of every seed's bucket, DP_UNROLL independent 16-byte reductions in flight per thread
   const int64_t chunk = (a.n4 + a.world - 1) / a.world;
   const int64_t lo = a.rank * chunk, hi = (lo + chunk < a.n4) ? lo + chunk : a.n4;
   const int64_t per_seed = hi > lo ? hi - lo : 0;
-  for (int64_t i = (int64_t)b * blockDim.x + tid; i < per_seed * a.S; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t s = i / per_seed, e = a.off + (int64_t)s * a.arena + (lo + (i - s * per_seed)) * 4;
-    float4 v;
+  const int64_t total = per_seed * a.S, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)b * blockDim.x + tid; i0 < total; i0 += DP_UNROLL * stride) {
+    int64_t e[DP_UNROLL];
+    float4 v[DP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DP_UNROLL; u++) {
+      const int64_t i = i0 + u * stride;
+      e[u] = -1;
+      if (i < total) {
+        const int64_t s = i / per_seed;
+        e[u] = a.off + s * a.arena + (lo + (i - s * per_seed)) * 4;
+      }
+    }
     if (MC) {
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                   : "l"(a.mc + e)
-                   : "memory");
-      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.mc + e), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                   : "memory");
+#pragma unroll
+      for (int u = 0; u < DP_UNROLL; u++)
+        if (e[u] >= 0) v[u] = mc_ld_reduce(a.mc + e[u]);
+#pragma unroll
+      for (int u = 0; u < DP_UNROLL; u++)
+        if (e[u] >= 0) mc_st(a.mc + e[u], v[u]);
     } else {
-      float4 p[FQL_DP_MAX_RANKS];
 #pragma unroll
-      for (int r = 0; r < FQL_DP_MAX_RANKS; r++)
-        if (r < a.world) p[r] = __ldcg(reinterpret_cast<const float4*>(a.base[r] + e));   // all peers' loads in flight together
-      v = p[0];
+      for (int u = 0; u < DP_UNROLL; u++) {
+        if (e[u] < 0) continue;
+        float4 p[FQL_DP_MAX_RANKS];
 #pragma unroll
-      for (int r = 1; r < FQL_DP_MAX_RANKS; r++)
-        if (r < a.world) { v.x += p[r].x; v.y += p[r].y; v.z += p[r].z; v.w += p[r].w; }
+        for (int r = 0; r < FQL_DP_MAX_RANKS; r++)
+          if (r < a.world) p[r] = __ldcg(reinterpret_cast<const float4*>(a.base[r] + e[u]));   // all peers' loads in flight together
+        float4 t = p[0];
 #pragma unroll
-      for (int r = 0; r < FQL_DP_MAX_RANKS; r++)
-        if (r < a.world) __stcg(reinterpret_cast<float4*>(a.base[r] + e), v);
+        for (int r = 1; r < FQL_DP_MAX_RANKS; r++)
+          if (r < a.world) { t.x += p[r].x; t.y += p[r].y; t.z += p[r].z; t.w += p[r].w; }
+        v[u] = t;
+      }
+#pragma unroll
+      for (int u = 0; u < DP_UNROLL; u++) {
+        if (e[u] < 0) continue;
+#pragma unroll
+        for (int r = 0; r < FQL_DP_MAX_RANKS; r++)
+          if (r < a.world) __stcg(reinterpret_cast<float4*>(a.base[r] + e[u]), v[u]);
+      }
     }
   }
   // the metric accumulators of this rank -> slot [rank] of every rank's gather buffer (fql_finalize_info_seed reduces them)
@@ -105,16 +149,27 @@ __global__ void __launch_bounds__(512) dp_reduce_kernel(const DpArgs a) {
       __stcg(a.base[r] + a.o_raw + (int64_t)a.rank * n + k, a.raw_local[k]);
     }
   }
-  // ---- 3. everything I wrote is visible system-wide before any peer is told so
+  // ---- 3. everything this rank wrote is visible system-wide before any peer is told so: the last CTA to arrive tells the peers
+  //         and waits for theirs -- when the kernel ends on a rank, every rank's share has landed in its arena
   __threadfence_system();
   __syncthreads();
+  if (tid == 0) {
+    const uint32_t t = atomicAdd(my_count, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
   if (tid < a.world) {
-    uint32_t* peer = reinterpret_cast<uint32_t*>(a.base[tid] + a.o_flags) + ((int64_t)a.bucket * DP_MAX_CTAS + b) * FQL_DP_MAX_RANKS + a.rank;
+    uint32_t* peer = reinterpret_cast<uint32_t*>(a.base[tid] + a.o_flags) + (int64_t)a.bucket * DP_MAX_CTAS * FQL_DP_MAX_RANKS + a.rank;
     st_release_sys(peer, e2);
     wait_flag(my_flags + tid, e2, a.bucket, b, tid);
   }
   __syncthreads();
-  if (tid == 0) *my_epoch = e2;
+  if (tid == 0) {
+    *my_count = 0;
+    *my_epoch = e2;
+  }
 }
 
 }  // namespace
@@ -142,14 +197,29 @@ int dp_reduce_bucket(const DpState& dp, int bucket, int64_t off, int64_t n, cons
   a.arena = dp.arena; a.off = off; a.n4 = n / 4;
   a.o_flags = dp.lay.flags; a.o_epochs = dp.lay.epochs; a.o_raw = dp.lay.raw_all;
   a.raw_local = raw_local;
-  // one CTA per 8192 float4 of this rank's share (>= 4 float4 in flight per thread), every rank launches the same grid
+  // one CTA per 1024 float4 of this rank's share (two reductions in flight per thread), at most one CTA per SM pair
   const int64_t share = (a.n4 + a.world - 1) / a.world * dp.S;
-  int ctas = (int)((share + 8191) / 8192);
-  ctas = ctas < 1 ? 1 : (ctas > DP_MAX_CTAS ? DP_MAX_CTAS : ctas);
-  if (a.mc) dp_reduce_kernel<true><<<ctas, 512, 0, st>>>(a);
-  else dp_reduce_kernel<false><<<ctas, 512, 0, st>>>(a);
+  static const int max_ctas = getenv("FQL_DP_CTAS") ? atoi(getenv("FQL_DP_CTAS")) : DP_REDUCE_CTAS;
+  static const int unroll = getenv("FQL_DP_UNROLL") ? atoi(getenv("FQL_DP_UNROLL")) : 4;
+  static const int threads = getenv("FQL_DP_THREADS") ? atoi(getenv("FQL_DP_THREADS")) : 512;
+  int ctas = (int)((share + 1023) / 1024);
+  ctas = ctas < 1 ? 1 : (ctas > max_ctas ? max_ctas : ctas);
+  if (a.mc) {
+    if (unroll >= 8) dp_reduce_kernel<true, 8><<<ctas, threads, 0, st>>>(a);
+    else if (unroll >= 4) dp_reduce_kernel<true, 4><<<ctas, threads, 0, st>>>(a);
+    else dp_reduce_kernel<true, 1><<<ctas, threads, 0, st>>>(a);
+  } else {
+    if (unroll >= 4) dp_reduce_kernel<false, 4><<<ctas, threads, 0, st>>>(a);
+    else dp_reduce_kernel<false, 1><<<ctas, threads, 0, st>>>(a);
+  }
   FQL_CHECK_LAUNCH();
   return 0;
+}
+
+// Stand-alone exchange of grads[s][off, off + n) of every seed (callers that drive fql_step_grads / fql_step_apply themselves, and
+// profiles/micro/dp_reduce_bench.py).  Enqueue-only; every rank must call it with the same arguments.
+int dp_allreduce_range(const DpState& dp, int bucket, long long off, long long n, cudaStream_t st) {
+  return dp_reduce_bucket(dp, bucket, off, n, nullptr, st);
 }
 
 extern "C" size_t fql_dp_symmetric_bytes(const FqlDims* d, int32_t world) {

@@ -2,7 +2,8 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int DP_MAX_CTAS = 64;     // CTAs of one bucket-reduce launch (each synchronises with its namesake on every peer)
+constexpr int DP_MAX_CTAS = 64;     // flag / epoch words reserved per bucket in the symmetric buffer
+constexpr int DP_REDUCE_CTAS = 96;  // CTAs of one bucket-reduce launch
 constexpr int DP_BUCKETS = 4;       // flag sets: bc-flow | critic | one-step actor (+ metric gather) | whole arena (fp32 schedule)
 
 struct DpLayout {                   // float offsets inside one rank's symmetric buffer
@@ -39,3 +40,4 @@ DpLamArgs dp_lam_args(const DpState& dp);
 // gathers the [S][FQL_NUM_RAW] metric accumulators into every rank's raw_all[rank].
 int dp_reduce_bucket(const DpState& dp, int bucket, int64_t off, int64_t n, const float* raw_local, cudaStream_t st);
 inline const float* dp_raw_all(const DpState& dp) { return reinterpret_cast<const float*>(dp.comm.base[dp.comm.rank]) + dp.lay.raw_all; }
+int dp_allreduce_range(const DpState& dp, int bucket, long long off, long long n, cudaStream_t st);

@@ -430,6 +430,10 @@ struct FqlContext {
   int split_adam = 0;        // FQL_B200_SPLIT_ADAM: 0 = one optimizer pass at the end (default: the others measured within noise), 1 = bc-flow's part right behind the Euler chain,
                              // 2 = bc-flow and critic parts before the one-step actor's gradients are complete
   int adam_done_blk = 0;     // blocks [0, adam_done_blk) were already applied by enqueue_grads_tc in this enqueue
+  int dp_early_adam = 1;     // FQL_B200_DP_EARLY_ADAM=0: data parallel, one optimizer pass at the end.  Default: the bc-flow + critic part
+                             // runs behind their bucket reductions, under the one-step actor's bucket exchange
+  int dp_bc_late = 0;        // FQL_B200_DP_BC_LATE=1: bc-flow's bucket is exchanged together with the critic's (one launch) instead of
+                             // under the Euler chain
   int use_critic_chain = 0;
   int use_big_bwd = 1;       // FQL_B200_BIG_BWD=0: per-layer backward (tc_gemm + row kernels) also at large batch
   int chain_min_tiles = 48;  // row tiles (x seeds) from which the fused per-tile chain kernels replace the per-layer GEMMs
@@ -449,6 +453,13 @@ extern "C" int64_t fql_early_grads_floats(const FqlDims* d) {
   Layout L;
   if (fql_build_layout(d, &L)) return -1;
   return L.net[FQL_NET_ACTOR_ONESTEP_FLOW].begin;
+}
+extern "C" int fql_dp_allreduce(FqlContext* c, int32_t bucket, int64_t off, int64_t n, void* stream) {
+  FQL_REQUIRE(c && c->dp.active, "fql_dp_allreduce: no communicator attached (fql_dp_attach)");
+  const long long before = g_fql_launches;
+  const int rc = dp_allreduce_range(c->dp, bucket, off, n, reinterpret_cast<cudaStream_t>(stream));
+  c->launches += g_fql_launches - before;
+  return rc;
 }
 extern "C" int fql_dp_attach(FqlContext* c, const FqlDims* d, const FqlDpComm* comm) {
   FQL_REQUIRE(c != nullptr, "context is NULL");
@@ -531,6 +542,10 @@ extern "C" int fql_context_create(FqlContext** out) {
   }
   const char* sa = getenv("FQL_B200_SPLIT_ADAM");
   if (sa) c->split_adam = atoi(sa);
+  const char* dea = getenv("FQL_B200_DP_EARLY_ADAM");
+  if (dea) c->dp_early_adam = atoi(dea);
+  const char* dbl = getenv("FQL_B200_DP_BC_LATE");
+  if (dbl) c->dp_bc_late = atoi(dbl);
   const char* cm = getenv("FQL_B200_CHAIN_MIN_TILES");
   if (cm) c->chain_min_tiles = atoi(cm);
   const char* bb = getenv("FQL_B200_BIG_BWD");
@@ -712,7 +727,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   if (c.do_backward && big_bwd) {
     FQL_TRY(tc_actor_backward_big(fbc, w.dpred, w.F_dOutb, w.F_dZb, false, S2));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], S2));
-    if (dp_grads) {
+    if (dp_grads && !ctx->dp_bc_late) {
       const NetView& nb = L.net[FQL_NET_ACTOR_BC_FLOW];
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[16], 0));
       FQL_TRY(dp_reduce_bucket(ctx->dp, 0, nb.begin, nb.end - nb.begin, nullptr, ctx->sc));
@@ -723,10 +738,12 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[53], ctx->s7));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s3, ctx->ev[53], 0));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], ctx->s3));
-    if (dp_grads) {  // bc-flow's gradients are final long before the rest: its bucket crosses NVLink under the remaining backward
+    if (dp_grads && !ctx->dp_bc_late) {  // bc-flow's gradients are final long before the rest: its bucket crosses NVLink under the remaining backward
       const NetView& nb = L.net[FQL_NET_ACTOR_BC_FLOW];
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[16], 0));
+      FQL_TRY(stamp(ctx, 20, ctx->sc));   // bc-flow bucket: gradients final
       FQL_TRY(dp_reduce_bucket(ctx->dp, 0, nb.begin, nb.end - nb.begin, nullptr, ctx->sc));
+      FQL_TRY(stamp(ctx, 21, ctx->sc));   // bc-flow bucket reduced
     }
     FQL_TRY(stamp(ctx, 4, S2));   // bc-flow dgrad chain done (weight gradients on s3 may still run)
   }
@@ -822,7 +839,15 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     if (dp_grads) {
       const NetView& nc = L.net[FQL_NET_CRITIC];
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[36], 0));
-      FQL_TRY(dp_reduce_bucket(ctx->dp, 1, nc.begin, nc.end - nc.begin, nullptr, ctx->sc));
+      int64_t b0 = nc.begin;
+      if (ctx->dp_bc_late) {              // bc-flow | critic are adjacent in the arena: one exchange for both
+        FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[16], 0));
+        b0 = L.net[FQL_NET_ACTOR_BC_FLOW].begin;
+        FQL_REQUIRE(L.net[FQL_NET_ACTOR_BC_FLOW].end == nc.begin, "arena order: bc-flow is not followed by the critic");
+      }
+      FQL_TRY(stamp(ctx, 22, ctx->sc));   // critic bucket: gradients final
+      FQL_TRY(dp_reduce_bucket(ctx->dp, 1, b0, nc.end - b0, nullptr, ctx->sc));
+      FQL_TRY(stamp(ctx, 23, ctx->sc));   // critic bucket reduced
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[59], ctx->sc));
     }
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[36], 0));
@@ -837,6 +862,20 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     if (big_bwd) FQL_TRY(tc_critic_backward_big(q, w.C_XHb, w.C_DGb, S0));
     else FQL_TRY(tc_critic_backward(q, S0, nullptr, nullptr, &ctx->ev[44]));
     FQL_TRY(stamp(ctx, 6, S0));   // critic input-gradient chain done
+    if (dp_grads && c.do_apply && ctx->dp_early_adam && ctx->split_adam == 0 && d->reserved[0] == 0) {
+      // data parallel: bc-flow's and the critic's part of the optimizer pass (+ Polyak) right behind their bucket exchanges on the
+      // communication stream, under the one-step actor's backward and bucket exchange.  Last readers of their weights: the Euler
+      // chain (bc-flow) and the critic input-gradient chain that S0 has just enqueued; the critic's own backward precedes ev[36].
+      const int blk1 = (int)(L.net[FQL_NET_ACTOR_ONESTEP_FLOW].begin / FQL_LEAF_PAD);
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[52], S0));
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[52], 0));
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ev_euler, 0));
+      FQL_TRY(launch_adam_polyak_stats(L, hp, S, c.st->params, c.st->mu, c.st->nu, c.st->grads, w.gstats + S * 4, w.partials, c.st->shadow,
+                                       tc_shadow_seed_elems(d, L), ctx->sc, 0, blk1));
+      FQL_TRY(stamp(ctx, 9, ctx->sc));  // early optimizer pass done
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[59], ctx->sc));
+      ctx->adam_done_blk = blk1;
+    }
     if (c.do_apply && ctx->split_adam == 1 && d->reserved[0] == 0) {
       // bc-flow is finished with once the Euler chain (the last reader of its weights) has ended and its gradients are complete:
       // its quarter of the optimizer pass runs behind the Euler kernel, beside the one-step actor's dgrad chain
@@ -909,7 +948,9 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   if (early_adam_s1) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[58], 0));
   if (dp_grads) {  // the one-step actor's bucket + the metric accumulators close the exchange; the optimizer pass follows on S0
     const NetView& no = L.net[FQL_NET_ACTOR_ONESTEP_FLOW];
+    FQL_TRY(stamp(ctx, 24, S0));          // one-step bucket: gradients final
     FQL_TRY(dp_reduce_bucket(ctx->dp, 2, no.begin, no.end - no.begin, raw, S0));
+    FQL_TRY(stamp(ctx, 25, S0));          // one-step bucket reduced
     FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[59], 0));
   }
   return 0;

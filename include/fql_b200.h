@@ -166,6 +166,10 @@ typedef struct FqlDpComm {
 } FqlDpComm;
 size_t fql_dp_symmetric_bytes(const FqlDims* d, int32_t world);
 int fql_dp_attach(FqlContext* ctx, const FqlDims* d, const FqlDpComm* comm); /* comm == NULL detaches */
+/* Stand-alone exchange: floats [off, off + n) of every seed's gradient arena are summed over the ranks, in place on every rank
+ * (what an ncclAllReduce of that range would do).  bucket in [0, 4) selects the flag set: launches that may be in
+ * flight at the same time must use different buckets.  Enqueue-only; every rank calls it with the same arguments. */
+int fql_dp_allreduce(FqlContext* ctx, int32_t bucket, int64_t off, int64_t n, void* stream);
 
 /* Forward-only total_loss(grad_params=None) (agents/fql.py:94-111 as called from main.py:284): 10 info floats
  * [0..9] and the scalar loss in info[FQL_NUM_INFO-3] slot order documented in fql_info_name. */

