@@ -30,7 +30,7 @@ WORKLOADS = {  # BASELINE.json configs 1-4 (state-based); SURVEY 8d hyper-parame
     'antmaze-large': dict(F=29, A=8, cfg=dict(q_agg='min', alpha=10.0)),
     'humanoidmaze-medium': dict(F=69, A=21, cfg=dict(discount=0.995, alpha=30.0)),
     'puzzle-4x4': dict(F=83, A=5, cfg=dict(normalize_q_loss=True, alpha=1000.0)),  # F=83 assumed (unverified)
-    # BASELINE config 5: 64x64x3 pixels, frame_stack 3 -> 64x64x9 uint8, impala_small encoders (fp32 CUDA-core kernels this round)
+    # BASELINE config 5: 64x64x3 pixels, frame_stack 3 -> 64x64x9 uint8, impala_small encoders (tcgen05 implicit-GEMM convolutions)
     'visual-cube-single': dict(F=512, A=5, image=(64, 64, 9), cfg=dict(alpha=300.0, encoder='impala_small')),
 }
 
@@ -186,7 +186,7 @@ def time_config(name, batch, seeds, mode, world, rank, pg, stream, flush, steps=
     cfg = get_config()
     cfg.update(wl['cfg'])
     cfg['batch_size'] = batch
-    precision = 'fp32' if wl.get('image') and not PIXEL_BF16 else 'bf16'
+    precision = 'bf16'
     ex_obs = np.zeros((1,) + tuple(wl['image']), np.uint8) if wl.get('image') else np.zeros((1, F), np.float32)
     out = dict(workload=name, batch_per_gpu=batch, seeds_per_gpu=seeds, n_gpus=world, mode=mode, precision=precision)
     try:
@@ -227,9 +227,6 @@ def time_config(name, batch, seeds, mode, world, rank, pg, stream, flush, steps=
     return out
 
 
-PIXEL_BF16 = False   # the pixel configuration runs its MLPs/encoders in fp32 until the tensor-core encoder lands
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -246,8 +243,7 @@ def main():
     ap.add_argument('--no-scaling-configs', action='store_true')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if wl.get('image'):
-        args.precision = 'fp32'  # the pixel path is fp32 this round
+    # pixel workloads: --precision bf16 = the ImpalaEncoders on tcgen05 in bf16 (FQL_PRECISION_BF16_ENC), MLPs behind them in fp32
     F, A = wl['F'], wl['A']
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -397,7 +393,8 @@ def main():
                 algorithmic_flops_per_step_per_gpu=flops_gpu, algorithmic_bytes_per_step_per_gpu=bytes_gpu,
                 tensor_tflops_achieved=flops_gpu / t_s / 1e12, tensor_frac=flops_gpu / t_s / 1e12 / peaks['tc'],
                 hbm_gbs_achieved=bytes_gpu / t_s / 1e9, t_min_us=max(t_tc, t_hbm) * 1e6,
-                arithmetic='fp32 FFMA (parity mode)' if args.precision == 'fp32' else 'bf16 tcgen05, fp32 accumulate')
+                arithmetic='fp32 FFMA (parity mode)' if args.precision == 'fp32' else
+                ('bf16 tcgen05 implicit-GEMM encoders (fp32 accumulate), fp32 FFMA MLPs' if wl.get('image') else 'bf16 tcgen05, fp32 accumulate'))
     if n == 1 and args.precision == 'bf16' and not wl.get('image') and args.seeds == 1:
         # the dominant kernel, timed alone on its launching stream with CUDA events (L2 flushed between launches): the persistent
         # cluster kernel of compute_flow_actions = the longest dependent chain of the step (concat + pad + ONE cluster launch)
@@ -465,7 +462,7 @@ def main():
                                                  note='preallocated buffers, pinned staging, one H2D + 3 kernels + one D2H + stream sync')
         except Exception as e:
             out['sample_actions_latency'] = dict(error=repr(e)[:200])
-    if n == 1 and args.precision == 'bf16' and not args.no_fp32_leg:
+    if n == 1 and args.precision == 'bf16' and not args.no_fp32_leg and not wl.get('image'):
         with torch.cuda.stream(stream):
             a32 = FQLAgent.create(0, np.zeros((1, F), np.float32), np.zeros((1, A), np.float32), cfg, num_seeds=args.seeds, precision='fp32')
             b32 = a32.stage(batches[0])

@@ -15,7 +15,7 @@ NUM_INFO = 13
 NUM_RAW = 16
 NET_NAMES = ('actor_bc_flow', 'actor_onestep_flow', 'critic', 'target_critic')
 LEAF_KINDS = ('kernel', 'bias', 'scale', 'bias', 'kernel', 'bias', 'kernel', 'bias')
-PRECISION_FP32, PRECISION_BF16_TC = 0, 1
+PRECISION_FP32, PRECISION_BF16_TC, PRECISION_BF16_ENC = 0, 1, 2
 
 
 class FqlDims(C.Structure):
@@ -79,6 +79,11 @@ _SIGS = {
     'fql_dp_symmetric_bytes': (C.c_size_t, [C.POINTER(FqlDims), C.c_int32]),
     'fql_dp_attach': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlDpComm)]),
     'fql_dp_allreduce': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]),
+    'fql_conv3x3_workspace_bytes': (C.c_size_t, []),
+    'fql_conv3x3_bf16': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'fql_conv3x3_wgrad_bf16': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'fql_set_early_grads_event': (C.c_int, [C.c_void_p, C.c_void_p]),
     'fql_early_grads_floats': (C.c_int64, [C.POINTER(FqlDims)]),
     'fql_total_loss': (C.c_int, [C.c_void_p, C.POINTER(FqlDims), C.POINTER(FqlHparams), C.POINTER(FqlBatch), C.POINTER(FqlState),

@@ -40,12 +40,15 @@ int fql_validate_dims(const FqlDims* d) {
   FQL_REQUIRE(d->hidden >= 1 && d->num_hidden >= 1 && d->num_hidden + 1 <= FQL_MAXL, "hidden=%d num_hidden=%d", d->hidden, d->num_hidden);
   FQL_REQUIRE(d->num_seeds >= 1, "num_seeds=%d", d->num_seeds);
   FQL_REQUIRE(d->flow_steps >= 1, "flow_steps=%d", d->flow_steps);
-  FQL_REQUIRE(d->precision == FQL_PRECISION_FP32 || d->precision == FQL_PRECISION_BF16_TC, "precision=%d", d->precision);
+  FQL_REQUIRE(d->precision == FQL_PRECISION_FP32 || d->precision == FQL_PRECISION_BF16_TC || d->precision == FQL_PRECISION_BF16_ENC,
+              "precision=%d", d->precision);
+  FQL_REQUIRE(d->precision != FQL_PRECISION_BF16_ENC || d->reserved[0] > 0, "FQL_PRECISION_BF16_ENC is a pixel-config mode (encoder='impala_small')");
   if (d->reserved[0] > 0) {  // pixel observations through ImpalaEncoder('impala_small')
     FQL_REQUIRE(d->reserved[1] > 0 && d->reserved[2] > 0 && d->reserved[2] <= 32, "image dims %dx%dx%d", d->reserved[0], d->reserved[1], d->reserved[2]);
     FQL_REQUIRE(d->obs_dim == 512, "pixel configs: obs_dim is the encoder output width and must be 512 (got %d)", d->obs_dim);
     FQL_REQUIRE(d->num_seeds == 1, "pixel configs are built for num_seeds == 1");
-    FQL_REQUIRE(d->precision == FQL_PRECISION_FP32, "pixel configs run in FQL_PRECISION_FP32 in this version (encoders are fp32 CUDA-core kernels)");
+    FQL_REQUIRE(d->precision == FQL_PRECISION_FP32 || d->precision == FQL_PRECISION_BF16_ENC,
+                "pixel configs run in FQL_PRECISION_FP32 (fp32 CUDA-core encoders) or FQL_PRECISION_BF16_ENC (tcgen05 encoders, fp32 MLPs)");
   }
   return 0;
 }

@@ -21,7 +21,13 @@ struct PassBuf {               // activations of one grouped MLP pass: [G][Mcap]
   int G, Mcap;
 };
 
+struct EncTc {                // bf16 NHWC activations / prepared weights of one tensor-core encoder pass (encoder_tc.cu)
+  void *img, *y0, *p[3], *r1[3], *r2[3], *xs[3], *flat;
+  void *wf, *wd, *wdense;     // [9][320][64] forward / input-gradient matrices of the convolutions, [flat][512] Dense kernel
+  void *dzb, *da, *db, *dc;
+};
 struct EncBuf {               // activations of one encoder pass over B images (encoder.cu)
+  EncTc tc;                   // FQL_PRECISION_BF16_ENC
   float *pl[3], *c1[3], *x[3];
   uint8_t* arg[3];
   float *flat, *z, *scratch;
@@ -325,4 +331,10 @@ int enc_forward(const FqlDims* d, const EncView& v, const float* params, const u
                 cudaStream_t st);
 int enc_backward(const FqlDims* d, const EncView& v, const float* params, float* grads, const uint8_t* obs, int64_t B, const EncBuf& e,
                  const float* dfeat, cudaStream_t st);
+// encoder_tc.cu -- the same three entry points on tcgen05 (FQL_PRECISION_BF16_ENC); encoder.cu dispatches to them
+size_t enc_tc_carve(const FqlDims* d, int64_t B, void* base, EncBuf* e, bool for_backward);
+int enc_tc_forward(const FqlDims* d, const EncView& v, const float* params, const uint8_t* obs, int64_t B, const EncBuf& e, float* feat,
+                   cudaStream_t st);
+int enc_tc_backward(const FqlDims* d, const EncView& v, const float* params, float* grads, const uint8_t* obs, int64_t B, const EncBuf& e,
+                    const float* dfeat, cudaStream_t st);
 int launch_extract_feat_grad(const float* dX0, float* out, int E, int64_t M, int K0, int F, cudaStream_t st);

@@ -37,7 +37,9 @@ enum { FQL_LEAF_KERNEL = 0, FQL_LEAF_BIAS = 1, FQL_LEAF_LN_SCALE = 2, FQL_LEAF_L
        FQL_LEAF_CONV_KERNEL = 4, FQL_LEAF_CONV_BIAS = 5, FQL_LEAF_ENC_DENSE_KERNEL = 6, FQL_LEAF_ENC_DENSE_BIAS = 7 };
 /* Arithmetic mode of the contractions. */
 enum { FQL_PRECISION_FP32 = 0,      /* fp32 FFMA everywhere: parity mode (1e-5 vs the fp32/fp64 oracle)          */
-       FQL_PRECISION_BF16_TC = 1 }; /* bf16 operands on tcgen05, fp32 accumulate/epilogue, fp32 master weights   */
+       FQL_PRECISION_BF16_TC = 1,   /* bf16 operands on tcgen05, fp32 accumulate/epilogue, fp32 master weights   */
+       FQL_PRECISION_BF16_ENC = 2 };/* pixel configs: the ImpalaEncoders (89 % of the FLOPs) as bf16 implicit-GEMM
+                                     * convolutions on tcgen05 (fp32 accumulate, bf16 activations), MLPs in fp32  */
 
 /* Static problem description: agents/fql.py:249-270 (get_config) + shapes fixed at create() (:192-194). */
 typedef struct FqlDims {
@@ -216,6 +218,20 @@ int fql_fill_noise_rows(const FqlDims* d, uint64_t seed, uint64_t step, int64_t 
 /* %globaltimer stamps taken at the schedule points of the last step when the context was created with FQL_B200_STAMPS=1
  * (profiles/dbg_timeline.py); fails otherwise.  Synchronises the device: not for the hot path. */
 int fql_debug_stamps(FqlContext* ctx, unsigned long long* host_out, int n);
+
+/* ---- 3x3 SAME convolutions of ImpalaEncoder (utils/encoders.py:17-57) on tcgen05, stand-alone -------------------------
+ * x: bf16 NHWC [B,H,W,cin] (cin, cout in {16, 32}); w_hwio: fp32 [3,3,cin,cout] (nn.Conv kernel layout), rounded to bf16 for the
+ * tensor cores; fp32 accumulation.  out = epilogue(conv(x) + bias): optional relu-mask of a saved bf16 tensor (mask > 0), optional
+ * bf16 addend (skip connection / upstream gradient), optional relu; bf16 NHWC.  input_gradient != 0: x is dY [B,H,W,cout] and out
+ * is dX [B,H,W,cin] (jax.grad of the same convolution with respect to its input).  The weight gradient returns fp32
+ * gw [3,3,cin,cout] and gb [cout] (sums over all pixels, reduced in a fixed order).  These are the kernels FQL_PRECISION_BF16_ENC
+ * runs inside fql_update_step; they are exported for exact arithmetic checks. */
+size_t fql_conv3x3_workspace_bytes(void);
+int fql_conv3x3_bf16(const void* x, const float* w_hwio, const float* bias, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout,
+                     int32_t input_gradient, const void* mask, const void* add, int32_t relu_out, void* out, void* workspace,
+                     size_t ws_bytes, void* stream);
+int fql_conv3x3_wgrad_bf16(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout, float* gw, float* gb,
+                           void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

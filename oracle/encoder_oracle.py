@@ -90,53 +90,68 @@ def pool_bwd(dy, arg, in_shape, pad_lo):
     return dxp[:, pad_lo[0]:pad_lo[0] + H, pad_lo[1]:pad_lo[1] + W, :]
 
 
-def encoder_forward(p, obs_u8, dtype=None, save=False):
-    """obs_u8 [B,H,W,C] uint8 -> features [B,512].  With save=True also returns the cache for encoder_backward."""
+def bf16_round(x):
+    """round-to-nearest-even to bfloat16 (returned in x's dtype): the storage rounding of the tensor-core encoder path"""
+    x = np.asarray(x)
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((b + np.uint32(0x7FFF) + ((b >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)).view(np.float32)
+    return r.astype(x.dtype)
+
+
+def encoder_forward(p, obs_u8, dtype=None, save=False, q=None):
+    """obs_u8 [B,H,W,C] uint8 -> features [B,512].  With save=True also returns the cache for encoder_backward.
+    q (optional, e.g. bf16_round): the same mathematics with every STORED activation and every matrix-product weight operand rounded
+    by q -- the reference's arithmetic as FQL_PRECISION_BF16_ENC evaluates it (fql_b200/csrc/encoder_tc.cu: bf16 NHWC activations,
+    bf16 weight operands, fp32 accumulation, fp32 biases; the 0..255 frames are exact in bf16 and 1/255 scales the accumulator)."""
     dt = dtype or p['MLP_0']['Dense_0']['kernel'].dtype
+    q = q or (lambda a: a)
     x = obs_u8.astype(dt) / dt.type(255.0)
     cache = []
     for i in range(len(STACKS)):
         blk = p[f'stack_blocks_{i}']
         x_in = x
-        c0 = conv_fwd(x_in, blk['Conv_0']['kernel'], blk['Conv_0']['bias'])
+        c0 = q(conv_fwd(x_in, q(blk['Conv_0']['kernel']), blk['Conv_0']['bias']))
         pl, arg, pad_lo = pool_fwd(c0)
         r1 = np.maximum(pl, 0)
-        c1 = conv_fwd(r1, blk['Conv_1']['kernel'], blk['Conv_1']['bias'])
-        r2 = np.maximum(c1, 0)
-        c2 = conv_fwd(r2, blk['Conv_2']['kernel'], blk['Conv_2']['bias'])
-        x = c2 + pl
+        c1 = conv_fwd(r1, q(blk['Conv_1']['kernel']), blk['Conv_1']['bias'])
+        r2 = q(np.maximum(c1, 0))
+        c2 = conv_fwd(r2, q(blk['Conv_2']['kernel']), blk['Conv_2']['bias'])
+        x = q(c2 + pl)
         cache.append((x_in, c0.shape, arg, pad_lo, pl, r1, c1, r2))
     xr = np.maximum(x, 0)
     flat = xr.reshape(xr.shape[0], -1)
     d = p['MLP_0']['Dense_0']
-    z = flat @ d['kernel'] + d['bias']
+    z = flat @ q(d['kernel']) + d['bias']
     out = gelu_tanh(z)
     if save:
         return out, (cache, x, flat, z)
     return out
 
 
-def encoder_backward(p, saved, dout):
-    """-> grads with the layout of p (no input gradient: the input is pixels)."""
+def encoder_backward(p, saved, dout, q=None):
+    """-> grads with the layout of p (no input gradient: the input is pixels).  q: see encoder_forward (gradient tensors that the
+    tensor-core path stores -- dz as a GEMM operand, dx, dc1, dpool, dc0 -- are rounded by q; parameter gradients are fp32 sums)."""
     cache, x_last, flat, z = saved
+    q = q or (lambda a: a)
     g = {}
     d = p['MLP_0']['Dense_0']
     dz = dout * gelu_tanh_grad(z)
-    g['MLP_0'] = {'Dense_0': {'kernel': flat.T @ dz, 'bias': dz.sum(0)}}
-    dx = (dz @ d['kernel'].T).reshape(x_last.shape) * (x_last > 0)
+    dzq = q(dz)
+    g['MLP_0'] = {'Dense_0': {'kernel': flat.T @ dzq, 'bias': dz.sum(0)}}
+    dx = q((dzq @ q(d['kernel']).T).reshape(x_last.shape) * (x_last > 0))
     for i in reversed(range(len(STACKS))):
         blk = p[f'stack_blocks_{i}']
         x_in, c0_shape, arg, pad_lo, pl, r1, c1, r2 = cache[i]
         gb = {}
-        dpl = dx.copy()                                            # skip connection
-        dr2, dW2, db2 = conv_bwd(r2, blk['Conv_2']['kernel'], dx)
+        dr2, dW2, db2 = conv_bwd(r2, q(blk['Conv_2']['kernel']), dx)
         gb['Conv_2'] = {'kernel': dW2, 'bias': db2}
-        dc1 = dr2 * (c1 > 0)
-        dr1, dW1, db1 = conv_bwd(r1, blk['Conv_1']['kernel'], dc1)
+        dc1 = q(dr2 * (c1 > 0))
+        dr1, dW1, db1 = conv_bwd(r1, q(blk['Conv_1']['kernel']), dc1)
         gb['Conv_1'] = {'kernel': dW1, 'bias': db1}
-        dpl += dr1 * (pl > 0)
-        dc0 = pool_bwd(dpl, arg, c0_shape, pad_lo)
-        dx, dW0, db0 = conv_bwd(x_in, blk['Conv_0']['kernel'], dc0)
+        dpl = q(dx + dr1 * (pl > 0))                               # skip connection + residual branch
+        dc0 = q(pool_bwd(dpl, arg, c0_shape, pad_lo))
+        dx, dW0, db0 = conv_bwd(x_in, q(blk['Conv_0']['kernel']), dc0)
+        dx = q(dx)
         gb['Conv_0'] = {'kernel': dW0, 'bias': db0}
         g[f'stack_blocks_{i}'] = gb
     return g

@@ -37,10 +37,11 @@ def init_params(seed, in_ch, action_dim, cfg, dtype=np.float32, hw=64, jitter=0.
     return params
 
 
-def total_loss(params, cfg, batch, noise, with_grads=True):
+def total_loss(params, cfg, batch, noise, with_grads=True, enc_q=None):
+    """enc_q (optional): storage rounding of the encoders' activations / weight operands (oracle/encoder_oracle.py bf16_round)."""
     obs, nobs = batch['observations'], batch['next_observations']
     dt = batch['actions'].dtype
-    enc = lambda p, x, save=False: E.encoder_forward(p, x, dtype=dt, save=save)
+    enc = lambda p, x, save=False: E.encoder_forward(p, x, dtype=dt, save=save, q=enc_q)
     fC, sC = enc(params['modules_critic']['encoder'], obs, True)
     fF, sF = enc(params['modules_actor_bc_flow_encoder'], obs, True)
     fO, sO = enc(params['modules_actor_onestep_flow']['encoder'], obs, True)
@@ -49,16 +50,16 @@ def total_loss(params, cfg, batch, noise, with_grads=True):
     loss, info, grads, dfeat = O.total_loss(params, cfg, batch, noise, with_grads=with_grads, feats=feats)
     if not with_grads:
         return loss, info, None
-    grads['modules_critic']['encoder'] = E.encoder_backward(params['modules_critic']['encoder'], sC, dfeat['C'])
-    grads['modules_actor_bc_flow_encoder'] = E.encoder_backward(params['modules_actor_bc_flow_encoder'], sF, dfeat['F'])
-    grads['modules_actor_onestep_flow']['encoder'] = E.encoder_backward(params['modules_actor_onestep_flow']['encoder'], sO, dfeat['O'])
+    grads['modules_critic']['encoder'] = E.encoder_backward(params['modules_critic']['encoder'], sC, dfeat['C'], q=enc_q)
+    grads['modules_actor_bc_flow_encoder'] = E.encoder_backward(params['modules_actor_bc_flow_encoder'], sF, dfeat['F'], q=enc_q)
+    grads['modules_actor_onestep_flow']['encoder'] = E.encoder_backward(params['modules_actor_onestep_flow']['encoder'], sO, dfeat['O'], q=enc_q)
     return loss, info, grads
 
 
-def update(state, cfg, batch, noise):
+def update(state, cfg, batch, noise, enc_q=None):
     """agents/fql.py:122-133 for the pixel configuration (same optimizer / Polyak as the state oracle)."""
     params = state['params']
-    loss, info, grads = total_loss(params, cfg, batch, noise)
+    loss, info, grads = total_loss(params, cfg, batch, noise, enc_q=enc_q)
     gmax, gmin, gnorm = O.grad_stats(grads)
     info['grad/max'], info['grad/min'], info['grad/norm'] = gmax, gmin, gnorm
     new_p, new_m, new_v, new_count = O.adam_update(params, grads, state['mu'], state['nu'], state['count'], cfg['lr'])

@@ -19,11 +19,11 @@ from tests.helpers import f32, info_close, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def make_agent(cfg, B, hw, ch, A):
+def make_agent(cfg, B, hw, ch, A, precision='fp32'):
     from fql_b200 import FQLAgent
     c = dict(cfg)
     c['batch_size'] = B
-    return FQLAgent.create(0, np.zeros((1, hw, hw, ch), np.uint8), np.zeros((1, A), np.float32), c)
+    return FQLAgent.create(0, np.zeros((1, hw, hw, ch), np.uint8), np.zeros((1, A), np.float32), c, precision=precision)
 
 
 @pytest.mark.parametrize('name,B,hw,ch,A,hidden,over', [
@@ -74,6 +74,72 @@ def test_pixel_update_parity(name, B, hw, ch, A, hidden, over):
     fa = agent.compute_flow_actions(batch['observations'], noise['z'].astype(np.float32))
     ff = PO.E.encoder_forward(p64['modules_actor_bc_flow_encoder'], batch['observations'], dtype=np.dtype(np.float64))
     assert rel_err(fa, O.compute_flow_actions(p64, cfg, ff, noise['z'])) <= 2e-5
+
+
+# bf16 tensor-core encoders (FQL_PRECISION_BF16_ENC: implicit-GEMM convolutions on tcgen05, bf16 activations, fp32 accumulate; the MLPs
+# behind them in fp32).  Two references:
+#  (a) the reference's mathematics with the SAME storage rounding (oracle/encoder_oracle.py `q=bf16_round`: every stored activation /
+#      gradient tensor and every weight operand of the encoders rounded to bf16, everything else fp64).  The device must reproduce
+#      it: metrics 1e-3, every gradient leaf TOL_Q (what is left is fp32-vs-fp64 accumulation moving a value across a bf16 rounding
+#      boundary or a relu / max-pool decision; measured <= 2e-2 on the smallest-magnitude leaves);
+#  (b) the unrounded fp64 oracle, the stated bf16 tolerance: metrics 5e-2, MLP gradient leaves 3e-2.  The ENCODER leaves are reported
+#      and bounded only loosely (TOL_ENC_64, plus cosine >= 0.85): rounding an activation to 8 significant bits flips a small
+#      fraction of the relu masks and max-pool argmaxes, every flip re-routes that element's gradient completely, and on these
+#      uniform-noise frames (neighbouring pixels independent: the worst case) that is 5-40 % of a leaf's largest entry -- a property
+#      of bf16 storage in this non-smooth network (the fp64 oracle run with the same rounding shows it, (a)), not of the kernels,
+#      whose arithmetic is checked exactly in tests/test_conv_tc_gpu.py.
+TOL_Q, TOL_MLP_64, TOL_ENC_64 = 4e-2, 3e-2, 0.6
+
+
+@pytest.mark.parametrize('name,B,hw,ch,A,hidden,over', [
+    ('tc-small-16px', 6, 16, 6, 3, 64, dict(alpha=10.0)),
+    ('tc-odd-20px', 5, 20, 3, 2, 64, dict(q_agg='min', alpha=10.0)),
+    ('tc-visual-cube-single-b8', 8, 64, 9, 5, 512, dict(alpha=300.0)),
+    ('tc-visual-cube-single-b256', 256, 64, 9, 5, 512, dict(alpha=300.0)),   # BASELINE config 5 at its batch size
+])
+def test_pixel_update_parity_tensor_core_encoders(name, B, hw, ch, A, hidden, over):
+    from oracle.encoder_oracle import bf16_round
+    from tests.helpers import check_update_delta
+    cfg = dict(O.DEFAULT_CONFIG)
+    cfg.update(over)
+    cfg.update(actor_hidden_dims=(hidden,) * 4, value_hidden_dims=(hidden,) * 4, encoder='impala_small')
+    params = PO.init_params(3, ch, A, cfg, dtype=np.float64, hw=hw, jitter=0.05, target_equals_critic=False)
+    params['modules_actor_onestep_flow']['mlp']['Dense_4']['bias'][0] += 1.1
+    state = O.init_state(params, warm=True, seed=3)
+    batch = PO.make_pixel_batch(4, B, A, hw=hw, ch=ch, dtype=np.float64)
+    noise = O.make_noise(5, B, A, np.float64)
+    stq, infoq, gradsq = PO.update(copy.deepcopy(state), cfg, batch, noise, enc_q=bf16_round)
+    st64, info64, grads64 = PO.update(copy.deepcopy(state), cfg, batch, noise)
+    agent = make_agent(cfg, B, hw, ch, A, precision='bf16')
+    agent.load_tree(f32(state['params']), f32(state['mu']), f32(state['nu']), state['count'])
+    b32 = {k: (v if v.dtype == np.uint8 else v.astype(np.float32)) for k, v in batch.items()}
+    _, info = agent.update(b32, noise=f32(noise))
+    for k in O.INFO_KEYS[:10]:
+        info_close(k, info[k], infoq, 1e-3)
+        info_close(k, info[k], info64, 5e-2)
+    got = agent.export_tree('grads')
+    worst_q, worst_mlp, worst_enc, worst_cos = 0.0, 0.0, 0.0, 1.0
+    for (path, r64), (_, rq), (_, g) in zip(O.tree_leaves(grads64), O.tree_leaves(gradsq), O.tree_leaves(got)):
+        if np.abs(r64).max() == 0:
+            continue
+        eq, e64 = rel_err(g, rq), rel_err(g, r64)
+        assert eq <= TOL_Q, ('vs the bf16-storage oracle', '/'.join(path), eq)
+        worst_q = max(worst_q, eq)
+        if any('stack_blocks' in p for p in path):
+            cos = float(np.vdot(g, r64) / (np.linalg.norm(g) * np.linalg.norm(r64)))
+            assert e64 <= TOL_ENC_64 and cos >= 0.85, ('encoder leaf vs fp64', '/'.join(path), e64, cos)
+            worst_enc, worst_cos = max(worst_enc, e64), min(worst_cos, cos)
+        else:
+            assert e64 <= TOL_MLP_64, ('vs fp64', '/'.join(path), e64)
+            worst_mlp = max(worst_mlp, e64)
+    print(name, f'gradient leaves: worst vs bf16-storage oracle {worst_q:.2e}; vs fp64: MLP/Dense leaves {worst_mlp:.2e}, encoder conv leaves '
+                f'{worst_enc:.2e} (cosine >= {worst_cos:.3f})')
+    check_update_delta(state['params'], stq['params'], agent.export_tree('params'), 0.9, what=name, opt=dict(state=state, cfg=cfg, grads=got))
+    # forward entry point through the tensor-core encoder (the device parameters are the update by the device gradients: bf16 tolerance)
+    a = agent.sample_actions(batch['observations'][:8], noise=noise['z'][:8].astype(np.float32))
+    pq = O.cast_tree(stq['params'], np.float64)
+    feats = PO.E.encoder_forward(pq['modules_actor_onestep_flow']['encoder'], batch['observations'][:8], dtype=np.dtype(np.float64), q=bf16_round)
+    assert rel_err(a, O.sample_actions_given_noise(pq, cfg, feats, noise['z'][:8])) <= 2e-2
 
 
 def test_pixel_param_count_matches_survey():
