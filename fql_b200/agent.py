@@ -155,10 +155,9 @@ class FQLAgent:
             self.world = dist.get_world_size(process_group)
         if world_size is not None:
             self.world = int(world_size)  # explicit override: the caller drives grads_phase / apply_phase itself
-        self._precision = {'fp32': _lib.PRECISION_FP32, 'bf16': _lib.PRECISION_BF16_TC}[precision]
-        if cfg.get('encoder') is not None and precision == 'bf16':
-            # pixel configs: the ImpalaEncoders run as bf16 implicit-GEMM convolutions on tcgen05, the MLPs behind them in fp32
-            self._precision = _lib.PRECISION_BF16_ENC
+        # 'bf16': every contraction on tcgen05 (pixel configs: implicit-GEMM encoders + layer-by-layer MLPs); 'bf16-enc' (pixel
+        # configs only): tcgen05 encoders, the MLPs behind them in fp32
+        self._precision = {'fp32': _lib.PRECISION_FP32, 'bf16': _lib.PRECISION_BF16_TC, 'bf16-enc': _lib.PRECISION_BF16_ENC}[precision]
         self._hidden, self._num_hidden = ah[0], len(ah)
         self._image = ob_dims if cfg.get('encoder') is not None else None
         self._feat = 512 if self._image else ob_dims[0]

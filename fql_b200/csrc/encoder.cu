@@ -300,7 +300,7 @@ int conv_wgrad(const float* in_f, const uint8_t* in_u8, const float* dout, float
 // buffers of one encoder pass
 // ---------------------------------------------------------------------------------------------------------------
 size_t enc_carve(const FqlDims* d, int64_t B, void* base, EncBuf* e, bool for_backward) {
-  if (d->precision == FQL_PRECISION_BF16_ENC) return enc_tc_carve(d, B, base, e, for_backward);
+  if (d->precision != FQL_PRECISION_FP32) return enc_tc_carve(d, B, base, e, for_backward);
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
   auto take = [&](int64_t nfloats) {
@@ -348,7 +348,7 @@ size_t enc_carve(const FqlDims* d, int64_t B, void* base, EncBuf* e, bool for_ba
 // features [B, 512] = encoder(obs_u8 [B,H,W,C]); `enc` = offsets of this encoder's leaves, params = arena of the seed
 int enc_forward(const FqlDims* d, const EncView& v, const float* params, const uint8_t* obs, int64_t B, const EncBuf& e, float* feat,
                 cudaStream_t st) {
-  if (d->precision == FQL_PRECISION_BF16_ENC) return enc_tc_forward(d, v, params, obs, B, e, feat, st);
+  if (d->precision != FQL_PRECISION_FP32) return enc_tc_forward(d, v, params, obs, B, e, feat, st);
   int H = d->reserved[0], W = d->reserved[1], C = d->reserved[2];
   const float* xin_f = nullptr;
   const uint8_t* xin_u8 = obs;
@@ -379,7 +379,7 @@ int enc_forward(const FqlDims* d, const EncView& v, const float* params, const u
 // parameter gradients of one encoder given d(loss)/d(features) [B,512]; grads = gradient arena of the seed
 int enc_backward(const FqlDims* d, const EncView& v, const float* params, float* grads, const uint8_t* obs, int64_t B, const EncBuf& e,
                  const float* dfeat, cudaStream_t st) {
-  if (d->precision == FQL_PRECISION_BF16_ENC) return enc_tc_backward(d, v, params, grads, obs, B, e, dfeat, st);
+  if (d->precision != FQL_PRECISION_FP32) return enc_tc_backward(d, v, params, grads, obs, B, e, dfeat, st);
   const int F = d->obs_dim;
   FQL_TRY(launch1d(gelu_grad_mul_kernel, B * F, st, dfeat, e.z, e.dz, B * F));
   GemmArgs a;  // dWd = flat^T dz

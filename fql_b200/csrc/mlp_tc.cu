@@ -448,10 +448,12 @@ int64_t tc_shadow_seed_elems(const FqlDims* d, const Layout& L) {
   return n;
 }
 
-int tc_supported(const FqlDims* d) {
+int tc_supported(const FqlDims* d, bool fused_kernels) {
   FQL_REQUIRE(d->hidden % 64 == 0 && d->hidden >= 64 && d->hidden <= 512 && (d->hidden & (d->hidden - 1)) == 0,
               "FQL_PRECISION_BF16_TC needs hidden in {64,128,256,512} (got %d)", d->hidden);
-  FQL_REQUIRE(d->obs_dim + d->action_dim + 1 <= 128, "FQL_PRECISION_BF16_TC needs obs_dim+action_dim+1 <= 128");
+  // the fused chain / cluster kernels keep the first-layer operand tile resident in shared memory (two 64-wide K blocks); wider
+  // inputs (pixel configs: 512 encoder features + action + time) run layer by layer through tc_gemm
+  FQL_REQUIRE(!fused_kernels || !tc_wide_input(d), "the fused tensor-core MLP kernels need obs_dim+action_dim+1 <= 128");
   FQL_REQUIRE(d->action_dim <= MAX_A, "FQL_PRECISION_BF16_TC needs action_dim <= %d", MAX_A);
   FQL_REQUIRE(!d->actor_layer_norm, "FQL_PRECISION_BF16_TC does not implement actor_layer_norm=True (non-default, agents/fql.py:260); "
                                     "use FQL_PRECISION_FP32");
@@ -459,7 +461,7 @@ int tc_supported(const FqlDims* d) {
 }
 
 int tc_refresh_shadow(const FqlDims* d, const Layout& L, const float* params, void* shadow, cudaStream_t st) {
-  FQL_TRY(tc_supported(d));
+  FQL_TRY(tc_supported(d, false));
   FQL_REQUIRE(shadow != nullptr, "shadow buffer is NULL (FQL_PRECISION_BF16_TC needs fql_shadow_bytes() bytes)");
   const int64_t seed = tc_shadow_seed_elems(d, L);
   dim3 g1((unsigned)((L.arena / 4 + 255) / 256), d->num_seeds);

@@ -47,8 +47,8 @@ int fql_validate_dims(const FqlDims* d) {
     FQL_REQUIRE(d->reserved[1] > 0 && d->reserved[2] > 0 && d->reserved[2] <= 32, "image dims %dx%dx%d", d->reserved[0], d->reserved[1], d->reserved[2]);
     FQL_REQUIRE(d->obs_dim == 512, "pixel configs: obs_dim is the encoder output width and must be 512 (got %d)", d->obs_dim);
     FQL_REQUIRE(d->num_seeds == 1, "pixel configs are built for num_seeds == 1");
-    FQL_REQUIRE(d->precision == FQL_PRECISION_FP32 || d->precision == FQL_PRECISION_BF16_ENC,
-                "pixel configs run in FQL_PRECISION_FP32 (fp32 CUDA-core encoders) or FQL_PRECISION_BF16_ENC (tcgen05 encoders, fp32 MLPs)");
+    // FQL_PRECISION_FP32: fp32 CUDA-core encoders and MLPs; FQL_PRECISION_BF16_ENC: tcgen05 encoders, fp32 MLPs;
+    // FQL_PRECISION_BF16_TC: tcgen05 encoders and MLPs (the MLPs layer by layer: their first-layer input is 512 + A (+ 1) wide)
   }
   return 0;
 }
@@ -656,6 +656,11 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4], ev_pad = ctx->ev[5];
   const int kO = (int)round_up64(sh.F + sh.A, 64), kF = (int)round_up64(sh.F + sh.A + 1, 64);
   const bool dp_grads = ctx->dp.active && c.do_backward;   // data parallel: per-network bucket reductions on ctx->sc
+  // pixel configs (512 encoder features in front of the action columns): every MLP layer by layer through tc_gemm, and the
+  // first-layer input gradients of the three trainable networks feed their encoders' backward
+  const bool wide = tc_wide_input(d), pix = d->reserved[0] > 0;
+  FQL_REQUIRE(!(pix && ctx->dp.active), "data-parallel pixel configs run in FQL_PRECISION_FP32 / FQL_PRECISION_BF16_ENC (one exchange at the end of the "
+                                         "backward); the bucketed tensor-core schedule does not cover the encoder gradients yet");
   FQL_TRY(stamp(ctx, 0, S0));   // step start
   FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0, w.cpost_ticket, 3 * S));
   FQL_TRY(encode_observations(c, L, w, S0));
@@ -683,7 +688,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   if (!fused_prep) FQL_TRY(tc_pad_bf16(w.XF, w.XFb, (int64_t)S * 2 * B, sh.F + sh.A + 1, kF, S1));
   FQL_CHECK_CUDA(cudaEventRecord(ev_pad, S1));
   const int row_tiles = S * ((B + 127) / 128);
-  const bool many_tiles = row_tiles >= ctx->chain_min_tiles;  // enough 128-row tiles to fill the GPU: fused per-tile chain kernels
+  const bool many_tiles = row_tiles >= ctx->chain_min_tiles && !wide;  // enough 128-row tiles to fill the GPU: fused per-tile chain kernels
   // ... and the whole backward as chain launches on bf16 gelu' / xhat saves (chain2_tc.cu, tc_path.cu "large-batch backward")
   const bool big_bwd = many_tiles && ctx->use_big_bwd && tc_mlp_chain2_supported(d) && d->critic_layer_norm && d->reserved[0] == 0;
   auto chain = [&](int net, const void* X0b, int rows_cap, int r0_in, int M, void* const* Hb, void* const* Zb, float* out, int n_steps,
@@ -698,7 +703,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   };
   if (many_tiles) {
     FQL_TRY(chain(FQL_NET_ACTOR_BC_FLOW, w.XFb, 2 * B, B, B, nullptr, nullptr, nullptr, sh.flow_steps, S1));
-  } else if (H == 512 && ctx->use_euler_cluster) {
+  } else if (H == 512 && ctx->use_euler_cluster && !wide) {
     TcEulerSpec e;
     memset(&e, 0, sizeof(e));
     e.d = d; e.L = &L; e.params = P; e.shadow = shadow; e.X0b = w.XFb; e.Mcap0 = 2 * B; e.r0_in = B; e.M = B;
@@ -738,6 +743,10 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     FQL_TRY(stamp(ctx, 4, S2));
   } else if (c.do_backward) {
     FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.F_dZf, S2, ctx->s3, ctx->s7, &ctx->ev[8]));
+    if (pix) {  // d(BC loss)/d(features) -> actor_bc_flow_encoder (agents/fql.py:58, 230-232)
+      FQL_TRY(tc_actor_input_grad(fbc, w.F_dZb[0], w.dX0F, S2));
+      FQL_TRY(encoder_grads(c, L, w, FQL_NET_ACTOR_BC_FLOW, w.dX0F, 1, sh.F + sh.A + 1, w.dfeat[1], 4, S2));
+    }
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[53], ctx->s7));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s3, ctx->ev[53], 0));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], ctx->s3));
@@ -761,7 +770,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   } else {
     // small batch: the same cluster-of-16 chain kernel as the Euler integration (2.7 us per layer instead of a GEMM launch each)
     int rc = 1;
-    if (ctx->use_euler_cluster && ctx->use_cluster_fwd) {
+    if (ctx->use_euler_cluster && ctx->use_cluster_fwd && !wide) {
       // rows (s',z') and (s,z) feed the critic passes that everything else waits for; the (s,z'') rows only feed the mse metric
       // and go layer by layer on a side stream (the GPU holds 7 clusters of 16: 2 Euler + 4 here)
       TcClusterFwdSpec cf;
@@ -791,7 +800,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   cr.d = d; cr.L = &L; cr.params = P; cr.shadow = shadow; cr.M = B; cr.K0pad = kO; cr.x_ss = (long long)B * kO; cr.buf = &w.pC; cr.Hb = w.C_Hb;
   cr.cs_scratch = w.cs_scratch[2];
   bool split_cpost = false;
-  if (ctx->use_critic_chain || many_tiles) {   // enough row tiles to fill the GPU: the three critic problems x 2 heads as ONE fused launch
+  if ((ctx->use_critic_chain && !wide) || many_tiles) {   // enough row tiles to fill the GPU: the three critic problems x 2 heads as ONE fused launch
     TcChainSpec t;
     memset(&t, 0, sizeof(t));
     t.d = d; t.L = &L; t.P = 3; t.net[0] = FQL_NET_TARGET_CRITIC; t.net[1] = FQL_NET_CRITIC; t.net[2] = FQL_NET_CRITIC;
@@ -830,11 +839,13 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     t.grads = c.st->grads; t.p = 1; t.X0b = reinterpret_cast<const bf16*>(w.XCb) + (int64_t)1 * S * B * kO;
     t.dOut = w.dq; t.dOutb = w.C1_dOutb;
     for (int l = 0; l < NH; l++) { t.dZb[l] = w.C1_dZb[l]; t.dZf[l] = w.C1_dZf[l]; t.dHf[l] = w.C1_dHf[l]; }
+    if (pix) t.dX0 = w.dX0C;   // d(critic loss)/d(features) of both heads -> the critic's encoder (agents/fql.py:36)
     if (big_bwd) {
       FQL_TRY(tc_critic_backward_big(t, w.C_XHb, w.C_DGb, S2));
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], S2));
     } else {
       FQL_TRY(tc_critic_backward(t, S2, ctx->s5, ctx->s8, &ctx->ev[28]));
+      if (pix) FQL_TRY(encoder_grads(c, L, w, FQL_NET_CRITIC, w.dX0C, 2, sh.F + sh.A, w.dfeat[0], 3, S2));
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[54], ctx->s8));
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s5, ctx->ev[54], 0));
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], ctx->s5));
@@ -914,7 +925,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   if (c.do_backward) {
     TcActor bo = actor(FQL_NET_ACTOR_ONESTEP_FLOW, w.XOb, kO, 3 * B, B, B, w.O_Hb, w.O_Zb, true);
     int rc = 1;
-    if (!many_tiles && ctx->use_euler_cluster && ctx->use_cluster_bwd) {
+    if (!many_tiles && ctx->use_euler_cluster && ctx->use_cluster_bwd && !wide) {
       // small batch: the dgrad chain as ONE cluster-of-16 launch (the Euler chain has finished: its clusters are free), then the
       // ten independent parameter-gradient launches dealt onto five idle side streams
       TcClusterBwdSpec cb;
@@ -939,6 +950,10 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
       FQL_TRY(tc_actor_backward_big(bo, w.dapi, w.O_dOutb, w.O_dZb, true, S0));
     } else if (rc == 1) {
       FQL_TRY(tc_actor_backward(bo, w.dapi, w.O_dOutb, w.O_dZb, w.O_dZf, S0, ctx->s4, ctx->s9, &ctx->ev[18], true));
+      if (pix) {  // d(alpha distill + Q loss)/d(features) -> the one-step actor's encoder (agents/fql.py:65)
+        FQL_TRY(tc_actor_input_grad(bo, w.O_dZb[0], w.dX0O, S0));
+        FQL_TRY(encoder_grads(c, L, w, FQL_NET_ACTOR_ONESTEP_FLOW, w.dX0O, 1, sh.F + sh.A, w.dfeat[2], 1, S0));
+      }
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[55], ctx->s9));
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s4, ctx->ev[55], 0));
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[26], ctx->s4));
@@ -965,7 +980,7 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
   FQL_TRY(check_common(c.d, c.ws, c.ws_bytes, &L, &w));
   const bool tcm = c.d->precision == FQL_PRECISION_BF16_TC;
   if (tcm) {
-    FQL_TRY(tc_supported(c.d));
+    FQL_TRY(tc_supported(c.d, false));
     FQL_REQUIRE(c.st->shadow != nullptr, "FQL_PRECISION_BF16_TC needs FqlState.shadow (fql_shadow_bytes() bytes, kept by fql_refresh_shadow)");
   }
   const StepShape sh = make_shape(c.d);
@@ -1170,7 +1185,7 @@ int run_step_on(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     WsPtrs w;
     FQL_TRY(check_common(c.d, c.ws, c.ws_bytes, &L, &w));
     if (c.d->precision == FQL_PRECISION_BF16_TC) {
-      FQL_TRY(tc_supported(c.d));
+      FQL_TRY(tc_supported(c.d, false));
       FQL_REQUIRE(c.st->shadow != nullptr, "FQL_PRECISION_BF16_TC needs FqlState.shadow");
     }
   }
@@ -1329,7 +1344,7 @@ extern "C" int fql_sample_actions(FqlContext*, const FqlDims* d, const float* pa
     obs = feat;
   }
   FQL_TRY(launch_concat(obs, d->obs_dim, noise, d->action_dim, 0.f, 0, X, R, st));
-  if (d->precision == FQL_PRECISION_BF16_TC) {
+  if (d->precision == FQL_PRECISION_BF16_TC && !tc_wide_input(d)) {
     FQL_REQUIRE(shadow != nullptr, "FQL_PRECISION_BF16_TC needs the bf16 shadow");
     const int kp = (int)round_up64(nv.in_dim, 64);
     FQL_TRY(tc_pad_bf16(X, Xb, R, nv.in_dim, kp, st));
@@ -1367,7 +1382,7 @@ extern "C" int fql_compute_flow_actions(FqlContext*, const FqlDims* d, const flo
     obs = feat;
   }
   FQL_TRY(launch_concat(obs, d->obs_dim, noise, d->action_dim, 0.f, 1, X, R, st));
-  if (d->precision == FQL_PRECISION_BF16_TC) {
+  if (d->precision == FQL_PRECISION_BF16_TC && !tc_wide_input(d)) {
     FQL_REQUIRE(shadow != nullptr, "FQL_PRECISION_BF16_TC needs the bf16 shadow");
     const int kp = (int)round_up64(nv.in_dim, 64);
     FQL_TRY(tc_pad_bf16(X, Xb, R, nv.in_dim, kp, st));

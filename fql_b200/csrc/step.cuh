@@ -186,7 +186,8 @@ struct TcChain2BwdSpec {
   float* dX0;            // out (optional): fp32 [S][ens][Mcap_dz][K0] input gradient
 };
 int tc_mlp_chain2_backward(const TcChain2BwdSpec& f, cudaStream_t st);
-int tc_supported(const FqlDims* d);
+int tc_supported(const FqlDims* d, bool fused_kernels = true);   // fused_kernels: also the limits of the chain / cluster kernels
+inline bool tc_wide_input(const FqlDims* d) { return d->obs_dim + d->action_dim + 1 > 128; }   // pixel configs: 512 encoder features
 int64_t tc_shadow_seed_elems(const FqlDims* d, const Layout& L);
 int tc_refresh_shadow(const FqlDims* d, const Layout& L, const float* params, void* shadow, cudaStream_t st);
 int tc_refresh_shadow_lastlayer(const FqlDims* d, const Layout& L, const float* params, void* shadow, cudaStream_t st);
@@ -225,6 +226,8 @@ struct TcGemmSpec {
 // column sums over rows of a bf16 tensor [G][M][N] ADDED into fp32 out[g * out_stride + n] (bias gradients from the bf16 dZ saves)
 int launch_colsum_bf16(const void* X, int64_t G, int64_t M, int N, float* out, int64_t out_stride_g0, int G0, int64_t out_stride_g1, cudaStream_t st);
 int tc_gemm(const TcGemmSpec& s, cudaStream_t st);
+struct TcActor;
+int tc_actor_input_grad(const TcActor& t, const void* dZ0b, float* dX0, cudaStream_t st);
 
 // tc_path.cu -- layer-by-layer tensor-core schedules
 struct TcActor {

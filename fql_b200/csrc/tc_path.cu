@@ -288,6 +288,24 @@ int tc_actor_forward(const TcActor& t, float* out, long long out_ss, int clip, c
 // ---------------------------------------------------------------------------------------------------------------
 // actor backward: dOut fp32 [S][M][A] -> parameter gradients (fp32, into the arena)
 // ---------------------------------------------------------------------------------------------------------------
+// dX0 [S][M][K0] = dZ_0 W_0^T in fp32: the gradient of an actor's loss with respect to its first-layer input (pixel configs: the first
+// obs_dim columns are the encoder features, agents/fql.py:58, 65 -> utils/encoders.py backward)
+int tc_actor_input_grad(const TcActor& t, const void* dZ0b, float* dX0, cudaStream_t st) {
+  const FqlDims* d = t.d;
+  const Layout& L = *t.L;
+  const NetView& nv = L.net[t.net];
+  const int H = d->hidden, S = d->num_seeds, K0 = nv.in_dim;
+  const bf16* sh = reinterpret_cast<const bf16*>(t.shadow);
+  TcGemmSpec g;
+  memset(&g, 0, sizeof(g));
+  g.M = t.M; g.N = K0; g.K = H; g.G0 = 1; g.G1 = S; g.a_mn = 0; g.b_mn = 0;
+  g.A = op(dZ0b, H, t.M, H, 1, 0, S, (long long)t.M * H);
+  g.B = op(sh + nv.off_w[0], H, K0, H, 1, 0, S, tc_shadow_seed_elems(d, L));
+  g.mode = TC_MODE_STORE_F32;
+  g.out_f = tp(dX0, 0, (long long)t.M * K0, K0);
+  return tc_gemm(g, st);
+}
+
 int tc_actor_backward(const TcActor& t, const float* dOut, void* dOutb, void* const dZb[FQL_MAXL], float* const dZf[FQL_MAXL],
                       cudaStream_t st, cudaStream_t side, cudaStream_t side2, cudaEvent_t* ev, bool dOutb_ready) {
   // side: weight-gradient GEMMs, side2: bias-gradient column sums (one stream for both was measured to be the longest chain of

@@ -88,16 +88,20 @@ def test_pixel_update_parity(name, B, hw, ch, A, hidden, over):
 #      uniform-noise frames (neighbouring pixels independent: the worst case) that is 5-40 % of a leaf's largest entry -- a property
 #      of bf16 storage in this non-smooth network (the fp64 oracle run with the same rounding shows it, (a)), not of the kernels,
 #      whose arithmetic is checked exactly in tests/test_conv_tc_gpu.py.
-TOL_Q, TOL_MLP_64, TOL_ENC_64 = 4e-2, 3e-2, 0.6
+# mode 'bf16' (FQL_PRECISION_BF16_TC on a pixel config) additionally runs the MLPs on tcgen05, layer by layer (their first-layer input is
+# 512 + A (+1) wide): the MLPs' own bf16 error (measured 1e-2 on their gradient leaves) then also enters d(loss)/d(features), so the
+# comparison with the bf16-storage oracle (whose MLPs are exact) is bounded at TOL_Q_FULL instead of TOL_Q.
+TOL_Q, TOL_Q_FULL, TOL_MLP_64, TOL_ENC_64 = 4e-2, 8e-2, 4e-2, 0.6
 
 
+@pytest.mark.parametrize('mode', ['bf16-enc', 'bf16'])
 @pytest.mark.parametrize('name,B,hw,ch,A,hidden,over', [
     ('tc-small-16px', 6, 16, 6, 3, 64, dict(alpha=10.0)),
     ('tc-odd-20px', 5, 20, 3, 2, 64, dict(q_agg='min', alpha=10.0)),
     ('tc-visual-cube-single-b8', 8, 64, 9, 5, 512, dict(alpha=300.0)),
     ('tc-visual-cube-single-b256', 256, 64, 9, 5, 512, dict(alpha=300.0)),   # BASELINE config 5 at its batch size
 ])
-def test_pixel_update_parity_tensor_core_encoders(name, B, hw, ch, A, hidden, over):
+def test_pixel_update_parity_tensor_core_encoders(name, B, hw, ch, A, hidden, over, mode):
     from oracle.encoder_oracle import bf16_round
     from tests.helpers import check_update_delta
     cfg = dict(O.DEFAULT_CONFIG)
@@ -110,12 +114,13 @@ def test_pixel_update_parity_tensor_core_encoders(name, B, hw, ch, A, hidden, ov
     noise = O.make_noise(5, B, A, np.float64)
     stq, infoq, gradsq = PO.update(copy.deepcopy(state), cfg, batch, noise, enc_q=bf16_round)
     st64, info64, grads64 = PO.update(copy.deepcopy(state), cfg, batch, noise)
-    agent = make_agent(cfg, B, hw, ch, A, precision='bf16')
+    agent = make_agent(cfg, B, hw, ch, A, precision=mode)
     agent.load_tree(f32(state['params']), f32(state['mu']), f32(state['nu']), state['count'])
     b32 = {k: (v if v.dtype == np.uint8 else v.astype(np.float32)) for k, v in batch.items()}
     _, info = agent.update(b32, noise=f32(noise))
+    tol_q = TOL_Q if mode == 'bf16-enc' else TOL_Q_FULL
     for k in O.INFO_KEYS[:10]:
-        info_close(k, info[k], infoq, 1e-3)
+        info_close(k, info[k], infoq, 1e-3 if mode == 'bf16-enc' else 5e-2)
         info_close(k, info[k], info64, 5e-2)
     got = agent.export_tree('grads')
     worst_q, worst_mlp, worst_enc, worst_cos = 0.0, 0.0, 0.0, 1.0
@@ -123,7 +128,7 @@ def test_pixel_update_parity_tensor_core_encoders(name, B, hw, ch, A, hidden, ov
         if np.abs(r64).max() == 0:
             continue
         eq, e64 = rel_err(g, rq), rel_err(g, r64)
-        assert eq <= TOL_Q, ('vs the bf16-storage oracle', '/'.join(path), eq)
+        assert eq <= tol_q, ('vs the bf16-storage oracle', '/'.join(path), eq)
         worst_q = max(worst_q, eq)
         if any('stack_blocks' in p for p in path):
             cos = float(np.vdot(g, r64) / (np.linalg.norm(g) * np.linalg.norm(r64)))
@@ -132,14 +137,14 @@ def test_pixel_update_parity_tensor_core_encoders(name, B, hw, ch, A, hidden, ov
         else:
             assert e64 <= TOL_MLP_64, ('vs fp64', '/'.join(path), e64)
             worst_mlp = max(worst_mlp, e64)
-    print(name, f'gradient leaves: worst vs bf16-storage oracle {worst_q:.2e}; vs fp64: MLP/Dense leaves {worst_mlp:.2e}, encoder conv leaves '
+    print(name, mode, f'gradient leaves: worst vs bf16-storage oracle {worst_q:.2e}; vs fp64: MLP/Dense leaves {worst_mlp:.2e}, encoder conv leaves '
                 f'{worst_enc:.2e} (cosine >= {worst_cos:.3f})')
     check_update_delta(state['params'], stq['params'], agent.export_tree('params'), 0.9, what=name, opt=dict(state=state, cfg=cfg, grads=got))
     # forward entry point through the tensor-core encoder (the device parameters are the update by the device gradients: bf16 tolerance)
     a = agent.sample_actions(batch['observations'][:8], noise=noise['z'][:8].astype(np.float32))
     pq = O.cast_tree(stq['params'], np.float64)
     feats = PO.E.encoder_forward(pq['modules_actor_onestep_flow']['encoder'], batch['observations'][:8], dtype=np.dtype(np.float64), q=bf16_round)
-    assert rel_err(a, O.sample_actions_given_noise(pq, cfg, feats, noise['z'][:8])) <= 2e-2
+    assert rel_err(a, O.sample_actions_given_noise(pq, cfg, feats, noise['z'][:8])) <= 3e-2
 
 
 def test_pixel_param_count_matches_survey():
