@@ -10,12 +10,15 @@
 //                           MMAs produce the bias gradient; per-CTA partials are reduced in CTA order (deterministic)
 // Activations are NHWC bf16 with 16 or 32 channels (the uint8 frames become 16-channel bf16 INTEGERS 0..255, exact in bf16; the
 // 1/255 of encoders.py:84 is applied in fp32 to the accumulator).  Nothing is ever materialised as an im2col matrix in HBM:
-//   warps 1-4  producers: thread r owns pixel r of the tile; for each of the 9 taps it copies that neighbour's channels (16-byte
-//              chunks, zeros outside the image = SAME padding) straight from L2/HBM into the K-major SWIZZLE_128B operand blocks
-//              ([128 rows][64 k] bf16) the MMAs read -- the same blocks serve as the MN-major A operand of the weight gradient;
-//   warp 0     one thread issues tcgen05.mma (M=128, N=64, K=16); the prepared weights [Kpad][64] arrive once per CTA by TMA and
-//              stay resident; operand buffers and accumulators are double-buffered so tile i+1 is gathered while tile i multiplies;
-//   warps 5-8  epilogue: thread per pixel reads its accumulator row from TMEM: x scale + bias, x relu-mask of a saved tensor,
+//   warps 1-8  producers, two groups of four (group g fills operand buffer g, i.e. every second tile: a gather is one L2 round trip
+//              per tile, two tiles in flight hide it): thread r owns pixel r of the tile; for each of the 9 taps it copies that
+//              neighbour's channels (16-byte chunks, zeros outside the image = SAME padding) straight from L2/HBM into the K-major
+//              SWIZZLE_128B operand blocks ([128 rows][64 k] bf16) the MMAs read -- the same blocks serve as the MN-major A operand
+//              of the weight gradient;
+//   warps 0,13 one thread each issues tcgen05.mma (M=128, N=64, K=16) for every second tile of the CTA into its own accumulator set
+//              (the ~80 ns issue cost of an MMA is per warp); the prepared weights [Kpad][64] arrive once per CTA by TMA and stay
+//              resident; operand buffers and accumulators are double-buffered so tile i+1 is gathered while tile i multiplies;
+//   warps 9-12 epilogue: thread per pixel reads its accumulator row from TMEM: x scale + bias, x relu-mask of a saved tensor,
 //              + skip / upstream gradient, relu, bf16 NHWC stores (16-byte vectors).
 // Pooling (3x3/2, first maximum wins, argmax routing in the backward) and the element-wise pieces are bf16 kernels below; the final
 // Dense runs through tc_gemm.cu.
@@ -32,7 +35,7 @@ namespace {
 constexpr int kStacks[3] = {16, 32, 32};
 constexpr int TM = 128;
 constexpr int BLK = TM * 128;            // one operand block: [128 rows][64 bf16]
-constexpr int CT_THREADS = 32 * 9;
+constexpr int CT_THREADS = 32 * 14;   // MMA warp 0, 2 x 4 producer warps (one group per operand buffer), 4 epilogue warps, MMA warp 13
 constexpr int KPAD_MAX = 320;            // round_up(9 * 32, 64)
 constexpr int WSLOT = KPAD_MAX * 64;     // elements of one prepared weight matrix [Kpad][64]
 enum { CT_CONV = 0, CT_WGRAD = 1 };
@@ -66,38 +69,44 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   constexpr int NKB = (9 * CIN + 1 + 63) / 64;      // operand blocks per buffer that hold data
   constexpr int NMT = (9 * CIN + 1 + 127) / 128;    // M tiles of the weight gradient
   constexpr int NBLK = (MODE == CT_WGRAD) ? 2 * NMT : NKB;   // blocks allocated per buffer
+  // operand buffers: a tile's gather (one L2 round trip) and its MMAs (~0.7 us) overlap with other tiles only across buffers, so the
+  // 16-channel forward / input-gradient kernels, whose buffers are 48 KB, keep four of them (two per producer group / MMA issuer)
+  constexpr int NBUF = (MODE == CT_CONV && CIN == 16) ? 4 : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                                         // [2][NBLK][BLK]
-  uint8_t* sB = sA + 2 * NBLK * BLK;                          // CT_CONV: weights [NKB * 64 k][64 n]; CT_WGRAD: dY tiles [2][BLK]
-  constexpr int SB_BYTES = (MODE == CT_WGRAD) ? 2 * BLK : NKB * 64 * 128;
+  uint8_t* sA = smem;                                         // [NBUF][NBLK][BLK]
+  uint8_t* sB = sA + NBUF * NBLK * BLK;                       // CT_CONV: weights [NKB * 64 k][64 n]; CT_WGRAD: dY tiles [NBUF][BLK]
+  constexpr int SB_BYTES = (MODE == CT_WGRAD) ? NBUF * BLK : NKB * 64 * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SB_BYTES);
-  uint64_t* a_full = bars;          // [2] operand buffer gathered                 (4 producer warps)
-  uint64_t* a_empty = bars + 2;     // [2] the MMAs have consumed the buffer       (tcgen05.commit)
-  uint64_t* acc_full = bars + 4;    // [2] accumulator complete                    (tcgen05.commit)
-  uint64_t* acc_free = bars + 6;    // [2] accumulator read                        (4 epilogue warps)
-  uint64_t* b_full = bars + 8;      //     weights landed                          (TMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* a_full = bars;          // [4] operand buffer gathered                 (4 producer warps)
+  uint64_t* a_empty = bars + 4;     // [4] the MMAs have consumed the buffer       (tcgen05.commit)
+  uint64_t* acc_full = bars + 8;    // [2] accumulator complete                    (tcgen05.commit)
+  uint64_t* acc_free = bars + 10;   // [2] accumulator read                        (4 epilogue warps)
+  uint64_t* b_full = bars + 12;     //     weights landed                          (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntl = (a.tiles > (int)blockIdx.x) ? (a.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // tiles of this CTA
 
   if (warp == 0 && lane == 0) {
     if (MODE == CT_CONV) tma_prefetch_desc(&mapW);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 4; i++) {
       mbar_init(&a_full[i], 4);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 4);
     }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  constexpr uint32_t TCOLS = (MODE == CT_WGRAD) ? 512u : 128u;   // CT_WGRAD: two sets of NMT x 64 columns
+  if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
   // the padding columns of the operand blocks are written once: zeros (and never touched by the gather)
   {
     uint4* z = reinterpret_cast<uint4*>(sA);
-    const int n16 = (2 * NBLK * BLK + ((MODE == CT_WGRAD) ? 2 * BLK : 0)) / 16;
+    const int n16 = (NBUF * NBLK * BLK + ((MODE == CT_WGRAD) ? NBUF * BLK : 0)) / 16;
     for (int i = threadIdx.x; i < n16; i += CT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();
@@ -106,61 +115,69 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================= MMA issuer (+ the one-time weight load) =================
+  if (warp == 0 || warp == 13) {
+    // ================= MMA issuers (+ the one-time weight load) =================
+    // A tcgen05.mma costs its issuing warp ~80 ns whatever N is, and the cost is per warp (profiles/micro/mma_bench.cu): warp 0 issues
+    // the even tiles of this CTA into accumulator set 0, warp 13 the odd tiles into set 1.  Descriptor offsets are compile-time constants.
+    const int g = (warp == 0) ? 0 : 1;
     if (lane == 0 && ntl > 0) {
       if (MODE == CT_CONV) {
-        mbar_expect_tx(b_full, NKB * 64 * 128);
-        for (int i = 0; i < NKB * 2; i++) tma_load_2d(sB + i * 4096, &mapW, b_full, 0, i * 32);
+        if (g == 0) {
+          mbar_expect_tx(b_full, NKB * 64 * 128);
+          for (int i = 0; i < NKB * 2; i++) tma_load_2d(sB + i * 4096, &mapW, b_full, 0, i * 32);
+        }
         mbar_wait(b_full, 0);
       }
       const uint32_t sa0 = smem_u32(sA) >> 4, sb0 = smem_u32(sB) >> 4;
       if (MODE == CT_CONV) {
         const uint32_t idesc = make_idesc_bf16(128, 64, false, true);
-        const uint64_t a_t = make_smem_desc(0, 16, 1024);
-        const uint64_t b_t = make_smem_desc(0, 4096, 1024) + (uint64_t)sb0;
-        for (int it = 0; it < ntl; it++) {
-          const int buf = it & 1;
-          mbar_wait(&a_full[buf], (it >> 1) & 1);
-          if (it >= 2) mbar_wait(&acc_free[buf], ((it >> 1) - 1) & 1);
+        const uint64_t a_t = make_smem_desc(0, 16, 1024) + (uint64_t)sa0;
+        const uint64_t bb = make_smem_desc(0, 4096, 1024) + (uint64_t)sb0;
+        const uint32_t tacc = tmem_base + g * 64;
+        for (int it = g; it < ntl; it += 2) {
+          const int buf = it % NBUF;
+          mbar_wait(&a_full[buf], (it / NBUF) & 1);
+          if (it >= 2) mbar_wait(&acc_free[g], ((it >> 1) - 1) & 1);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + buf * 64;
-          const uint64_t ab = a_t + (uint64_t)(sa0 + buf * NBLK * (BLK >> 4));
-#pragma unroll 1
-          for (int j = 0; j < NK16; j++)
-            umma_bf16(tacc, ab + (uint64_t)((j >> 2) * (BLK >> 4) + (j & 3) * 2), b_t + (uint64_t)(j * (2048 >> 4)), idesc, j > 0);
+          const uint64_t ab = a_t + (uint64_t)(buf * NBLK * (BLK >> 4));
+#pragma unroll
+          for (int kb = 0; kb < NK16 / 4; kb++)      // one 64-wide K block = four K steps (A: +32 B, B: +16 rows of 128 B)
+            umma_bf16_x4(tacc, ab + (uint64_t)(kb * (BLK >> 4)), bb + (uint64_t)(kb * 4 * (2048 >> 4)), 2, 2048 >> 4, idesc, kb > 0);
+          if (NK16 % 4 >= 2)
+            umma_bf16_x2(tacc, ab + (uint64_t)((NK16 / 4) * (BLK >> 4)), bb + (uint64_t)((NK16 / 4) * 4 * (2048 >> 4)), 2, 2048 >> 4, idesc, 1);
+          if (NK16 % 2 == 1)
+            umma_bf16(tacc, ab + (uint64_t)((NK16 / 4) * (BLK >> 4) + ((NK16 % 4) - 1) * 2), bb + (uint64_t)((NK16 - 1) * (2048 >> 4)), idesc, 1);
           umma_commit(&a_empty[buf]);
-          umma_commit(&acc_full[buf]);
+          umma_commit(&acc_full[g]);
         }
       } else {
         const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
-        const uint64_t a_t = make_smem_desc(0, BLK, 1024);
-        const uint64_t b_t = make_smem_desc(0, BLK, 1024);
-        for (int it = 0; it < ntl; it++) {
-          const int buf = it & 1;
-          mbar_wait(&a_full[buf], (it >> 1) & 1);
+        const uint64_t a_t = make_smem_desc(0, BLK, 1024) + (uint64_t)(sa0 + g * NBLK * (BLK >> 4));
+        const uint64_t bb = make_smem_desc(0, BLK, 1024) + (uint64_t)(sb0 + g * (BLK >> 4));
+        const uint32_t tacc = tmem_base + g * NMT * 64;
+        for (int it = g; it < ntl; it += 2) {
+          mbar_wait(&a_full[g], (it >> 1) & 1);
           tc_fence_after();
-          const uint64_t bb = b_t + (uint64_t)(sb0 + buf * (BLK >> 4));
-#pragma unroll 1
+#pragma unroll
           for (int mt = 0; mt < NMT; mt++) {
-            const uint64_t ab = a_t + (uint64_t)(sa0 + (buf * NBLK + 2 * mt) * (BLK >> 4));
-#pragma unroll 1
-            for (int ks = 0; ks < 8; ks++)
-              umma_bf16(tmem_base + mt * 64, ab + (uint64_t)(ks * (2048 >> 4)), bb + (uint64_t)(ks * (2048 >> 4)), idesc, (it > 0) || (ks > 0));
+            const uint64_t ab = a_t + (uint64_t)(2 * mt * (BLK >> 4));
+            umma_bf16_x4(tacc + mt * 64, ab, bb, 2048 >> 4, 2048 >> 4, idesc, it >= 2);
+            umma_bf16_x4(tacc + mt * 64, ab + (uint64_t)(4 * (2048 >> 4)), bb + (uint64_t)(4 * (2048 >> 4)), 2048 >> 4, 2048 >> 4, idesc, 1);
           }
-          umma_commit(&a_empty[buf]);
+          umma_commit(&a_empty[g]);
         }
-        umma_commit(&acc_full[0]);
+        if (ntl > g) umma_commit(&acc_full[g]);
       }
     }
-  } else if (warp <= 4) {
+  } else if (warp <= 8) {
     // ================= producers: implicit im2col into the swizzled operand blocks =================
-    const int r = (warp - 1) * 32 + lane;
+    const int grp = (warp - 1) >> 2;
+    const int r = ((warp - 1) & 3) * 32 + lane;
     const int HW = a.H * a.W;
-    for (int it = 0; it < ntl; it++) {
-      const int buf = it & 1;
+    for (int it = grp; it < ntl; it += 2) {
+      const int buf = it % NBUF;
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (it >= 2) mbar_wait(&a_empty[buf], ((it >> 1) - 1) & 1);
+      if (it >= NBUF) mbar_wait(&a_empty[buf], ((it / NBUF) - 1) & 1);
       uint8_t* A = sA + buf * NBLK * BLK;
       const long long p = tile * TM + r;
       const bool valid = p < a.npix;
@@ -264,12 +281,20 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     } else if (ntl > 0) {
       mbar_wait(&acc_full[0], 0);
+      if (ntl > 1) mbar_wait(&acc_full[1], 0);
       tc_fence_after();
       float* part = a.partial + (long long)blockIdx.x * a.krows * COUT;
 #pragma unroll 1
       for (int mt = 0; mt < NMT; mt++) {
         tmem_ld32(t_lane + mt * 64, rg);
         tmem_wait_ld();
+        if (ntl > 1) {      // the odd tiles accumulated into the second set
+          uint32_t r2[32];
+          tmem_ld32(t_lane + (NMT + mt) * 64, r2);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; c++) rg[c] = __float_as_uint(__uint_as_float(rg[c]) + __uint_as_float(r2[c]));
+        }
         const int kr = mt * 128 + row;
         if (kr < a.krows) {
 #pragma unroll
@@ -286,28 +311,41 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
 }
 
-// gw[tap][ci][co] = scale * sum_cta partial[cta][tap * CIN + ci][co] (ci < cin_real); gb[co] = sum_cta partial[cta][9 * CIN][co]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int krows, int CIN, int cin_real, int COUT, float scale,
-                                    float* __restrict__ gw, float* __restrict__ gb) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// gw[tap][ci][co] = scale * sum_cta partial[cta][tap * CIN + ci][co] (ci < cin_real); gb[co] = sum_cta partial[cta][9 * CIN][co].
+// 32 outputs per block; the CTA partials of an output are split over 8 threads and combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int krows, int CIN, int cin_real, int COUT,
+                                                           float scale, float* __restrict__ gw, float* __restrict__ gb) {
+  __shared__ float red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
   const int n_w = 9 * cin_real * COUT;
-  if (i >= n_w + COUT) return;
-  int kr, co;
-  if (i < n_w) {
-    co = i % COUT;
-    const int t = i / COUT, ci = t % cin_real, tap = t / cin_real;
-    kr = tap * CIN + ci;
-  } else {
-    co = i - n_w;
-    kr = 9 * CIN;
+  const bool live = i < n_w + COUT;
+  int kr = 0, co = 0;
+  if (live) {
+    if (i < n_w) {
+      co = i % COUT;
+      const int t = i / COUT, ci = t % cin_real, tap = t / cin_real;
+      kr = tap * CIN + ci;
+    } else {
+      co = i - n_w;
+      kr = 9 * CIN;
+    }
   }
   float s = 0.f;
-  for (int c = 0; c < nctas; c++) s += partial[((long long)c * krows + kr) * COUT + co];
-  if (i < n_w) gw[i] = s * scale;
-  else gb[co] = s;
+  if (live)
+    for (int c = ty; c < nctas; c += 8) s += partial[((long long)c * krows + kr) * COUT + co];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && live) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += red[k][tx];
+    if (i < n_w) gw[i] = t * scale;
+    else gb[co] = t;
+  }
 }
 
 // ---- prepared bf16 weights of one encoder -----------------------------------------------------------------------
@@ -501,7 +539,8 @@ template <int MODE, int CIN, int COUT>
 int launch_conv_t(const CUtensorMap& mapW, const ConvTcArgs& a, int grid, cudaStream_t st) {
   constexpr int NKB = (9 * CIN + 1 + 63) / 64, NMT = (9 * CIN + 1 + 127) / 128;
   constexpr int NBLK = (MODE == CT_WGRAD) ? 2 * NMT : NKB;
-  constexpr int SMEM = 2 * NBLK * BLK + ((MODE == CT_WGRAD) ? 2 * BLK : NKB * 64 * 128) + 256 + 1024;
+  constexpr int NBUF = (MODE == CT_CONV && CIN == 16) ? 4 : 2;
+  constexpr int SMEM = NBUF * NBLK * BLK + ((MODE == CT_WGRAD) ? NBUF * BLK : NKB * 64 * 128) + 256 + 1024;
   static_assert(SMEM <= 232448, "conv_tc_kernel: shared memory");
   auto kern = conv_tc_kernel<MODE, CIN, COUT>;
   static bool attr_set[FQL_MAX_DEVICES] = {};
@@ -561,7 +600,7 @@ int conv_wgrad_tc(const bf16* x, int cin, int cin_real, int cout, const bf16* dy
   else if (cin == 32 && cout == 32) FQL_TRY((launch_conv_t<CT_WGRAD, 32, 32>(mapW, a, grid, st)));
   else FQL_REQUIRE(false, "conv_wgrad_tc: unsupported channel counts %d -> %d", cin, cout);
   const int n = 9 * cin_real * cout + cout;
-  wgrad_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, grid, a.krows, cin, cin_real, cout, scale, gw, gb);
+  wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(partial, grid, a.krows, cin, cin_real, cout, scale, gw, gb);
   FQL_CHECK_LAUNCH();
   return 0;
 }
