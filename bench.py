@@ -11,8 +11,9 @@ A "step" is one FQLAgent.update (agents/fql.py:122-133) on one synthetic batch o
 N > 1 is data parallel, weak scaling: every rank holds `--batch` rows of a global batch of N*batch; the gradient buckets are
 reduced by the library's own kernels over NVLink peer memory / NVLS multicast inside the step graph (FQL_DP_BACKEND=nccl: NCCL
 all-reduce instead); value = global samples/s.  `--seeds S` with N > 1 shards SEEDS: every rank trains its own S independent
-agents, no collective on the step.  Every line also carries `scaling_configs`: the two sharded north_star configurations
-(humanoidmaze-medium batch 8192/GPU data parallel; puzzle-4x4 8 seeds/GPU seed-sharded) timed in the same run at this N.
+agents, no collective on the step.  Every line also carries `scaling_configs`: the sharded north_star configurations
+(humanoidmaze-medium batch 8192/GPU data parallel; puzzle-4x4 8 seeds/GPU seed-sharded; visual-cube-single pixels batch 256/GPU data
+parallel) timed in the same run at this N, and BASELINE config 1 beside the headline config 2 at N = 1.
 """
 import argparse
 import json
@@ -363,6 +364,7 @@ def main():
     if not args.no_scaling_configs:
         scaling_configs.append(time_config('humanoidmaze-medium', 8192, 1, 'dp', world, rank, pg, stream, flush))
         scaling_configs.append(time_config('puzzle-4x4', 256, 8, 'seeds', world, rank, pg, stream, flush))
+        scaling_configs.append(time_config('visual-cube-single', 256, 1, 'dp' if world > 1 else 'single', world, rank, pg, stream, flush))
         if world == 1:
             scaling_configs.append(time_config('cube-single', 256, 1, 'single', world, rank, pg, stream, flush, steps=50))
     if rank != 0:

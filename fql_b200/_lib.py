@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libfql_b200.so')
 NUM_INFO = 13
 NUM_RAW = 16
 NET_NAMES = ('actor_bc_flow', 'actor_onestep_flow', 'critic', 'target_critic')
+NET_ACTOR_BC_FLOW, NET_ACTOR_ONESTEP_FLOW, NET_CRITIC, NET_TARGET_CRITIC = 0, 1, 2, 3
 LEAF_KINDS = ('kernel', 'bias', 'scale', 'bias', 'kernel', 'bias', 'kernel', 'bias')
 PRECISION_FP32, PRECISION_BF16_TC, PRECISION_BF16_ENC = 0, 1, 2
 

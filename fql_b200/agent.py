@@ -674,6 +674,44 @@ class FQLAgent:
     def compute_flow_actions(self, observations, noises):
         return self._fwd_call(self._lib.fql_compute_flow_actions, observations, noises)
 
+    def q_values(self, observations, actions, target=False):
+        """Q_h(s, a) of both critic heads, [2, rows] (utils/networks.py:178-195 `Value.__call__`; state observations).  Evaluated in
+        fp32 from the master parameters (fql_mlp_forward) whatever the training precision: this is the evaluation-side call of
+        best-of-N action selection (agents/ifql.py:146-149), not part of the update."""
+        if self._image is not None:
+            raise NotImplementedError('q_values takes state observations')
+        obs = torch.as_tensor(np.asarray(observations), dtype=torch.float32, device=self.device).reshape(-1, self._feat)
+        act = torch.as_tensor(np.asarray(actions), dtype=torch.float32, device=self.device).reshape(obs.shape[0], -1)
+        rows = int(obs.shape[0])
+        d = _lib.FqlDims.from_buffer_copy(self._dims(int(self.config.get('batch_size', 256))))
+        d.precision, d.num_seeds = _lib.PRECISION_FP32, 1
+        if self.num_seeds != 1:
+            raise NotImplementedError('q_values: one agent (num_seeds == 1)')
+        x = torch.cat([obs, act], dim=1).contiguous()
+        y = torch.empty(2, rows, dtype=torch.float32, device=self.device)
+        wsb = int(self._lib.fql_forward_workspace_bytes(C.byref(d), rows))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.fql_mlp_forward(self._ctx, C.byref(d), _lib.NET_TARGET_CRITIC if target else _lib.NET_CRITIC, _ptr(self._params),
+                                                 _ptr(x), _ptr(y), rows, _ptr(ws), wsb, self._stream()), 'fql_mlp_forward')
+            torch.cuda.current_stream(self.device).synchronize()
+        return y.cpu().numpy()
+
+    def sample_actions_best_of_n(self, observation, num_samples=32, seed=None, noise=None):
+        """IFQLAgent.sample_actions (agents/ifql.py:122-149) on this agent's networks -- the reuse of the Euler kernel SURVEY 8(f)4
+        names: `num_samples` noises are integrated through the bc-flow velocity field (compute_flow_actions: ONE persistent kernel
+        for all samples), clipped, and the action with the largest min-over-heads Q is returned.  `observation`: one state [F]."""
+        ob = np.asarray(observation, np.float32).reshape(1, self._feat)
+        A = self.config['action_dim']
+        if noise is None:
+            key = np.ravel(np.asarray(seed if seed is not None else self.rng)).astype(np.uint64)
+            noise = np.random.Generator(np.random.Philox(key=int(key[0]) | (int(key[-1]) << 32))).standard_normal((num_samples, A)).astype(np.float32)
+        noise = np.asarray(noise, np.float32).reshape(-1, A)
+        obs_n = np.repeat(ob, noise.shape[0], axis=0)
+        actions = self.compute_flow_actions(obs_n, noise)
+        q = self.q_values(obs_n, actions).min(axis=0)
+        return actions[int(np.argmax(q))]
+
     def __del__(self):
         try:
             if getattr(self, '_ctx', None):

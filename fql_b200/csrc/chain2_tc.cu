@@ -707,6 +707,8 @@ int launch_chain2(const Chain2Args& a0, int nkb_x, int npar, bool ln, const CUte
   const int fixed = (NKB + nkb_x) * KB_BYTES + 2 * npar * HID * 4 + (ln ? 2 * TILE_M * 2 * 4 : 0) + 512 + 1024;
   int nstage = (232448 - fixed) / STAGE_BYTES;
   if (nstage > 8) nstage = 8;
+  static const int cap = getenv("FQL_B200_CHAIN2_STAGES") ? atoi(getenv("FQL_B200_CHAIN2_STAGES")) : 0;   // diagnostics: shallower weight ring
+  if (cap >= 2 && nstage > cap) nstage = cap;
   FQL_REQUIRE(nstage >= 2, "not enough shared memory for the weight pipeline");
   a.nstage = nstage;
   const int smem = fixed + nstage * STAGE_BYTES;

@@ -659,8 +659,9 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   // pixel configs (512 encoder features in front of the action columns): every MLP layer by layer through tc_gemm, and the
   // first-layer input gradients of the three trainable networks feed their encoders' backward
   const bool wide = tc_wide_input(d), pix = d->reserved[0] > 0;
-  FQL_REQUIRE(!(pix && ctx->dp.active), "data-parallel pixel configs run in FQL_PRECISION_FP32 / FQL_PRECISION_BF16_ENC (one exchange at the end of the "
-                                         "backward); the bucketed tensor-core schedule does not cover the encoder gradients yet");
+  // data parallel: state configs exchange per-network buckets as soon as each is final; pixel configs (encoder gradients finish on other
+  // streams) exchange the whole trainable prefix of the arena once, behind the complete backward
+  const bool dp_bucketed = dp_grads && !pix;
   FQL_TRY(stamp(ctx, 0, S0));   // step start
   FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0, w.cpost_ticket, 3 * S));
   FQL_TRY(encode_observations(c, L, w, S0));
@@ -735,7 +736,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   if (c.do_backward && big_bwd) {
     FQL_TRY(tc_actor_backward_big(fbc, w.dpred, w.F_dOutb, w.F_dZb, false, S2));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], S2));
-    if (dp_grads && !ctx->dp_bc_late) {
+    if (dp_bucketed && !ctx->dp_bc_late) {
       const NetView& nb = L.net[FQL_NET_ACTOR_BC_FLOW];
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[16], 0));
       FQL_TRY(dp_reduce_bucket(ctx->dp, 0, nb.begin, nb.end - nb.begin, nullptr, ctx->sc));
@@ -750,7 +751,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[53], ctx->s7));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s3, ctx->ev[53], 0));
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[16], ctx->s3));
-    if (dp_grads && !ctx->dp_bc_late) {  // bc-flow's gradients are final long before the rest: its bucket crosses NVLink under the remaining backward
+    if (dp_bucketed && !ctx->dp_bc_late) {  // bc-flow's gradients are final long before the rest: its bucket crosses NVLink under the remaining backward
       const NetView& nb = L.net[FQL_NET_ACTOR_BC_FLOW];
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[16], 0));
       FQL_TRY(stamp(ctx, 20, ctx->sc));   // bc-flow bucket: gradients final
@@ -850,7 +851,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s5, ctx->ev[54], 0));
       FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[36], ctx->s5));
     }
-    if (dp_grads) {
+    if (dp_bucketed) {
       const NetView& nc = L.net[FQL_NET_CRITIC];
       FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[36], 0));
       int64_t b0 = nc.begin;
@@ -876,7 +877,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     if (big_bwd) FQL_TRY(tc_critic_backward_big(q, w.C_XHb, w.C_DGb, S0));
     else FQL_TRY(tc_critic_backward(q, S0, nullptr, nullptr, &ctx->ev[44]));
     FQL_TRY(stamp(ctx, 6, S0));   // critic input-gradient chain done
-    if (dp_grads && c.do_apply && ctx->dp_early_adam && ctx->split_adam == 0 && d->reserved[0] == 0) {
+    if (dp_bucketed && c.do_apply && ctx->dp_early_adam && ctx->split_adam == 0 && d->reserved[0] == 0) {
       // data parallel: bc-flow's and the critic's part of the optimizer pass (+ Polyak) right behind their bucket exchanges on the
       // communication stream, under the one-step actor's backward and bucket exchange.  Last readers of their weights: the Euler
       // chain (bc-flow) and the critic input-gradient chain that S0 has just enqueued; the critic's own backward precedes ev[36].
@@ -964,7 +965,11 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   }
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_s2, 0));
   if (early_adam_s1) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[58], 0));
-  if (dp_grads) {  // the one-step actor's bucket + the metric accumulators close the exchange; the optimizer pass follows on S0
+  if (dp_grads && !dp_bucketed) {
+    const int64_t t0 = L.net[FQL_NET_TARGET_CRITIC].begin;
+    FQL_TRY(dp_reduce_bucket(ctx->dp, 3, 0, t0, raw, S0));
+  }
+  if (dp_bucketed) {  // the one-step actor's bucket + the metric accumulators close the exchange; the optimizer pass follows on S0
     const NetView& no = L.net[FQL_NET_ACTOR_ONESTEP_FLOW];
     FQL_TRY(stamp(ctx, 24, S0));          // one-step bucket: gradients final
     FQL_TRY(dp_reduce_bucket(ctx->dp, 2, no.begin, no.end - no.begin, raw, S0));

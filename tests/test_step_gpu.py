@@ -140,6 +140,32 @@ def test_sample_actions_and_flow_actions(rows):
     assert np.array_equal(s1, s2) and np.abs(s1).max() <= 1.0
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_q_values_and_best_of_n_action_selection(precision):
+    """IFQLAgent.sample_actions (agents/ifql.py:122-149) on the FQL networks: Euler-integrate N noises through the bc-flow field, pick the
+    action with the largest min-over-heads Q.  Q values against the oracle's critic (1e-5); the chosen action is the oracle's argmax
+    (or, in bf16 where the Euler integration carries 1e-3, an action whose oracle Q is within 1e-2 of the best)."""
+    cfg, state, _, _ = make_case(dict(), 8, 29, 8, seed=23, hidden=512)
+    agent = cuda_agent_from_state(cfg, state, 8, 29, 8, precision=precision)
+    agent.load_tree(f32(state['params']))
+    rng = np.random.default_rng(3)
+    ob = rng.standard_normal(29)
+    nz = rng.standard_normal((32, 8))
+    obs_n = np.repeat(ob[None], 32, 0)
+    acts = O.compute_flow_actions(state['params'], cfg, obs_n, nz)
+    q_ref = O.critic_forward(state['params']['modules_critic'], cfg, obs_n, acts)
+    q = agent.q_values(obs_n.astype(np.float32), acts.astype(np.float32))
+    assert q.shape == (2, 32) and rel_err(q, q_ref) <= TOL
+    a = agent.sample_actions_best_of_n(ob.astype(np.float32), noise=nz.astype(np.float32))
+    qmin = np.asarray(q_ref).min(axis=0)
+    best = int(np.argmax(qmin))
+    if precision == 'fp32':
+        assert rel_err(a, acts[best]) <= TOL
+    else:
+        k = int(np.argmin(np.abs(acts - a[None]).max(axis=1)))           # which sample the device picked
+        assert np.abs(acts[k] - a).max() <= 5e-2 and qmin[k] >= qmin[best] - 1e-2 * np.abs(qmin).max()
+
+
 def test_large_batch_properties():
     """BASELINE config 3 at a large batch: checked against the oracle through size-independent properties:
     (a) info of a batch made of 8 copies of a 256-row block == info of the block (means are replication-invariant),
