@@ -87,8 +87,10 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
   dg = 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * (FQL_GELU_C * (1.0f + 3.0f * FQL_GELU_A * x2));
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float u = FQL_GELU_C * (x + FQL_GELU_A * x * x * x);
-  return 0.5f * x * (1.0f + tanh_approx(u));
+  // 0.5 x (1 + tanh(c (x + a x^3))) as 3 FMUL + 2 FFMA + 1 MUFU
+  const float p = fmaf(x * x, FQL_GELU_C * FQL_GELU_A, FQL_GELU_C);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(x * p), hx);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -276,8 +278,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
               tc_fence_after();
               const uint64_t adesc = a_t + (uint64_t)(abase + kb * (KB_BYTES >> 4) + (ks & 1) * 4);
               const uint64_t bdesc = b_t + (uint64_t)(sw0 + stage * (STAGE_BYTES >> 4));
-              umma_bf16(tacc, adesc, bdesc, idesc_h, ks > 0);
-              if (K - ks * KS > 16) umma_bf16(tacc, adesc + 2, bdesc + b_k16, idesc_h, 1);
+              // both K steps of a stage from ONE asm block: the uniform-register descriptors are materialised once (a run-time
+              // descriptor costs the issuing thread more than the ~80 ns of the MMA itself)
+              if (K - ks * KS > 16) umma_bf16_x2(tacc, adesc, bdesc, 2, b_k16, idesc_h, ks > 0);
+              else umma_bf16(tacc, adesc, bdesc, idesc_h, ks > 0);
               umma_commit(&empty[stage]);
               if (++stage == a.nstage) { stage = 0; phase ^= 1; }
               if (it > 0 && h == 1 && (ks & 1) == 1 && kb < 4) umma_commit(&a_free[kb]);
@@ -298,8 +302,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
             tc_fence_after();
             const uint64_t adesc = a_t + (uint64_t)(sa0 + kb * (KB_BYTES >> 4) + (ks & 1) * 4);
             const uint64_t bdesc = b_t + (uint64_t)(sw0 + stage * (STAGE_BYTES >> 4));
-            umma_bf16(tmem_base, adesc, bdesc, idesc_t, ks > 0);
-            umma_bf16(tmem_base, adesc + 2, bdesc + b_k16, idesc_t, 1);
+            umma_bf16_x2(tmem_base, adesc, bdesc, 2, b_k16, idesc_t, ks > 0);
             umma_commit(&empty[stage]);
             if (++stage == a.nstage) { stage = 0; phase ^= 1; }
           }
@@ -361,22 +364,26 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
           for (int h = 0; h < 2; h++) {
             mbar_wait(&acc_full[h], (nf[h]++) & 1);
             tc_fence_after();
-#pragma unroll 1
+            // software-pipelined TMEM reads: chunk jj + 1 is in flight while chunk jj is evaluated (two register buffers)
+            uint32_t rb[2][32];
+            tmem_ld32(t_lane + (h * 8 + pw) * 32, rb[0]);
+#pragma unroll
             for (int jj = 0; jj < 4; jj++) {
               const int j = h * 8 + jj * 2 + pw;
-              tmem_ld32(t_lane + j * 32, r);
               tmem_wait_ld();
+              if (jj < 3) tmem_ld32(t_lane + (j + 2) * 32, rb[(jj + 1) & 1]);
+              const uint32_t (&rr)[32] = rb[jj & 1];
               float hv[32];
               if (DGb) {        // z -> gelu(z) for the next layer, gelu'(z) saved for the backward (the large-batch backward reads no z)
                 float dv[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) gelu_and_grad(__uint_as_float(r[i]) + par[j * 32 + i], hv[i], dv[i]);
+                for (int i = 0; i < 32; i++) gelu_and_grad(__uint_as_float(rr[i]) + par[j * 32 + i], hv[i], dv[i]);
                 store_bf16x32(DGb + j * 32, dv);
               } else {
                 float zv[32];
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
-                  zv[i] = __uint_as_float(r[i]) + par[j * 32 + i];
+                  zv[i] = __uint_as_float(rr[i]) + par[j * 32 + i];
                   hv[i] = gelu_fast(zv[i]);
                 }
                 if (Zb) store_bf16x32(Zb + j * 32, zv);

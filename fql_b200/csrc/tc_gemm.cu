@@ -217,24 +217,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         float* o = a.out_f.at<float>(g0, g1) + (int64_t)m * a.out_f.ld + nb;
         float dg = 0.f, dbt = 0.f;
         const bool vec = (nb + 32 <= a.N) && ((a.out_f.ld & 3) == 0);
+        if (vec) {
+          // 16-byte accesses: a thread owns 32 consecutive floats of its row (one 128-byte line of W and of dW)
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          if (nb + i < a.N) {
-            const float gacc = __uint_as_float(r[i]);    // no bias in this mode: v[] == the accumulator
-            const float w = vec ? __ldg(wrow + i) : wrow[i];
-            const float dbn = db[nb + i];
-            dg = fmaf(w, gacc, dg);
-            if (kz == 0) dbt = fmaf(w, dbn, dbt);
-            const float dw = gam * gacc + (kz == 0 ? bet * dbn : 0.f);
-            if (a.ksplit > 1) atomicAdd(o + i, dw);      // K split over CTAs: partial tiles add into the zeroed leaf
-            else o[i] = dw;
+          for (int i4 = 0; i4 < 8; i4++) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow) + i4);
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(db + nb) + i4);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            float ov[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const float gacc = __uint_as_float(r[i4 * 4 + k]);
+              dg = fmaf(wv[k], gacc, dg);
+              if (kz == 0) dbt = fmaf(wv[k], dv[k], dbt);
+              ov[k] = gam * gacc + (kz == 0 ? bet * dv[k] : 0.f);
+            }
+            if (a.ksplit > 1) atomicAdd(reinterpret_cast<float4*>(o) + i4, make_float4(ov[0], ov[1], ov[2], ov[3]));   // red.global.add.v4.f32
+            else reinterpret_cast<float4*>(o)[i4] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            if (nb + i < a.N) {
+              const float gacc = __uint_as_float(r[i]);    // no bias in this mode: v[] == the accumulator
+              const float w = wrow[i];
+              const float dbn = db[nb + i];
+              dg = fmaf(w, gacc, dg);
+              if (kz == 0) dbt = fmaf(w, dbn, dbt);
+              const float dw = gam * gacc + (kz == 0 ? bet * dbn : 0.f);
+              if (a.ksplit > 1) atomicAdd(o + i, dw);      // K split over CTAs: partial tiles add into the zeroed leaf
+              else o[i] = dw;
+            }
           }
         }
         atomicAdd(a.dln_s.at<float>(g0, g1) + m, dg);
         if (kz == 0) atomicAdd(a.dln_b.at<float>(g0, g1) + m, dbt);
       } else if constexpr (MODE == TC_MODE_STORE_F32) {
         float* o = a.out_f.at<float>(g0, g1) + (int64_t)m * a.out_f.ld + nb;
-        if (a.ksplit > 1) {
+        if (a.ksplit > 1 && nb + 32 <= a.N && (a.out_f.ld & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(o + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        } else if (a.ksplit > 1) {
 #pragma unroll
           for (int i = 0; i < 32; i++)
             if (nb + i < a.N) atomicAdd(o + i, v[i]);

@@ -55,6 +55,14 @@ int main() {
   unsigned long long* out; CK(cudaMalloc(&out, 64));
   CK(cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   const int n_mma = 64;
+  // one issuing warp, N = 256 (the chain kernels' MMA): 64 MMAs into ONE accumulator vs alternating between TWO accumulators
+  for (int nacc : {1, 2}) {
+    bench<<<1, 128, 65536>>>(256, 1, n_mma, nacc, out, 1);
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[8]; CK(cudaMemcpy(h, out, 64, cudaMemcpyDeviceToHost));
+    printf("N=256 issuing warps=1 accumulators=%d: %d MMAs issued in %7.1f ns, complete after %7.1f ns -> %5.1f ns per MMA (math floor 65 ns)\n", nacc, n_mma,
+           (double)h[0], (double)h[1], (double)h[1] / n_mma);
+  }
   for (int N : {64, 128})
     for (int nw : {1, 2, 4}) {
       if (N * nw > 512) continue;
