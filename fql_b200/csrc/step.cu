@@ -433,6 +433,7 @@ struct FqlContext {
   int split_adam = 0;        // FQL_B200_SPLIT_ADAM: 0 = one optimizer pass at the end (default: the others measured within noise), 1 = bc-flow's part right behind the Euler chain,
                              // 2 = bc-flow and critic parts before the one-step actor's gradients are complete
   int adam_done_blk = 0;     // blocks [0, adam_done_blk) were already applied by enqueue_grads_tc in this enqueue
+  int enc_streams = 1;       // FQL_B200_ENC_STREAMS=0: pixel configs, the five tensor-core encoder forwards on one stream
   int dp_early_adam = 1;     // FQL_B200_DP_EARLY_ADAM=0: data parallel, one optimizer pass at the end.  Default: the bc-flow + critic part
                              // runs behind their bucket reductions, under the one-step actor's bucket exchange
   int dp_bc_late = 0;        // FQL_B200_DP_BC_LATE=1: bc-flow's bucket is exchanged together with the critic's (one launch) instead of
@@ -545,6 +546,8 @@ extern "C" int fql_context_create(FqlContext** out) {
   }
   const char* sa = getenv("FQL_B200_SPLIT_ADAM");
   if (sa) c->split_adam = atoi(sa);
+  const char* ens = getenv("FQL_B200_ENC_STREAMS");
+  if (ens) c->enc_streams = atoi(ens);
   const char* dea = getenv("FQL_B200_DP_EARLY_ADAM");
   if (dea) c->dp_early_adam = atoi(dea);
   const char* dbl = getenv("FQL_B200_DP_BC_LATE");
@@ -608,7 +611,7 @@ int check_common(const FqlDims* d, const void* ws, size_t ws_bytes, Layout* L, W
 
 // What every call site reads as "observations": the batch itself (state configs) or the output of that network's encoder.
 // Five unique encoder forwards per step: onestep(next_obs), onestep(obs), target critic(next_obs), critic(obs), bc flow(obs).
-int encode_observations(const StepCall& c, const Layout& L, WsPtrs& w, cudaStream_t st) {
+int encode_observations(const StepCall& c, const Layout& L, WsPtrs& w, cudaStream_t st, FqlContext* ctx = nullptr) {
   const FqlBatch& b = *c.b;
   if (c.d->reserved[0] == 0) {
     w.src[0] = w.src[2] = b.next_observations;
@@ -619,11 +622,27 @@ int encode_observations(const StepCall& c, const Layout& L, WsPtrs& w, cudaStrea
   const uint8_t* nobs = reinterpret_cast<const uint8_t*>(b.next_observations);
   const float* P = c.st->params;
   const int64_t B = c.d->batch;
+  // tensor-core encoders: the five independent forwards on three streams (a pass is ~30 short launches, many of them smaller than
+  // the GPU: the tails and the small layers of one pass fill the gaps of another)
+  cudaStream_t sa = st, sb = st;
+  const bool fork = ctx && c.d->precision != FQL_PRECISION_FP32 && ctx->enc_streams;
+  if (fork) {
+    sa = ctx->s5; sb = ctx->s6;
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[60], st));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(sa, ctx->ev[60], 0));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(sb, ctx->ev[60], 0));
+  }
   FQL_TRY(enc_forward(c.d, L.net[FQL_NET_ACTOR_ONESTEP_FLOW].enc, P, nobs, B, w.enc[0], w.feat[0], st));
+  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_TARGET_CRITIC].enc, P, nobs, B, w.enc[2], w.feat[2], sa));
+  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_ACTOR_BC_FLOW].enc, P, obs, B, w.enc[4], w.feat[4], sb));
   FQL_TRY(enc_forward(c.d, L.net[FQL_NET_ACTOR_ONESTEP_FLOW].enc, P, obs, B, w.enc[1], w.feat[1], st));
-  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_TARGET_CRITIC].enc, P, nobs, B, w.enc[2], w.feat[2], st));
-  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_CRITIC].enc, P, obs, B, w.enc[3], w.feat[3], st));
-  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_ACTOR_BC_FLOW].enc, P, obs, B, w.enc[4], w.feat[4], st));
+  FQL_TRY(enc_forward(c.d, L.net[FQL_NET_CRITIC].enc, P, obs, B, w.enc[3], w.feat[3], sa));
+  if (fork) {
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[61], sa));
+    FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[62], sb));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(st, ctx->ev[61], 0));
+    FQL_CHECK_CUDA(cudaStreamWaitEvent(st, ctx->ev[62], 0));
+  }
   for (int i = 0; i < 5; i++) w.src[i] = w.feat[i];
   return 0;
 }
@@ -664,7 +683,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   const bool dp_bucketed = dp_grads && !pix;
   FQL_TRY(stamp(ctx, 0, S0));   // step start
   FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0, w.cpost_ticket, 3 * S));
-  FQL_TRY(encode_observations(c, L, w, S0));
+  FQL_TRY(encode_observations(c, L, w, S0, ctx));
   const bool fused_prep = ctx->fused_prep;
   FQL_TRY(launch_prep(sh, b, w, S0, fused_prep ? kF : 0, fused_prep ? kO : 0));  // also writes the bf16 first-layer operands XFb / XOb
   FQL_TRY(stamp(ctx, 1, S0));   // prep done
@@ -1007,7 +1026,7 @@ int enqueue_step(FqlContext* ctx, const StepCall& c, cudaStream_t S0) {
     cudaStream_t S1 = ctx->s1, S2 = ctx->s2;
     cudaEvent_t ev_prep = ctx->ev[0], ev_f0 = ctx->ev[1], ev_cpost = ctx->ev[2], ev_euler = ctx->ev[3], ev_s2 = ctx->ev[4];
     FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0, w.cpost_ticket, 3 * S));
-    FQL_TRY(encode_observations(c, L, w, S0));
+    FQL_TRY(encode_observations(c, L, w, S0, ctx));
     FQL_TRY(launch_prep(sh, b, w, S0));
     const bool pix = c.d->reserved[0] > 0;
     FQL_CHECK_CUDA(cudaEventRecord(ev_prep, S0));
