@@ -39,6 +39,9 @@ constexpr int CT_THREADS = 32 * 14;   // MMA warp 0, 2 x 4 producer warps (one g
 constexpr int KPAD_MAX = 320;            // round_up(9 * 32, 64)
 constexpr int WSLOT = KPAD_MAX * 64;     // elements of one prepared weight matrix [Kpad][64]
 enum { CT_CONV = 0, CT_WGRAD = 1 };
+#ifndef FQL_CONV_NBUF16
+#define FQL_CONV_NBUF16 3   // measured at the 64x64 layer: 2 buffers 66 us, 3: 43 us, 4: 47 us (a fourth buffer costs the L1 its room)
+#endif
 
 struct ConvTcArgs {
   const bf16* x;        // input activations, NHWC [npix][CIN]
@@ -70,8 +73,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   constexpr int NMT = (9 * CIN + 1 + 127) / 128;    // M tiles of the weight gradient
   constexpr int NBLK = (MODE == CT_WGRAD) ? 2 * NMT : NKB;   // blocks allocated per buffer
   // operand buffers: a tile's gather (one L2 round trip) and its MMAs (~0.7 us) overlap with other tiles only across buffers, so the
-  // 16-channel forward / input-gradient kernels, whose buffers are 48 KB, keep four of them (two per producer group / MMA issuer)
-  constexpr int NBUF = (MODE == CT_CONV && CIN == 16) ? 4 : 2;
+  // 16-channel forward / input-gradient kernels, whose buffers are 48 KB, keep three of them
+  constexpr int NBUF = (MODE == CT_CONV && CIN == 16) ? FQL_CONV_NBUF16 : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                         // [NBUF][NBLK][BLK]
@@ -539,7 +542,7 @@ template <int MODE, int CIN, int COUT>
 int launch_conv_t(const CUtensorMap& mapW, const ConvTcArgs& a, int grid, cudaStream_t st) {
   constexpr int NKB = (9 * CIN + 1 + 63) / 64, NMT = (9 * CIN + 1 + 127) / 128;
   constexpr int NBLK = (MODE == CT_WGRAD) ? 2 * NMT : NKB;
-  constexpr int NBUF = (MODE == CT_CONV && CIN == 16) ? 4 : 2;
+  constexpr int NBUF = (MODE == CT_CONV && CIN == 16) ? FQL_CONV_NBUF16 : 2;
   constexpr int SMEM = NBUF * NBLK * BLK + ((MODE == CT_WGRAD) ? NBUF * BLK : NKB * 64 * 128) + 256 + 1024;
   static_assert(SMEM <= 232448, "conv_tc_kernel: shared memory");
   auto kern = conv_tc_kernel<MODE, CIN, COUT>;

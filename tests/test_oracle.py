@@ -354,3 +354,25 @@ def test_torch_cpu_restatement_matches_pixel_oracle():
         np.testing.assert_allclose(g, r, rtol=1e-7, atol=1e-11, err_msg=str(path))
     for (path, r), (_, g) in zip(O.tree_leaves(new_state['params']), O.tree_leaves(ta.tree('p'))):
         np.testing.assert_allclose(g, r, rtol=1e-8, atol=1e-12, err_msg=str(path))
+
+
+def test_bf16_storage_rounding_hook_of_the_encoder_oracle():
+    """oracle/encoder_oracle.py `q=bf16_round` (the reference for FQL_PRECISION_BF16_ENC / BF16_TC on pixel configs): the rounding is
+    torch's round-to-nearest-even bfloat16 cast, the rounded forward stays within bf16 distance of the exact one, and the rounded
+    backward is a gradient of about the same function (cosine with the exact gradient)."""
+    import torch
+    from oracle import encoder_oracle as E
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(4096) * np.exp(rng.uniform(-20, 20, 4096))
+    assert np.array_equal(E.bf16_round(x), torch.tensor(x, dtype=torch.float32).to(torch.bfloat16).double().numpy())
+    p = E.init_encoder(rng, 6, np.float64, hw=16, jitter=0.05)
+    obs = rng.integers(0, 256, (4, 16, 16, 6), dtype=np.uint8)
+    f0, s0 = E.encoder_forward(p, obs, dtype=np.dtype(np.float64), save=True)
+    fq, sq = E.encoder_forward(p, obs, dtype=np.dtype(np.float64), save=True, q=E.bf16_round)
+    assert np.abs(fq - f0).max() <= 2e-2 * np.abs(f0).max()
+    dout = rng.standard_normal(f0.shape)
+    g0, gq = E.encoder_backward(p, s0, dout), E.encoder_backward(p, sq, dout, q=E.bf16_round)
+    a, b = g0['MLP_0']['Dense_0']['kernel'].ravel(), gq['MLP_0']['Dense_0']['kernel'].ravel()
+    assert np.vdot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b)) >= 0.999
+    a, b = g0['stack_blocks_0']['Conv_0']['kernel'].ravel(), gq['stack_blocks_0']['Conv_0']['kernel'].ravel()
+    assert np.vdot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b)) >= 0.9
