@@ -10,15 +10,15 @@
 //                           MMAs produce the bias gradient; per-CTA partials are reduced in CTA order (deterministic)
 // Activations are NHWC bf16 with 16 or 32 channels (the uint8 frames become 16-channel bf16 INTEGERS 0..255, exact in bf16; the
 // 1/255 of encoders.py:84 is applied in fp32 to the accumulator).  Nothing is ever materialised as an im2col matrix in HBM:
-//   warps 1-8  producers, two groups of four (group g fills operand buffer g, i.e. every second tile: a gather is one L2 round trip
-//              per tile, two tiles in flight hide it): thread r owns pixel r of the tile; for each of the 9 taps it copies that
+//   producers  one group of four warps per operand buffer (2 or 3: group g fills buffer g, i.e. every second / third tile: a gather
+//              is one L2 round trip per tile, several tiles in flight hide it): thread r owns pixel r of the tile; for each of the 9 taps it copies that
 //              neighbour's channels (16-byte chunks, zeros outside the image = SAME padding) straight from L2/HBM into the K-major
 //              SWIZZLE_128B operand blocks ([128 rows][64 k] bf16) the MMAs read -- the same blocks serve as the MN-major A operand
 //              of the weight gradient;
-//   warps 0,13 one thread each issues tcgen05.mma (M=128, N=64, K=16) for every second tile of the CTA into its own accumulator set
+//   2 issuers  (warp 0 and the last warp) one thread each issues tcgen05.mma (M=128, N=64, K=16) for every second tile of the CTA into its own accumulator set
 //              (the ~80 ns issue cost of an MMA is per warp); the prepared weights [Kpad][64] arrive once per CTA by TMA and stay
 //              resident; operand buffers and accumulators are double-buffered so tile i+1 is gathered while tile i multiplies;
-//   warps 9-12 epilogue: thread per pixel reads its accumulator row from TMEM: x scale + bias, x relu-mask of a saved tensor,
+//   4 warps    epilogue: thread per pixel reads its accumulator row from TMEM: x scale + bias, x relu-mask of a saved tensor,
 //              + skip / upstream gradient, relu, bf16 NHWC stores (16-byte vectors).
 // Pooling (3x3/2, first maximum wins, argmax routing in the backward) and the element-wise pieces are bf16 kernels below; the final
 // Dense runs through tc_gemm.cu.
@@ -35,13 +35,20 @@ namespace {
 constexpr int kStacks[3] = {16, 32, 32};
 constexpr int TM = 128;
 constexpr int BLK = TM * 128;            // one operand block: [128 rows][64 bf16]
-constexpr int CT_THREADS = 32 * 14;   // MMA warp 0, 2 x 4 producer warps (one group per operand buffer), 4 epilogue warps, MMA warp 13
+#ifndef FQL_CONV_NBUF16
+#define FQL_CONV_NBUF16 4   // measured at the 64x64 layer (kernel alone): 2 buffers 66 us, 4 buffers 47 us; must be even (see below)
+#endif
+// operand buffers = producer groups of a kernel instantiation: the 16-channel forward / input-gradient kernels (48 KB buffers) keep three
+__host__ __device__ constexpr int conv_nbuf(int mode, int cin) { return (mode == 0 && cin == 16) ? FQL_CONV_NBUF16 : 2; }
+// warps: NGRP MMA issuers | NGRP producer groups of 4 warps | 4 epilogue warps.  Tile i of a CTA uses operand buffer i % NBUF and
+// belongs to lane i % NGRP (one producer group, one issuing warp, one accumulator set per lane).  NBUF is a multiple of NGRP, so a
+// buffer is always filled and consumed by the same lane: every mbarrier has ONE waiter that sees every one of its phases (a waiter that
+// skipped a phase would take the parity of an older phase for the one it waits for -- the failure an odd NBUF produced).
+constexpr int NGRP = 2;
+__host__ __device__ constexpr int conv_threads(int, int) { return 32 * (5 * NGRP + 4); }
 constexpr int KPAD_MAX = 320;            // round_up(9 * 32, 64)
 constexpr int WSLOT = KPAD_MAX * 64;     // elements of one prepared weight matrix [Kpad][64]
 enum { CT_CONV = 0, CT_WGRAD = 1 };
-#ifndef FQL_CONV_NBUF16
-#define FQL_CONV_NBUF16 3   // measured at the 64x64 layer: 2 buffers 66 us, 3: 43 us, 4: 47 us (a fourth buffer costs the L1 its room)
-#endif
 
 struct ConvTcArgs {
   const bf16* x;        // input activations, NHWC [npix][CIN]
@@ -65,7 +72,7 @@ struct ConvTcArgs {
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 template <int MODE, int CIN, int COUT>
-__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapW, const ConvTcArgs a) {
+__global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapW, const ConvTcArgs a) {
   constexpr int CH = CIN / 8;                       // 16-byte chunks per (pixel, tap)
   constexpr int NCH = 9 * CH;                       // chunks of real K per pixel row
   constexpr int NK16 = (9 * CIN + 15) / 16;         // MMA K steps (CT_CONV)
@@ -74,7 +81,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   constexpr int NBLK = (MODE == CT_WGRAD) ? 2 * NMT : NKB;   // blocks allocated per buffer
   // operand buffers: a tile's gather (one L2 round trip) and its MMAs (~0.7 us) overlap with other tiles only across buffers, so the
   // 16-channel forward / input-gradient kernels, whose buffers are 48 KB, keep three of them
-  constexpr int NBUF = (MODE == CT_CONV && CIN == 16) ? FQL_CONV_NBUF16 : 2;
+  constexpr int NBUF = conv_nbuf(MODE, CIN);
+  constexpr int NTHR = conv_threads(MODE, CIN);
+  constexpr int W_EPI = 5 * NGRP;              // first epilogue warp (warps [0, NGRP): MMA issuers, [NGRP, 5 NGRP): producers)
+  static_assert(NBUF % NGRP == 0, "a buffer must always belong to the same producer group / MMA issuer");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                         // [NBUF][NBLK][BLK]
@@ -83,10 +93,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SB_BYTES);
   uint64_t* a_full = bars;          // [4] operand buffer gathered                 (4 producer warps)
   uint64_t* a_empty = bars + 4;     // [4] the MMAs have consumed the buffer       (tcgen05.commit)
-  uint64_t* acc_full = bars + 8;    // [2] accumulator complete                    (tcgen05.commit)
-  uint64_t* acc_free = bars + 10;   // [2] accumulator read                        (4 epilogue warps)
-  uint64_t* b_full = bars + 12;     //     weights landed                          (TMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* acc_full = bars + 8;    // [4] accumulator complete                    (tcgen05.commit)
+  uint64_t* acc_free = bars + 12;   // [4] accumulator read                        (4 epilogue warps)
+  uint64_t* b_full = bars + 16;     //     weights landed                          (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntl = (a.tiles > (int)blockIdx.x) ? (a.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // tiles of this CTA
@@ -96,21 +106,21 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int i = 0; i < 4; i++) {
       mbar_init(&a_full[i], 4);
       mbar_init(&a_empty[i], 1);
-    }
-    for (int i = 0; i < 2; i++) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 4);
     }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
-  constexpr uint32_t TCOLS = (MODE == CT_WGRAD) ? 512u : 128u;   // CT_WGRAD: two sets of NMT x 64 columns
-  if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
+  // accumulators: CT_CONV one 64-column set per slot, CT_WGRAD NMT x 64 columns per slot
+  constexpr uint32_t TCOLS = (MODE == CT_WGRAD) ? 512u : 128u;
+  static_assert(NGRP * NMT * 64 <= 512, "weight-gradient accumulators exceed TMEM");
+  if (warp == NGRP) tmem_alloc(tmem_slot, TCOLS);
   // the padding columns of the operand blocks are written once: zeros (and never touched by the gather)
   {
     uint4* z = reinterpret_cast<uint4*>(sA);
     const int n16 = (NBUF * NBLK * BLK + ((MODE == CT_WGRAD) ? NBUF * BLK : 0)) / 16;
-    for (int i = threadIdx.x; i < n16; i += CT_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < n16; i += NTHR) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -118,11 +128,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 || warp == 13) {
+  if (warp < NGRP) {
     // ================= MMA issuers (+ the one-time weight load) =================
-    // A tcgen05.mma costs its issuing warp ~80 ns whatever N is, and the cost is per warp (profiles/micro/mma_bench.cu): warp 0 issues
-    // the even tiles of this CTA into accumulator set 0, warp 13 the odd tiles into set 1.  Descriptor offsets are compile-time constants.
-    const int g = (warp == 0) ? 0 : 1;
+    // A tcgen05.mma costs its issuing warp ~80 ns whatever N is, and the cost is per warp (profiles/micro/mma_bench.cu): warp g issues
+    // the tiles of slot g into accumulator set g.  Descriptor offsets are compile-time constants.
+    const int g = warp;
     if (lane == 0 && ntl > 0) {
       if (MODE == CT_CONV) {
         if (g == 0) {
@@ -137,10 +147,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         const uint64_t a_t = make_smem_desc(0, 16, 1024) + (uint64_t)sa0;
         const uint64_t bb = make_smem_desc(0, 4096, 1024) + (uint64_t)sb0;
         const uint32_t tacc = tmem_base + g * 64;
-        for (int it = g; it < ntl; it += 2) {
-          const int buf = it % NBUF;
+        for (int it = g; it < ntl; it += NGRP) {
+          const int buf = it % NBUF, use = it / NGRP;
           mbar_wait(&a_full[buf], (it / NBUF) & 1);
-          if (it >= 2) mbar_wait(&acc_free[g], ((it >> 1) - 1) & 1);
+          if (use >= 1) mbar_wait(&acc_free[g], (use - 1) & 1);
           tc_fence_after();
           const uint64_t ab = a_t + (uint64_t)(buf * NBLK * (BLK >> 4));
 #pragma unroll
@@ -158,13 +168,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         const uint64_t a_t = make_smem_desc(0, BLK, 1024) + (uint64_t)(sa0 + g * NBLK * (BLK >> 4));
         const uint64_t bb = make_smem_desc(0, BLK, 1024) + (uint64_t)(sb0 + g * (BLK >> 4));
         const uint32_t tacc = tmem_base + g * NMT * 64;
-        for (int it = g; it < ntl; it += 2) {
-          mbar_wait(&a_full[g], (it >> 1) & 1);
+        static_assert(MODE != 1 || NBUF == NGRP, "the weight-gradient kernel keeps one buffer per lane");
+        for (int it = g; it < ntl; it += NGRP) {
+          mbar_wait(&a_full[g], (it / NBUF) & 1);
           tc_fence_after();
 #pragma unroll
           for (int mt = 0; mt < NMT; mt++) {
             const uint64_t ab = a_t + (uint64_t)(2 * mt * (BLK >> 4));
-            umma_bf16_x4(tacc + mt * 64, ab, bb, 2048 >> 4, 2048 >> 4, idesc, it >= 2);
+            umma_bf16_x4(tacc + mt * 64, ab, bb, 2048 >> 4, 2048 >> 4, idesc, it >= NBUF);
             umma_bf16_x4(tacc + mt * 64, ab + (uint64_t)(4 * (2048 >> 4)), bb + (uint64_t)(4 * (2048 >> 4)), 2048 >> 4, 2048 >> 4, idesc, 1);
           }
           umma_commit(&a_empty[g]);
@@ -172,12 +183,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         if (ntl > g) umma_commit(&acc_full[g]);
       }
     }
-  } else if (warp <= 8) {
+  } else if (warp < W_EPI) {
     // ================= producers: implicit im2col into the swizzled operand blocks =================
-    const int grp = (warp - 1) >> 2;
-    const int r = ((warp - 1) & 3) * 32 + lane;
+    const int grp = (warp - NGRP) >> 2;        // group g gathers tiles g, g + NGRP, ...
+    const int r = ((warp - NGRP) & 3) * 32 + lane;
     const int HW = a.H * a.W;
-    for (int it = grp; it < ntl; it += 2) {
+    for (int it = grp; it < ntl; it += NGRP) {
       const int buf = it % NBUF;
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
       if (it >= NBUF) mbar_wait(&a_empty[buf], ((it / NBUF) - 1) & 1);
@@ -224,11 +235,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
       for (int c = 0; c < COUT; c++) bias[c] = a.bias ? __ldg(a.bias + c) : 0.f;
       for (int it = 0; it < ntl; it++) {
-        const int buf = it & 1;
+        const int buf = it % NGRP;               // accumulator set of the tile's lane
         const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
         const long long p = tile * TM + row;
         const bool valid = p < a.npix;
-        mbar_wait(&acc_full[buf], (it >> 1) & 1);
+        mbar_wait(&acc_full[buf], (it / NGRP) & 1);
         tc_fence_after();
         tmem_ld32(t_lane + buf * 64, rg);
         tmem_wait_ld();
@@ -283,17 +294,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
     } else if (ntl > 0) {
-      mbar_wait(&acc_full[0], 0);
-      if (ntl > 1) mbar_wait(&acc_full[1], 0);
+      for (int g = 0; g < NGRP && g < ntl; g++) mbar_wait(&acc_full[g], 0);
       tc_fence_after();
       float* part = a.partial + (long long)blockIdx.x * a.krows * COUT;
 #pragma unroll 1
       for (int mt = 0; mt < NMT; mt++) {
         tmem_ld32(t_lane + mt * 64, rg);
         tmem_wait_ld();
-        if (ntl > 1) {      // the odd tiles accumulated into the second set
+        for (int g = 1; g < NGRP && g < ntl; g++) {      // the other lanes' tiles accumulated into their own sets
           uint32_t r2[32];
-          tmem_ld32(t_lane + (NMT + mt) * 64, r2);
+          tmem_ld32(t_lane + (g * NMT + mt) * 64, r2);
           tmem_wait_ld();
 #pragma unroll
           for (int c = 0; c < 32; c++) rg[c] = __float_as_uint(__uint_as_float(rg[c]) + __uint_as_float(r2[c]));
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
+  if (warp == NGRP) tmem_dealloc(tmem_base, TCOLS);
 }
 
 // gw[tap][ci][co] = scale * sum_cta partial[cta][tap * CIN + ci][co] (ci < cin_real); gb[co] = sum_cta partial[cta][9 * CIN][co].
@@ -542,7 +552,7 @@ template <int MODE, int CIN, int COUT>
 int launch_conv_t(const CUtensorMap& mapW, const ConvTcArgs& a, int grid, cudaStream_t st) {
   constexpr int NKB = (9 * CIN + 1 + 63) / 64, NMT = (9 * CIN + 1 + 127) / 128;
   constexpr int NBLK = (MODE == CT_WGRAD) ? 2 * NMT : NKB;
-  constexpr int NBUF = (MODE == CT_CONV && CIN == 16) ? FQL_CONV_NBUF16 : 2;
+  constexpr int NBUF = conv_nbuf(MODE, CIN);
   constexpr int SMEM = NBUF * NBLK * BLK + ((MODE == CT_WGRAD) ? NBUF * BLK : NKB * 64 * 128) + 256 + 1024;
   static_assert(SMEM <= 232448, "conv_tc_kernel: shared memory");
   auto kern = conv_tc_kernel<MODE, CIN, COUT>;
@@ -552,7 +562,7 @@ int launch_conv_t(const CUtensorMap& mapW, const ConvTcArgs& a, int grid, cudaSt
     FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set[dev] = true;
   }
-  kern<<<grid, CT_THREADS, SMEM, st>>>(mapW, a);
+  kern<<<grid, conv_threads(MODE, CIN), SMEM, st>>>(mapW, a);
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -32,7 +32,7 @@ def conv_ref(x, w, b):
 
 
 @pytest.mark.parametrize('B,H,W,cin,cout', [(3, 8, 8, 16, 16), (2, 16, 16, 16, 32), (5, 20, 12, 32, 32), (1, 5, 3, 32, 32), (64, 32, 32, 16, 16),
-                                            (300, 8, 8, 32, 32)])
+                                            (300, 8, 8, 32, 32), (128, 64, 64, 16, 16), (192, 32, 32, 32, 32)])   # the last two: ~28 / ~10 tiles per persistent CTA
 def test_conv3x3_forward_dgrad_wgrad_exact(B, H, W, cin, cout):
     from fql_b200 import _lib
     lib = _lib.lib()
