@@ -55,6 +55,9 @@ struct EulerArgs {
   const float* params;
   long long arena;
   long long off_b[FQL_MAXL];
+  const float* c0;              // optional [S][M][H]: per-ROW additive term of layer 0 in place of its bias (pixel configs: the constant
+                                // part obs_features @ W0[:F] + b0 of the first layer, hoisted out of the Euler loop; X0b then holds only
+                                // the action / time columns and w_row[0] points at row F of W0)
   const float* a0;              // [S][M][A] initial actions (noise)
   float* target;                // [S][M][A] clip(final)
   __nv_bfloat16* hx;            // exchange scratch [2][S*tiles*128][H]
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     const bool lastl = (l == NL - 1);
     const int N = lastl ? a.A : a.H;
     const int col = lastl ? c : (int)j * NCOL + c;
-    sBias[i] = (c < NCOL && col < N) ? a.params[(int64_t)s * a.arena + a.off_b[l] + col] : 0.f;
+    sBias[i] = (c < NCOL && col < N && !(l == 0 && a.c0)) ? a.params[(int64_t)s * a.arena + a.off_b[l] + col] : 0.f;
   }
   if (threadIdx.x <= a.n_steps) sT[threadIdx.x] = (float)((double)threadIdx.x / (double)a.n_steps);
   tc_fence_before();
@@ -399,6 +402,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
         } else if (!last) {
           if constexpr (MODE == MODE_EULER) {
             uint4* dst = reinterpret_cast<uint4*>(a.hx + (int64_t)buf * a.hx_buf_elems + (int64_t)(hx_row + row) * a.H + j * NCOL + half * 32);
+            if (l == 0 && a.c0) {   // hoisted first layer: + (features @ W0[:F] + b0) of this row (sBias of layer 0 is zero)
+              const float4* cp = reinterpret_cast<const float4*>(a.c0 + ((int64_t)s * a.M + (valid ? grow : 0)) * a.H + j * NCOL + half * 32);
+#pragma unroll
+              for (int c = 0; c < 8; c++) {
+                const float4 cv = __ldg(cp + c);
+                r0[c * 4 + 0] = __float_as_uint(__uint_as_float(r0[c * 4 + 0]) + cv.x);
+                r0[c * 4 + 1] = __float_as_uint(__uint_as_float(r0[c * 4 + 1]) + cv.y);
+                r0[c * 4 + 2] = __float_as_uint(__uint_as_float(r0[c * 4 + 2]) + cv.z);
+                r0[c * 4 + 3] = __float_as_uint(__uint_as_float(r0[c * 4 + 3]) + cv.w);
+              }
+            }
 #pragma unroll
             for (int c = 0; c < 4; c++) {
               float h[8];
@@ -571,8 +585,8 @@ int launch_euler(const EulerArgs& a, const TcEulerSpec& f, cudaStream_t st, bool
 }  // namespace
 
 namespace {
-int fill_args(EulerArgs& a, const FqlDims* d, const Layout& L, int net, const float* params, int M, int Mcap0, int r0_in) {
-  FQL_TRY(tc_supported(d));
+int fill_args(EulerArgs& a, const FqlDims* d, const Layout& L, int net, const float* params, int M, int Mcap0, int r0_in, bool hoisted = false) {
+  FQL_TRY(tc_supported(d, !hoisted));
   FQL_REQUIRE(d->hidden == 512, "euler_cluster_kernel is built for hidden = 512 (16 exchange units of 32 columns)");
   const NetView& nv = L.net[net];
   memset(&a, 0, sizeof(a));
@@ -615,8 +629,15 @@ int max_clusters16(const EulerArgs& a, const TcEulerSpec& f) {
 int tc_euler_cluster(const TcEulerSpec& f, cudaStream_t st) {
   const FqlDims* d = f.d;
   EulerArgs a;
-  FQL_TRY(fill_args(a, d, *f.L, FQL_NET_ACTOR_BC_FLOW, f.params, f.M, f.Mcap0, f.r0_in));
+  FQL_TRY(fill_args(a, d, *f.L, FQL_NET_ACTOR_BC_FLOW, f.params, f.M, f.Mcap0, f.r0_in, f.c0 != nullptr));
   a.A = d->action_dim; a.n_steps = d->flow_steps;
+  if (f.c0) {
+    // hoisted first layer (agents/fql.py:162-169: the observation features are constant over the flow steps): the kernel's first layer
+    // is [action | t] @ W0[F:] + c0[row], X0b holds those A + 1 columns only
+    a.c0 = f.c0;
+    a.K0 = d->action_dim + 1; a.K0pad = 64; a.F = 0;
+    a.w_row[0] += d->obs_dim;
+  }
   a.a0 = f.a0; a.target = f.target;
   a.hx = reinterpret_cast<__nv_bfloat16*>(f.scratch);
   a.hx_buf_elems = (long long)a.S * a.tiles * TILE_M * a.H;

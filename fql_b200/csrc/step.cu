@@ -433,6 +433,7 @@ struct FqlContext {
   int split_adam = 0;        // FQL_B200_SPLIT_ADAM: 0 = one optimizer pass at the end (default: the others measured within noise), 1 = bc-flow's part right behind the Euler chain,
                              // 2 = bc-flow and critic parts before the one-step actor's gradients are complete
   int adam_done_blk = 0;     // blocks [0, adam_done_blk) were already applied by enqueue_grads_tc in this enqueue
+  int euler_hoist = 1;       // FQL_B200_EULER_HOIST=0: pixel configs, Euler integration layer by layer instead of hoisted first layer + cluster kernel
   int enc_streams = 1;       // FQL_B200_ENC_STREAMS=0: pixel configs, the five tensor-core encoder forwards on one stream
   int dp_early_adam = 1;     // FQL_B200_DP_EARLY_ADAM=0: data parallel, one optimizer pass at the end.  Default: the bc-flow + critic part
                              // runs behind their bucket reductions, under the one-step actor's bucket exchange
@@ -546,6 +547,8 @@ extern "C" int fql_context_create(FqlContext** out) {
   }
   const char* sa = getenv("FQL_B200_SPLIT_ADAM");
   if (sa) c->split_adam = atoi(sa);
+  const char* ehs = getenv("FQL_B200_EULER_HOIST");
+  if (ehs) c->euler_hoist = atoi(ehs);
   const char* ens = getenv("FQL_B200_ENC_STREAMS");
   if (ens) c->enc_streams = atoi(ens);
   const char* dea = getenv("FQL_B200_DP_EARLY_ADAM");
@@ -681,6 +684,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   // data parallel: state configs exchange per-network buckets as soon as each is final; pixel configs (encoder gradients finish on other
   // streams) exchange the whole trainable prefix of the arena once, behind the complete backward
   const bool dp_bucketed = dp_grads && !pix;
+  bool bc_enc_forked = false;
   FQL_TRY(stamp(ctx, 0, S0));   // step start
   FQL_TRY(launch_zero_bc(raw, (int64_t)S * FQL_NUM_RAW, c.do_apply ? c.st->count : nullptr, hp, w.gstats + S * 4, S0, w.cpost_ticket, 3 * S));
   FQL_TRY(encode_observations(c, L, w, S0, ctx));
@@ -723,6 +727,31 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
   };
   if (many_tiles) {
     FQL_TRY(chain(FQL_NET_ACTOR_BC_FLOW, w.XFb, 2 * B, B, B, nullptr, nullptr, nullptr, sh.flow_steps, S1));
+  } else if (H == 512 && ctx->use_euler_cluster && wide && S == 1 && ctx->euler_hoist) {
+    // pixel configs: the observation features are constant over the flow steps (agents/fql.py:162-169), so their part of the first
+    // layer, c0 = features @ W0[:F] + b0, is one GEMM in front of the loop and the cluster kernel integrates with the first layer
+    // reduced to [action | t] @ W0[F:] + c0[row]  (10 x 5 layer-by-layer GEMM launches -> one GEMM + one persistent launch)
+    const NetView& nb = L.net[FQL_NET_ACTOR_BC_FLOW];
+    const bf16* sh16 = reinterpret_cast<const bf16*>(shadow);
+    float* c0 = w.dF[0];                                   // fp32 scratch of the SIMT schedule, free in this one
+    TcGemmSpec g;
+    memset(&g, 0, sizeof(g));
+    g.M = B; g.N = H; g.K = sh.F; g.G0 = 1; g.G1 = 1; g.a_mn = 0; g.b_mn = 1;
+    g.A.ptr = reinterpret_cast<const bf16*>(w.XFb) + (int64_t)B * kF; g.A.inner = sh.F; g.A.rows = B; g.A.ld = kF; g.A.g0 = 1; g.A.g1 = 1;
+    g.B.ptr = sh16 + nb.off_w[0]; g.B.inner = H; g.B.rows = sh.F; g.B.ld = H; g.B.g0 = 1; g.B.g1 = 1;
+    g.mode = TC_MODE_STORE_F32;
+    g.bias.base = const_cast<float*>(P + nb.off_b[0]);
+    g.out_f.base = c0; g.out_f.ld = H;
+    FQL_TRY(tc_gemm(g, S1));
+    float* xa = w.dF[1];                                   // [B][A + 1] = (noise | t = 0)
+    void* xab = w.dO[0];                                   // bf16 [B][64]
+    FQL_TRY(launch_concat(b.z, sh.A, b.z, 0, 0.f, 1, xa, B, S1));
+    FQL_TRY(tc_pad_bf16(xa, xab, B, sh.A + 1, 64, S1));
+    TcEulerSpec e;
+    memset(&e, 0, sizeof(e));
+    e.d = d; e.L = &L; e.params = P; e.shadow = shadow; e.X0b = xab; e.Mcap0 = B; e.r0_in = 0; e.M = B;
+    e.a0 = b.z; e.c0 = c0; e.target = w.target; e.scratch = w.euler_hx;
+    FQL_TRY(tc_euler_cluster(e, S1));
   } else if (H == 512 && ctx->use_euler_cluster && !wide) {
     TcEulerSpec e;
     memset(&e, 0, sizeof(e));
@@ -763,9 +792,14 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
     FQL_TRY(stamp(ctx, 4, S2));
   } else if (c.do_backward) {
     FQL_TRY(tc_actor_backward(fbc, w.dpred, w.F_dOutb, w.F_dZb, w.F_dZf, S2, ctx->s3, ctx->s7, &ctx->ev[8]));
-    if (pix) {  // d(BC loss)/d(features) -> actor_bc_flow_encoder (agents/fql.py:58, 230-232)
+    if (pix) {  // d(BC loss)/d(features) -> actor_bc_flow_encoder (agents/fql.py:58, 230-232), on its own stream: S2 goes on to the
+                // critic's backward (the three encoder backwards are ~30 short launches each and overlap each other's gaps)
       FQL_TRY(tc_actor_input_grad(fbc, w.F_dZb[0], w.dX0F, S2));
-      FQL_TRY(encoder_grads(c, L, w, FQL_NET_ACTOR_BC_FLOW, w.dX0F, 1, sh.F + sh.A + 1, w.dfeat[1], 4, S2));
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[63], S2));
+      FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->sc, ctx->ev[63], 0));   // (the communication stream: idle in pixel configs)
+      FQL_TRY(encoder_grads(c, L, w, FQL_NET_ACTOR_BC_FLOW, w.dX0F, 1, sh.F + sh.A + 1, w.dfeat[1], 4, ctx->sc));
+      FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[37], ctx->sc));
+      bc_enc_forked = true;
     }
     FQL_CHECK_CUDA(cudaEventRecord(ctx->ev[53], ctx->s7));
     FQL_CHECK_CUDA(cudaStreamWaitEvent(ctx->s3, ctx->ev[53], 0));
@@ -936,6 +970,7 @@ int enqueue_grads_tc(FqlContext* ctx, const StepCall& c, const Layout& L, WsPtrs
       FQL_TRY(stamp(ctx, 9, S2)); // early optimizer pass done
     }
   }
+  if (bc_enc_forked) FQL_CHECK_CUDA(cudaStreamWaitEvent(S2, ctx->ev[37], 0));
   FQL_CHECK_CUDA(cudaEventRecord(ev_s2, S2));
   FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ev_euler, 0));
   if (split_metric) FQL_CHECK_CUDA(cudaStreamWaitEvent(S0, ctx->ev[57], 0));

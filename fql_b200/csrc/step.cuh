@@ -289,6 +289,7 @@ struct TcEulerSpec {
   const void* X0b;     // bf16 [S][Mcap0][K0pad] first-layer operand (obs | noise | t = 0)
   int Mcap0, r0_in, M;
   const float* a0;     // [S][M][A]
+  const float* c0;     // optional fp32 [S][M][H]: features @ W0[:F] + b0 (pixel configs); X0b is then bf16 [S][Mcap0][64] = (noise | t = 0)
   float* target;       // [S][M][A]
   void* scratch;       // tc_euler_scratch_elems() bf16 elements
   void* dbg;           // optional timestamp buffer (diagnostics)
