@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barriers, TMEM, zeroed operand padding) overlapped the previous kernel's tail; from
+  // here on this kernel reads what its predecessors wrote, and its successor may start its own prologue
+  FQL_PDL_SYNC();
 
   if (warp < NGRP) {
     // ================= MMA issuers (+ the one-time weight load) =================
@@ -562,7 +565,7 @@ int launch_conv_t(const CUtensorMap& mapW, const ConvTcArgs& a, int grid, cudaSt
     FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set[dev] = true;
   }
-  kern<<<grid, conv_threads(MODE, CIN), SMEM, st>>>(mapW, a);
+  FQL_CHECK_CUDA(fql_launch_pdl(kern, dim3(grid), dim3(conv_threads(MODE, CIN)), SMEM, st, mapW, a));
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -145,6 +145,9 @@ def test_pixel_update_parity_tensor_core_encoders(name, B, hw, ch, A, hidden, ov
     pq = O.cast_tree(stq['params'], np.float64)
     feats = PO.E.encoder_forward(pq['modules_actor_onestep_flow']['encoder'], batch['observations'][:8], dtype=np.dtype(np.float64), q=bf16_round)
     assert rel_err(a, O.sample_actions_given_noise(pq, cfg, feats, noise['z'][:8])) <= 3e-2
+    # one frame, like the online loop (main.py:225): a single image is 32 / 8 / 2 / half a pixel tile at the four resolutions
+    a1 = agent.sample_actions(batch['observations'][0], noise=noise['z'][0].astype(np.float32))
+    assert a1.shape == (A,) and np.abs(a1 - a[0]).max() <= 1e-3
 
 
 def test_pixel_param_count_matches_survey():
