@@ -10,8 +10,9 @@
 //                           MMAs produce the bias gradient; per-CTA partials are reduced in CTA order (deterministic)
 // Activations are NHWC bf16 with 16 or 32 channels (the uint8 frames become 16-channel bf16 INTEGERS 0..255, exact in bf16; the
 // 1/255 of encoders.py:84 is applied in fp32 to the accumulator).  Nothing is ever materialised as an im2col matrix in HBM:
-//   producers  one group of four warps per operand buffer (2 or 3: group g fills buffer g, i.e. every second / third tile: a gather
-//              is one L2 round trip per tile, several tiles in flight hide it): thread r owns pixel r of the tile; for each of the 9 taps it copies that
+//   producers  NGRP groups of four warps.  A tile's zero-padded neighbourhood [R + 2][W + 2][Cin] arrives by ONE 4-D TMA per tile into a
+//              small ring (out-of-bounds elements read as zero = SAME padding), prefetched a tile ahead, and the producers copy it
+//              shared -> shared (odd image sizes: direct gather from L2, one round trip per tile): thread r owns pixel r of the tile; for each of the 9 taps it copies that
 //              neighbour's channels (16-byte chunks, zeros outside the image = SAME padding) straight from L2/HBM into the K-major
 //              SWIZZLE_128B operand blocks ([128 rows][64 k] bf16) the MMAs read -- the same blocks serve as the MN-major A operand
 //              of the weight gradient;
@@ -36,7 +37,7 @@ constexpr int kStacks[3] = {16, 32, 32};
 constexpr int TM = 128;
 constexpr int BLK = TM * 128;            // one operand block: [128 rows][64 bf16]
 #ifndef FQL_CONV_NBUF16
-#define FQL_CONV_NBUF16 4   // measured at the 64x64 layer (kernel alone): 2 buffers 66 us, 4 buffers 47 us; must be even (see below)
+#define FQL_CONV_NBUF16 2   // a multiple of NGRP (see below); the halo ring prefetches the gathers, the operand buffers only cover the MMAs
 #endif
 // operand buffers = producer groups of a kernel instantiation: the 16-channel forward / input-gradient kernels (48 KB buffers) keep three
 __host__ __device__ constexpr int conv_nbuf(int mode, int cin) { return (mode == 0 && cin == 16) ? FQL_CONV_NBUF16 : 2; }
@@ -67,18 +68,33 @@ struct ConvTcArgs {
   const bf16* dy;       // [npix][COUT]
   float* partial;       // [gridDim.x][krows][COUT]
   int krows;            // 9 * CIN + 1
+  // halo staging (halo != 0): a tile = NB images x R rows x W pixels; its zero-padded neighbourhood [NB][R + 2][W + 2][CIN] arrives by ONE
+  // TMA (mapX: the NHWC tensor, box {CIN, W + 2, R + 2, NB}, out-of-bounds = zeros = SAME padding) into a ring slot
+  int halo, R, NB, tiles_per_image, halo_bytes;
 };
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// halo ring: slots per lane and bytes per slot (W <= 64 for 16 channels: 4 x 66 pixels; W <= 32 for 32 channels: 6 x 34 pixels)
+__host__ __device__ constexpr int halo_nstg(int cin) { return cin == 16 ? 2 : 1; }
+__host__ __device__ constexpr int halo_slot(int cin) { return cin == 16 ? 9216 : 13312; }
 
 template <int MODE, int CIN, int COUT>
-__global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapW, const ConvTcArgs a) {
+__global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const ConvTcArgs a) {
   constexpr int CH = CIN / 8;                       // 16-byte chunks per (pixel, tap)
   constexpr int NCH = 9 * CH;                       // chunks of real K per pixel row
   constexpr int NK16 = (9 * CIN + 15) / 16;         // MMA K steps (CT_CONV)
   constexpr int NKB = (9 * CIN + 1 + 63) / 64;      // operand blocks per buffer that hold data
   constexpr int NMT = (9 * CIN + 1 + 127) / 128;    // M tiles of the weight gradient
-  constexpr int NBLK = (MODE == CT_WGRAD) ? 2 * NMT : NKB;   // blocks allocated per buffer
+  // blocks per buffer.  The weight gradient's last M tile reads a second 64-column chunk one block past the buffer: whatever lies there
+  // (the next buffer / the dY tiles: finite bf16 data) only reaches accumulator rows >= 9 CIN + 1, which nobody reads
+  constexpr int NBLK = NKB;
+  constexpr int NSTG = halo_nstg(CIN), HSLOT = halo_slot(CIN);
   // operand buffers: a tile's gather (one L2 round trip) and its MMAs (~0.7 us) overlap with other tiles only across buffers, so the
   // 16-channel forward / input-gradient kernels, whose buffers are 48 KB, keep three of them
   constexpr int NBUF = conv_nbuf(MODE, CIN);
@@ -89,14 +105,18 @@ __global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                         // [NBUF][NBLK][BLK]
   uint8_t* sB = sA + NBUF * NBLK * BLK;                       // CT_CONV: weights [NKB * 64 k][64 n]; CT_WGRAD: dY tiles [NBUF][BLK]
-  constexpr int SB_BYTES = (MODE == CT_WGRAD) ? NBUF * BLK : NKB * 64 * 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SB_BYTES);
+  constexpr int NBOX = (NK16 + 1) / 2;                         // 32-row boxes of the prepared weights that hold real K rows
+  constexpr int SB_BYTES = (MODE == CT_WGRAD) ? NBUF * BLK : NBOX * 4096;
+  uint8_t* sH = sB + ((SB_BYTES + 1023) & ~1023);             // halo ring [NGRP][NSTG][HSLOT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sH + NGRP * NSTG * HSLOT);
   uint64_t* a_full = bars;          // [4] operand buffer gathered                 (4 producer warps)
   uint64_t* a_empty = bars + 4;     // [4] the MMAs have consumed the buffer       (tcgen05.commit)
   uint64_t* acc_full = bars + 8;    // [4] accumulator complete                    (tcgen05.commit)
   uint64_t* acc_free = bars + 12;   // [4] accumulator read                        (4 epilogue warps)
   uint64_t* b_full = bars + 16;     //     weights landed                          (TMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* h_full = bars + 17;     // [NGRP][2] halo slot landed                  (TMA)
+  uint64_t* h_empty = bars + 21;    // [NGRP][2] halo slot copied into the operand (4 producer warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntl = (a.tiles > (int)blockIdx.x) ? (a.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // tiles of this CTA
@@ -110,6 +130,11 @@ __global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(con
       mbar_init(&acc_free[i], 4);
     }
     mbar_init(b_full, 1);
+    for (int i = 0; i < 4; i++) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&h_empty[i], 4);
+    }
+    if (a.halo) tma_prefetch_desc(&mapX);
     fence_barrier_init();
   }
   // accumulators: CT_CONV one 64-column set per slot, CT_WGRAD NMT x 64 columns per slot
@@ -139,8 +164,9 @@ __global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(con
     if (lane == 0 && ntl > 0) {
       if (MODE == CT_CONV) {
         if (g == 0) {
-          mbar_expect_tx(b_full, NKB * 64 * 128);
-          for (int i = 0; i < NKB * 2; i++) tma_load_2d(sB + i * 4096, &mapW, b_full, 0, i * 32);
+          // rows [0, NK16 * 16) of the prepared matrix as boxes of 32 rows
+          mbar_expect_tx(b_full, NBOX * 4096);
+          for (int i = 0; i < NBOX; i++) tma_load_2d(sB + i * 4096, &mapW, b_full, 0, i * 32);
         }
         mbar_wait(b_full, 0);
       }
@@ -191,26 +217,63 @@ __global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(con
     const int grp = (warp - NGRP) >> 2;        // group g gathers tiles g, g + NGRP, ...
     const int r = ((warp - NGRP) & 3) * 32 + lane;
     const int HW = a.H * a.W;
-    for (int it = grp; it < ntl; it += NGRP) {
+    const bool issuer = ((warp - NGRP) & 3) == 0 && lane == 0;   // the group's TMA thread (halo staging)
+    // halo staging: this pixel's position inside the tile's zero-padded neighbourhood is the same for every tile
+    const int PI = a.R * a.W;                  // pixels of one image inside a tile
+    const int hb = a.halo ? r / PI : 0, hr = a.halo ? (r % PI) / a.W : 0, hw = a.halo ? r % a.W : 0;
+    const int hrow = (a.W + 2) * CIN * 2;      // bytes of one halo row
+    const uint32_t hoff = (uint32_t)((hb * (a.R + 2) + hr) * hrow + hw * CIN * 2);
+    auto halo_fetch = [&](int it, int slot) {  // TMA of tile it's neighbourhood into ring slot `slot` of this group
+      const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+      const int b0 = (a.NB > 1) ? (int)(tile * a.NB) : (int)(tile / a.tiles_per_image);
+      const int h0 = (a.NB > 1) ? 0 : (int)(tile % a.tiles_per_image) * a.R;
+      uint64_t* bar = &h_full[grp * 2 + slot];
+      mbar_expect_tx(bar, a.halo_bytes);
+      tma_load_4d(sH + (grp * NSTG + slot) * HSLOT, &mapX, bar, 0, -1, h0 - 1, b0);
+    };
+    if (a.halo && issuer)
+      for (int k = 0; k < NSTG && grp + k * NGRP < ntl; k++) halo_fetch(grp + k * NGRP, k);
+    int k = 0;                                 // this group's tile counter
+    for (int it = grp; it < ntl; it += NGRP, k++) {
       const int buf = it % NBUF;
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (it >= NBUF) mbar_wait(&a_empty[buf], ((it / NBUF) - 1) & 1);
-      uint8_t* A = sA + buf * NBLK * BLK;
       const long long p = tile * TM + r;
       const bool valid = p < a.npix;
-      const int pin = valid ? (int)(p % HW) : 0;
-      const int h = pin / a.W, w = pin - h * a.W;
-      const bf16* img = a.x + (valid ? (p - pin) : 0) * CIN;
+      uint4 dyv[COUT / 8];
+      if (MODE == CT_WGRAD) {                  // the dY row of this pixel: in flight while the waits below pass
 #pragma unroll
-      for (int tap = 0; tap < 9; tap++) {
-        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-        const bool inb = valid && hh >= 0 && hh < a.H && ww >= 0 && ww < a.W;
-        const bf16* src = img + (long long)(hh * a.W + ww) * CIN;
+        for (int c = 0; c < COUT / 8; c++) dyv[c] = valid ? ldg16(a.dy + p * COUT + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (it >= NBUF) mbar_wait(&a_empty[buf], ((it / NBUF) - 1) & 1);
+      uint8_t* A = sA + buf * NBLK * BLK;
+      if (a.halo) {
+        const int slot = k % NSTG;
+        mbar_wait(&h_full[grp * 2 + slot], (k / NSTG) & 1);
+        const uint8_t* hp = sH + (grp * NSTG + slot) * HSLOT + hoff;
 #pragma unroll
-        for (int c = 0; c < CH; c++) {
-          const int kc = tap * CH + c;
-          const uint4 v = inb ? ldg16(src + c * 8) : make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(A + (kc >> 3) * BLK + sw128_off(r, kc & 7)) = v;
+        for (int tap = 0; tap < 9; tap++) {
+          const uint8_t* src = hp + (tap / 3) * hrow + (tap % 3) * CIN * 2;
+#pragma unroll
+          for (int c = 0; c < CH; c++) {
+            const int kc = tap * CH + c;
+            *reinterpret_cast<uint4*>(A + (kc >> 3) * BLK + sw128_off(r, kc & 7)) = *reinterpret_cast<const uint4*>(src + c * 16);
+          }
+        }
+      } else {
+        const int pin = valid ? (int)(p % HW) : 0;
+        const int h = pin / a.W, w = pin - h * a.W;
+        const bf16* img = a.x + (valid ? (p - pin) : 0) * CIN;
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+          const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+          const bool inb = valid && hh >= 0 && hh < a.H && ww >= 0 && ww < a.W;
+          const bf16* src = img + (long long)(hh * a.W + ww) * CIN;
+#pragma unroll
+          for (int c = 0; c < CH; c++) {
+            const int kc = tap * CH + c;
+            const uint4 v = inb ? ldg16(src + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(A + (kc >> 3) * BLK + sw128_off(r, kc & 7)) = v;
+          }
         }
       }
       if (MODE == CT_WGRAD) {
@@ -218,14 +281,20 @@ __global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(con
         *reinterpret_cast<uint4*>(A + (NCH >> 3) * BLK + sw128_off(r, NCH & 7)) = make_uint4(valid ? 0x3F80u : 0u, 0u, 0u, 0u);
         uint8_t* Bt = sB + buf * BLK;
 #pragma unroll
-        for (int c = 0; c < COUT / 8; c++) {
-          const uint4 v = valid ? ldg16(a.dy + p * COUT + c * 8) : make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(Bt + sw128_off(r, c)) = v;
-        }
+        for (int c = 0; c < COUT / 8; c++) *reinterpret_cast<uint4*>(Bt + sw128_off(r, c)) = dyv[c];
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[buf]);
+      if (a.halo) {
+        // the slot is free once all four warps have copied it out; the group's TMA thread then refills it NSTG tiles ahead
+        const int slot = k % NSTG;
+        if (lane == 0) mbar_arrive(&h_empty[grp * 2 + slot]);
+        if (issuer && it + NSTG * NGRP < ntl) {
+          mbar_wait(&h_empty[grp * 2 + slot], (k / NSTG) & 1);
+          halo_fetch(it + NSTG * NGRP, slot);
+        }
+      }
     }
   } else {
     // ================= epilogue =================
@@ -551,12 +620,40 @@ int make_map_w(CUtensorMap* m, const void* base, int rows) {
   return 0;
 }
 
+// Halo staging applies when a 128-pixel tile is R full rows of one image (W divides 128, R = 128 / W divides H) or NB whole images
+// (H W divides 128), and the neighbourhood fits the ring slot; other geometries (odd image sizes) use the direct gather.
+// mapX: the NHWC activation tensor {C, W, H, B} with box {C, W + 2, R + 2, NB}, no swizzle, out-of-bounds elements read as zero.
+int conv_halo_setup(ConvTcArgs& a, CUtensorMap* mapX, const void* x, int cin, long long B) {
+  memset(mapX, 0, sizeof(*mapX));
+  a.halo = 0; a.R = 1; a.NB = 1; a.tiles_per_image = 1; a.halo_bytes = 0;
+  static const bool off = getenv("FQL_B200_CONV_HALO") && getenv("FQL_B200_CONV_HALO")[0] == '0';
+  if (off) return 0;
+  const int H = a.H, W = a.W;
+  int R = 0, NB = 0;
+  if (W <= TM && TM % W == 0 && H % (TM / W) == 0) { R = TM / W; NB = 1; }
+  else if (H * W < TM && TM % (H * W) == 0) { R = H; NB = TM / (H * W); }
+  else return 0;
+  const long long bytes = (long long)NB * (R + 2) * (W + 2) * cin * 2;
+  if (bytes > halo_slot(cin) || W + 2 > 256 || R + 2 > 256) return 0;
+  auto enc = get_encode();
+  FQL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
+  cuuint32_t box[4] = {(cuuint32_t)cin, (cuuint32_t)(W + 2), (cuuint32_t)(R + 2), (cuuint32_t)NB};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(mapX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FQL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(conv halo) failed (%d): C %d W %d H %d B %lld box %d x %d x %d", (int)r, cin, W, H, B, W + 2, R + 2, NB);
+  a.halo = 1; a.R = R; a.NB = NB; a.tiles_per_image = (NB == 1) ? H / R : 1; a.halo_bytes = (int)bytes;
+  return 0;
+}
+
 template <int MODE, int CIN, int COUT>
-int launch_conv_t(const CUtensorMap& mapW, const ConvTcArgs& a, int grid, cudaStream_t st) {
-  constexpr int NKB = (9 * CIN + 1 + 63) / 64, NMT = (9 * CIN + 1 + 127) / 128;
-  constexpr int NBLK = (MODE == CT_WGRAD) ? 2 * NMT : NKB;
+int launch_conv_t(const CUtensorMap& mapW, const CUtensorMap& mapX, const ConvTcArgs& a, int grid, cudaStream_t st) {
+  constexpr int NKB = (9 * CIN + 1 + 63) / 64, NK16 = (9 * CIN + 15) / 16, NBOX = (NK16 + 1) / 2;
   constexpr int NBUF = conv_nbuf(MODE, CIN);
-  constexpr int SMEM = NBUF * NBLK * BLK + ((MODE == CT_WGRAD) ? NBUF * BLK : NKB * 64 * 128) + 256 + 1024;
+  constexpr int SB = ((MODE == CT_WGRAD) ? NBUF * BLK : NBOX * 4096);
+  constexpr int SMEM = NBUF * NKB * BLK + ((SB + 1023) & ~1023) + NGRP * halo_nstg(CIN) * halo_slot(CIN) + 256 + 1024;
   static_assert(SMEM <= 232448, "conv_tc_kernel: shared memory");
   auto kern = conv_tc_kernel<MODE, CIN, COUT>;
   static bool attr_set[FQL_MAX_DEVICES] = {};
@@ -565,7 +662,7 @@ int launch_conv_t(const CUtensorMap& mapW, const ConvTcArgs& a, int grid, cudaSt
     FQL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set[dev] = true;
   }
-  FQL_CHECK_CUDA(fql_launch_pdl(kern, dim3(grid), dim3(conv_threads(MODE, CIN)), SMEM, st, mapW, a));
+  FQL_CHECK_CUDA(fql_launch_pdl(kern, dim3(grid), dim3(conv_threads(MODE, CIN)), SMEM, st, mapW, mapX, a));
   FQL_CHECK_LAUNCH();
   return 0;
 }
@@ -590,12 +687,13 @@ int conv_tc(const bf16* x, int cin, int cout, const bf16* wb, long long B, int H
   a.scale = scale; a.bias = bias; a.mask = mask; a.add = add; a.relu_out = relu_out; a.out = out; a.out_relu = out_relu;
   const int grid = a.tiles < num_sms() ? a.tiles : num_sms();
   if (grid <= 0) return 0;
-  CUtensorMap mapW;
+  CUtensorMap mapW, mapX;
   FQL_TRY(make_map_w(&mapW, wb, KPAD_MAX));
-  if (cin == 16 && cout == 16) return launch_conv_t<CT_CONV, 16, 16>(mapW, a, grid, st);
-  if (cin == 16 && cout == 32) return launch_conv_t<CT_CONV, 16, 32>(mapW, a, grid, st);
-  if (cin == 32 && cout == 32) return launch_conv_t<CT_CONV, 32, 32>(mapW, a, grid, st);
-  if (cin == 32 && cout == 16) return launch_conv_t<CT_CONV, 32, 16>(mapW, a, grid, st);
+  FQL_TRY(conv_halo_setup(a, &mapX, x, cin, B));
+  if (cin == 16 && cout == 16) return launch_conv_t<CT_CONV, 16, 16>(mapW, mapX, a, grid, st);
+  if (cin == 16 && cout == 32) return launch_conv_t<CT_CONV, 16, 32>(mapW, mapX, a, grid, st);
+  if (cin == 32 && cout == 32) return launch_conv_t<CT_CONV, 32, 32>(mapW, mapX, a, grid, st);
+  if (cin == 32 && cout == 16) return launch_conv_t<CT_CONV, 32, 16>(mapW, mapX, a, grid, st);
   FQL_REQUIRE(false, "conv_tc: unsupported channel counts %d -> %d", cin, cout);
   return 1;
 }
@@ -609,11 +707,12 @@ int conv_wgrad_tc(const bf16* x, int cin, int cin_real, int cout, const bf16* dy
   a.dy = dy; a.partial = partial; a.krows = 9 * cin + 1;
   const int grid = a.tiles < num_sms() ? a.tiles : num_sms();
   if (grid <= 0) return 0;
-  CUtensorMap mapW;
+  CUtensorMap mapW, mapX;
   memset(&mapW, 0, sizeof(mapW));
-  if (cin == 16 && cout == 16) FQL_TRY((launch_conv_t<CT_WGRAD, 16, 16>(mapW, a, grid, st)));
-  else if (cin == 16 && cout == 32) FQL_TRY((launch_conv_t<CT_WGRAD, 16, 32>(mapW, a, grid, st)));
-  else if (cin == 32 && cout == 32) FQL_TRY((launch_conv_t<CT_WGRAD, 32, 32>(mapW, a, grid, st)));
+  FQL_TRY(conv_halo_setup(a, &mapX, x, cin, B));
+  if (cin == 16 && cout == 16) FQL_TRY((launch_conv_t<CT_WGRAD, 16, 16>(mapW, mapX, a, grid, st)));
+  else if (cin == 16 && cout == 32) FQL_TRY((launch_conv_t<CT_WGRAD, 16, 32>(mapW, mapX, a, grid, st)));
+  else if (cin == 32 && cout == 32) FQL_TRY((launch_conv_t<CT_WGRAD, 32, 32>(mapW, mapX, a, grid, st)));
   else FQL_REQUIRE(false, "conv_wgrad_tc: unsupported channel counts %d -> %d", cin, cout);
   const int n = 9 * cin_real * cout + cout;
   wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(partial, grid, a.krows, cin, cin_real, cout, scale, gw, gb);
