@@ -7,7 +7,7 @@ from oracle import fql_oracle as O
 from oracle import fql_pixel_oracle as PO
 from tests.helpers import f32, rel_err
 from fql_b200 import FQLAgent
-B, hw, ch, A, hidden = int(os.environ.get('B', 6)), int(os.environ.get('HW', 16)), int(os.environ.get('CH', 6)), 3, 64
+B, hw, ch, A, hidden = int(os.environ.get('B', 6)), int(os.environ.get('HW', 16)), int(os.environ.get('CH', 6)), 3, int(os.environ.get('HIDDEN', 64))
 cfg = dict(O.DEFAULT_CONFIG); cfg.update(alpha=10.0)
 cfg.update(actor_hidden_dims=(hidden,) * 4, value_hidden_dims=(hidden,) * 4, encoder='impala_small')
 params = PO.init_params(3, ch, A, cfg, dtype=np.float64, hw=hw, jitter=0.05, target_equals_critic=False)

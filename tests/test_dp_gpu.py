@@ -138,6 +138,66 @@ def test_two_ranks_data_parallel_step(backend, precision, over):
     assert ret.get(timeout=5) == 'ok'
 
 
+def _dp_pixel_worker(rank, world, port, ret, precision):
+    """Pixel configuration, two ranks: rows shard, the encoder + MLP gradients of the whole trainable arena are exchanged once behind
+    the backward (the encoder backwards finish on forked streams), every rank applies the same update."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(f'cuda:{rank}'))
+    from fql_b200 import FQLAgent, dist as fdist
+    from oracle import fql_pixel_oracle as PO
+    from oracle.encoder_oracle import bf16_round
+    B, hw, ch, A, hidden = 8, 16, 6, 3, 512
+    cfg = dict(O.DEFAULT_CONFIG)
+    cfg.update(alpha=10.0, actor_hidden_dims=(hidden,) * 4, value_hidden_dims=(hidden,) * 4, encoder='impala_small')
+    params = PO.init_params(3, ch, A, cfg, dtype=np.float64, hw=hw, jitter=0.05, target_equals_critic=False)
+    state = O.init_state(params, warm=True, seed=3)
+    # frames on which no max-pool window is decided by fp32 rounding (seed 4 has a 1.3e-8 near-tie at 8 rows: the pooling gradient
+    # of one channel then lands on another pixel than in the fp64 oracle -- measured, profiles/dbg_pix_fp32.py)
+    batch, _ = PO.well_posed_pixel_batch(params, B, A, hw, ch, dtype=np.float64, first_seed=4)
+    noise = O.make_noise(5, B, A, np.float64)
+    q = None if precision == 'fp32' else bf16_round
+    new_state, ref_info, ref_grads = PO.update(copy.deepcopy(state), cfg, batch, noise, enc_q=q)
+    c = dict(cfg)
+    c['batch_size'] = B // world
+    agent = FQLAgent.create(0, np.zeros((1, hw, hw, ch), np.uint8), np.zeros((1, A), np.float32), c, process_group=dist.group.WORLD, precision=precision)
+    agent.load_tree(f32(state['params']), f32(state['mu']), f32(state['nu']), state['count'])
+    sh = lambda d: {k: (v if v.dtype == np.uint8 else v.astype(np.float32)) for k, v in fdist.shard_rows(d, rank, world).items()}
+    _, info = agent.update(sh(batch), noise=sh(noise))
+    tol_info, tol_grad = (3e-5, 1e-4) if precision == 'fp32' else (5e-2, 8e-2)
+    for k in O.INFO_KEYS[:10]:
+        info_close(k, info[k], ref_info, tol_info)
+    for (path, r), (_, g) in zip(O.tree_leaves(ref_grads), O.tree_leaves(agent.export_tree('grads'))):
+        if np.abs(r).max() > 0:
+            assert rel_err(g, r) <= tol_grad, ('grads', path, rel_err(g, r))      # the arena holds the REDUCED gradient
+    mine = agent._params.view(torch.int32).sum(dtype=torch.int64).reshape(1)
+    both = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    assert all(int(x) == int(both[0]) for x in both), [int(x) for x in both]
+    if rank == 0:
+        ret.put('ok')
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_two_ranks_data_parallel_pixel_step(precision):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_dp_pixel_worker, args=(r, 2, port, ret, precision)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(420)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 'ok'
+
+
 def _nccl_worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
