@@ -51,6 +51,17 @@ constexpr int NKB = HID / 64;
 
 enum { C2_FWD = 0, C2_EULER = 1, C2_FWD_LN = 2, C2_BWD = 3, C2_BWD_LN = 4 };
 
+#ifdef FQL_C2_DBG   // diagnostics build only (make EXTRA=-DFQL_C2_DBG): per-stage %globaltimer stamps of CTA 0, iteration FQL_C2_DBG_N
+__device__ unsigned long long g_c2_dbg[256];
+__device__ __forceinline__ unsigned long long c2_gt() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#ifndef FQL_C2_DBG_N
+#define FQL_C2_DBG_N 7
+#endif
+#define C2_STAMP(cond, idx) do { if ((cond) && el && blockIdx.x == 0) g_c2_dbg[idx] = c2_gt(); } while (0)
+#else
+#define C2_STAMP(cond, idx) do { } while (0)
+#endif
+
 struct Chain2Args {
   int NL, K0, K0pad, out_dim;
   int P, S, E, M, tiles;
@@ -205,6 +216,11 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
   tc_fence_after();
   if (PAIR) cluster_sync_();     // both CTAs' barriers are initialised before any remote arrive / completion
   const uint32_t tmem_base = *tmem_slot;
+  // The TMA producer and the MMA issuer are ONE thread each, but all 32 lanes of their warps run the loops (waits, descriptor arithmetic):
+  // warp-uniform control flow keeps the descriptors in uniform registers, and only the instruction itself is predicated on the elected
+  // lane.  With the whole loop under `if (lane == 0)` ptxas wraps every tcgen05.mma / tcgen05.commit / TMA in an ELECT + 5 R2UR.BROADCAST
+  // waterfall: 178 instead of 139 ns per two MMAs + commit in isolation (profiles/micro/mma_dual_bench.cu), 370 ns per stage in here.
+  bool el = false;     // set at the top of the two roles' branches (straight from elect.sync: ptxas then knows the region is single-lane)
   // arrive on a barrier the leader's MMA thread waits on
   auto arrive_lead = [&](uint64_t* bar) {
     if (!PAIR || rank == 0) mbar_arrive(bar);
@@ -213,18 +229,21 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
   // wait on a barrier that takes arrivals from the peer CTA (remote arrive / multicast commit / the peer's TMA)
   auto wait_x = [&](uint64_t* bar, uint32_t parity) {
     if (PAIR) mbar_wait_cl(bar, parity);
+    else if (warp <= 1) mbar_wait_u(bar, parity);
     else mbar_wait(bar, parity);
   };
   // TMA load of this CTA's part of a stage; completion bytes go to the leader's barrier
   auto load2d = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    if (!el) return;
     if (PAIR && rank != 0) tma_load_2d_pair(dst, m, bar, c0, c1);
     else tma_load_2d(dst, m, bar, c0, c1);
   };
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      if (rank == 0) mbar_expect_tx(x_full, NCTA * nkb_x * KB_BYTES);
+    el = elect_one();
+    {
+      if (el && rank == 0) mbar_expect_tx(x_full, NCTA * nkb_x * KB_BYTES);
       const int xrow = a.x_row0[p] + s * a.x_rows_s + e * a.x_rows_e + tile * TILE_M;
       for (int kb = 0; kb < nkb_x; kb++) load2d(sX + kb * KB_BYTES, &mapX, x_full, kb * 64, xrow);
       int stage = 0;
@@ -241,12 +260,13 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
           for (int h = 0; h < 2; h++)
             for (int ks = 0; ks < nst; ks++) {
               wait_x(&empty[stage], phase ^ 1);
+              C2_STAMP(n == FQL_C2_DBG_N && MODE == C2_EULER, 128 + h * 16 + ks);
               uint8_t* dst = sW + stage * SLOT;
-              if (rank == 0) mbar_expect_tx(&full[stage], STAGE_BYTES);
+              if (el && rank == 0) mbar_expect_tx(&full[stage], STAGE_BYTES);
               if (BWD) {     // this CTA's 256 / NCTA input rows of the half
                 load2d(dst, it == 0 ? &mapWL : &mapW, &full[stage], ks * KS, row0 + h * NHALF + (int)rank * (NHALF / NCTA));
               } else if (!PAIR && a.w3d) {
-                tma_load_3d(dst, &mapW, &full[stage], 0, row0 + ks * KS, h * 4);
+                if (el) tma_load_3d(dst, &mapW, &full[stage], 0, row0 + ks * KS, h * 4);
               } else {       // this CTA's 4 / NCTA chunks of 64 output columns of the half
                 for (int c = 0; c < 4 / NCTA; c++)
                   load2d(dst + c * CHUNK_BYTES, &mapW, &full[stage], (h * 4 + (int)rank * (4 / NCTA) + c) * 64, row0 + ks * KS);
@@ -260,7 +280,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
             wait_x(&empty[stage], phase ^ 1);
             // backward: this CTA's K0pad / NCTA input rows; forward: the padded 64 output columns (the pair: N = 128, both CTAs load
             // the same chunk, the leader's copy gives columns [0, 64) of every row of both tiles)
-            if (rank == 0) mbar_expect_tx(&full[stage], BWD ? a.K0pad * 64 : NCTA * KS * 128);
+            if (el && rank == 0) mbar_expect_tx(&full[stage], BWD ? a.K0pad * 64 : NCTA * KS * 128);
             if (BWD) load2d(sW + stage * SLOT, &mapW0, &full[stage], ks * KS, row0 + (int)rank * (a.K0pad / NCTA));
             else load2d(sW + stage * SLOT, &mapWL, &full[stage], 0, row0 + ks * KS);
             if (++stage == a.nstage) { stage = 0; phase ^= 1; }
@@ -270,18 +290,23 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ================= MMA issuer (the leader's only) =================
-    if (lane == 0 && rank == 0) {
+    el = elect_one();
+    if (rank == 0) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // uniform copy (the shared-memory load is per-thread to ptxas)
       const uint32_t idesc_h = make_idesc_bf16(128 * NCTA, NHALF, false, !BWD);
       const uint32_t idesc_t = make_idesc_bf16(128 * NCTA, (!BWD && PAIR) ? 128 : ntail, false, !BWD);
       auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+        if (!el) return;
         if (PAIR) umma2_bf16(d, ad, bd, id, acc);
         else umma_bf16(d, ad, bd, id, acc);
       };
       auto mma_x2 = [&](uint32_t d, uint64_t ad, uint64_t bd, uint64_t as, uint64_t bs, uint32_t id, uint32_t acc) {
+        if (!el) return;
         if (PAIR) umma2_bf16_x2(d, ad, bd, as, bs, id, acc);
         else umma_bf16_x2(d, ad, bd, as, bs, id, acc);
       };
       auto commit = [&](uint64_t* bar) {
+        if (!el) return;
         if (PAIR) umma2_commit(bar);
         else umma_commit(bar);
       };
@@ -310,15 +335,17 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
               wait_x(&acc_free[h], (uses[h] - 1) & 1);
               tc_fence_after();
             }
-            const uint32_t tacc = tmem_base + h * NHALF;
+            const uint32_t tacc = tmem_u + h * NHALF;
             for (int ks = 0; ks < nst; ks++) {
               const int kb = ks >> 1;
               if (it > 0 && h == 0 && (ks & 1) == 0) {
                 wait_x(&a_ready[kb], (n_ar - 1) & 1);
                 tc_fence_after();
               }
+              C2_STAMP(n == FQL_C2_DBG_N && MODE == C2_EULER, h * 48 + ks * 3 + 0);
               wait_x(&full[stage], phase);
               tc_fence_after();
+              C2_STAMP(n == FQL_C2_DBG_N && MODE == C2_EULER, h * 48 + ks * 3 + 1);
               const uint64_t adesc = a_t + (uint64_t)(abase + kb * (KB_BYTES >> 4) + (ks & 1) * 4);
               const uint64_t bdesc = b_t + (uint64_t)(sw0 + stage * (SLOT >> 4));
               // both K steps of a stage from ONE asm block: the uniform-register descriptors are materialised once (a run-time
@@ -326,6 +353,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
               if (K - ks * KS > 16) mma_x2(tacc, adesc, bdesc, 2, b_k16, idesc_h, ks > 0);
               else mma(tacc, adesc, bdesc, idesc_h, ks > 0);
               commit(&empty[stage]);
+              C2_STAMP(n == FQL_C2_DBG_N && MODE == C2_EULER, h * 48 + ks * 3 + 2);
               if (++stage == a.nstage) { stage = 0; phase ^= 1; }
               if (it > 0 && h == 1 && (ks & 1) == 1 && kb < 4) commit(&a_free[kb]);
             }
@@ -345,7 +373,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
             tc_fence_after();
             const uint64_t adesc = a_t + (uint64_t)(sa0 + kb * (KB_BYTES >> 4) + (ks & 1) * 4);
             const uint64_t bdesc = b_t + (uint64_t)(sw0 + stage * (SLOT >> 4));
-            mma_x2(tmem_base, adesc, bdesc, 2, b_k16, idesc_t, ks > 0);
+            mma_x2(tmem_u, adesc, bdesc, 2, b_k16, idesc_t, ks > 0);
             commit(&empty[stage]);
             if (++stage == a.nstage) { stage = 0; phase ^= 1; }
           }
@@ -682,6 +710,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
     else tmem_dealloc(tmem_base, 512);
   }
 }
+
+#ifdef FQL_C2_DBG
+}  // namespace
+extern "C" int fql_debug_chain2_stamps(unsigned long long* host_out, int n) {
+  FQL_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_c2_dbg, (n < 256 ? n : 256) * sizeof(unsigned long long)));
+  return 0;
+}
+namespace {
+#endif
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;

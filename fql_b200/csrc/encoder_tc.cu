@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(con
   uint64_t* h_empty = bars + 21;    // [NGRP][2] halo slot copied into the operand (4 producer warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform to ptxas as well
   const int ntl = (a.tiles > (int)blockIdx.x) ? (a.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // tiles of this CTA
 
   if (warp == 0 && lane == 0) {
@@ -158,58 +158,65 @@ __global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(con
 
   if (warp < NGRP) {
     // ================= MMA issuers (+ the one-time weight load) =================
-    // A tcgen05.mma costs its issuing warp ~80 ns whatever N is, and the cost is per warp (profiles/micro/mma_bench.cu): warp g issues
-    // the tiles of slot g into accumulator set g.  Descriptor offsets are compile-time constants.
+    // Warp g issues the tiles of slot g into accumulator set g.  All 32 lanes run the loop (waits, descriptor arithmetic in uniform
+    // registers); the tcgen05 / TMA instructions are predicated on the elected lane -- under `if (lane == 0)` each of them sat in an
+    // ELECT + R2UR.BROADCAST waterfall (tc_prims.cuh, profiles/micro/mma_dual_bench.cu).
     const int g = warp;
-    if (lane == 0 && ntl > 0) {
+    const bool el = elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    if (ntl > 0) {
       if (MODE == CT_CONV) {
-        if (g == 0) {
+        if (g == 0 && el) {
           // rows [0, NK16 * 16) of the prepared matrix as boxes of 32 rows
           mbar_expect_tx(b_full, NBOX * 4096);
           for (int i = 0; i < NBOX; i++) tma_load_2d(sB + i * 4096, &mapW, b_full, 0, i * 32);
         }
-        mbar_wait(b_full, 0);
+        mbar_wait_u(b_full, 0);
       }
       const uint32_t sa0 = smem_u32(sA) >> 4, sb0 = smem_u32(sB) >> 4;
       if (MODE == CT_CONV) {
         const uint32_t idesc = make_idesc_bf16(128, 64, false, true);
         const uint64_t a_t = make_smem_desc(0, 16, 1024) + (uint64_t)sa0;
         const uint64_t bb = make_smem_desc(0, 4096, 1024) + (uint64_t)sb0;
-        const uint32_t tacc = tmem_base + g * 64;
+        const uint32_t tacc = tmem_u + g * 64;
         for (int it = g; it < ntl; it += NGRP) {
           const int buf = it % NBUF, use = it / NGRP;
-          mbar_wait(&a_full[buf], (it / NBUF) & 1);
-          if (use >= 1) mbar_wait(&acc_free[g], (use - 1) & 1);
+          mbar_wait_u(&a_full[buf], (it / NBUF) & 1);
+          if (use >= 1) mbar_wait_u(&acc_free[g], (use - 1) & 1);
           tc_fence_after();
           const uint64_t ab = a_t + (uint64_t)(buf * NBLK * (BLK >> 4));
+          if (el) {
 #pragma unroll
-          for (int kb = 0; kb < NK16 / 4; kb++)      // one 64-wide K block = four K steps (A: +32 B, B: +16 rows of 128 B)
-            umma_bf16_x4(tacc, ab + (uint64_t)(kb * (BLK >> 4)), bb + (uint64_t)(kb * 4 * (2048 >> 4)), 2, 2048 >> 4, idesc, kb > 0);
-          if (NK16 % 4 >= 2)
-            umma_bf16_x2(tacc, ab + (uint64_t)((NK16 / 4) * (BLK >> 4)), bb + (uint64_t)((NK16 / 4) * 4 * (2048 >> 4)), 2, 2048 >> 4, idesc, 1);
-          if (NK16 % 2 == 1)
-            umma_bf16(tacc, ab + (uint64_t)((NK16 / 4) * (BLK >> 4) + ((NK16 % 4) - 1) * 2), bb + (uint64_t)((NK16 - 1) * (2048 >> 4)), idesc, 1);
-          umma_commit(&a_empty[buf]);
-          umma_commit(&acc_full[g]);
+            for (int kb = 0; kb < NK16 / 4; kb++)      // one 64-wide K block = four K steps (A: +32 B, B: +16 rows of 128 B)
+              umma_bf16_x4(tacc, ab + (uint64_t)(kb * (BLK >> 4)), bb + (uint64_t)(kb * 4 * (2048 >> 4)), 2, 2048 >> 4, idesc, kb > 0);
+            if (NK16 % 4 >= 2)
+              umma_bf16_x2(tacc, ab + (uint64_t)((NK16 / 4) * (BLK >> 4)), bb + (uint64_t)((NK16 / 4) * 4 * (2048 >> 4)), 2, 2048 >> 4, idesc, 1);
+            if (NK16 % 2 == 1)
+              umma_bf16(tacc, ab + (uint64_t)((NK16 / 4) * (BLK >> 4) + ((NK16 % 4) - 1) * 2), bb + (uint64_t)((NK16 - 1) * (2048 >> 4)), idesc, 1);
+            umma_commit(&a_empty[buf]);
+            umma_commit(&acc_full[g]);
+          }
         }
       } else {
         const uint32_t idesc = make_idesc_bf16(128, 64, true, true);
         const uint64_t a_t = make_smem_desc(0, BLK, 1024) + (uint64_t)(sa0 + g * NBLK * (BLK >> 4));
         const uint64_t bb = make_smem_desc(0, BLK, 1024) + (uint64_t)(sb0 + g * (BLK >> 4));
-        const uint32_t tacc = tmem_base + g * NMT * 64;
+        const uint32_t tacc = tmem_u + g * NMT * 64;
         static_assert(MODE != 1 || NBUF == NGRP, "the weight-gradient kernel keeps one buffer per lane");
         for (int it = g; it < ntl; it += NGRP) {
-          mbar_wait(&a_full[g], (it / NBUF) & 1);
+          mbar_wait_u(&a_full[g], (it / NBUF) & 1);
           tc_fence_after();
+          if (el) {
 #pragma unroll
-          for (int mt = 0; mt < NMT; mt++) {
-            const uint64_t ab = a_t + (uint64_t)(2 * mt * (BLK >> 4));
-            umma_bf16_x4(tacc + mt * 64, ab, bb, 2048 >> 4, 2048 >> 4, idesc, it >= NBUF);
-            umma_bf16_x4(tacc + mt * 64, ab + (uint64_t)(4 * (2048 >> 4)), bb + (uint64_t)(4 * (2048 >> 4)), 2048 >> 4, 2048 >> 4, idesc, 1);
+            for (int mt = 0; mt < NMT; mt++) {
+              const uint64_t ab = a_t + (uint64_t)(2 * mt * (BLK >> 4));
+              umma_bf16_x4(tacc + mt * 64, ab, bb, 2048 >> 4, 2048 >> 4, idesc, it >= NBUF);
+              umma_bf16_x4(tacc + mt * 64, ab + (uint64_t)(4 * (2048 >> 4)), bb + (uint64_t)(4 * (2048 >> 4)), 2048 >> 4, 2048 >> 4, idesc, 1);
+            }
+            umma_commit(&a_empty[g]);
           }
-          umma_commit(&a_empty[g]);
         }
-        if (ntl > g) umma_commit(&acc_full[g]);
+        if (ntl > g && el) umma_commit(&acc_full[g]);
       }
     }
   } else if (warp < W_EPI) {
@@ -400,10 +407,13 @@ __global__ void __launch_bounds__(conv_threads(MODE, CIN), 1) conv_tc_kernel(con
 }
 
 // gw[tap][ci][co] = scale * sum_cta partial[cta][tap * CIN + ci][co] (ci < cin_real); gb[co] = sum_cta partial[cta][9 * CIN][co].
-// 32 outputs per block; the CTA partials of an output are split over 8 threads and combined in a fixed order (deterministic).
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int krows, int CIN, int cin_real, int COUT,
-                                                           float scale, float* __restrict__ gw, float* __restrict__ gb) {
-  __shared__ float red[8][32];
+// 32 outputs per block; the CTA partials of an output are split over 32 threads (<= 5 independent loads each at 148 CTAs: the
+// 8-way split of round 2 was a chain of 19 dependent L2 round trips = 22 us per launch, 27 launches per step) and combined in a
+// fixed order (deterministic).
+constexpr int WR_SPLIT = 32;
+__global__ void __launch_bounds__(32 * WR_SPLIT) wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int krows, int CIN, int cin_real,
+                                                                     int COUT, float scale, float* __restrict__ gw, float* __restrict__ gb) {
+  __shared__ float red[WR_SPLIT][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx;
   const int n_w = 9 * cin_real * COUT;
@@ -420,14 +430,22 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
   }
   float s = 0.f;
-  if (live)
-    for (int c = ty; c < nctas; c += 8) s += partial[((long long)c * krows + kr) * COUT + co];
+  if (live) {
+    const float* src = partial + (long long)kr * COUT + co;
+    const long long stride = (long long)krows * COUT;
+    int c = ty;
+    for (; c + 3 * WR_SPLIT < nctas; c += 4 * WR_SPLIT) {
+      const float v0 = src[c * stride], v1 = src[(c + WR_SPLIT) * stride], v2 = src[(c + 2 * WR_SPLIT) * stride], v3 = src[(c + 3 * WR_SPLIT) * stride];
+      s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; c < nctas; c += WR_SPLIT) s += src[c * stride];
+  }
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && live) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; k++) t += red[k][tx];
+    for (int k = 0; k < WR_SPLIT; k++) t += red[k][tx];
     if (i < n_w) gw[i] = t * scale;
     else gb[co] = t;
   }
@@ -715,7 +733,7 @@ int conv_wgrad_tc(const bf16* x, int cin, int cin_real, int cout, const bf16* dy
   else if (cin == 32 && cout == 32) FQL_TRY((launch_conv_t<CT_WGRAD, 32, 32>(mapW, mapX, a, grid, st)));
   else FQL_REQUIRE(false, "conv_wgrad_tc: unsupported channel counts %d -> %d", cin, cout);
   const int n = 9 * cin_real * cout + cout;
-  wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(partial, grid, a.krows, cin, cin_real, cout, scale, gw, gb);
+  wgrad_reduce_kernel<<<(n + 31) / 32, 32 * WR_SPLIT, 0, st>>>(partial, grid, a.krows, cin, cin_real, cout, scale, gw, gb);
   FQL_CHECK_LAUNCH();
   return 0;
 }

@@ -129,6 +129,15 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
+// (loop inside the asm block: see mbar_wait_u in tc_prims.cuh)
+__device__ __forceinline__ void mbar_wait_cluster_u(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1, P2;\n\t.reg .u32 c;\n\tmov.u32 c, 0;\n"
+      "WC_LOOP:\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra WC_DONE;\n\t"
+      "add.u32 c, c, 1;\n\tsetp.lt.u32 P2, c, 0x4000000;\n\t@P2 bra WC_LOOP;\n\ttrap;\n"
+      "WC_DONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
@@ -167,8 +176,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
   uint64_t* half_ready = bars + 21; // [2] count NEPI: 32 columns of this CTA's layer output are in the exchange scratch
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t j = cluster_ctarank();                  // column slice
+  // warp index and cluster rank through a shuffle: warp-uniform to ptxas as well (operands of TMA / tcgen05 instructions derived from
+  // them then live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t j = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);   // column slice
   const int cl = blockIdx.x / NC;                        // cluster id = (seed, tile)
   const int tile = cl % a.tiles, s = cl / a.tiles;
   const int NL = a.NL;
@@ -210,10 +221,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
 
   if (warp == 0) {
     // ================= TMA producer / publisher =================
-    if (lane == 0) {
-      mbar_expect_tx(x_full, nkb_x * A_BLK);
+    // One thread's role, but all 32 lanes run the loop and only the instructions are predicated on the elected lane: with the loop
+    // under `if (lane == 0)` ptxas wraps every TMA / tcgen05 instruction in an ELECT + R2UR.BROADCAST waterfall (tc_prims.cuh).
+    const bool el = elect_one();
+    {
+      if (el) mbar_expect_tx(x_full, nkb_x * A_BLK);
       const int xrow = s * a.x_rows_s + a.x_row0 + tile * TILE_M;
-      for (int kb = 0; kb < nkb_x; kb++) tma_load_2d(sX + kb * A_BLK, &mapX, x_full, kb * KB, xrow);
+      for (int kb = 0; kb < nkb_x; kb++)
+        if (el) tma_load_2d(sX + kb * A_BLK, &mapX, x_full, kb * KB, xrow);
       int n_pub = 0;
       int l = 0;
       for (int it = 0; it < total; it++, l = (l + 1 == NL) ? 0 : l + 1) {
@@ -221,9 +236,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
         const int K = (l == 0) ? a.K0 : a.H;
         const int kblocks = (K + KB - 1) / KB;
         // weights of this layer: sB is free once the previous layer's MMAs have completed
-        if (it > 0) mbar_wait(acc_full, (it - 1) & 1);
-        mbar_expect_tx(full_b, kblocks * B_BLK);
+        if (it > 0) mbar_wait_u(acc_full, (it - 1) & 1);
+        if (el) mbar_expect_tx(full_b, kblocks * B_BLK);
         for (int kb = 0; kb < kblocks; kb++) {
+          if (!el) continue;
           if constexpr (MODE == MODE_DGRAD) {  // K-major: box = [NCOL input rows][64 k]
             if (l == 0) tma_load_2d(sB, &mapWL, full_b, 0, a.wl_row + s * a.wl_rows_s + (int)j * NCOL);
             else tma_load_2d(sB + kb * B_BLK, &mapW, full_b, kb * KB, a.w_row[l] + s * a.w_rows_s + (int)j * NCOL);
@@ -236,20 +252,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
           // arm the per-sub-block barriers, then publish this CTA's slice of the layer input (= the previous layer's output, which
           // its epilogue is producing right now) 32 columns at a time: one TMA multicast lands them in all CTAs' smem and
           // completes their barriers directly
-          for (int sbk = 0; sbk < NSUB; sbk++) mbar_expect_tx(&full_a[sbk], A_SUB);
+          for (int sbk = 0; sbk < NSUB; sbk++)
+            if (el) mbar_expect_tx(&full_a[sbk], A_SUB);
           const int buf = n_pub & 1;
           for (int h = 0; h < HALVES; h++) {
-            mbar_wait(&half_ready[h], n_pub & 1);
+            mbar_wait_u(&half_ready[h], n_pub & 1);
             asm volatile("fence.proxy.async.global;" ::: "memory");  // the epilogue's st.global (acquired above) -> this thread's TMA read
-            if (h == 0) mbar_wait_cluster(free_a, (it - 1) & 1);     // every CTA finished reading sA for the previous layer
-            if (dbg && it == DBG_IT) dbg[3 + h] = gtime();
+            if (h == 0) mbar_wait_cluster_u(free_a, (it - 1) & 1);   // every CTA finished reading sA for the previous layer
+            if (dbg && el && it == DBG_IT) dbg[3 + h] = gtime();
             const int sbk = (int)j * HALVES + h;
-            asm volatile(
-                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-                ::"r"(smem_u32(sA + sbk * A_SUB)), "l"(reinterpret_cast<uint64_t>(MODE != MODE_EULER ? &mapsH.m[l - 1] : &mapsH.m[0])),
-                "r"(smem_u32(&full_a[sbk])), "r"(sbk * SUB),
-                "r"(MODE != MODE_EULER ? s * a.rows_cap + a.r0 + tile * TILE_M : buf * (a.S * a.tiles * TILE_M) + hx_row), "h"(MASK)
-                : "memory");
+            if (el)
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                  ::"r"(smem_u32(sA + sbk * A_SUB)), "l"(reinterpret_cast<uint64_t>(MODE != MODE_EULER ? &mapsH.m[l - 1] : &mapsH.m[0])),
+                  "r"(smem_u32(&full_a[sbk])), "r"(sbk * SUB),
+                  "r"(MODE != MODE_EULER ? s * a.rows_cap + a.r0 + tile * TILE_M : buf * (a.S * a.tiles * TILE_M) + hx_row), "h"(MASK)
+                  : "memory");
           }
           n_pub++;
         }
@@ -257,10 +275,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     }
   } else if (warp <= NMMA) {
     // ================= MMA issuers =================
-    // One tcgen05.mma costs its issuing warp ~80 ns for any N (profiles/micro/mma_bench.cu) but the cost is per warp, so four
-    // warps issue a quarter of the K range each into their own TMEM columns (summed by the epilogue).
-    if (lane == 0) {
+    // Four warps issue a quarter of the K range each into their own TMEM columns (summed by the epilogue): the sub-blocks of a layer's
+    // input land one after the other, and a warp starts on its four as soon as they are there.  All 32 lanes of an issuer warp run
+    // the loop; the tcgen05 instructions are predicated on the elected lane (uniform-register operands, no waterfall -- see above).
+    const bool el = elect_one();
+    {
       const int mw = warp - 1;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = make_idesc_bf16(TILE_M, NCOL, false, MODE != MODE_DGRAD);
       const uint64_t ax_t = make_smem_desc(0, 16, 1024);            // first-layer operand: [128][64] bf16 blocks, SWIZZLE_128B
       const uint64_t a64_t0 = make_smem_desc_sw64(0, 16, 512);      // [128][32] bf16 sub-blocks, SWIZZLE_64B: 8-row groups 512 B apart
@@ -276,40 +297,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
       for (int it = 0; it < total; it++, l = (l + 1 == NL) ? 0 : l + 1) {
         const int K = (l == 0) ? a.K0 : a.H;
         const int kblocks = (K + KB - 1) / KB;
-        const uint32_t tacc = tmem_base + (it & 1) * ACC_SET + mw * NCOL;
+        const uint32_t tacc = tmem_u + (it & 1) * ACC_SET + mw * NCOL;
         if (l == 0) {
-          if (it == 0) mbar_wait(x_full, 0);
-          else { mbar_wait(a_ready, (n_step - 1) & 1); }
+          if (it == 0) mbar_wait_u(x_full, 0);
+          else { mbar_wait_u(a_ready, (n_step - 1) & 1); }
           n_step++;
-          if (dbg && mw == 0 && it == DBG_IT) dbg[8] = gtime();
+          if (dbg && el && mw == 0 && it == DBG_IT) dbg[8] = gtime();
         }
-        mbar_wait(full_b, it & 1);
+        mbar_wait_u(full_b, it & 1);
         tc_fence_after();
-        if (dbg && mw == 0 && it == DBG_IT && l == 0) dbg[9] = gtime();
+        if (dbg && el && mw == 0 && it == DBG_IT && l == 0) dbg[9] = gtime();
         if (l >= 1) {
           // hidden / last layers (K = H): warp w owns four of the 16 sub-blocks, in the order they are published
           for (int i = 0; i < 4; i++) {
             const int sbk = (NC == 8) ? (mw * 2 + (i & 1)) * 2 + (i >> 1) : mw * 4 + i;
-            mbar_wait(&full_a[sbk], n_a & 1);
+            mbar_wait_u(&full_a[sbk], n_a & 1);
             tc_fence_after();
-            if (dbg && mw == 0 && it == DBG_IT && i == 0) dbg[5] = gtime();
-            if (dbg && mw == NMMA - 1 && it == DBG_IT && i == 3) dbg[6] = gtime();
-            umma_bf16_x2(tacc, a64_t0 + (uint64_t)(sa0 + sbk * (A_SUB >> 4)),
-                         b_t0 + (uint64_t)(sb0 + (sbk >> 1) * (B_BLK >> 4) + (sbk & 1) * B_SUBH), 2, B_KSTEP, idesc, i != 0);
+            if (dbg && el && mw == 0 && it == DBG_IT && i == 0) dbg[5] = gtime();
+            if (dbg && el && mw == NMMA - 1 && it == DBG_IT && i == 3) dbg[6] = gtime();
+            if (el)
+              umma_bf16_x2(tacc, a64_t0 + (uint64_t)(sa0 + sbk * (A_SUB >> 4)),
+                           b_t0 + (uint64_t)(sb0 + (sbk >> 1) * (B_BLK >> 4) + (sbk & 1) * B_SUBH), 2, B_KSTEP, idesc, i != 0);
           }
         } else {
           // first layer (K0 <= 128): k-step w of every block -> warp w
           for (int kb = 0; kb < kblocks; kb++)
-            if (mw < (a.K0 - kb * KB + 15) / 16)
+            if (el && mw < (a.K0 - kb * KB + 15) / 16)
               umma_bf16(tacc, ax_t + (uint64_t)(sx0 + kb * (A_BLK >> 4) + mw * 2), b_t0 + (uint64_t)(sb0 + kb * (B_BLK >> 4) + mw * B_KSTEP), idesc,
                         kb != 0);
         }
         if (l >= 1) n_a++;
-        if (dbg && mw == 0 && it == DBG_IT && l == 0) dbg[10] = gtime();
-        umma_commit(acc_full);
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(free_a)),
-                     "h"(MASK)
-                     : "memory");
+        if (dbg && el && mw == 0 && it == DBG_IT && l == 0) dbg[10] = gtime();
+        if (el) {
+          umma_commit(acc_full);
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(free_a)),
+                       "h"(MASK)
+                       : "memory");
+        }
       }
     }
   } else {

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
   uint64_t* acc_full = bars + 2 * NSTAGE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform to ptxas as well
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int zg = blockIdx.z / a.ksplit, kz = blockIdx.z % a.ksplit;
   const int g0 = zg % a.G0, g1 = zg / a.G0;
@@ -132,49 +132,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: one thread's role, all 32 lanes run the loop and the instructions are predicated on the elected lane (uniform-register
+    // operands; under `if (lane == 0)` every TMA / tcgen05 instruction sits in an ELECT + R2UR.BROADCAST waterfall, tc_prims.cuh)
+    const bool el = elect_one();
+    {
       const int ga0 = a.a_bcast0 ? 0 : g0, gb0 = a.b_bcast0 ? 0 : g0;
       for (int kb = 0; kb < nkb; kb++) {
         const int st = kb % NSTAGE;
-        if (kb >= NSTAGE) mbar_wait(&empty[st], ((kb / NSTAGE) - 1) & 1);
+        if (kb >= NSTAGE) mbar_wait_u(&empty[st], ((kb / NSTAGE) - 1) & 1);
         uint8_t* sa = smem + st * STAGE;
         uint8_t* sb = sa + A_STAGE;
-        mbar_expect_tx(&full[st], STAGE);
         const int kc = (kb0 + kb) * BK;
-        if (!a.a_mn) {
-          tma_load_4d(sa, &mapA, &full[st], kc, m0, ga0, g1);
-        } else {
-          tma_load_4d(sa, &mapA, &full[st], m0, kc, ga0, g1);
-          tma_load_4d(sa + A_STAGE / 2, &mapA, &full[st], m0 + 64, kc, ga0, g1);
+        if (el) {
+          mbar_expect_tx(&full[st], STAGE);
+          if (!a.a_mn) {
+            tma_load_4d(sa, &mapA, &full[st], kc, m0, ga0, g1);
+          } else {
+            tma_load_4d(sa, &mapA, &full[st], m0, kc, ga0, g1);
+            tma_load_4d(sa + A_STAGE / 2, &mapA, &full[st], m0 + 64, kc, ga0, g1);
+          }
+          if (!a.b_mn) tma_load_4d(sb, &mapB, &full[st], kc, n0, gb0, g1);
+          else tma_load_4d(sb, &mapB, &full[st], n0, kc, gb0, g1);
         }
-        if (!a.b_mn) tma_load_4d(sb, &mapB, &full[st], kc, n0, gb0, g1);
-        else tma_load_4d(sb, &mapB, &full[st], n0, kc, gb0, g1);
       }
     }
   } else if (warp <= NACC) {
     // ---------------- MMA issuers ----------------
-    // A tcgen05.mma costs its issuing warp ~80 ns whatever N is (measured, profiles/micro/mma_bench.cu: 81 ns at N=16..256),
-    // and the cost is per warp: four warps issue at ~3x the rate of one.  Warp w therefore owns k-step w of every 64-wide K
-    // block and accumulates into its own 64 TMEM columns; the epilogue adds the four partial accumulators.
-    if (lane == 0) {
+    // Warp w owns k-step w of every 64-wide K block and accumulates into its own 64 TMEM columns; the epilogue adds the four partial
+    // accumulators.  (Round 1 measured ~80 ns per tcgen05.mma per issuing warp and split the K steps over four warps for it; most of
+    // that was the waterfall around every instruction of an `if (lane == 0)` loop -- profiles/micro/mma_dual_bench.cu.)
+    const bool el = elect_one();
+    {
       const int mw = warp - 1;
       const uint32_t idesc = make_idesc_bf16(BM, BN, a.a_mn != 0, a.b_mn != 0);
       const uint64_t a_t = (a.a_mn ? make_smem_desc(0, A_STAGE / 2, 1024) : make_smem_desc(0, 16, 1024)) + (uint64_t)(mw * (a.a_mn ? (2048 >> 4) : (32 >> 4)));
       const uint64_t b_t = (a.b_mn ? make_smem_desc(0, B_STAGE, 1024) : make_smem_desc(0, 16, 1024)) + (uint64_t)(mw * (a.b_mn ? (2048 >> 4) : (32 >> 4)));
       const uint32_t s0 = smem_u32(smem) >> 4;
-      const uint32_t tacc = tmem_base + mw * 64;
+      const uint32_t tacc = __shfl_sync(0xffffffffu, tmem_base, 0) + mw * 64;
       int st = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < nkb; kb++) {
-        mbar_wait(&full[st], ph);
+        mbar_wait_u(&full[st], ph);
         tc_fence_after();
-        if (dbg && mw == 0 && kb == 0) dbg[2] = gtime();
-        if (dbg && mw == 0 && kb == nkb - 1) dbg[3] = gtime();
-        umma_bf16(tacc, a_t + (uint64_t)(s0 + st * (STAGE >> 4)), b_t + (uint64_t)(s0 + st * (STAGE >> 4) + (A_STAGE >> 4)), idesc, kb != 0);
-        umma_commit(&empty[st]);
+        if (dbg && el && mw == 0 && kb == 0) dbg[2] = gtime();
+        if (dbg && el && mw == 0 && kb == nkb - 1) dbg[3] = gtime();
+        if (el) {
+          umma_bf16(tacc, a_t + (uint64_t)(s0 + st * (STAGE >> 4)), b_t + (uint64_t)(s0 + st * (STAGE >> 4) + (A_STAGE >> 4)), idesc, kb != 0);
+          umma_commit(&empty[st]);
+        }
         if (++st == NSTAGE) { st = 0; ph ^= 1; }
       }
-      umma_commit(acc_full);
+      if (el) umma_commit(acc_full);
     }
   } else {
     // ---------------- epilogue: thread per row, 64 accumulator columns ----------------

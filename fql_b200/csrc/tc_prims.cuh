@@ -43,6 +43,17 @@ static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity)
   printf("fql_b200: mbarrier timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x, (void*)bar, parity);
   __trap();
 }
+// The same bounded wait with the spin loop INSIDE the asm block, for warps whose 32 lanes run a single-thread role's loop together
+// (TMA producer, MMA issuer): a C++ loop with a per-lane exit makes every value carried around it "possibly divergent" to the
+// compiler, and each tcgen05.mma / tcgen05.commit / TMA behind it is then wrapped in an ELECT + R2UR.BROADCAST waterfall.
+__device__ __forceinline__ void mbar_wait_u(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1, P2;\n\t.reg .u32 c;\n\tmov.u32 c, 0;\n"
+      "W_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra W_DONE;\n\t"
+      "add.u32 c, c, 1;\n\tsetp.lt.u32 P2, c, 0x4000000;\n\t@P2 bra W_LOOP;\n\ttrap;\n"
+      "W_DONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
