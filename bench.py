@@ -228,6 +228,32 @@ def time_config(name, batch, seeds, mode, world, rank, pg, stream, flush, steps=
     return out
 
 
+def euler_kernel_traffic_from_profile():
+    """DRAM bytes (read + write) of one launch of the Euler cluster kernel, read from the newest committed `ncu --set full` summary under
+    profiles/ (the capture is made with the same bench command; bench.py itself never runs under a profiler)."""
+    import glob
+    import re
+    here = os.path.dirname(os.path.abspath(__file__))
+    unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for path in sorted(glob.glob(os.path.join(here, 'profiles', 'r*_ncu_full_cluster_kernels.txt')), reverse=True):
+        try:
+            blocks = open(path).read().split('----')
+        except OSError:
+            continue
+        for b in blocks:
+            if 'euler_cluster_kernel<16, 8, 0>' not in b:
+                continue
+            tot = 0.0
+            for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                m = re.search(re.escape(name) + r' \[(\w+)\] = ([0-9.]+)', b)
+                if not m:
+                    break
+                tot += float(m.group(2)) * unit.get(m.group(1), 1.0)
+            else:
+                return int(tot), 'profiles/' + os.path.basename(path)
+    return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -419,20 +445,21 @@ def main():
             k_flops = int(cfg['flow_steps']) * 2 * ((F + A + 1) * Hh + 3 * Hh * Hh + Hh * A) * args.batch
             k_tf = k_flops / (k_us * 1e-6) / 1e12
             default_wl = args.workload == 'antmaze-large' and args.batch == 256
+            ncu_traffic = euler_kernel_traffic_from_profile()
             step_level = roof
             # the object the contract asks for: the dominant kernel against the roofline that bounds it (tensor: it is a chain of
             # dense contractions), peak = the burst figure because the kernel is timed alone; the whole-step view is kept in `step`
             roof = dict(
                 bound='tensor', achieved=k_tf, peak=peaks['tc_burst'], unit='TFLOP/s', frac=k_tf / peaks['tc_burst'],
-                traffic=(1783040 + 130816) if default_wl else None,
-                traffic_source='profiles/r1b_ncu_full_cluster_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum of one launch '
-                               '(algorithmic: 1.7 MB of bf16 weights read once + 40 KB of inputs/outputs)' if default_wl else None,
+                traffic=ncu_traffic[0] if default_wl else None,
+                traffic_source=(ncu_traffic[1] + ': dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full; '
+                                'algorithmic: 1.7 MB of bf16 weights read once + 40 KB of inputs/outputs)') if default_wl and ncu_traffic[0] else None,
                 kernel='euler_cluster_kernel<16,8,EULER> = compute_flow_actions, the longest dependent chain of the step',
                 us_per_launch=k_us, timed='alone through fql_compute_flow_actions (concat + bf16 pad + ONE cluster launch, ~8 us of the '
                                           'figure are the two small kernels), CUDA events on the launching stream, L2 flushed between launches',
                 algorithmic_flops_per_launch=k_flops, share_of_step=k_us / (ms_per_step * 1e3), peak_source=peaks['src'],
                 why_small='latency-bound by construction: flow_steps x 5 dependent layers on batch/128 = 2 row tiles (32 CTAs); one layer = '
-                          'TMEM read of the 4 partial accumulators + ~1 us multicast-TMA round trip + 8 MMA issues per issuer warp (profiles/)',
+                          'TMEM read of the 2 partial accumulators + ~1 us multicast-TMA round trip + 16 MMA issues per issuer warp (profiles/)',
                 step=step_level)
         except Exception as e:  # a diagnostic, never the reason a bench line is missing
             roof['dominant_kernel_error'] = repr(e)

@@ -39,7 +39,14 @@ constexpr int SUB = 32;               // exchange granularity (columns)
 constexpr int A_SUB = TILE_M * SUB * 2;  // 8 KB: [128][32] bf16, SWIZZLE_64B
 constexpr int NSUB = 16;              // sub-blocks per hidden layer (H / SUB)
 constexpr int MAX_A = 32;
-constexpr int NMMA = 4;                // MMA-issuer warps, each with its own partial accumulator
+constexpr int NMMA = 4;                // MMA warps in the launch (TMEM columns of an accumulator set = NMMA * NCOL)
+#ifndef FQL_EULER_NISS
+#define FQL_EULER_NISS 2
+#endif
+constexpr int NISS = FQL_EULER_NISS;   // warps that actually issue, each with its own partial accumulator (summed by the epilogue: its TMEM
+                                       // reads, 64 B/clk, are the floor of a layer's epilogue).  4 when an `if (lane == 0)` issuer cost ~80 ns
+                                       // per tcgen05.mma; with warp-uniform issue two warps keep up with the sub-blocks as they land.
+static_assert(NISS == 1 || NISS == 2 || NISS == 4, "NISS");
 constexpr int NEPI = 4;                // epilogue warps: one thread per row (TMEM-read bound: more warps were measured slower)
 constexpr int NTHREADS = 32 * (1 + NMMA + NEPI);
 constexpr int EPI0 = 32 * (1 + NMMA);  // first epilogue thread
@@ -197,8 +204,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     mbar_init(&half_ready[0], NEPI);
     mbar_init(&half_ready[1], NEPI);
     mbar_init(full_b, 1);
-    mbar_init(acc_full, NMMA);
-    mbar_init(free_a, NC * NMMA);
+    mbar_init(acc_full, NISS);
+    mbar_init(free_a, NC * NISS);
     mbar_init(a_ready, NEPI);
     mbar_init(x_full, 1);
     fence_barrier_init();
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
     // input land one after the other, and a warp starts on its four as soon as they are there.  All 32 lanes of an issuer warp run
     // the loop; the tcgen05 instructions are predicated on the elected lane (uniform-register operands, no waterfall -- see above).
     const bool el = elect_one();
-    {
+    if (warp <= NISS) {
       const int mw = warp - 1;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = make_idesc_bf16(TILE_M, NCOL, false, MODE != MODE_DGRAD);
@@ -308,23 +315,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
         tc_fence_after();
         if (dbg && el && mw == 0 && it == DBG_IT && l == 0) dbg[9] = gtime();
         if (l >= 1) {
-          // hidden / last layers (K = H): warp w owns four of the 16 sub-blocks, in the order they are published
-          for (int i = 0; i < 4; i++) {
-            const int sbk = (NC == 8) ? (mw * 2 + (i & 1)) * 2 + (i >> 1) : mw * 4 + i;
+          // hidden / last layers (K = H): warp w owns NSUB / NISS of the 16 sub-blocks, in the order they are published (clusters of 8:
+          // every CTA publishes its first 32 columns, then its second)
+          constexpr int PER = NSUB / NISS;
+          for (int i = 0; i < PER; i++) {
+            const int sbk = (NC == 8) ? (mw * (PER / 2) + (i % (PER / 2))) * 2 + (i / (PER / 2)) : mw * PER + i;
             mbar_wait_u(&full_a[sbk], n_a & 1);
             tc_fence_after();
             if (dbg && el && mw == 0 && it == DBG_IT && i == 0) dbg[5] = gtime();
-            if (dbg && el && mw == NMMA - 1 && it == DBG_IT && i == 3) dbg[6] = gtime();
+            if (dbg && el && mw == NISS - 1 && it == DBG_IT && i == PER - 1) dbg[6] = gtime();
             if (el)
               umma_bf16_x2(tacc, a64_t0 + (uint64_t)(sa0 + sbk * (A_SUB >> 4)),
                            b_t0 + (uint64_t)(sb0 + (sbk >> 1) * (B_BLK >> 4) + (sbk & 1) * B_SUBH), 2, B_KSTEP, idesc, i != 0);
           }
         } else {
-          // first layer (K0 <= 128): k-step w of every block -> warp w
+          // first layer (K0 <= 128): k-steps w, w + NISS, ... of every block -> warp w
           for (int kb = 0; kb < kblocks; kb++)
-            if (el && mw < (a.K0 - kb * KB + 15) / 16)
-              umma_bf16(tacc, ax_t + (uint64_t)(sx0 + kb * (A_BLK >> 4) + mw * 2), b_t0 + (uint64_t)(sb0 + kb * (B_BLK >> 4) + mw * B_KSTEP), idesc,
-                        kb != 0);
+            for (int ks = mw; ks < 4; ks += NISS)
+              if (el && ks < (a.K0 - kb * KB + 15) / 16)
+                umma_bf16(tacc, ax_t + (uint64_t)(sx0 + kb * (A_BLK >> 4) + ks * 2), b_t0 + (uint64_t)(sb0 + kb * (B_BLK >> 4) + ks * B_KSTEP), idesc,
+                          !(kb == 0 && ks == mw));
         }
         if (l >= 1) n_a++;
         if (dbg && el && mw == 0 && it == DBG_IT && l == 0) dbg[10] = gtime();
@@ -369,8 +379,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) euler_cluster_kernel(const __grid
       tc_fence_after();
       if (dbg && et == 0 && it == DBG_IT - 1) dbg[0] = gtime();
       if (dbg && et == 0 && it == DBG_IT) dbg[7] = gtime();
-      // partial accumulators of the NMMA issuer warps, loads issued in pairs (a first layer with K0 < 64 has ceil(K0/16) of them)
-      const int live = (l == 0 && a.K0 < KB) ? (a.K0 + 15) / 16 : NMMA;
+      // partial accumulators of the NISS issuer warps, loads issued in pairs (a first layer with K0 < 16 NISS has ceil(K0/16) of them)
+      const int live = (l == 0 && (a.K0 + 15) / 16 < NISS) ? (a.K0 + 15) / 16 : NISS;
       const int buf = n_exch & 1;
       if (!last) n_exch++;
 #pragma unroll 1
