@@ -144,7 +144,7 @@ __device__ __forceinline__ float bf16_at(const uint4 (&q)[4], int i) {
 
 // PAIR: two CTAs of a 2-CTA cluster (consecutive 128-row tiles of one group) run as a cta_group::2 pair: ONE tcgen05.mma issued by the
 // leader covers both tiles (M = 256), each CTA holds half of every weight stage (its 128 of the 256 columns of an N-half) and its own
-// activations / accumulator rows / epilogue.  The single MMA-issuing thread is what bounds this kernel (profiles/r2d_*): the pair does
+// activations / accumulator rows / epilogue.  The serial work of the single MMA-issuing thread bounds this kernel (profiles/r2f_chain2_*): the pair does
 // the same number of tcgen05.mma / tcgen05.commit per 256 rows that one CTA needs per 128.  Barriers the leader's MMA thread waits on
 // (full, a_ready, acc_free, x_full, x_ready) live in the leader and take the peer's arrivals remotely; barriers the epilogue / producer
 // warps wait on (empty, a_free, acc_full) are signalled in both CTAs by multicast tcgen05.commit.
@@ -348,8 +348,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) mlp_chain2_kernel(const __grid_
               C2_STAMP(n == FQL_C2_DBG_N && MODE == C2_EULER, h * 48 + ks * 3 + 1);
               const uint64_t adesc = a_t + (uint64_t)(abase + kb * (KB_BYTES >> 4) + (ks & 1) * 4);
               const uint64_t bdesc = b_t + (uint64_t)(sw0 + stage * (SLOT >> 4));
-              // both K steps of a stage from ONE asm block: the uniform-register descriptors are materialised once (a run-time
-              // descriptor costs the issuing thread more than the ~80 ns of the MMA itself)
+              // both K steps of a stage from ONE asm block (the second descriptor pair is a constant add inside PTX)
               if (K - ks * KS > 16) mma_x2(tacc, adesc, bdesc, 2, b_k16, idesc_h, ks > 0);
               else mma(tacc, adesc, bdesc, idesc_h, ks > 0);
               commit(&empty[stage]);
@@ -792,8 +791,8 @@ int fill_common(Chain2Args& a, const FqlDims* d, const Layout& L, int P, const i
 }
 
 // FQL_B200_CHAIN2_PAIR=1: CTA pairs (cta_group::2) when a group has at least two row tiles.  Parity-tested, but OFF by default: measured
-// slower (B=16384 step 2.71 vs 2.24 ms).  The kernel is bound by its MMA-issuing thread (~83 ns per tcgen05.mma / tcgen05.commit per
-// warp); a pair halves the instructions per row but also halves the issuing threads per SM, so a layer of 256 rows takes 15.4 us on two
+// slower (B=16384 step 2.71 vs 2.24 ms, measured before the issuer loops became warp-uniform).  The kernel is bound by the serial work of
+// its MMA-issuing thread (barrier waits, tcgen05.mma, tcgen05.commit); a pair halves the instructions per row but also halves the issuing threads per SM, so a layer of 256 rows takes 15.4 us on two
 // SMs against 12.4 us for two independent 128-row CTAs (in-kernel stamps), and the peer's remote barrier arrivals lengthen the epilogue.
 bool chain2_pair(int tiles) {
   static const bool on = []() {

@@ -17,7 +17,7 @@
 //              SWIZZLE_128B operand blocks ([128 rows][64 k] bf16) the MMAs read -- the same blocks serve as the MN-major A operand
 //              of the weight gradient;
 //   2 issuers  (warp 0 and the last warp) one thread each issues tcgen05.mma (M=128, N=64, K=16) for every second tile of the CTA into its own accumulator set
-//              (the ~80 ns issue cost of an MMA is per warp); the prepared weights [Kpad][64] arrive once per CTA by TMA and stay
+//              (each issuing warp serialises its own barrier waits and instructions); the prepared weights [Kpad][64] arrive once per CTA by TMA and stay
 //              resident; operand buffers and accumulators are double-buffered so tile i+1 is gathered while tile i multiplies;
 //   4 warps    epilogue: thread per pixel reads its accumulator row from TMEM: x scale + bias, x relu-mask of a saved tensor,
 //              + skip / upstream gradient, relu, bf16 NHWC stores (16-byte vectors).

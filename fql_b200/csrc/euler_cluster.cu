@@ -14,10 +14,10 @@
 //        profiles/micro: DSMEM bulk copies 15 GB/s/SM, unicast gather + remote arrives 7.6 us/layer.)
 //     B: the CTA's [K][H/NC] weight slice (MN-major, straight from the Flax [in,out] bf16 shadow), prefetched by TMA while the
 //        previous layer's epilogue and exchange run (weights do not depend on activations)
-//     D: fp32 in TMEM, one partial accumulator per MMA-issuer warp (a tcgen05.mma costs its issuing warp ~80 ns whatever its
-//        N), two sets so that layer l+1 can start while the epilogue still reads layer l.  TMEM reads run at 64 B/clk/SM, so
-//        the epilogue's floor is (issuers x 128 x H/NC x 4 B) / 64 B/clk: 1.07 us at NC = 8, 0.53 us at NC = 16 -- with the
-//        ~1.1 us issue-to-landed latency of the multicast this is what bounds a layer, hence the cluster of 16.
+//     D: fp32 in TMEM, one partial accumulator per issuing warp (NISS = 2 warps, each taking the sub-blocks of half the cluster as
+//        they land), two sets so that layer l+1 can start while the epilogue still reads layer l.  TMEM reads run at 64 B/clk/SM, so
+//        the epilogue's floor is (issuers x 128 x H/NC x 4 B) / 64 B/clk: 0.53 us at NC = 8, 0.27 us at NC = 16 -- with the
+//        ~1.0 us issue-to-landed latency of the multicast this is what bounds a layer, hence the cluster of 16.
 //        Epilogue: one thread per row: sum of the partials + bias, GELU(tanh), bf16.
 //   the narrow last Dense (N = action_dim <= 32, zero-padded) is computed redundantly by every CTA, so each CTA applies
 //   a += v / flow_steps to ITS copy of the first-layer operand tile (resident in smem for all steps) with no exchange.

@@ -4,7 +4,7 @@
 //   warp 0   TMA producer : streams the bf16 shadow weights of every layer as MN-major SWIZZLE_128B B-tiles
 //                           (kernel leaves are Flax [in,out] row-major, so a [16 k][64 n] box IS the canonical MN-major atom)
 //   warps 1-2 MMA issuers : tcgen05.mma kind::f16, M=128, N<=256 per instruction, one 256-column half of the accumulator each
-//                           (a tcgen05.mma costs its issuing warp ~80 ns); fp32 accumulators in all 512 TMEM columns
+//                           ; fp32 accumulators in all 512 TMEM columns
 //   warps 3-6 epilogue    : one thread per row (tcgen05.ld 32x32b): + bias, GELU(tanh), optional LayerNorm with per-thread row
 //                           statistics (the 128x512 fp32 accumulator is exactly one SM's TMEM, so LN needs no cross-thread
 //                           reduction), bf16 re-pack straight into the next layer's K-major SWIZZLE_128B A operand in smem.
@@ -64,7 +64,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-constexpr int CH_NMMA = 2;   // MMA-issuer warps: one per 256-column half of the accumulator (a tcgen05.mma costs its issuing warp ~80 ns)
+constexpr int CH_NMMA = 2;   // MMA-issuer warps: one per 256-column half of the accumulator
 constexpr int CH_THREADS = 32 * (1 + CH_NMMA + 4);
 constexpr int CH_EPI0 = 32 * (1 + CH_NMMA);
 
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const __gri
   uint64_t* a_ready = bars + 18;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform to ptxas as well
   const int tile = blockIdx.x % a.tiles, g = blockIdx.x / a.tiles;
   const int e = g % a.E, s = (g / a.E) % a.S, p = g / (a.E * a.S);
   const int NL = a.n_layers;
@@ -115,10 +115,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const __gri
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      mbar_expect_tx(x_full, nkb_x * KB_BYTES);
+    // (single-thread roles run warp-uniform, the instruction predicated on the elected lane: tc_prims.cuh)
+    const bool el = elect_one();
+    {
+      if (el) mbar_expect_tx(x_full, nkb_x * KB_BYTES);
       const int xrow = a.x_row0[p] + s * a.x_rows_s + tile * TILE_M;
-      for (int kb = 0; kb < nkb_x; kb++) tma_load_2d(sX + kb * KB_BYTES, &mapX, x_full, kb * 64, xrow);
+      for (int kb = 0; kb < nkb_x; kb++)
+        if (el) tma_load_2d(sX + kb * KB_BYTES, &mapX, x_full, kb * 64, xrow);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < total_iters; it++) {
@@ -127,16 +130,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const __gri
         const int K = (l == 0) ? a.K0 : a.H;
         const int ksteps = (K + STAGE_K - 1) / STAGE_K;
         for (int ks = 0; ks < ksteps; ks++) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait_u(&empty[stage], phase ^ 1);
           uint8_t* dst = sB + stage * stage_bytes;
-          if (!last) {
-            mbar_expect_tx(&full[stage], stage_bytes);
-            const int row = a.w_row[p][l] + s * a.w_rows_s + e * K + ks * STAGE_K;
-            for (int c = 0; c < nchunk; c++) tma_load_2d(dst + c * CHUNK_BYTES, &mapW, &full[stage], c * 64, row);
-          } else {
-            mbar_expect_tx(&full[stage], CHUNK_BYTES);
-            const int row = a.wl_row[p] + s * a.wl_rows_s + e * a.H + ks * STAGE_K;
-            tma_load_2d(dst, &mapWL, &full[stage], 0, row);
+          if (el) {
+            if (!last) {
+              mbar_expect_tx(&full[stage], stage_bytes);
+              const int row = a.w_row[p][l] + s * a.w_rows_s + e * K + ks * STAGE_K;
+              for (int c = 0; c < nchunk; c++) tma_load_2d(dst + c * CHUNK_BYTES, &mapW, &full[stage], c * 64, row);
+            } else {
+              mbar_expect_tx(&full[stage], CHUNK_BYTES);
+              const int row = a.wl_row[p] + s * a.wl_rows_s + e * a.H + ks * STAGE_K;
+              tma_load_2d(dst, &mapWL, &full[stage], 0, row);
+            }
           }
           if (++stage == a.nstage) { stage = 0; phase ^= 1; }
         }
@@ -145,7 +150,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const __gri
   } else if (warp <= CH_NMMA) {
     // ================= MMA issuers =================
     const int mw = warp - 1;
-    if (lane == 0 && mw < n_issuers) {
+    const bool el = elect_one();
+    if (mw < n_issuers) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       const int n_mma = (a.H > 256) ? 256 : a.H;          // N per instruction for hidden layers
@@ -156,26 +163,28 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_tc_kernel(const __gri
       for (int it = 0; it < total_iters; it++) {
         const int l = it % NL;
         const bool last = (l == NL - 1);
-        if (it == 0) mbar_wait(x_full, 0);
-        else mbar_wait(a_ready, (it - 1) & 1);
+        if (it == 0) mbar_wait_u(x_full, 0);
+        else mbar_wait_u(a_ready, (it - 1) & 1);
         tc_fence_after();
         const int K = (l == 0) ? a.K0 : a.H;
         const int ksteps = (K + STAGE_K - 1) / STAGE_K;
         const uint32_t a0 = (l == 0) ? sx0 : sa0;
         for (int ks = 0; ks < ksteps; ks++) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait_u(&full[stage], phase);
           tc_fence_after();
           const uint64_t adesc = a_t + (uint64_t)(a0 + (ks >> 2) * (KB_BYTES >> 4) + (ks & 3) * 2);
           const uint32_t b0 = sb0 + stage * (stage_bytes >> 4);
-          if (!last) {
-            umma_bf16(tmem_base + mw * n_mma, adesc, b_t + (uint64_t)(b0 + mw * (n_mma / 64) * (CHUNK_BYTES >> 4)), idesc_h, ks > 0);
-          } else if (mw == 0) {
-            umma_bf16(tmem_base, adesc, b_t + (uint64_t)b0, idesc_l, ks > 0);
+          if (el) {
+            if (!last) {
+              umma_bf16(tmem_u + mw * n_mma, adesc, b_t + (uint64_t)(b0 + mw * (n_mma / 64) * (CHUNK_BYTES >> 4)), idesc_h, ks > 0);
+            } else if (mw == 0) {
+              umma_bf16(tmem_u, adesc, b_t + (uint64_t)b0, idesc_l, ks > 0);
+            }
+            umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
           if (++stage == a.nstage) { stage = 0; phase ^= 1; }
         }
-        umma_commit(acc_full);
+        if (el) umma_commit(acc_full);
       }
     }
   } else {
