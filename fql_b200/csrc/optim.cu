@@ -123,12 +123,12 @@ __global__ void __launch_bounds__(1024) grad_stats_final_kernel(Layout L, const 
     float mx = -INFINITY, mn = INFINITY, sq = 0.f;
     const int bend = L.leaf_blk[leaf + 1];
     const float4* p4 = reinterpret_cast<const float4*>(part);
-    for (int b0 = L.leaf_blk[leaf] + lane; b0 < bend; b0 += 128) {  // four independent 16-byte loads in flight per lane
-      float4 v[4];
+    for (int b0 = L.leaf_blk[leaf] + lane; b0 < bend; b0 += 256) {  // eight independent 16-byte loads in flight per lane: a 512 x 512 leaf
+      float4 v[8];                                                   // (256 blocks) is ONE round trip, the critic's [2,512,512] two
 #pragma unroll
-      for (int u = 0; u < 4; u++) v[u] = (b0 + 32 * u < bend) ? p4[b0 + 32 * u] : make_float4(-INFINITY, INFINITY, 0.f, 0.f);
+      for (int u = 0; u < 8; u++) v[u] = (b0 + 32 * u < bend) ? p4[b0 + 32 * u] : make_float4(-INFINITY, INFINITY, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < 8; u++) {
         mx = fmaxf(mx, v[u].x);
         mn = fminf(mn, v[u].y);
         sq += v[u].z;
