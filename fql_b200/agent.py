@@ -191,6 +191,8 @@ class FQLAgent:
         self._ring, self._ring_i = [], 0
         self._host_step = 0          # updates enqueued so far == optax count: the Philox step of the next noise draw
         self.last_h2d_bytes = 0
+        self._copy_stream = None     # host batches of update() go up on this stream, under the previous step (two input sets)
+        self._overlap_h2d = os.environ.get('FQL_B200_OVERLAP_H2D', '1') != '0'
         self.rank = 0
         if process_group is not None:
             import torch.distributed as dist
@@ -389,8 +391,29 @@ class FQLAgent:
         info = torch.zeros(S, _lib.NUM_INFO, dtype=torch.float32, device=self.device)
         raw = torch.zeros(S, _lib.NUM_RAW, dtype=torch.float32, device=self.device)
         self._bufs[B] = dict(d=d, dev=dev, dev_block=dev_block, pins=pins, pin_i=0, offs=offs, ws=ws, ws_bytes=ws_bytes, fb=fb, st=st,
-                             info=info, raw=raw)
+                             info=info, raw=raw, shapes=shapes, dt=dt, read_done=torch.cuda.Event(), ready=torch.cuda.Event(), flip=0)
         return self._bufs[B]
+
+    def _input_sets(self, base):
+        """The two input sets of the overlapped host path (`update(host batch)`): the base buffers and a second device block + pinned
+        ring + FqlBatch with everything else (dims, state, workspace, metrics) shared.  While the step graph of one set runs, the next
+        batch goes up into the other on the copy stream (the library caches one CUDA graph per argument set, so there are two)."""
+        if 'sets' not in base:
+            offs, shapes, dt = base['offs'], base['shapes'], base['dt']
+            size = base['dev_block'].numel()
+            view = lambda blk, k: blk[offs[k][0]:offs[k][0] + offs[k][1]].view(dt(k)).view(shapes[k])
+            dev_block = torch.empty(size, dtype=torch.uint8, device=self.device)
+            dev = {k: view(dev_block, k) for k in shapes}
+            pins = []
+            for _ in range(_PIN_RING):
+                blk = torch.empty(size, dtype=torch.uint8).pin_memory()
+                pins.append(dict(block=blk, views={k: view(blk, k) for k in shapes}, event=torch.cuda.Event(), pending=False))
+            alt = dict(base)
+            alt.update(dev=dev, dev_block=dev_block, pins=pins, pin_i=0, fb=_lib.FqlBatch(*[dev[k].data_ptr() for k in _BATCH_KEYS + NOISE_KEYS]),
+                       read_done=torch.cuda.Event(), ready=torch.cuda.Event())
+            alt.pop('sets', None)
+            base['sets'] = [base, alt]
+        return base['sets']
 
     def _stage(self, bufs, items):
         """items: [(key, source)], keys in buffer order.  Host sources are packed into the next pinned staging block and sent with
@@ -452,8 +475,40 @@ class FQLAgent:
     def update(self, batch, noise=None):
         """One training step.  `batch`: dict of host numpy arrays (main.py:201) or torch tensors, [B,...] (or [S,B,...]
         when num_seeds>1).  Returns (self, info)."""
+        if self._overlap_h2d and (self.world == 1 or self._dp_peer) and self._all_host(batch, noise):
+            return self, self._update_overlapped(batch, noise)
         bufs = self.stage(batch, noise)
         return self, self.step(bufs, fill_noise=noise is None)
+
+    @staticmethod
+    def _all_host(batch, noise):
+        vals = [batch[k] for k in _BATCH_KEYS] + ([noise[k] for k in NOISE_KEYS] if noise is not None else [])
+        return not any(isinstance(v, torch.Tensor) and v.is_cuda for v in vals)
+
+    def _update_overlapped(self, batch, noise):
+        """update(host batch) with the host-to-device copy (and the device noise draw) of THIS step on the copy stream, into the input set
+        the previous step is not reading: they run under the previous step's graph instead of in front of this one (main.py:201-204 hands
+        a fresh host batch to every update).  FQL_B200_OVERLAP_H2D=0 restores the single-stream path."""
+        B = int(np.shape(batch['actions'])[-2])
+        base = self._step_bufs(B)
+        sets = self._input_sets(base)
+        cur = sets[base['flip']]
+        base['flip'] ^= 1
+        with torch.cuda.device(self.device):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            cs, main = self._copy_stream, torch.cuda.current_stream(self.device)
+            cs.wait_event(cur['read_done'])          # the last consumer of this set (two steps ago) has finished reading it
+            items = [(k, batch[k]) for k in _BATCH_KEYS]
+            if noise is not None:
+                items += [(k, noise[k]) for k in NOISE_KEYS]
+            with torch.cuda.stream(cs):
+                self.last_h2d_bytes = self._stage(cur, items)
+                if noise is None:
+                    self._fill_noise(cur, self._host_step)
+                cur['ready'].record(cs)
+            main.wait_event(cur['ready'])
+            return self.step(cur, fill_noise=False)
 
     def stage(self, batch, noise=None):
         """Copy one batch (and optionally explicit noise) into the static device buffers of its batch size."""
@@ -479,6 +534,7 @@ class FQLAgent:
                                                      _ptr(bufs['ws']), bufs['ws_bytes'], self._stream()), 'fql_update_step')
             else:
                 self._dp_step(bufs)
+            bufs['read_done'].record(torch.cuda.current_stream(self.device))
             return self._info_out(bufs['info'])
 
     def _dp_step(self, bufs):
@@ -590,6 +646,7 @@ class FQLAgent:
             _lib.check(self._lib.fql_total_loss(self._ctx, C.byref(bufs['d']), C.byref(self._hp), C.byref(bufs['fb']),
                                                 C.byref(bufs['st']), _ptr(bufs['info']), _ptr(bufs['ws']), bufs['ws_bytes'],
                                                 self._stream()), 'fql_total_loss')
+            bufs['read_done'].record(torch.cuda.current_stream(self.device))
             info = self._info_out(bufs['info'])
         vals = {k: info[k] for k in INFO_KEYS[:10]}
         return vals['critic/critic_loss'] + vals['actor/actor_loss'], vals
