@@ -376,3 +376,20 @@ def test_bf16_storage_rounding_hook_of_the_encoder_oracle():
     assert np.vdot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b)) >= 0.999
     a, b = g0['stack_blocks_0']['Conv_0']['kernel'].ravel(), gq['stack_blocks_0']['Conv_0']['kernel'].ravel()
     assert np.vdot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b)) >= 0.9
+
+
+def test_pixel_batch_conditioning_helper():
+    """The max-pool gradient goes to the argmax (encoders.py:41): a window whose two largest entries differ by less than the rounding
+    noise of the arithmetic under test is decided by rounding.  `min_pool_gap` measures the closest call of a batch; seed 4 at 8 frames
+    of 16x16x6 is the near-tie (1.3e-8) that the 2-GPU fp32 pixel test ran into, and `well_posed_pixel_batch` steps past it."""
+    from oracle import fql_pixel_oracle as PO
+    hw, ch, A, hidden = 16, 6, 3, 32
+    cfg = dict(O.DEFAULT_CONFIG)
+    cfg.update(alpha=10.0, actor_hidden_dims=(hidden,) * 4, value_hidden_dims=(hidden,) * 4, encoder='impala_small')
+    params = PO.init_params(3, ch, A, cfg, dtype=np.float64, hw=hw, jitter=0.05, target_equals_critic=False)
+    tie = PO.make_pixel_batch(4, 8, A, hw=hw, ch=ch, dtype=np.float64)
+    assert PO.min_pool_gap(params, tie) < 1e-7
+    ok = PO.make_pixel_batch(4, 6, A, hw=hw, ch=ch, dtype=np.float64)
+    assert PO.min_pool_gap(params, ok) > 2e-6
+    batch, seed = PO.well_posed_pixel_batch(params, 8, A, hw, ch, first_seed=4)
+    assert seed > 4 and PO.min_pool_gap(params, batch) > 2e-6
