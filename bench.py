@@ -469,7 +469,9 @@ def main():
                value_l2_warm=(samples_per_step / (warm_ms / K / 1e3)) if n == 1 else None,
                ms_per_step_l2_warm=(warm_ms / K) if n == 1 else None,
                e2e=dict(value=samples_per_step * K / e2e_s, unit='samples/s', steps_per_sec=K / e2e_s, h2d_bytes_per_step=h2d,
-                        d2h_bytes_per_step=13 * 4 * args.seeds, api='FQLAgent.update(host numpy batch)'),
+                        d2h_bytes_per_step=13 * 4 * args.seeds, api='FQLAgent.update(host numpy batch)',
+                        note='wall clock over K public-API calls, a fresh host batch each; its H2D copy runs on a copy stream under the previous step '
+                             '(two input sets) and the metrics come back every step; no L2 flush in this loop: compare with value_l2_warm'),
                gpu_launches=launches, gpu_launches_per_step=launches / K, roofline=roof, clocks=clk, last_critic_loss=last_loss,
                scaling_configs=scaling_configs, dp_transport=getattr(agent, 'dp_transport', None))
     if n == 1 and not wl.get('image'):
